@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- GAT 2-layer forward on a synthetic Reddit-shape graph (BASELINE.json
+configs[1]) through the B200-native sparse path, plus per-kernel roofline numbers.
+
+  python bench.py --gpus N --steps K --warmup W              # our arm
+  python bench.py --impl reference --gpus N --steps K ...    # reference CPU arm
+
+One "step" = one 2-layer GAT inference forward over the whole graph (dense transforms
+via libtorch/cuBLAS as in the generated program + 2 launches of the fused GAT kernel).
+Metric: ms per step (lower is better).  See DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gala-gnn-acceleration-language_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "GAT 2-layer forward ms (Reddit-shape, 233K nodes / 114.6M edges / 602 feats / hidden 32)"
+SHAPE = "reddit"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_graph(device, n, e, seed=0):
+    from gala_b200 import synth
+
+    return synth.powerlaw_csr_torch(n, e, seed=seed, device=device)
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_gat_forward(orc, use_ref, n, offset, ids, X, m, rows=None):
+    """The same 2-layer GAT forward on the host cores: dense parts torch-CPU, weighted
+    aggregation through the reference's gSpMM (oracle/_ref, src/ops/aggregators.h:55-127)
+    when available, edge kernels through the C restatement (they exist in the reference
+    only as CUDA text).  `rows` bounds the sparse work to the first `rows` rows.
+    Returns (logits, dense seconds, sparse seconds, edges processed)."""
+    import torch.nn.functional as F
+
+    rows = n if rows is None else rows
+    off = np.ascontiguousarray(offset[:rows + 1])
+    nv = int(off[-1])
+    idv = np.ascontiguousarray(ids[:nv])
+    g = orc.Tiled.from_csr(rows, n, off, idv)
+    t = {"dense": 0.0, "sparse": 0.0}
+
+    def dense(fn):
+        t0 = time.perf_counter()
+        r = fn()
+        t["dense"] += time.perf_counter() - t0
+        return r
+
+    def gat_layer(att_src, feat, wl, wr):
+        aL = dense(lambda: F.linear(att_src, *wl).reshape(-1).numpy())
+        aR = dense(lambda: F.linear(att_src, *wr).reshape(-1).numpy())
+        t0 = time.perf_counter()
+        att = orc.sddvv(g, aL[:rows], aR, "add")
+        att = orc.leaky_relu(att, 0.2)
+        alpha, _ = orc.edge_softmax_fwd(g, att)
+        fn_ = np.ascontiguousarray(feat.numpy())
+        if use_ref:
+            y = orc.ref_gspmm_wsum(rows, n, off, idv, alpha, fn_)
+        else:
+            y = orc.spmm(g, fn_, vals=alpha)
+        t["sparse"] += time.perf_counter() - t0
+        return torch.from_numpy(y)
+
+    res = dense(lambda: F.linear(X, *m.fc0))
+    h = torch.relu(gat_layer(res, res, m.efc0, m.efc1))
+    if rows < n:   # layer 2 gathers rows of every column: pad the sample with layer-1 input rows
+        h = torch.cat([h, res[rows:]], 0)
+    tt = dense(lambda: F.linear(h, *m.fc1))
+    agg = gat_layer(tt, h, m.efc2, m.efc3)
+    out = dense(lambda: F.linear(agg, *m.fc1))
+    return out, t["dense"], t["sparse"], nv
+
+
+class _CpuModel:
+    def __init__(self, m):
+        for k in ("fc0", "efc0", "efc1", "fc1", "efc2", "efc3"):
+            setattr(self, k, tuple(t.cpu() for t in getattr(m, k)))
+
+
+def cpu_arm(n, e, feats, offset, ids, X_cpu, model, reps, warm, frac=None):
+    """Times the CPU path; returns (ms per full-workload step, info dict)."""
+    from oracle import orc
+
+    orc.lib()
+    use_ref = orc.have_ref()
+    if use_ref:
+        try:
+            orc.ref()
+        except OSError:
+            use_ref = False
+    cm = _CpuModel(model)
+    cores = orc.lib().orc_num_threads()
+    torch.set_num_threads(cores)
+    nvals = int(offset[-1])
+    # bounded sample: calibrate on 1/32 of the rows, then size the sample for ~10-20 s total
+    r0 = max(n // 32, 1)
+    t0 = time.perf_counter()
+    _, td, ts, nv0 = cpu_gat_forward(orc, use_ref, n, offset, ids, X_cpu, cm, rows=r0)
+    est_full = td + ts * (nvals / max(nv0, 1))
+    budget = 20.0
+    if frac is None:
+        frac = min(1.0, budget / max(est_full * (reps + warm), 1e-3))
+    rows = n if frac >= 0.999 else max(int(n * frac), 1)
+    times = []
+    for i in range(warm + reps):
+        _, td, ts, nv = cpu_gat_forward(orc, use_ref, n, offset, ids, X_cpu, cm, rows=rows)
+        if i >= warm:
+            times.append((td + ts * (nvals / max(nv, 1))) * 1e3)
+    info = {"cores": int(cores), "kind": "reference" if use_ref else "port",
+            "sample": (f"first {rows} of {n} rows ({nv} of {nvals} edges) of the same graph, sparse time "
+                       f"scaled by edge ratio, dense transforms in full; {reps} timed + {warm} warm-up passes; "
+                       + ("weighted aggregation = reference gSpMM<wsumAgg> (oracle/_ref), "
+                          if use_ref else "weighted aggregation = C port, ")
+                       + "SDDVV/LeakyReLU/edge-softmax = C port (CUDA-only in the reference)")}
+    return float(np.mean(times)), info
+
+
+# ------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=None, help="override graph size (debug)")
+    ap.add_argument("--edges", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels", action="store_true", help="also report the kernel sweep (SpMM/SDDMM GB/s)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    from gala_b200 import synth
+
+    n, e, feats, hidden, classes = synth.SHAPES[SHAPE]
+    if args.nodes:
+        n, e = args.nodes, args.edges or args.nodes * 50
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"synthetic {SHAPE}-shape power-law graph: {n} nodes, {e} directed edges incl. self loops, "
+                          f"{feats} feats, hidden {hidden}, {classes} classes; 2-layer GAT inference forward; "
+                          "schedule col_tile(370000) -> 1 column segment (tests/GALA-DSL/gat/Reddit/h100.txt)",
+              "l2": "inputs exceed L2: 458 MB of column indices are streamed per layer (no explicit flush)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+        from gala_b200.gat_model import GAT2
+
+        offset, ids = build_graph(dev, n, e)
+        model = GAT2(feats, hidden, classes, dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1)
+        X = (torch.rand(n, feats, generator=gen, device=dev) - 0.5).cpu()
+        ms, info = cpu_arm(n, e, feats, offset.cpu().numpy(), ids.cpu().numpy(), X, model,
+                           max(args.steps, 1), args.warmup)
+        info["value"] = ms
+        info["unit"] = "ms"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": config, "cpu_baseline": info,
+                          "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; gala_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    from gala_b200 import ops
+    from gala_b200.gat_model import GAT2
+
+    torch.backends.cuda.matmul.allow_tf32 = False   # libtorch default: the reference's Linear is fp32
+    offset, ids = build_graph(dev, n, e)
+    nvals = int(ids.numel())
+    model = GAT2(feats, hidden, classes, dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1)
+    X = torch.rand(n, feats, generator=gen, device=dev) - 0.5
+
+    if world > 1:
+        from gala_b200 import dist_gat
+
+        runner = dist_gat.PartitionedGAT(model, offset, ids, n, rank, world, dev)
+        X_in = X[runner.row_lo:runner.row_hi].contiguous()
+        step_fn = lambda hook=None: runner.forward(X_in, hook)   # noqa: E731
+        launches_per_step = runner.launches_per_step
+        config["parallelism"] = f"1D row partition over {world} GPUs (nnz-balanced), NCCL all-gather of hidden features"
+    else:
+        g = ops.TiledGraph(offset, ids, n).build_plan()
+        X_in = X
+        step_fn = lambda hook=None: model.forward(g, X_in, hook)   # noqa: E731
+        launches_per_step = 2
+        config["parallelism"] = "single GPU"
+        config["hub_rows"] = int(g.plan.n_hub)
+        config["hub_threshold"] = int(g.plan.hub_threshold)
+
+    ktimes = {}
+
+    def hook(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        ktimes.setdefault(name, []).append((a, b))
+        return out
+
+    for _ in range(args.warmup):
+        step_fn()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_beg.record()
+    for _ in range(args.steps):
+        out = step_fn(hook)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = t_beg.elapsed_time(t_end)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    kern_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in ktimes.items()}
+
+    # ---- end-to-end through the public call with HOST buffers (pinned), copies inside the timed region
+    X_host = X_in.cpu().pin_memory()
+    out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+    X_stage = torch.empty_like(X_in)
+
+    def e2e_step():
+        X_stage.copy_(X_host, non_blocking=True)
+        o = (runner.forward(X_stage) if world > 1 else model.forward(g, X_stage))
+        out_host.copy_(o, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(min(args.steps, 10), 1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    b.record()
+    torch.cuda.synchronize()
+    e2e_ms = a.elapsed_time(b) / e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused GAT layer, inference: alpha not stored)
+    # algorithmic bytes: 4(N+1) rowptr + 4E cols + 8N (aL, aR) + 8NK (X read once, Y written once)
+    peak, peak_src = peaks()
+    rows_local = (runner.row_hi - runner.row_lo) if world > 1 else n
+    e_local = runner.local_nvals if world > 1 else nvals
+    alg_bytes = 4 * (rows_local + 1) + 4 * e_local + 4 * (rows_local + n) + 4 * hidden * (n + rows_local)
+    kms = float(np.mean([kern_ms[k] for k in ("gat_layer1", "gat_layer2") if k in kern_ms]))
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    gather_bytes = 4 * (rows_local + 1) + 4 * e_local + 4 * e_local + 4 * hidden * e_local + 4 * hidden * rows_local
+    roofline = {"kernel": "gala::spmm_kernel<4,8,1,MODE_GAT> (fused SDDVV+LeakyReLU+edge-softmax+SpMM, K=32)",
+                "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kms, 4),
+                "no_reuse_gather_gbs": round(gather_bytes / (kms * 1e-3) / 1e9, 1),
+                "note": "X (N*K*4 = 29.8 MB) is L2-resident; the 4*E*K gather bytes are served by L2/L1, not HBM "
+                        "(SURVEY.md section 7), so frac against the compulsory-byte model is L2/LSU-limited"}
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tfile):
+        try:
+            roofline["traffic"] = json.load(open(tfile)).get("gat_fused_k32_bytes_per_launch")
+        except (ValueError, OSError):
+            pass
+
+    line = {"metric": METRIC, "value": round(ms_per_step, 4), "unit": "ms", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+            "e2e": {"value": round(e2e_ms, 4), "unit": "ms",
+                    "h2d_bytes_per_step": int(X_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4)},
+            "roofline": roofline, "kernel_ms": {k: round(v, 4) for k, v in kern_ms.items()}}
+
+    if args.kernels and world == 1:
+        line["kernels"] = kernel_sweep(g, n, nvals, hidden, peak, dev)
+
+    if world == 1 and not args.no_cpu_baseline:
+        ms, info = cpu_arm(n, e, feats, offset.cpu().numpy(), ids.cpu().numpy(), X.cpu(), model, 1, 0)
+        info["value"] = round(ms, 2)
+        info["unit"] = "ms"
+        line["cpu_baseline"] = info
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_op(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def kernel_sweep(g, n, nvals, K, peak, dev):
+    """SpMM / SDDMM / edge kernels alone on the same graph: ms, compulsory-byte GB/s, fraction."""
+    from gala_b200 import ops
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3)
+    X = torch.rand(n, K, generator=gen, device=dev) - 0.5
+    Z = torch.rand(n, K, generator=gen, device=dev) - 0.5
+    a = torch.rand(n, generator=gen, device=dev)
+    w = torch.rand(nvals, generator=gen, device=dev)
+    Y = torch.empty(n, K, device=dev)
+    ev = torch.empty(nvals, device=dev)
+    res = {}
+
+    def rec(name, ms, nbytes):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        res[name] = {"ms": round(ms, 4), "alg_GB": round(nbytes / 1e9, 4), "GBps": round(gbs, 1),
+                     "frac_of_hbm_peak": round(gbs / peak, 4)}
+
+    rp = 4 * (n + 1)
+    rec("spmm_k32_unweighted", time_op(lambda: ops.spmm(g, X, out=Y)), rp + 4 * nvals + 8 * n * K)
+    rec("spmm_k32_weighted", time_op(lambda: ops.spmm(g, X, vals=w, out=Y)), rp + 8 * nvals + 8 * n * K)
+    rec("sddmm_k32", time_op(lambda: ops.sddmm(g, Z, X, out=ev)), rp + 4 * nvals + 8 * n * K + 4 * nvals)
+    rec("sddvv_add", time_op(lambda: ops.sddvv(g, a, a, "add", out=ev)), rp + 4 * nvals + 8 * n + 4 * nvals)
+    rec("edge_softmax_fwd", time_op(lambda: ops.edge_softmax_fwd(g, w, out=ev)), rp + 8 * nvals)
+    rec("edge_rowsum", time_op(lambda: ops.edge_rowsum(g, w)), rp + 4 * nvals + 4 * n)
+    return res
+
+
+if __name__ == "__main__":
+    main()

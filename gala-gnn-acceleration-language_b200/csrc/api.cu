@@ -1,0 +1,368 @@
+// api.cu -- the C-ABI (include/gala_b200.h): argument checks, shape dispatch, launches.
+#include <cstdio>
+#include <cstring>
+
+#include "edge_ops.cuh"
+#include "spmm.cuh"
+
+using namespace gala;
+
+namespace {
+
+inline cudaStream_t S(gala_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+int check_graph(const gala_graph_t* g) {
+    if (!g) return GALA_ERR_NULL_POINTER;
+    if (g->nrows < 0 || g->ncols < 0 || g->nvals < 0 || g->segments < 1) return GALA_ERR_BAD_SHAPE;
+    if (g->nvals > 0x7fffffffLL) return GALA_ERR_UNSUPPORTED;  // int32 edge ids (common.h:1682)
+    if (g->segments > kMaxSeg) return GALA_ERR_UNSUPPORTED;
+    if (g->nrows > 0 && !g->offsets) return GALA_ERR_NULL_POINTER;
+    if (g->nvals > 0 && !g->cols) return GALA_ERR_NULL_POINTER;
+    if (g->segments > 1 && !g->bounds) return GALA_ERR_NULL_POINTER;
+    return GALA_OK;
+}
+
+GraphDev make_dev(const gala_graph_t* g) {
+    GraphDev d;
+    d.offsets = g->offsets;
+    d.cols = g->cols;
+    d.nrows = g->nrows;
+    d.S = g->segments;
+    for (int s = 0; s < kMaxSeg; ++s) d.seg_base[s] = 0;
+    if (g->bounds)
+        for (int s = 0; s < g->segments; ++s) d.seg_base[s] = g->bounds[2 * s];
+    return d;
+}
+
+struct HubView {
+    const int* rows;
+    int n, thr;
+};
+HubView hub_of(const gala_plan_t* plan) {
+    if (plan && plan->n_hub > 0 && plan->hub_rows) return {plan->hub_rows, plan->n_hub, plan->hub_threshold};
+    return {nullptr, 0, 0x7fffffff};
+}
+
+inline int last_error() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GALA_OK : (int)e;
+}
+
+// Pick the vector width / lanes-per-row / accumulators-per-lane for a feature width.
+struct Shape {
+    int vec, lpr, acc;
+};
+Shape pick_shape(int K, bool a16, bool a8) {
+    Shape s;
+    s.vec = (K % 4 == 0 && a16) ? 4 : (K % 2 == 0 && a8) ? 2 : 1;
+    int units = K / s.vec;
+    s.lpr = 1;
+    while (s.lpr < units && s.lpr < 32) s.lpr <<= 1;
+    s.acc = units <= 32 ? 1 : units <= 64 ? 2 : 4;
+    return s;
+}
+
+#define GALA_SHAPE_SWITCH(SH, CALL)                                        \
+    do {                                                                   \
+        const int key_ = (SH).vec * 10000 + (SH).lpr * 100 + (SH).acc;     \
+        switch (key_) {                                                    \
+            case 10101: CALL(1, 1, 1); break;                              \
+            case 10201: CALL(1, 2, 1); break;                              \
+            case 10401: CALL(1, 4, 1); break;                              \
+            case 10801: CALL(1, 8, 1); break;                              \
+            case 11601: CALL(1, 16, 1); break;                             \
+            case 13201: CALL(1, 32, 1); break;                             \
+            case 13202: CALL(1, 32, 2); break;                             \
+            case 13204: CALL(1, 32, 4); break;                             \
+            case 20101: CALL(2, 1, 1); break;                              \
+            case 20201: CALL(2, 2, 1); break;                              \
+            case 20401: CALL(2, 4, 1); break;                              \
+            case 20801: CALL(2, 8, 1); break;                              \
+            case 21601: CALL(2, 16, 1); break;                             \
+            case 23201: CALL(2, 32, 1); break;                             \
+            case 23202: CALL(2, 32, 2); break;                             \
+            case 23204: CALL(2, 32, 4); break;                             \
+            case 40101: CALL(4, 1, 1); break;                              \
+            case 40201: CALL(4, 2, 1); break;                              \
+            case 40401: CALL(4, 4, 1); break;                              \
+            case 40801: CALL(4, 8, 1); break;                              \
+            case 41601: CALL(4, 16, 1); break;                             \
+            case 43201: CALL(4, 32, 1); break;                             \
+            case 43202: CALL(4, 32, 2); break;                             \
+            case 43204: CALL(4, 32, 4); break;                             \
+            default: return GALA_ERR_UNSUPPORTED;                          \
+        }                                                                  \
+    } while (0)
+
+template <int MODE>
+int launch_spmm(const SpmmParams& p, cudaStream_t st) {
+    if (p.g.nrows == 0 || p.K == 0) return GALA_OK;
+    const bool a16 = aligned(p.X, 16) && aligned(p.Y, 16);
+    const bool a8 = aligned(p.X, 8) && aligned(p.Y, 8);
+    Shape sh = pick_shape(p.K, a16, a8);
+    const int tw = sh.vec * sh.lpr * sh.acc;
+    dim3 grid(p.n_hub + (p.g.nrows + kWarpsPerCta - 1) / kWarpsPerCta, (p.K + tw - 1) / tw);
+#define CALL(V, L, A) spmm_kernel<V, L, A, MODE><<<grid, kCtaThreads, 0, st>>>(p)
+    GALA_SHAPE_SWITCH(sh, CALL);
+#undef CALL
+    return last_error();
+}
+
+__global__ void plan_scan_kernel(GraphDev g, int thr, int* count, int* hub_rows) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= g.nrows) return;
+    if (row_degree(g, row) > thr) hub_rows[atomicAdd(count, 1)] = row;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gala_b200_abi_version(void) { return GALA_B200_ABI_VERSION; }
+
+const char* gala_b200_error_string(int code) {
+    switch (code) {
+        case GALA_OK: return "success";
+        case GALA_ERR_NULL_POINTER: return "gala_b200: required pointer is NULL";
+        case GALA_ERR_BAD_SHAPE: return "gala_b200: negative or inconsistent size";
+        case GALA_ERR_UNSUPPORTED: return "gala_b200: unsupported configuration (segments > 64, nvals >= 2^31, ...)";
+        case GALA_ERR_WORKSPACE: return "gala_b200: workspace too small";
+        case GALA_ERR_MISALIGNED: return "gala_b200: pointer is not 4-byte aligned";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "gala_b200: unknown error";
+    }
+}
+
+size_t gala_plan_workspace_bytes(const gala_graph_t* g) {
+    if (!g || g->nrows < 0) return 0;
+    return ((size_t)g->nrows + 4) * sizeof(int32_t);
+}
+
+int gala_plan_build(const gala_graph_t* g, int32_t hub_threshold, void* workspace, size_t workspace_bytes,
+                    gala_plan_t* plan, gala_stream_t stream) {
+    if (int rc = check_graph(g)) return rc;
+    if (!plan || !workspace) return GALA_ERR_NULL_POINTER;
+    if (workspace_bytes < gala_plan_workspace_bytes(g)) return GALA_ERR_WORKSPACE;
+    if (hub_threshold < 1) return GALA_ERR_BAD_SHAPE;
+    int* ws = static_cast<int*>(workspace);
+    plan->hub_rows = ws + 4;
+    plan->n_hub = 0;
+    plan->hub_threshold = hub_threshold;
+    if (g->nrows == 0) return GALA_OK;
+    cudaStream_t st = S(stream);
+    cudaError_t e = cudaMemsetAsync(ws, 0, 4 * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    GraphDev d = make_dev(g);
+    plan_scan_kernel<<<(g->nrows + 255) / 256, 256, 0, st>>>(d, hub_threshold, ws, ws + 4);
+    if (int rc = last_error()) return rc;
+    int n = 0;
+    e = cudaMemcpyAsync(&n, ws, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return (int)e;
+    plan->n_hub = n;
+    return GALA_OK;
+}
+
+int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int32_t K, float* Y,
+                  const gala_epilogue_t* ep, const gala_plan_t* plan, gala_stream_t stream) {
+    if (int rc = check_graph(g)) return rc;
+    if (K < 0) return GALA_ERR_BAD_SHAPE;
+    if ((g->nrows > 0 && K > 0) && (!X || !Y)) return GALA_ERR_NULL_POINTER;
+    if (!aligned(X, 4) || !aligned(Y, 4)) return GALA_ERR_MISALIGNED;
+    SpmmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.g = make_dev(g);
+    p.vals = vals;
+    p.X = X;
+    p.Y = Y;
+    p.K = K;
+    if (ep) {
+        p.row_scale = ep->row_scale;
+        p.col_scale = ep->col_scale;
+        p.accumulate = ep->accumulate;
+        p.relu = ep->relu;
+    }
+    HubView h = hub_of(plan);
+    p.hub_rows = h.rows;
+    p.n_hub = h.n;
+    p.hub_threshold = h.thr;
+    return launch_spmm<MODE_PLAIN>(p, S(stream));
+}
+
+int gala_gat_forward_f32(const gala_graph_t* g, const float* aL, const float* aR, const float* X, int32_t K,
+                         float slope, float* Y, float* alpha_out, int32_t relu, const gala_plan_t* plan,
+                         gala_stream_t stream) {
+    if (int rc = check_graph(g)) return rc;
+    if (K < 0) return GALA_ERR_BAD_SHAPE;
+    if (g->nrows > 0 && (!aL || !aR || (K > 0 && (!X || !Y)))) return GALA_ERR_NULL_POINTER;
+    if (!aligned(X, 4) || !aligned(Y, 4)) return GALA_ERR_MISALIGNED;
+    if (K == 0) return GALA_ERR_UNSUPPORTED;
+    SpmmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.g = make_dev(g);
+    p.X = X;
+    p.Y = Y;
+    p.K = K;
+    p.relu = relu;
+    p.aL = aL;
+    p.aR = aR;
+    p.slope = slope;
+    p.alpha_out = alpha_out;
+    p.seed_total = (float)g->segments * 1e-12f;
+    HubView h = hub_of(plan);
+    p.hub_rows = h.rows;
+    p.n_hub = h.n;
+    p.hub_threshold = h.thr;
+    return launch_spmm<MODE_GAT>(p, S(stream));
+}
+
+int gala_spmm_sampled_f32(const gala_graph_t* g, const float* vals, const float* X, int32_t K, float* Y,
+                          int32_t nsamples, int32_t ra, int32_t rb, int32_t accumulate, gala_stream_t stream) {
+    if (int rc = check_graph(g)) return rc;
+    if (K < 0 || nsamples < 0) return GALA_ERR_BAD_SHAPE;
+    if ((g->nrows > 0 && K > 0) && (!X || !Y)) return GALA_ERR_NULL_POINTER;
+    if (!aligned(X, 4) || !aligned(Y, 4)) return GALA_ERR_MISALIGNED;
+    if (g->nrows == 0 || K == 0) return GALA_OK;
+    SampledParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.g = make_dev(g);
+    p.vals = vals;
+    p.X = X;
+    p.Y = Y;
+    p.K = K;
+    p.nsamples = nsamples;
+    p.ra = ra;
+    p.rb = rb;
+    p.accumulate = accumulate;
+    const bool a16 = aligned(X, 16) && aligned(Y, 16);
+    const bool a8 = aligned(X, 8) && aligned(Y, 8);
+    Shape sh = pick_shape(K, a16, a8);
+    const int tw = sh.vec * sh.lpr * sh.acc;
+    dim3 grid((g->nrows + kWarpsPerCta - 1) / kWarpsPerCta, (K + tw - 1) / tw);
+    cudaStream_t st = S(stream);
+#define CALL(V, L, A) spmm_sampled_kernel<V, L, A><<<grid, kCtaThreads, 0, st>>>(p)
+    GALA_SHAPE_SWITCH(sh, CALL);
+#undef CALL
+    return last_error();
+}
+
+static int edge_common(const gala_graph_t* g, const gala_plan_t* plan, EdgeParams& p, dim3& grid) {
+    if (int rc = check_graph(g)) return rc;
+    std::memset(&p, 0, sizeof(p));
+    p.g = make_dev(g);
+    HubView h = hub_of(plan);
+    p.hub_rows = h.rows;
+    p.n_hub = h.n;
+    p.hub_threshold = h.thr;
+    p.slope = 1.0f;
+    grid = dim3(h.n + (g->nrows + kWarpsPerCta - 1) / kWarpsPerCta);
+    return GALA_OK;
+}
+
+int gala_edge_rowsum_f32(const gala_graph_t* g, const float* vals, float* out, float seed,
+                         const gala_plan_t* plan, gala_stream_t stream) {
+    EdgeParams p;
+    dim3 grid;
+    if (int rc = edge_common(g, plan, p, grid)) return rc;
+    if (g->nrows == 0) return GALA_OK;
+    if (!out || (g->nvals > 0 && !vals)) return GALA_ERR_NULL_POINTER;
+    p.a = vals;
+    p.out = out;
+    // reference: `local_C = 1e-12` once per segment, then C += local_C (cuda.h:512-522)
+    p.seed = (float)g->segments * seed;
+    edge_rowsum_kernel<<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    return last_error();
+}
+
+int gala_edge_scale_rows_f32(const gala_graph_t* g, float* vals, const float* rowval, const gala_plan_t* plan,
+                             gala_stream_t stream) {
+    EdgeParams p;
+    dim3 grid;
+    if (int rc = edge_common(g, plan, p, grid)) return rc;
+    if (g->nrows == 0 || g->nvals == 0) return GALA_OK;
+    if (!vals || !rowval) return GALA_ERR_NULL_POINTER;
+    p.a = rowval;
+    p.out = vals;
+    edge_scale_kernel<<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    return last_error();
+}
+
+int gala_sddvv_f32(const gala_graph_t* g, const float* A, const float* B, float* out, int32_t op,
+                   float leaky_slope, const gala_plan_t* plan, gala_stream_t stream) {
+    EdgeParams p;
+    dim3 grid;
+    if (int rc = edge_common(g, plan, p, grid)) return rc;
+    if (op != GALA_SDDVV_ADD && op != GALA_SDDVV_MUL) return GALA_ERR_UNSUPPORTED;
+    if (g->nrows == 0 || g->nvals == 0) return GALA_OK;
+    if (!A || !B || !out) return GALA_ERR_NULL_POINTER;
+    p.a = A;
+    p.b = B;
+    p.out = out;
+    p.op = op;
+    p.slope = leaky_slope;
+    sddvv_kernel<<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    return last_error();
+}
+
+int gala_edge_softmax_fwd_f32(const gala_graph_t* g, const float* x, float* alpha, float* recip,
+                              const gala_plan_t* plan, gala_stream_t stream) {
+    EdgeParams p;
+    dim3 grid;
+    if (int rc = edge_common(g, plan, p, grid)) return rc;
+    if (g->nrows == 0) return GALA_OK;
+    if (g->nvals > 0 && (!x || !alpha)) return GALA_ERR_NULL_POINTER;
+    p.a = x;
+    p.out = alpha;
+    p.out2 = recip;
+    p.seed = (float)g->segments * 1e-12f;
+    edge_softmax_fwd_kernel<<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    return last_error();
+}
+
+int gala_edge_softmax_bwd_f32(const gala_graph_t* g, const float* alpha, const float* dalpha, float* out,
+                              const gala_plan_t* plan, gala_stream_t stream) {
+    EdgeParams p;
+    dim3 grid;
+    if (int rc = edge_common(g, plan, p, grid)) return rc;
+    if (g->nrows == 0 || g->nvals == 0) return GALA_OK;
+    if (!alpha || !dalpha || !out) return GALA_ERR_NULL_POINTER;
+    p.a = alpha;
+    p.b = dalpha;
+    p.out = out;
+    p.seed = (float)g->segments * 1e-12f;
+    edge_softmax_bwd_kernel<<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    return last_error();
+}
+
+int gala_sddmm_f32(const gala_graph_t* g, const float* A, const float* B, int32_t K, float* out,
+                   const gala_plan_t* plan, gala_stream_t stream) {
+    if (int rc = check_graph(g)) return rc;
+    if (K < 0) return GALA_ERR_BAD_SHAPE;
+    if (g->nrows == 0 || g->nvals == 0) return GALA_OK;
+    if (!out || (K > 0 && (!A || !B))) return GALA_ERR_NULL_POINTER;
+    if (!aligned(A, 4) || !aligned(B, 4)) return GALA_ERR_MISALIGNED;
+    SddmmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.g = make_dev(g);
+    HubView h = hub_of(plan);
+    p.hub_rows = h.rows;
+    p.n_hub = h.n;
+    p.hub_threshold = h.thr;
+    p.A = A;
+    p.B = B;
+    p.out = out;
+    p.K = K;
+    const bool a16 = aligned(A, 16) && aligned(B, 16);
+    const bool a8 = aligned(A, 8) && aligned(B, 8);
+    Shape sh = pick_shape(K > 0 ? K : 1, a16, a8);
+    dim3 grid(h.n + (g->nrows + kWarpsPerCta - 1) / kWarpsPerCta);
+    cudaStream_t st = S(stream);
+#define CALL(V, L, A_) sddmm_kernel<V, L, A_><<<grid, kCtaThreads, 0, st>>>(p)
+    GALA_SHAPE_SWITCH(sh, CALL);
+#undef CALL
+    return last_error();
+}
+
+}  // extern "C"

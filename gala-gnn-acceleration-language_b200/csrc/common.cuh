@@ -1,0 +1,115 @@
+// common.cuh -- device-side helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gala_b200.h"
+
+namespace gala {
+
+constexpr int kMaxSeg = 64;       // column segments handled by one launch
+constexpr int kWarpsPerCta = 8;   // 256-thread CTAs everywhere
+constexpr int kCtaThreads = kWarpsPerCta * 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Device view of a column-tiled graph, passed by value in kernel params.
+struct GraphDev {
+    const int* __restrict__ offsets;  // [S*(N+1)]
+    const int* __restrict__ cols;     // [E]
+    int nrows;
+    int S;
+    int seg_base[kMaxSeg];            // bounds[2s] of the segments in this launch
+};
+
+// ---- cache-hinted loads / stores -------------------------------------------
+// Streams that are read exactly once (column indices, edge values) go through
+// ld.global.cs / st.global.cs so they are first in line for eviction and leave L1/L2
+// to the gathered feature rows, which are re-used.
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+    __device__ __forceinline__ void load_rw(const float* p) { v[0] = *p; }
+};
+template <>
+struct Vec<2> {
+    float v[2];
+    __device__ __forceinline__ void load(const float* p) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        v[0] = t.x; v[1] = t.y;
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    }
+    __device__ __forceinline__ void load_rw(const float* p) {
+        float2 t = *reinterpret_cast<const float2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    }
+};
+template <>
+struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ void load(const float* p) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __device__ __forceinline__ void load_rw(const float* p) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+    return x;
+}
+
+// exp -> clamp(0, 1e12) of the reference's edge-softmax (common.h:760-761).
+// expf (not __expf): the 1e-5 parity bound leaves no room for ex2.approx at large |x|.
+__device__ __forceinline__ float softmax_num(float x) {
+    float e = expf(x);
+    return e > 1e12f ? 1e12f : e;
+}
+
+__device__ __forceinline__ float leaky(float x, float slope) { return x > 0.0f ? x : x * slope; }
+
+// Visit the pieces of row `row` that fall inside [lo, hi) of the row's edge list
+// taken as the concatenation of its per-segment chunks (segment order == column
+// order == the order of the untiled CSR row).  f(e0, e1) receives absolute edge
+// ranges into cols / vals.
+template <class F>
+__device__ __forceinline__ void for_each_chunk(const GraphDev& g, int row, int lo, int hi, F&& f) {
+    int pos = 0;
+#pragma unroll 1
+    for (int s = 0; s < g.S; ++s) {
+        const int* off = g.offsets + (int64_t)s * (g.nrows + 1) + row;
+        int b = __ldg(off), e = __ldg(off + 1);
+        int len = e - b;
+        int a0 = max(lo - pos, 0), a1 = min(hi - pos, len);
+        if (a0 < a1) f(g.seg_base[s] + b + a0, g.seg_base[s] + b + a1);
+        pos += len;
+    }
+}
+
+__device__ __forceinline__ int row_degree(const GraphDev& g, int row) {
+    int d = 0;
+#pragma unroll 1
+    for (int s = 0; s < g.S; ++s) {
+        const int* off = g.offsets + (int64_t)s * (g.nrows + 1) + row;
+        d += __ldg(off + 1) - __ldg(off);
+    }
+    return d;
+}
+
+}  // namespace gala

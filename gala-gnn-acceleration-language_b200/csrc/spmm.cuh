@@ -1,0 +1,315 @@
+// spmm.cuh -- the gather-accumulate core shared by SpMM, sampled SpMM and the fused
+// GAT layer.  Written for sm_100a; see DESIGN.md "Kernels" for the byte model.
+//
+// Work decomposition
+//   * one warp per sparse row (8 rows per 256-thread CTA); rows whose total degree
+//     exceeds plan->hub_threshold are skipped by their warp and executed by a whole
+//     CTA instead (hub CTAs are the first blockIdx.x values so that the longest tasks
+//     start first).  Hub partials are combined through shared memory in fixed warp
+//     order: no atomics, bit-reproducible run to run.
+//   * a warp walks its edge list 32 edges at a time: one coalesced streaming load of
+//     32 column indices (+ weights), software-pipelined one chunk ahead, then
+//     the feature rows are gathered with 128-bit loads.  LPR lanes cover one feature
+//     row (K = 32 fp32 -> 8 lanes x float4 = one 128-byte line), so 32/LPR edges are
+//     in flight per load instruction and LPR independent loads per lane per chunk.
+//   * feature tiles wider than one warp pass are mapped to blockIdx.y.
+#pragma once
+#include "common.cuh"
+
+namespace gala {
+
+enum { MODE_PLAIN = 0, MODE_GAT = 1 };
+
+struct SpmmParams {
+    GraphDev g;
+    const float* __restrict__ vals;       // per-edge weights or nullptr
+    const float* __restrict__ X;          // [ncols, K]
+    float* __restrict__ Y;                // [nrows, K]
+    int K;
+    const float* __restrict__ row_scale;  // nullable
+    const float* __restrict__ col_scale;  // nullable
+    int accumulate;
+    int relu;
+    const int* __restrict__ hub_rows;
+    int n_hub;
+    int hub_threshold;
+    // MODE_GAT
+    const float* __restrict__ aL;
+    const float* __restrict__ aR;
+    float slope;
+    float* __restrict__ alpha_out;        // nullable
+    float seed_total;                     // S * 1e-12f
+};
+
+
+// Gather the feature rows of the (up to) 32 edges a warp holds one-per-lane and
+// accumulate them.  All loads of a batch are issued before the first FMA that
+// consumes them (UNR x ACC independent 16-byte loads in flight per lane); FULL
+// chunks carry no per-edge validity checks.
+template <int VEC, int LPR, int ACC, bool FULL>
+__device__ __forceinline__ void gather_chunk(const float* __restrict__ X, int K, int tile_base, int sub,
+                                             int grp, int c, float w, bool weighted,
+                                             const bool (&fvalid)[ACC], float (&acc)[ACC][VEC]) {
+    constexpr int EPI = 32 / LPR;
+    constexpr int UNR_ = 32 / (ACC * VEC) < 1 ? 1 : 32 / (ACC * VEC);
+    constexpr int UNR = UNR_ > LPR ? LPR : (UNR_ > 16 ? 16 : UNR_);
+#pragma unroll
+    for (int j0 = 0; j0 < LPR; j0 += UNR) {
+        int cj[UNR];
+        float wj[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            cj[u] = __shfl_sync(kFull, c, (j0 + u) * EPI + grp);
+            wj[u] = weighted ? __shfl_sync(kFull, w, (j0 + u) * EPI + grp) : 1.0f;
+        }
+        Vec<VEC> x[UNR][ACC];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int cc = FULL ? cj[u] : max(cj[u], 0);
+            const float* xr = X + (int64_t)cc * K + tile_base + sub * VEC;
+#pragma unroll
+            for (int a = 0; a < ACC; ++a) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) x[u][a].v[v] = 0.0f;
+                if (fvalid[a]) x[u][a].load(xr + a * LPR * VEC);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const bool ok = FULL || cj[u] >= 0;
+            const float ww = ok ? wj[u] : 0.0f;
+#pragma unroll
+            for (int a = 0; a < ACC; ++a)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    acc[a][v] = fmaf(ww, ok ? x[u][a].v[v] : 0.0f, acc[a][v]);
+        }
+    }
+}
+
+template <int VEC, int LPR, int ACC, int MODE>
+__global__ void __launch_bounds__(kCtaThreads)
+spmm_kernel(const __grid_constant__ SpmmParams p) {
+    constexpr int TW = VEC * LPR * ACC;  // features covered by one warp pass
+    constexpr int EPI = 32 / LPR;        // edges in flight per load instruction
+    const GraphDev& g = p.g;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int sub = lane % LPR;
+    const int grp = lane / LPR;
+    const int tile_base = blockIdx.y * TW;
+    const bool hub_cta = (int)blockIdx.x < p.n_hub;
+
+    int row, lo, hi;
+    if (hub_cta) {
+        row = __ldg(p.hub_rows + blockIdx.x);
+        int deg = row_degree(g, row);
+        int per = ((deg + kWarpsPerCta * 32 - 1) / (kWarpsPerCta * 32)) * 32;
+        lo = warp * per;
+        hi = min(deg, lo + per);
+    } else {
+        row = ((int)blockIdx.x - p.n_hub) * kWarpsPerCta + warp;
+        if (row >= g.nrows) return;
+        if (p.n_hub > 0 && row_degree(g, row) > p.hub_threshold) return;
+        lo = 0;
+        hi = 0x7fffffff;
+    }
+
+    bool fvalid[ACC];
+#pragma unroll
+    for (int a = 0; a < ACC; ++a) fvalid[a] = tile_base + (a * LPR + sub) * VEC < p.K;
+
+    float acc[ACC][VEC];
+#pragma unroll
+    for (int a = 0; a < ACC; ++a)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[a][v] = 0.0f;
+
+    const bool weighted = MODE == MODE_GAT || p.vals != nullptr || p.col_scale != nullptr;
+    float aL_row = 0.0f, rs = 0.0f;
+    if (MODE == MODE_GAT) aL_row = __ldg(p.aL + row);
+    const bool write_alpha = MODE == MODE_GAT && p.alpha_out != nullptr && blockIdx.y == 0;
+
+    // one edge per lane: column index and the weight the edge contributes with
+    auto fetch = [&](int idx, int e1, int& c, float& w) {
+        c = -1;
+        w = 0.0f;
+        if (idx < e1) {
+            c = ld_stream(g.cols + idx);
+            if (MODE == MODE_GAT) {
+                float e = softmax_num(leaky(aL_row + __ldg(p.aR + c), p.slope));
+                rs += e;
+                if (write_alpha) p.alpha_out[idx] = e;
+                w = e;
+            } else {
+                w = p.vals ? ld_stream(p.vals + idx) : 1.0f;
+                if (p.col_scale) w *= __ldg(p.col_scale + c);
+            }
+        }
+    };
+
+    for_each_chunk(g, row, lo, hi, [&](int e0, int e1) {
+        int c_nxt;
+        float w_nxt;
+        fetch(e0 + lane, e1, c_nxt, w_nxt);
+        for (int base = e0; base < e1; base += 32) {
+            const int c = c_nxt;
+            const float w = w_nxt;
+            if (base + 32 < e1) fetch(base + 32 + lane, e1, c_nxt, w_nxt);
+            if (base + 32 <= e1)
+                gather_chunk<VEC, LPR, ACC, true>(p.X, p.K, tile_base, sub, grp, c, w, weighted, fvalid, acc);
+            else
+                gather_chunk<VEC, LPR, ACC, false>(p.X, p.K, tile_base, sub, grp, c, w, weighted, fvalid, acc);
+        }
+    });
+
+    // combine the EPI edge groups of the warp (fixed tree -> deterministic)
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+        for (int a = 0; a < ACC; ++a)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[a][v] += __shfl_xor_sync(kFull, acc[a][v], o);
+    if (MODE == MODE_GAT) rs = warp_sum(rs);
+
+    float scale = p.row_scale ? __ldg(p.row_scale + row) : 1.0f;
+
+    if (!hub_cta) {
+        if (MODE == MODE_GAT) scale = 1.0f / (rs + p.seed_total);
+        if (grp == 0) {
+#pragma unroll
+            for (int a = 0; a < ACC; ++a) {
+                if (!fvalid[a]) continue;
+                float* y = p.Y + (int64_t)row * p.K + tile_base + (a * LPR + sub) * VEC;
+                Vec<VEC> o;
+                if (p.accumulate) o.load_rw(y);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    float t = acc[a][v] * scale;
+                    if (p.accumulate) t += o.v[v];
+                    if (p.relu) t = fmaxf(t, 0.0f);
+                    o.v[v] = t;
+                }
+                o.store(y);
+            }
+        }
+        if (write_alpha) {
+            for_each_chunk(g, row, lo, hi, [&](int e0, int e1) {
+                for (int e = e0 + lane; e < e1; e += 32) p.alpha_out[e] *= scale;
+            });
+        }
+        return;
+    }
+
+    // ---- hub row: combine the 8 warp partials in warp order ----
+    __shared__ float part[kWarpsPerCta * TW];
+    __shared__ float part_rs[kWarpsPerCta];
+    if (grp == 0) {
+#pragma unroll
+        for (int a = 0; a < ACC; ++a)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) part[warp * TW + (a * LPR + sub) * VEC + v] = acc[a][v];
+    }
+    if (MODE == MODE_GAT && lane == 0) part_rs[warp] = rs;
+    __syncthreads();
+    if (MODE == MODE_GAT) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) t += part_rs[w];
+        scale = 1.0f / (t + p.seed_total);
+    }
+    for (int f = threadIdx.x; f < TW; f += kCtaThreads) {
+        if (tile_base + f >= p.K) break;
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) t += part[w * TW + f];
+        float* y = p.Y + (int64_t)row * p.K + tile_base + f;
+        t *= scale;
+        if (p.accumulate) t += *y;
+        if (p.relu) t = fmaxf(t, 0.0f);
+        *y = t;
+    }
+    if (write_alpha) {
+        for_each_chunk(g, row, lo, hi, [&](int e0, int e1) {
+            for (int e = e0 + lane; e < e1; e += 32) p.alpha_out[e] *= scale;
+        });
+    }
+}
+
+// ---- sampled aggregation (K1s) ---------------------------------------------------
+struct SampledParams {
+    GraphDev g;
+    const float* __restrict__ vals;
+    const float* __restrict__ X;
+    float* __restrict__ Y;
+    int K;
+    int nsamples, ra, rb;
+    int accumulate;
+};
+
+template <int VEC, int LPR, int ACC>
+__global__ void __launch_bounds__(kCtaThreads)
+spmm_sampled_kernel(const __grid_constant__ SampledParams p) {
+    constexpr int TW = VEC * LPR * ACC;
+    constexpr int EPI = 32 / LPR;
+    const GraphDev& g = p.g;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int sub = lane % LPR;
+    const int grp = lane / LPR;
+    const int tile_base = blockIdx.y * TW;
+    const int row = blockIdx.x * kWarpsPerCta + warp;
+    if (row >= g.nrows) return;
+
+    bool fvalid[ACC];
+#pragma unroll
+    for (int a = 0; a < ACC; ++a) fvalid[a] = tile_base + (a * LPR + sub) * VEC < p.K;
+    float acc[ACC][VEC];
+#pragma unroll
+    for (int a = 0; a < ACC; ++a)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[a][v] = 0.0f;
+
+    for (int s = 0; s < g.S; ++s) {
+        const int* off = g.offsets + (int64_t)s * (g.nrows + 1) + row;
+        const int b = __ldg(off);
+        const int jmax = __ldg(off + 1) - b;
+        if (jmax <= 0) continue;
+        const int base = g.seg_base[s] + b;
+        for (int ji = grp; ji < p.nsamples; ji += EPI) {
+            const int j = (p.ra * ji + p.rb) % jmax;  // cuda.h:320, int arithmetic as emitted
+            const int c = __ldg(g.cols + base + j);
+            const float w = p.vals ? __ldg(p.vals + base + j) : 1.0f;
+            const float* xr = p.X + (int64_t)c * p.K + tile_base + sub * VEC;
+#pragma unroll
+            for (int a = 0; a < ACC; ++a) {
+                if (fvalid[a]) {
+                    Vec<VEC> x;
+                    x.load(xr + a * LPR * VEC);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[a][v] = fmaf(w, x.v[v], acc[a][v]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+        for (int a = 0; a < ACC; ++a)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[a][v] += __shfl_xor_sync(kFull, acc[a][v], o);
+    if (grp == 0) {
+#pragma unroll
+        for (int a = 0; a < ACC; ++a) {
+            if (!fvalid[a]) continue;
+            float* y = p.Y + (int64_t)row * p.K + tile_base + (a * LPR + sub) * VEC;
+            Vec<VEC> o;
+            if (p.accumulate) o.load_rw(y);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) o.v[v] = p.accumulate ? o.v[v] + acc[a][v] : acc[a][v];
+            o.store(y);
+        }
+    }
+}
+
+}  // namespace gala

@@ -1,0 +1,56 @@
+"""The 2-layer GAT forward as GALA generates it (reference src/codegen/common.h:622-675,
+735-810, 835-927), on top of the fused kernel.
+
+  layer 1: res = fc0(X); aL = efc0(res); aR = efc1(res)
+           res = relu( softmax_row(LeakyReLU_0.2(aL[row] + aR[col])) @ res )
+  layer 2 (FFN-recompute rewrite, src/middle-end/middle-end.h:324-375): the attention
+           logits come from fc1(res) but the aggregation runs at the narrower hidden
+           width and fc1 is applied after it:
+           t = fc1(res); aL = efc2(t); aR = efc3(t); res = fc1( attention @ res )
+
+The dense transforms are torch.nn.functional.linear (cuBLAS through libtorch, fp32),
+exactly what the generated program uses (common.h:1185-1281); they are adjacent to,
+not part of, the sparse hot path.  Random-init weights (nn.Linear default init under a
+fixed seed), since no checkpoint exists.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+def _linear_init(gen, out_f, in_f, device):
+    bound = 1.0 / math.sqrt(in_f)
+    w = (torch.rand(out_f, in_f, generator=gen, device=device) * 2 - 1) * bound
+    b = (torch.rand(out_f, generator=gen, device=device) * 2 - 1) * bound
+    return w, b
+
+
+class GAT2:
+    def __init__(self, in_feats, hidden, classes, device, seed=0):
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        self.fc0 = _linear_init(gen, hidden, in_feats, device)
+        self.efc0 = _linear_init(gen, 1, hidden, device)
+        self.efc1 = _linear_init(gen, 1, hidden, device)
+        self.fc1 = _linear_init(gen, classes, hidden, device)
+        self.efc2 = _linear_init(gen, 1, classes, device)
+        self.efc3 = _linear_init(gen, 1, classes, device)
+        self.slope = 0.2
+
+    def attention_inputs(self, t, wl, wr):
+        return F.linear(t, *wl).reshape(-1), F.linear(t, *wr).reshape(-1)
+
+    def forward(self, g, X, hook=None):
+        """g: TiledGraph (rows = output nodes, cols index X's rows).  `hook(name, fn)`
+        lets the benchmark time the sparse kernels individually."""
+        run = hook if hook is not None else (lambda name, fn: fn())
+        res = F.linear(X, *self.fc0)
+        aL, aR = self.attention_inputs(res, self.efc0, self.efc1)
+        res = run("gat_layer1", lambda: ops.gat_forward(g, aL, aR, res, self.slope, relu=True))
+        t = F.linear(res, *self.fc1)
+        aL, aR = self.attention_inputs(t, self.efc2, self.efc3)
+        agg = run("gat_layer2", lambda: ops.gat_forward(g, aL, aR, res, self.slope, relu=False))
+        return F.linear(agg, *self.fc1)

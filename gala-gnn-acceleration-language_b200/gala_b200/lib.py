@@ -1,0 +1,97 @@
+"""ctypes binding of libgala_b200.so (include/gala_b200.h).
+
+torch is used for device memory and streams only; every compute call goes through
+the C-ABI with raw device pointers.  There is no CPU fallback: if the shared
+library is missing, loading fails loudly.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_ROOT, "libgala_b200.so")
+
+EXPORTS = [
+    "gala_b200_abi_version", "gala_b200_error_string", "gala_plan_workspace_bytes",
+    "gala_plan_build", "gala_spmm_f32", "gala_spmm_sampled_f32", "gala_edge_rowsum_f32",
+    "gala_edge_scale_rows_f32", "gala_sddvv_f32", "gala_sddmm_f32", "gala_edge_softmax_fwd_f32",
+    "gala_edge_softmax_bwd_f32", "gala_gat_forward_f32",
+]
+
+
+class GalaGraph(C.Structure):
+    _fields_ = [("offsets", C.c_void_p), ("cols", C.c_void_p), ("bounds", C.c_void_p),
+                ("nrows", C.c_int32), ("ncols", C.c_int32), ("segments", C.c_int32),
+                ("nvals", C.c_int64)]
+
+
+class GalaPlan(C.Structure):
+    _fields_ = [("hub_rows", C.c_void_p), ("n_hub", C.c_int32), ("hub_threshold", C.c_int32)]
+
+
+class GalaEpilogue(C.Structure):
+    _fields_ = [("row_scale", C.c_void_p), ("col_scale", C.c_void_p), ("accumulate", C.c_int32),
+                ("relu", C.c_int32)]
+
+
+class GalaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gala_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no GPU needed to load or to list symbols)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C {_PKG_ROOT}` (or "
+            "__graft_entry__.build()).  gala_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.gala_b200_error_string.restype = C.c_char_p
+    lib.gala_b200_error_string.argtypes = [C.c_int]
+    lib.gala_plan_workspace_bytes.restype = C.c_size_t
+    lib.gala_plan_workspace_bytes.argtypes = [C.POINTER(GalaGraph)]
+    G, P, E = C.POINTER(GalaGraph), C.POINTER(GalaPlan), C.POINTER(GalaEpilogue)
+    vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+    sigs = {
+        "gala_plan_build": [G, i32, vp, C.c_size_t, P, vp],
+        "gala_spmm_f32": [G, vp, vp, i32, vp, E, P, vp],
+        "gala_spmm_sampled_f32": [G, vp, vp, i32, vp, i32, i32, i32, i32, vp],
+        "gala_edge_rowsum_f32": [G, vp, vp, f32, P, vp],
+        "gala_edge_scale_rows_f32": [G, vp, vp, P, vp],
+        "gala_sddvv_f32": [G, vp, vp, vp, i32, f32, P, vp],
+        "gala_sddmm_f32": [G, vp, vp, i32, vp, P, vp],
+        "gala_edge_softmax_fwd_f32": [G, vp, vp, vp, P, vp],
+        "gala_edge_softmax_bwd_f32": [G, vp, vp, vp, P, vp],
+        "gala_gat_forward_f32": [G, vp, vp, vp, i32, f32, vp, vp, i32, P, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        raise GalaError(code, load().gala_b200_error_string(code).decode())
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "gala_b200 takes contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,154 @@
+"""Host-side operator layer over the C-ABI.
+
+Two levels:
+  * `TiledGraph` + snake_case ops (spmm, sddvv, edge_softmax_fwd, gat_forward, ...):
+    one call = one launch of a hand-written sm_100a kernel;
+  * `emitted` (see emitted.py): functions with the exact names, argument order and
+    semantics of the wrappers GALA's code generator writes into gala.cu
+    (src/codegen/cuda.h:441-952 of the reference), built on the level above.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as _l
+
+DEFAULT_HUB_THRESHOLD = 2048
+
+
+class TiledGraph:
+    """Column-tiled CSR on the device, in the layout the generated code keeps in
+    global_offset_graph / global_columns_graph / global_bounds / global_segments
+    (reference src/codegen/common.h:1694-1705, src/ops/tiling.h:222-283)."""
+
+    def __init__(self, offsets, cols, nrows, ncols=None, bounds=None, segments=1, vals=None):
+        assert offsets.dtype == torch.int32 and cols.dtype == torch.int32
+        self.offsets, self.cols, self.vals = offsets.contiguous(), cols.contiguous(), vals
+        self.nrows = int(nrows)
+        self.ncols = int(ncols if ncols is not None else nrows)
+        self.segments = int(segments)
+        self.nvals = int(cols.numel())
+        if bounds is None:
+            assert self.segments == 1
+            bounds = [0, self.nvals]
+        if isinstance(bounds, torch.Tensor):
+            bounds = bounds.cpu().numpy()
+        self.bounds = np.ascontiguousarray(bounds, dtype=np.int32)  # host, as in the reference
+        assert self.bounds.shape[0] == 2 * self.segments
+        assert offsets.numel() == self.segments * (self.nrows + 1)
+        self.c = _l.GalaGraph(offsets=self.offsets.data_ptr(), cols=self.cols.data_ptr(),
+                              bounds=self.bounds.ctypes.data, nrows=self.nrows, ncols=self.ncols,
+                              segments=self.segments, nvals=self.nvals)
+        self.plan = None
+        self._plan_ws = None
+
+    @property
+    def device(self):
+        return self.cols.device
+
+    def build_plan(self, hub_threshold=DEFAULT_HUB_THRESHOLD):
+        """Find the hub rows once; every op then runs them on a whole CTA."""
+        lib = _l.load()
+        nbytes = lib.gala_plan_workspace_bytes(C.byref(self.c))
+        self._plan_ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+        plan = _l.GalaPlan()
+        _l.check(lib.gala_plan_build(C.byref(self.c), hub_threshold, _l.ptr(self._plan_ws), nbytes,
+                                     C.byref(plan), _l.stream_ptr()))
+        self.plan = plan
+        return self
+
+    def _p(self):
+        return C.byref(self.plan) if self.plan is not None else None
+
+
+def _f32(t):
+    assert t.dtype == torch.float32 and t.is_cuda
+    return t.contiguous()
+
+
+def spmm(g, X, vals=None, out=None, row_scale=None, col_scale=None, accumulate=False, relu=False):
+    """Y = A @ X (optionally weighted / scaled / accumulated / ReLU'd) in one launch."""
+    X = _f32(X)
+    K = X.shape[1] if X.dim() == 2 else 1
+    if out is None:
+        out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
+        assert not accumulate, "accumulate needs a caller-provided output"
+    ep = _l.GalaEpilogue(row_scale=row_scale.data_ptr() if row_scale is not None else None,
+                         col_scale=col_scale.data_ptr() if col_scale is not None else None,
+                         accumulate=int(accumulate), relu=int(relu))
+    _l.check(_l.load().gala_spmm_f32(C.byref(g.c), _l.ptr(vals), _l.ptr(X), K, _l.ptr(out),
+                                     C.byref(ep), g._p(), _l.stream_ptr()))
+    return out
+
+
+def spmm_sampled(g, X, nsamples, ra, rb, vals=None, out=None, accumulate=False):
+    X = _f32(X)
+    K = X.shape[1] if X.dim() == 2 else 1
+    if out is None:
+        out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
+    _l.check(_l.load().gala_spmm_sampled_f32(C.byref(g.c), _l.ptr(vals), _l.ptr(X), K, _l.ptr(out),
+                                             nsamples, ra, rb, int(accumulate), _l.stream_ptr()))
+    return out
+
+
+def edge_rowsum(g, vals, seed=1e-12, out=None):
+    if out is None:
+        out = torch.empty((g.nrows, 1), dtype=torch.float32, device=vals.device)
+    _l.check(_l.load().gala_edge_rowsum_f32(C.byref(g.c), _l.ptr(_f32(vals)), _l.ptr(out), seed,
+                                            g._p(), _l.stream_ptr()))
+    return out
+
+
+def edge_scale_rows_(g, vals, rowval):
+    """In place: vals[e] *= rowval[row(e)]."""
+    _l.check(_l.load().gala_edge_scale_rows_f32(C.byref(g.c), _l.ptr(vals), _l.ptr(_f32(rowval)),
+                                                g._p(), _l.stream_ptr()))
+    return vals
+
+
+def sddvv(g, A, B, op="add", leaky_slope=1.0, out=None):
+    if out is None:
+        out = torch.empty(g.nvals, dtype=torch.float32, device=A.device)
+    _l.check(_l.load().gala_sddvv_f32(C.byref(g.c), _l.ptr(_f32(A)), _l.ptr(_f32(B)), _l.ptr(out),
+                                      0 if op == "add" else 1, leaky_slope, g._p(), _l.stream_ptr()))
+    return out
+
+
+def sddmm(g, A, B, out=None):
+    A, B = _f32(A), _f32(B)
+    K = A.shape[1] if A.dim() == 2 else 1
+    if out is None:
+        out = torch.empty(g.nvals, dtype=torch.float32, device=A.device)
+    _l.check(_l.load().gala_sddmm_f32(C.byref(g.c), _l.ptr(A), _l.ptr(B), K, _l.ptr(out), g._p(),
+                                      _l.stream_ptr()))
+    return out
+
+
+def edge_softmax_fwd(g, x, out=None, recip=None):
+    if out is None:
+        out = torch.empty_like(x)
+    _l.check(_l.load().gala_edge_softmax_fwd_f32(C.byref(g.c), _l.ptr(_f32(x)), _l.ptr(out),
+                                                 _l.ptr(recip), g._p(), _l.stream_ptr()))
+    return out
+
+
+def edge_softmax_bwd(g, alpha, dalpha, out=None):
+    if out is None:
+        out = torch.empty_like(alpha)
+    _l.check(_l.load().gala_edge_softmax_bwd_f32(C.byref(g.c), _l.ptr(_f32(alpha)),
+                                                 _l.ptr(_f32(dalpha)), _l.ptr(out), g._p(),
+                                                 _l.stream_ptr()))
+    return out
+
+
+def gat_forward(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None):
+    """Fused SDDVV + LeakyReLU + edge-softmax + weighted SpMM (one pass over the edges)."""
+    X = _f32(X)
+    K = X.shape[1]
+    if out is None:
+        out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
+    _l.check(_l.load().gala_gat_forward_f32(C.byref(g.c), _l.ptr(_f32(aL)), _l.ptr(_f32(aR)),
+                                            _l.ptr(X), K, slope, _l.ptr(out), _l.ptr(alpha_out),
+                                            int(relu), g._p(), _l.stream_ptr()))
+    return out

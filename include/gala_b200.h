@@ -1,0 +1,179 @@
+/*
+ * gala_b200.h -- C-ABI of the B200-native (sm_100a) sparse aggregation library that
+ * replaces the kernels GALA's code generator emits as text into gala.cu.
+ *
+ * The reference has no FFI: its "operator interface" for this path is the set of
+ * free functions that CUDAGenerator::generateCudaCodeForCNode writes into every
+ * generated program (src/codegen/cuda.h:170-955 of ADAPT-uiuc/GALA, cited below as
+ * cuda.h:LINE) and that the emitted autograd classes call
+ * (src/codegen/common.h:622-977, cited as common.h:LINE).  Each entry point here
+ * names the emitted function / kernel it replaces.  The libtorch shim that
+ * re-creates the emitted names on top of this ABI is
+ * gala-gnn-acceleration-language_b200/host/gala_b200_torch.h; INTEGRATION.md shows the
+ * codegen edit.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is DEVICE memory unless
+ *     the parameter is documented as host;
+ *   - int32 indices, float32 values, row-major dense matrices
+ *     (common.h:1682-1693);
+ *   - every function returns int: 0 = success, > 0 = a cudaError_t,
+ *     < 0 = a GALA_ERR_* argument error.  Nothing exits or throws across the ABI
+ *     (the reference printf+exit()s, cuda.h:980-998);
+ *   - work is enqueued on the given stream (a cudaStream_t passed as void*;
+ *     NULL = the legacy default stream); no hidden synchronisation, no allocation
+ *     of caller-visible memory, no global state;
+ *   - outputs and workspaces are caller-provided.
+ *
+ * Graph layout ("column-tiled CSR", src/ops/tiling.h:222-283, Appendix B of
+ * SURVEY.md): `segments` consecutive LOCAL row-pointer arrays of length nrows+1
+ * in `offsets`; `cols` (and every per-edge value array) is segment-major,
+ * row-major inside a segment; segment s owns edges
+ * [bounds[2s], bounds[2s+1]) and row i of segment s owns
+ * bounds[2s] + offsets[s*(nrows+1)+i .. i+1).  A plain CSR is segments = 1.
+ * `bounds` is a HOST array exactly as in the generated code (cuda.h:472-475 reads
+ * it on the host); it may be NULL when segments == 1.
+ */
+#ifndef GALA_B200_H
+#define GALA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define GALA_B200_ABI_VERSION 1
+
+#define GALA_OK 0
+#define GALA_ERR_NULL_POINTER (-1)
+#define GALA_ERR_BAD_SHAPE (-2)
+#define GALA_ERR_UNSUPPORTED (-3)
+#define GALA_ERR_WORKSPACE (-4)
+#define GALA_ERR_MISALIGNED (-5)
+
+typedef void *gala_stream_t; /* cudaStream_t */
+
+typedef struct gala_graph {
+    const int32_t *offsets; /* device, [segments * (nrows + 1)]                      */
+    const int32_t *cols;    /* device, [nvals]                                       */
+    const int32_t *bounds;  /* HOST,   [2 * segments]; NULL allowed iff segments == 1 */
+    int32_t nrows;          /* rows of the sparse matrix == rows of every output     */
+    int32_t ncols;          /* columns == rows of the gathered dense operand         */
+    int32_t segments;       /* S >= 1                                                */
+    int64_t nvals;          /* E                                                     */
+} gala_graph_t;
+
+/*
+ * Load-balance plan for power-law graphs: the list of "hub" rows (total degree
+ * above `hub_threshold`) that are executed by a whole thread block instead of a
+ * single warp.  Built once per graph, reused by every call.  All kernels accept
+ * plan == NULL (pure warp-per-row).
+ */
+typedef struct gala_plan {
+    const int32_t *hub_rows; /* device, [n_hub] ascending row ids                   */
+    int32_t n_hub;
+    int32_t hub_threshold;
+} gala_plan_t;
+
+/* Fused epilogue / prologue of the SpMM (all fields optional):                   */
+/*   Y[i,:] = act( row_scale[i] * sum_e w_e * col_scale[col_e] * X[col_e,:]       */
+/*                 + (accumulate ? Y[i,:] : 0) )                                   */
+/* row_scale/col_scale fold the `norm * res` passes the generated GCN/SAGE models */
+/* run as separate ATen kernels (common.h:1128-1180, codegen/gala.cu:441-457).    */
+typedef struct gala_epilogue {
+    const float *row_scale; /* device [nrows] or NULL */
+    const float *col_scale; /* device [ncols] or NULL */
+    int32_t accumulate;     /* 0: Y is overwritten; 1: Y += (reference semantics
+                               of the per-segment `C = C + ...`, cuda.h:309-351)  */
+    int32_t relu;           /* apply max(.,0) last                                 */
+} gala_epilogue_t;
+
+int gala_b200_abi_version(void);
+const char *gala_b200_error_string(int code);
+
+/* ---- plan ------------------------------------------------------------------ */
+/* Bytes of device workspace gala_plan_build needs for this graph.               */
+size_t gala_plan_workspace_bytes(const gala_graph_t *g);
+/* Scans the row pointers on the device, writes the hub list into `workspace`    */
+/* and fills *plan (host struct).  Synchronises `stream` once to read the count. */
+int gala_plan_build(const gala_graph_t *g, int32_t hub_threshold, void *workspace,
+                    size_t workspace_bytes, gala_plan_t *plan, gala_stream_t stream);
+
+/* ---- node aggregation ------------------------------------------------------- */
+/* Replaces aggregate_node_mul_sum[_direct][_coarseN]_call + kernels K1/K2        */
+/* (cuda.h:282-503, launch tree :58-168; sample codegen/gala.cu:65-390) and the   */
+/* cuSPARSE flavour (cuda.h:211-280).  Y[nrows,K] = A * X[ncols,K]; `vals` is the  */
+/* per-edge weight array (value_graph) or NULL for an unweighted graph            */
+/* (cuda.h:292-295).  One launch covers every column segment and any K.          */
+int gala_spmm_f32(const gala_graph_t *g, const float *vals, const float *X, int32_t K, float *Y,
+                  const gala_epilogue_t *ep, const gala_plan_t *plan, gala_stream_t stream);
+
+/* Replaces the sampled flavour K1s (cuda.h:313-320, 389-396): per row and per    */
+/* segment, sum over j = (ra*ji + rb) % deg for ji in [0, nsamples).              */
+/* (ra, rb) = global_ra/global_rb (common.h:817-830).  Y is overwritten unless    */
+/* accumulate != 0.                                                              */
+int gala_spmm_sampled_f32(const gala_graph_t *g, const float *vals, const float *X, int32_t K,
+                          float *Y, int32_t nsamples, int32_t ra, int32_t rb, int32_t accumulate,
+                          gala_stream_t stream);
+
+/* ---- edge kernels ------------------------------------------------------------ */
+/* Replaces node_spmv_backward_of_sddmm_{nln,eaggr} + K3 (cuda.h:505-524,         */
+/* 565-600, 659-678, 737-772): out[i] = sum_s (seed + sum_{e in row i, seg s}     */
+/* vals[e]).  The reference seeds with 1e-12f once per segment.                   */
+int gala_edge_rowsum_f32(const gala_graph_t *g, const float *vals, float *out, float seed,
+                         const gala_plan_t *plan, gala_stream_t stream);
+
+/* Replaces inplace_softmax_sddvv[_mult] + K4 (cuda.h:525-562, 601-656):          */
+/* vals[e] *= rowval[row(e)] in place.                                            */
+int gala_edge_scale_rows_f32(const gala_graph_t *g, float *vals, const float *rowval,
+                             const gala_plan_t *plan, gala_stream_t stream);
+
+/* Replaces edge_sddvv + K5 (cuda.h:679-698, 773-807) when op == GALA_SDDVV_ADD   */
+/* and aggregate_edge_mul[_dir] + K7 (cuda.h:848-952) when op == GALA_SDDVV_MUL:  */
+/* out[e] = A[row(e)] (+|*) B[col(e)].  If leaky_slope != 1, LeakyReLU(slope) is   */
+/* applied to the result (the ATen pass at common.h:1180 fused in).               */
+#define GALA_SDDVV_ADD 0
+#define GALA_SDDVV_MUL 1
+int gala_sddvv_f32(const gala_graph_t *g, const float *A, const float *B, float *out, int32_t op,
+                   float leaky_slope, const gala_plan_t *plan, gala_stream_t stream);
+
+/* Replaces edge_sddmm + K6 (cuda.h:699-734, 808-845): out[e] = sum_k A[row,k] *   */
+/* B[col,k].  Implements the mathematical definition; the reference kernel's      */
+/* shared-memory aliasing between the 8 rows of a block (cuda.h:706-714) is not   */
+/* reproduced.                                                                    */
+int gala_sddmm_f32(const gala_graph_t *g, const float *A, const float *B, int32_t K, float *out,
+                   const gala_plan_t *plan, gala_stream_t stream);
+
+/* Replaces the 5-pass forward of non_lnr_op_softmax_AutoGrad (common.h:760-773): */
+/* alpha[e] = clamp(exp(x[e]),0,1e12) / (S*1e-12 + sum_row clamp(exp(x))).        */
+/* x and alpha may alias.  recip (nullable, [nrows]) receives 1/rowsum.           */
+int gala_edge_softmax_fwd_f32(const gala_graph_t *g, const float *x, float *alpha, float *recip,
+                              const gala_plan_t *plan, gala_stream_t stream);
+
+/* Replaces the backward of the same class (common.h:791-799):                    */
+/* out[e] = alpha*dalpha - alpha * (S*1e-12 + sum_row alpha*dalpha).               */
+int gala_edge_softmax_bwd_f32(const gala_graph_t *g, const float *alpha, const float *dalpha,
+                              float *out, const gala_plan_t *plan, gala_stream_t stream);
+
+/* ---- fused GAT layer (what the retargeted code generator emits) ---------------- */
+/* One pass over the edges: e = aL[row]+aR[col] -> LeakyReLU(slope) -> edge-       */
+/* softmax -> Y = alpha * X (-> ReLU if relu).  Equivalent to the emitted          */
+/* sequence edge_sddvv, LeakyReLU, non_lnr_op_softmax, aggregate_node_mul_sum      */
+/* (common.h:622-675, 735-810, 835-927).  alpha_out (nullable, [nvals]) receives   */
+/* the attention values for the backward pass.                                     */
+int gala_gat_forward_f32(const gala_graph_t *g, const float *aL, const float *aR, const float *X,
+                         int32_t K, float slope, float *Y, float *alpha_out, int32_t relu,
+                         const gala_plan_t *plan, gala_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* GALA_B200_H */

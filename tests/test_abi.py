@@ -1,0 +1,67 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/gala_b200.h
+declares; argument validation that needs no GPU; host-side logic."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from gala_b200 import lib as L
+from gala_b200 import ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gala_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gala_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported():
+    lib = L.load()
+    names = declared_symbols()
+    assert len(names) >= 13
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/gala_b200.h but not exported"
+    assert set(names) == set(L.EXPORTS)
+
+
+def test_abi_version_and_error_strings():
+    lib = L.load()
+    assert lib.gala_b200_abi_version() == 1
+    assert lib.gala_b200_error_string(0) == b"success"
+    for code in (-1, -2, -3, -4, -5):
+        assert b"gala_b200" in lib.gala_b200_error_string(code)
+
+
+def test_argument_errors_return_codes_not_exits():
+    """The reference printf+exit()s on error (cuda.h:980-998); the ABI returns codes."""
+    lib = L.load()
+    assert lib.gala_spmm_f32(None, None, None, 4, None, None, None, None) == -1
+    g = L.GalaGraph(offsets=None, cols=None, bounds=None, nrows=-3, ncols=0, segments=1, nvals=0)
+    assert lib.gala_spmm_f32(C.byref(g), None, None, 4, None, None, None, None) == -2
+    g = L.GalaGraph(offsets=None, cols=None, bounds=None, nrows=0, ncols=0, segments=1000, nvals=0)
+    assert lib.gala_spmm_f32(C.byref(g), None, None, 4, None, None, None, None) == -3
+    g = L.GalaGraph(offsets=None, cols=None, bounds=None, nrows=8, ncols=8, segments=1, nvals=0)
+    assert lib.gala_spmm_f32(C.byref(g), None, None, 4, None, None, None, None) == -1
+    with pytest.raises(L.GalaError):
+        L.check(-3)
+
+
+def test_tiled_graph_host_view():
+    off = torch.tensor([0, 1, 2, 0, 1, 1], dtype=torch.int32)
+    cols = torch.tensor([0, 1, 1], dtype=torch.int32)
+    g = ops.TiledGraph(off, cols, nrows=2, ncols=2, bounds=[0, 2, 2, 3], segments=2)
+    assert g.c.nrows == 2 and g.c.segments == 2 and g.c.nvals == 3
+    assert np.array_equal(g.bounds, [0, 2, 2, 3])
+    assert L.load().gala_plan_workspace_bytes(C.byref(g.c)) >= 4 * 2
+
+
+def test_no_cpu_fallback_when_library_missing(monkeypatch):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libgala_b200.so")
+    with pytest.raises(ImportError):
+        L.load()

@@ -1,0 +1,305 @@
+"""GPU parity tests (-m gpu): every kernel, called through the C-ABI, against the oracle
+on the same seeded inputs.  Integer / index work bit-exact; fp32 within 1e-5 relative
+error (BASELINE.json north_star), measured norm-wise per output with the
+double-accumulate arbiter alongside (SURVEY.md section 7 'summation order')."""
+import numpy as np
+import pytest
+import torch
+
+from gala_b200 import emitted, ops
+from util import FP32_TOL, GOLDEN_CASES, golden, make_csr, max_rel_to_rowscale, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def to_gpu_graph(t, plan_threshold=None):
+    g = ops.TiledGraph(dev(t.offsets), dev(t.cols), t.nrows, t.ncols, t.bounds, t.S)
+    if plan_threshold is not None:
+        g.build_plan(plan_threshold)
+    return g
+
+
+def graph_case(orc, n, e, seed, T=None, empty_rows=0):
+    offset, ids = make_csr(n, e, seed, empty_rows)
+    w = np.random.default_rng(seed).uniform(-1, 1, ids.shape[0]).astype(np.float32)
+    if T is None:
+        return orc.Tiled.from_csr(n, n, offset, ids, w)
+    return orc.col_tile(n, n, offset, ids, w, T)
+
+
+CASES = [
+    # n, e, seed, T (None = untiled), empty rows, hub threshold (None = no plan)
+    (2708, 13264, 1, None, 0, None),        # Cora shape
+    (2708, 13264, 1, 100000, 0, 64),        # Cora shape, shipped col_tile(100000) -> S=1, plan
+    (3000, 400000, 2, None, 0, 256),        # dense-ish power law, hub rows on CTAs
+    (3000, 400000, 2, 700, 0, 256),         # 5 column segments + hubs
+    (1500, 30000, 3, 400, 40, None),        # empty rows, 4 segments, no plan
+    (257, 3000, 4, 16, 5, 32),              # 17 segments
+]
+KS = [1, 7, 32, 41, 64, 100, 128, 602]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("K", KS)
+@pytest.mark.parametrize("weighted", [False, True])
+def test_spmm_matches_oracle(orc, case, K, weighted):
+    n, e, seed, T, empty, thr = case
+    t = graph_case(orc, n, e, seed, T, empty)
+    g = to_gpu_graph(t, thr)
+    X = np.random.default_rng(seed + K).uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    want = orc.spmm(t, X, weighted=weighted)
+    got = ops.spmm(g, dev(X), vals=dev(t.vals) if weighted else None).cpu().numpy()
+    exact = orc.spmm_f64(t, X, weighted=weighted)
+    assert rel_err(got, want) < FP32_TOL
+    # no worse than the reference's own serial fp32 order, judged by the fp64 arbiter
+    assert rel_err(got, exact) <= max(2.0 * rel_err(want, exact), 2e-7)
+    assert max_rel_to_rowscale(got, want) < 1e-4
+
+
+def test_spmm_degrees_are_exact(orc):
+    """SpMM(A, ones) = degrees: small integers, exact in fp32 whatever the order
+    (the generated GCN computes its normalisation this way, codegen/gala.cu:437)."""
+    t = graph_case(orc, 3000, 400000, 2, 700)
+    g = to_gpu_graph(t, 128)
+    got = ops.spmm(g, torch.ones(3000, 1, device=DEV)).cpu().numpy().ravel()
+    deg = np.zeros(3000, np.int64)
+    for s in range(t.S):
+        deg += np.diff(t.offsets[s * 3001:(s + 1) * 3001])
+    assert np.array_equal(got, deg.astype(np.float32))
+
+
+def test_spmm_epilogue_and_accumulate(orc):
+    n, K = 2000, 32
+    t = graph_case(orc, n, 60000, 5, 500)
+    g = to_gpu_graph(t, 128)
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    norm = rng.uniform(0.1, 1.0, n).astype(np.float32)
+    Y0 = rng.uniform(-1, 1, (n, K)).astype(np.float32)
+    # GCN layer body: norm * (A @ (norm * X)) then relu  (codegen/gala.cu:441-450)
+    want = norm[:, None] * orc.spmm(t, norm[:, None] * X, weighted=False)
+    got = ops.spmm(g, dev(X), row_scale=dev(norm), col_scale=dev(norm), relu=True).cpu().numpy()
+    assert rel_err(got, np.maximum(want, 0)) < FP32_TOL
+    # accumulate: Y += A @ X, the reference's per-segment `C = C + ...` (cuda.h:309-351)
+    out = dev(Y0.copy())
+    ops.spmm(g, dev(X), vals=dev(t.vals), out=out, accumulate=True)
+    assert rel_err(out.cpu().numpy(), orc.spmm(t, X, weighted=True, Y=Y0.copy())) < FP32_TOL
+
+
+@pytest.mark.parametrize("K", [1, 32, 47, 100])
+@pytest.mark.parametrize("T", [None, 600])
+def test_spmm_sampled_matches_oracle(orc, K, T):
+    n = 2500
+    t = graph_case(orc, n, 80000, 6, T)
+    g = to_gpu_graph(t)
+    X = np.random.default_rng(K).uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    for (s, ra, rb) in ((20, 5, 7), (3, 97, 13), (33, 0, 100)):
+        want = orc.spmm_sampled(t, X, s, ra, rb)
+        got = ops.spmm_sampled(g, dev(X), s, ra, rb).cpu().numpy()
+        assert rel_err(got, want) < FP32_TOL
+    want = orc.spmm_sampled(t, X, 20, 5, 7, weighted=True)
+    got = ops.spmm_sampled(g, dev(X), 20, 5, 7, vals=dev(t.vals)).cpu().numpy()
+    assert rel_err(got, want) < FP32_TOL
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_edge_kernels_match_oracle(orc, case):
+    n, e, seed, T, empty, thr = case
+    t = graph_case(orc, n, e, seed, T, empty)
+    g = to_gpu_graph(t, thr)
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=n).astype(np.float32)
+    B = rng.normal(size=n).astype(np.float32)
+    # K5 / K7: one rounding per edge -> bit-exact
+    for op in ("add", "mul"):
+        got = ops.sddvv(g, dev(A), dev(B), op).cpu().numpy()
+        assert np.array_equal(got, orc.sddvv(t, A, B, op))
+    got = ops.sddvv(g, dev(A), dev(B), "add", leaky_slope=0.2).cpu().numpy()
+    assert np.array_equal(got, orc.leaky_relu(orc.sddvv(t, A, B, "add"), 0.2))
+    # K4: bit-exact
+    v = dev(t.vals.copy())
+    ops.edge_scale_rows_(g, v, dev(A))
+    assert np.array_equal(v.cpu().numpy(), orc.edge_scale_rows(t, t.vals, A))
+    # K3
+    pos = np.abs(t.vals) + 0.01
+    got = ops.edge_rowsum(g, dev(pos)).cpu().numpy().ravel()
+    assert rel_err(got, orc.edge_rowsum(t, pos)) < FP32_TOL
+    deg = got * 0
+    for s in range(t.S):
+        deg += np.diff(t.offsets[s * (n + 1):(s + 1) * (n + 1)])
+    assert np.allclose(got[deg == 0], t.S * np.float32(1e-12), rtol=1e-6)   # per-segment seed
+    # softmax forward / backward
+    x = rng.normal(scale=2.0, size=t.nvals).astype(np.float32)
+    want, recip = orc.edge_softmax_fwd(t, x)
+    r = torch.empty(n, device=DEV)
+    got = ops.edge_softmax_fwd(g, dev(x), recip=r).cpu().numpy()
+    assert rel_err(got, want) < FP32_TOL
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-12)
+    assert rel_err(r.cpu().numpy()[deg > 0], recip[deg > 0]) < FP32_TOL
+    da = rng.normal(size=t.nvals).astype(np.float32)
+    got_b = ops.edge_softmax_bwd(g, dev(want), dev(da)).cpu().numpy()
+    want_b = orc.edge_softmax_bwd(t, want, da)
+    assert rel_err(got_b, want_b) < FP32_TOL
+    # in place (x aliases alpha), as the generated code does with val_exp
+    xi = dev(x.copy())
+    ops.edge_softmax_fwd(g, xi, out=xi)
+    assert np.array_equal(xi.cpu().numpy(), got)
+
+
+@pytest.mark.parametrize("case", CASES[:5])
+@pytest.mark.parametrize("K", [1, 7, 32, 64, 100, 602, 1433])
+def test_sddmm_matches_oracle(orc, case, K):
+    n, e, seed, T, empty, thr = case
+    if K > 602 and n > 2708:
+        pytest.skip("large K only on the Cora shape")
+    t = graph_case(orc, n, e, seed, T, empty)
+    g = to_gpu_graph(t, thr)
+    rng = np.random.default_rng(seed + K)
+    A = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    B = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    got = ops.sddmm(g, dev(A), dev(B)).cpu().numpy()
+    want = orc.sddmm(t, A, B)
+    assert rel_err(got, want) < FP32_TOL
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("K", [8, 32, 41, 128])
+def test_gat_fused_forward_matches_composition(orc, case, K):
+    """The fused kernel against the oracle's op-by-op composition of the emitted GAT layer
+    (edge_sddvv -> LeakyReLU -> softmax -> weighted SpMM)."""
+    n, e, seed, T, empty, thr = case
+    t = graph_case(orc, n, e, seed, T, empty)
+    g = to_gpu_graph(t, thr)
+    rng = np.random.default_rng(seed + K)
+    aL = rng.normal(size=n).astype(np.float32)
+    aR = rng.normal(size=n).astype(np.float32)
+    X = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    want_Y, want_alpha = orc.gat_forward(t, aL, aR, X)
+    alpha = torch.empty(t.nvals, device=DEV)
+    got_Y = ops.gat_forward(g, dev(aL), dev(aR), dev(X), alpha_out=alpha).cpu().numpy()
+    assert rel_err(got_Y, want_Y) < FP32_TOL
+    assert rel_err(alpha.cpu().numpy(), want_alpha) < FP32_TOL
+    got_relu = ops.gat_forward(g, dev(aL), dev(aR), dev(X), relu=True).cpu().numpy()
+    assert rel_err(got_relu, np.maximum(want_Y, 0)) < FP32_TOL
+    # and against the unfused sequence of our own kernels
+    att = ops.sddvv(g, dev(aL), dev(aR), "add", leaky_slope=0.2)
+    ops.edge_softmax_fwd(g, att, out=att)
+    unfused = ops.spmm(g, dev(X), vals=att).cpu().numpy()
+    assert rel_err(got_Y, unfused) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_fixtures_on_gpu(orc, name):
+    """The reference's own outputs (tests/golden) reproduced by the CUDA path."""
+    gd = golden(name)
+    n = int(gd["n"])
+    S = gd["tile_bounds"].shape[0] // 2
+    g = ops.TiledGraph(dev(gd["tile_offsets"]), dev(gd["tile_cols"]), n, n, gd["tile_bounds"], S)
+    g.build_plan(64)
+    got = ops.spmm(g, dev(gd["X"]), vals=dev(gd["tile_vals"])).cpu().numpy()
+    assert rel_err(got, gd["Y_w"]) < FP32_TOL
+    got = ops.spmm(g, dev(gd["X"])).cpu().numpy()
+    assert rel_err(got, gd["Y_1"]) < FP32_TOL
+    g1 = ops.TiledGraph(dev(gd["offset"]), dev(gd["ids"]), n)
+    got = ops.spmm(g1, dev(gd["X"]), vals=dev(gd["w"])).cpu().numpy()
+    assert rel_err(got, gd["Y_w"]) < FP32_TOL
+    # sampled kernel == SpMM over the reference's sampled graph
+    gs = ops.TiledGraph(dev(gd["s_offset"]), dev(gd["s_ids"]), n)
+    a = ops.spmm(gs, dev(gd["X"]), vals=dev(gd["s_vals"])).cpu().numpy()
+    b = ops.spmm_sampled(g1, dev(gd["X"]), 20, 5, 7, vals=dev(gd["w"])).cpu().numpy()
+    assert rel_err(a, b) < FP32_TOL
+
+
+def test_emitted_interface(orc):
+    """Calls spelled exactly as the generated gala.cu spells them (cuda.h:441-952)."""
+    n = 1200
+    t = graph_case(orc, n, 50000, 8, 300)
+    emitted.clear_cache()
+    emitted.global_nrows = n
+    off, col, val = dev(t.offsets), dev(t.cols), dev(t.vals)
+    bounds = torch.from_numpy(t.bounds)   # CPU tensor, as in the reference
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-0.5, 0.5, (n, 32)).astype(np.float32)
+    y = emitted.aggregate_node_mul_sum_call(dev(X), off, col, val, bounds, t.S)
+    assert rel_err(y.cpu().numpy(), orc.spmm(t, X, weighted=True)) < FP32_TOL
+    y = emitted.aggregate_node_mul_sum_direct_call(dev(X), off, col, val, bounds, t.S)
+    assert rel_err(y.cpu().numpy(), orc.spmm(t, X, weighted=False)) < FP32_TOL
+    ones = torch.ones(n, 1, device=DEV)
+    deg = emitted.aggregate_node_mul_sum_direct_call(ones, off, col, val, bounds, t.S)
+    a = rng.normal(size=(n, 1)).astype(np.float32)
+    b = rng.normal(size=(n, 1)).astype(np.float32)
+    att = emitted.edge_sddvv(dev(a), dev(b), off, col, val, bounds, n, t.S)
+    assert np.array_equal(att.cpu().numpy(), orc.sddvv(t, a.ravel(), b.ravel(), "add"))
+    att = torch.nn.functional.leaky_relu(att, 0.2)
+    # body of non_lnr_op_softmax_AutoGrad::forward, common.h:760-773, op by op
+    val_exp = torch.clamp(torch.exp(att), 0.0, 1e12)
+    row_sum = emitted.node_spmv_backward_of_sddmm_nln(off, col, val_exp, bounds, n, t.S)
+    row_sum = torch.reciprocal(row_sum)
+    val_exp = emitted.inplace_softmax_sddvv(row_sum, off, col, val_exp, bounds, n, t.S)
+    want, _ = orc.edge_softmax_fwd(t, orc.leaky_relu(orc.sddvv(t, a.ravel(), b.ravel(), "add")))
+    assert rel_err(val_exp.cpu().numpy(), want) < FP32_TOL
+    fused = emitted.non_lnr_op_softmax_forward(att, off, col, bounds, t.S)
+    assert rel_err(fused.cpu().numpy(), want) < FP32_TOL
+    nrm = torch.pow(deg, -0.5)
+    ev = emitted.aggregate_edge_mul(nrm, nrm, off, col, val, bounds, t.S)
+    dnp = deg.cpu().numpy().ravel() ** -0.5
+    assert rel_err(ev.cpu().numpy(), orc.sddvv(t, dnp.astype(np.float32), dnp.astype(np.float32), "mul")) < 1e-6
+    dz = rng.uniform(-0.5, 0.5, (n, 32)).astype(np.float32)
+    dd = emitted.edge_sddmm(dev(dz), dev(X), off, col, val, bounds, n, t.S)
+    assert rel_err(dd.cpu().numpy(), orc.sddmm(t, dz, X)) < FP32_TOL
+
+
+def test_empty_and_degenerate_graphs(orc):
+    # no rows
+    g = ops.TiledGraph(torch.zeros(1, dtype=torch.int32, device=DEV),
+                       torch.zeros(0, dtype=torch.int32, device=DEV), 0, 0)
+    assert ops.spmm(g, torch.zeros(0, 8, device=DEV)).shape == (0, 8)
+    # rows but no edges
+    g = ops.TiledGraph(torch.zeros(6, dtype=torch.int32, device=DEV),
+                       torch.zeros(0, dtype=torch.int32, device=DEV), 5, 5)
+    y = ops.spmm(g, torch.ones(5, 8, device=DEV))
+    assert torch.all(y == 0)
+    r = ops.edge_rowsum(g, torch.zeros(0, device=DEV))
+    assert torch.allclose(r, torch.full_like(r, 1e-12))
+    y = ops.gat_forward(g, torch.zeros(5, device=DEV), torch.zeros(5, device=DEV),
+                        torch.ones(5, 8, device=DEV))
+    assert torch.all(y == 0)
+    # one row holding every edge (max-size row on a hub CTA), K not a multiple of 4
+    n = 20000
+    offset = np.zeros(n + 1, np.int32)
+    offset[1:] = n
+    ids = np.arange(n, dtype=np.int32)
+    t = orc.Tiled.from_csr(n, n, offset, ids)
+    gg = to_gpu_graph(t, 1024)
+    assert gg.plan.n_hub == 1
+    X = np.random.default_rng(0).uniform(-0.5, 0.5, (n, 7)).astype(np.float32)
+    got = ops.spmm(gg, dev(X)).cpu().numpy()
+    assert rel_err(got[0], X.astype(np.float64).sum(0)) < FP32_TOL
+    assert np.all(got[1:] == 0)
+
+
+def test_misaligned_views_fall_back_to_narrow_loads(orc):
+    n, K = 500, 32
+    t = graph_case(orc, n, 8000, 10)
+    g = to_gpu_graph(t)
+    X = np.random.default_rng(1).uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    buf = torch.zeros(n * K + 1, device=DEV)
+    buf[1:] = dev(X).ravel()
+    Xv = buf[1:].view(n, K)                      # 4-byte aligned only
+    assert Xv.data_ptr() % 16 != 0
+    got = ops.spmm(g, Xv).cpu().numpy()
+    assert rel_err(got, orc.spmm(t, X, weighted=False)) < FP32_TOL
+
+
+def test_results_are_bit_reproducible(orc):
+    t = graph_case(orc, 3000, 400000, 2, 700)
+    g = to_gpu_graph(t, 256)
+    X = dev(np.random.default_rng(2).uniform(-0.5, 0.5, (3000, 32)).astype(np.float32))
+    a = ops.spmm(g, X, vals=dev(t.vals))
+    for _ in range(3):
+        assert torch.equal(a, ops.spmm(g, X, vals=dev(t.vals)))
