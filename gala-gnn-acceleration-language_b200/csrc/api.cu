@@ -1,8 +1,10 @@
 // api.cu -- the C-ABI (include/gala_b200.h): argument checks, shape dispatch, launches.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
 #include "edge_ops.cuh"
+#include "plan.cuh"
 #include "spmm.cuh"
 
 using namespace gala;
@@ -39,10 +41,32 @@ GraphDev make_dev(const gala_graph_t* g) {
 struct HubView {
     const int* rows;
     int n, thr;
+    const int* order;
+    int n_ordered;
 };
-HubView hub_of(const gala_plan_t* plan) {
-    if (plan && plan->n_hub > 0 && plan->hub_rows) return {plan->hub_rows, plan->n_hub, plan->hub_threshold};
-    return {nullptr, 0, 0x7fffffff};
+HubView hub_of(const gala_plan_t* plan, const gala_graph_t* g) {
+    HubView h = {nullptr, 0, 0x7fffffff, nullptr, g->nrows};
+    if (!plan) return h;
+    if (plan->n_hub > 0 && plan->hub_rows) {
+        h.rows = plan->hub_rows;
+        h.n = plan->n_hub;
+        h.thr = plan->hub_threshold;
+    }
+    if (plan->row_order && plan->n_ordered + plan->n_hub == g->nrows) {
+        h.order = plan->row_order;
+        h.n_ordered = plan->n_ordered;
+    }
+    return h;
+}
+
+TaskParams task_of(const HubView& h) {
+    TaskParams t;
+    t.hub_rows = h.rows;
+    t.row_order = h.order;
+    t.n_hub = h.n;
+    t.n_ordered = h.n_ordered;
+    t.hub_threshold = h.thr;
+    return t;
 }
 
 inline int last_error() {
@@ -103,17 +127,28 @@ int launch_spmm(const SpmmParams& p, cudaStream_t st) {
     const bool a8 = aligned(p.X, 8) && aligned(p.Y, 8);
     Shape sh = pick_shape(p.K, a16, a8);
     const int tw = sh.vec * sh.lpr * sh.acc;
-    dim3 grid(p.n_hub + (p.g.nrows + kWarpsPerCta - 1) / kWarpsPerCta, (p.K + tw - 1) / tw);
-#define CALL(V, L, A) spmm_kernel<V, L, A, MODE><<<grid, kCtaThreads, 0, st>>>(p)
+    dim3 grid(p.t.n_hub + (p.t.n_ordered + kWarpsPerCta - 1) / kWarpsPerCta, (p.K + tw - 1) / tw);
+    if (sh.vec == 4 && p.K % tw == 0) {
+        // K is a whole number of tiles: no per-lane feature predicates in the gather loop
+#define CALL(V, L, A) spmm_kernel<4, L, A, MODE, true><<<grid, kCtaThreads, 0, st>>>(p)
+        switch (sh.lpr * 100 + sh.acc) {
+            case 101: CALL(4, 1, 1); break;
+            case 201: CALL(4, 2, 1); break;
+            case 401: CALL(4, 4, 1); break;
+            case 801: CALL(4, 8, 1); break;
+            case 1601: CALL(4, 16, 1); break;
+            case 3201: CALL(4, 32, 1); break;
+            case 3202: CALL(4, 32, 2); break;
+            case 3204: CALL(4, 32, 4); break;
+            default: return GALA_ERR_UNSUPPORTED;
+        }
+#undef CALL
+        return last_error();
+    }
+#define CALL(V, L, A) spmm_kernel<V, L, A, MODE, false><<<grid, kCtaThreads, 0, st>>>(p)
     GALA_SHAPE_SWITCH(sh, CALL);
 #undef CALL
     return last_error();
-}
-
-__global__ void plan_scan_kernel(GraphDev g, int thr, int* count, int* hub_rows) {
-    int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= g.nrows) return;
-    if (row_degree(g, row) > thr) hub_rows[atomicAdd(count, 1)] = row;
 }
 
 }  // namespace
@@ -136,7 +171,7 @@ const char* gala_b200_error_string(int code) {
 
 size_t gala_plan_workspace_bytes(const gala_graph_t* g) {
     if (!g || g->nrows < 0) return 0;
-    return ((size_t)g->nrows + 4) * sizeof(int32_t);
+    return (2 * (size_t)g->nrows + 4 + 2 * kPlanBins) * sizeof(int32_t);
 }
 
 int gala_plan_build(const gala_graph_t* g, int32_t hub_threshold, void* workspace, size_t workspace_bytes,
@@ -146,15 +181,26 @@ int gala_plan_build(const gala_graph_t* g, int32_t hub_threshold, void* workspac
     if (workspace_bytes < gala_plan_workspace_bytes(g)) return GALA_ERR_WORKSPACE;
     if (hub_threshold < 1) return GALA_ERR_BAD_SHAPE;
     int* ws = static_cast<int*>(workspace);
-    plan->hub_rows = ws + 4;
+    int* hub_rows = ws + 4;
+    int* row_order = hub_rows + g->nrows;
+    int* hist = row_order + g->nrows;
+    int* cursor = hist + kPlanBins;
+    plan->hub_rows = hub_rows;
+    plan->row_order = row_order;
     plan->n_hub = 0;
+    plan->n_ordered = g->nrows;
     plan->hub_threshold = hub_threshold;
     if (g->nrows == 0) return GALA_OK;
     cudaStream_t st = S(stream);
     cudaError_t e = cudaMemsetAsync(ws, 0, 4 * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(hist, 0, 2 * kPlanBins * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
     GraphDev d = make_dev(g);
-    plan_scan_kernel<<<(g->nrows + 255) / 256, 256, 0, st>>>(d, hub_threshold, ws, ws + 4);
+    const int blocks = std::min((g->nrows + 255) / 256, 148 * 8);
+    plan_hist_kernel<<<blocks, 256, 0, st>>>(d, hub_threshold, ws, hub_rows, hist);
+    plan_scan_kernel<<<1, 1024, 0, st>>>(hist, cursor);
+    plan_scatter_kernel<<<blocks, 256, 0, st>>>(d, hub_threshold, cursor, row_order);
     if (int rc = last_error()) return rc;
     int n = 0;
     e = cudaMemcpyAsync(&n, ws, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -162,6 +208,7 @@ int gala_plan_build(const gala_graph_t* g, int32_t hub_threshold, void* workspac
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return (int)e;
     plan->n_hub = n;
+    plan->n_ordered = g->nrows - n;
     return GALA_OK;
 }
 
@@ -184,10 +231,8 @@ int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int3
         p.accumulate = ep->accumulate;
         p.relu = ep->relu;
     }
-    HubView h = hub_of(plan);
-    p.hub_rows = h.rows;
-    p.n_hub = h.n;
-    p.hub_threshold = h.thr;
+    HubView h = hub_of(plan, g);
+    p.t = task_of(h);
     return launch_spmm<MODE_PLAIN>(p, S(stream));
 }
 
@@ -211,10 +256,8 @@ int gala_gat_forward_f32(const gala_graph_t* g, const float* aL, const float* aR
     p.slope = slope;
     p.alpha_out = alpha_out;
     p.seed_total = (float)g->segments * 1e-12f;
-    HubView h = hub_of(plan);
-    p.hub_rows = h.rows;
-    p.n_hub = h.n;
-    p.hub_threshold = h.thr;
+    HubView h = hub_of(plan, g);
+    p.t = task_of(h);
     return launch_spmm<MODE_GAT>(p, S(stream));
 }
 
@@ -252,12 +295,10 @@ static int edge_common(const gala_graph_t* g, const gala_plan_t* plan, EdgeParam
     if (int rc = check_graph(g)) return rc;
     std::memset(&p, 0, sizeof(p));
     p.g = make_dev(g);
-    HubView h = hub_of(plan);
-    p.hub_rows = h.rows;
-    p.n_hub = h.n;
-    p.hub_threshold = h.thr;
+    HubView h = hub_of(plan, g);
+    p.t = task_of(h);
     p.slope = 1.0f;
-    grid = dim3(h.n + (g->nrows + kWarpsPerCta - 1) / kWarpsPerCta);
+    grid = dim3(h.n + (h.n_ordered + kWarpsPerCta - 1) / kWarpsPerCta);
     return GALA_OK;
 }
 
@@ -346,10 +387,8 @@ int gala_sddmm_f32(const gala_graph_t* g, const float* A, const float* B, int32_
     SddmmParams p;
     std::memset(&p, 0, sizeof(p));
     p.g = make_dev(g);
-    HubView h = hub_of(plan);
-    p.hub_rows = h.rows;
-    p.n_hub = h.n;
-    p.hub_threshold = h.thr;
+    HubView h = hub_of(plan, g);
+    p.t = task_of(h);
     p.A = A;
     p.B = B;
     p.out = out;
@@ -357,7 +396,7 @@ int gala_sddmm_f32(const gala_graph_t* g, const float* A, const float* B, int32_
     const bool a16 = aligned(A, 16) && aligned(B, 16);
     const bool a8 = aligned(A, 8) && aligned(B, 8);
     Shape sh = pick_shape(K > 0 ? K : 1, a16, a8);
-    dim3 grid(h.n + (g->nrows + kWarpsPerCta - 1) / kWarpsPerCta);
+    dim3 grid(h.n + (h.n_ordered + kWarpsPerCta - 1) / kWarpsPerCta);
     cudaStream_t st = S(stream);
 #define CALL(V, L, A_) sddmm_kernel<V, L, A_><<<grid, kCtaThreads, 0, st>>>(p)
     GALA_SHAPE_SWITCH(sh, CALL);

@@ -112,4 +112,49 @@ __device__ __forceinline__ int row_degree(const GraphDev& g, int row) {
     return d;
 }
 
+// ---- row -> warp / CTA assignment shared by every row-structured kernel -----------
+// blockIdx.x <  n_hub : hub row hub_rows[blockIdx.x], its edge list split over the 8 warps
+// blockIdx.x >= n_hub : 8 rows per CTA, one per warp, taken from row_order (degree-
+//                       descending, hubs excluded) or, without a plan, natural order.
+struct TaskParams {
+    const int* __restrict__ hub_rows;
+    const int* __restrict__ row_order;
+    int n_hub;
+    int n_ordered;
+    int hub_threshold;
+};
+
+struct RowTask {
+    int row, lo, hi;
+    bool hub, valid;
+};
+
+__device__ __forceinline__ RowTask row_task(const GraphDev& g, const TaskParams& tp) {
+    RowTask t;
+    const int warp = threadIdx.x >> 5;
+    t.hub = (int)blockIdx.x < tp.n_hub;
+    t.valid = true;
+    if (t.hub) {
+        t.row = __ldg(tp.hub_rows + blockIdx.x);
+        int deg = row_degree(g, t.row);
+        int per = ((deg + kWarpsPerCta * 32 - 1) / (kWarpsPerCta * 32)) * 32;
+        t.lo = warp * per;
+        t.hi = min(deg, t.lo + per);
+    } else {
+        const int slot = ((int)blockIdx.x - tp.n_hub) * kWarpsPerCta + warp;
+        t.row = 0;
+        t.lo = 0;
+        t.hi = 0x7fffffff;
+        if (slot >= tp.n_ordered) {
+            t.valid = false;
+        } else if (tp.row_order) {
+            t.row = __ldg(tp.row_order + slot);
+        } else {
+            t.row = slot;
+            if (tp.n_hub > 0 && row_degree(g, t.row) > tp.hub_threshold) t.valid = false;
+        }
+    }
+    return t;
+}
+
 }  // namespace gala

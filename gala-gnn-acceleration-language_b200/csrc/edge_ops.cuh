@@ -9,33 +9,6 @@
 
 namespace gala {
 
-struct RowTask {
-    int row, lo, hi;
-    bool hub, valid;
-};
-
-__device__ __forceinline__ RowTask row_task(const GraphDev& g, const int* hub_rows, int n_hub,
-                                            int hub_threshold) {
-    RowTask t;
-    const int warp = threadIdx.x >> 5;
-    t.hub = (int)blockIdx.x < n_hub;
-    t.valid = true;
-    if (t.hub) {
-        t.row = __ldg(hub_rows + blockIdx.x);
-        int deg = row_degree(g, t.row);
-        int per = ((deg + kWarpsPerCta * 32 - 1) / (kWarpsPerCta * 32)) * 32;
-        t.lo = warp * per;
-        t.hi = min(deg, t.lo + per);
-    } else {
-        t.row = ((int)blockIdx.x - n_hub) * kWarpsPerCta + warp;
-        t.lo = 0;
-        t.hi = 0x7fffffff;
-        if (t.row >= g.nrows) t.valid = false;
-        else if (n_hub > 0 && row_degree(g, t.row) > hub_threshold) t.valid = false;
-    }
-    return t;
-}
-
 // Sum over the CTA's warps in warp order (hub rows) -- all threads get the total.
 __device__ __forceinline__ float cta_sum_ordered(float warp_total) {
     __shared__ float s_part[kWarpsPerCta];
@@ -51,9 +24,7 @@ __device__ __forceinline__ float cta_sum_ordered(float warp_total) {
 
 struct EdgeParams {
     GraphDev g;
-    const int* __restrict__ hub_rows;
-    int n_hub;
-    int hub_threshold;
+    TaskParams t;
     const float* a;   // per-op meaning, see kernels
     const float* b;
     float* out;
@@ -65,7 +36,7 @@ struct EdgeParams {
 
 // ---- K3: out[row] = seed + sum vals -------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads) edge_rowsum_kernel(const __grid_constant__ EdgeParams p) {
-    RowTask t = row_task(p.g, p.hub_rows, p.n_hub, p.hub_threshold);
+    RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
     float s = 0.0f;
@@ -80,7 +51,7 @@ __global__ void __launch_bounds__(kCtaThreads) edge_rowsum_kernel(const __grid_c
 
 // ---- K4: vals[e] *= rowval[row] -------------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads) edge_scale_kernel(const __grid_constant__ EdgeParams p) {
-    RowTask t = row_task(p.g, p.hub_rows, p.n_hub, p.hub_threshold);
+    RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
     const float r = __ldg(p.a + t.row);
@@ -92,7 +63,7 @@ __global__ void __launch_bounds__(kCtaThreads) edge_scale_kernel(const __grid_co
 
 // ---- K5 / K7: out[e] = A[row] (+|*) B[col[e]]  (optional fused LeakyReLU) ---------------
 __global__ void __launch_bounds__(kCtaThreads) sddvv_kernel(const __grid_constant__ EdgeParams p) {
-    RowTask t = row_task(p.g, p.hub_rows, p.n_hub, p.hub_threshold);
+    RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
     const float ar = __ldg(p.a + t.row);
@@ -111,7 +82,7 @@ __global__ void __launch_bounds__(kCtaThreads) sddvv_kernel(const __grid_constan
 
 // ---- edge-softmax forward: alpha = clamp(exp(x)) / (seed + sum_row clamp(exp(x))) --------
 __global__ void __launch_bounds__(kCtaThreads) edge_softmax_fwd_kernel(const __grid_constant__ EdgeParams p) {
-    RowTask t = row_task(p.g, p.hub_rows, p.n_hub, p.hub_threshold);
+    RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
     float s = 0.0f;
@@ -132,7 +103,7 @@ __global__ void __launch_bounds__(kCtaThreads) edge_softmax_fwd_kernel(const __g
 
 // ---- edge-softmax backward: out = a*da - a * (seed + sum_row a*da) -----------------------
 __global__ void __launch_bounds__(kCtaThreads) edge_softmax_bwd_kernel(const __grid_constant__ EdgeParams p) {
-    RowTask t = row_task(p.g, p.hub_rows, p.n_hub, p.hub_threshold);
+    RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
     float s = 0.0f;
@@ -155,12 +126,14 @@ __global__ void __launch_bounds__(kCtaThreads) edge_softmax_bwd_kernel(const __g
 
 // ---- K6: out[e] = dot(A[row,:], B[col[e],:]) -----------------------------------------------
 // LPR lanes cover one feature row; the A row lives in registers (ACC*VEC per lane) when
-// K <= VEC*LPR*ACC, otherwise the kernel loops over feature tiles (GENERIC).
+// K <= VEC*LPR*ACC, further feature tiles are re-read from L1.  Each lane keeps one partial
+// dot product per edge of its group (LPR of them per 32-edge chunk); the partials are then
+// reduced ACROSS the LPR lanes by a halving exchange (LPR-1 shuffles for LPR edges instead
+// of LPR*log2(LPR)), which leaves lane `sub` holding the finished dot product of edge
+// `sub` of its group; the 32 results go out as one coalesced 128-byte store.
 struct SddmmParams {
     GraphDev g;
-    const int* __restrict__ hub_rows;
-    int n_hub;
-    int hub_threshold;
+    TaskParams t;
     const float* __restrict__ A;
     const float* __restrict__ B;
     float* __restrict__ out;
@@ -171,11 +144,12 @@ template <int VEC, int LPR, int ACC>
 __global__ void __launch_bounds__(kCtaThreads) sddmm_kernel(const __grid_constant__ SddmmParams p) {
     constexpr int EPI = 32 / LPR;
     constexpr int TW = VEC * LPR * ACC;
-    RowTask t = row_task(p.g, p.hub_rows, p.n_hub, p.hub_threshold);
+    RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR, grp = lane / LPR;
     const int ntiles = (p.K + TW - 1) / TW;
+    const uint32_t row_bytes = (uint32_t)p.K * 4u;
 
     float areg[ACC][VEC];
     bool fvalid[ACC];
@@ -191,28 +165,50 @@ __global__ void __launch_bounds__(kCtaThreads) sddmm_kernel(const __grid_constan
 #pragma unroll
         for (int v = 0; v < VEC; ++v) areg[a][v] = x.v[v];
     }
+    // lanes past K read the row start (A is zero there, so the product vanishes)
+    const char* blane = reinterpret_cast<const char*>(p.B + (sub * VEC < p.K ? sub * VEC : 0));
+    // after the halving exchange lane `sub` owns edge j = sub of its group, i.e. chunk
+    // position sub*EPI + grp
+    const int my_pos = sub * EPI + grp;
 
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
+        int c_nxt = (e0 + lane < e1) ? ld_stream(p.g.cols + e0 + lane) : -1;
         for (int base = e0; base < e1; base += 32) {
-            const int idx = base + lane;
-            const int c = idx < e1 ? ld_stream(p.g.cols + idx) : -1;
-            float mine = 0.0f;
+            const int c = c_nxt;
+            if (base + 32 < e1) c_nxt = (base + 32 + lane < e1) ? ld_stream(p.g.cols + base + 32 + lane) : -1;
+            float d[LPR];
+            constexpr int UNR = LPR < 8 ? LPR : 8;
 #pragma unroll
-            for (int j = 0; j < LPR; ++j) {
-                const int cj = __shfl_sync(kFull, c, j * EPI + grp);
-                float d = 0.0f;
-                if (cj >= 0) {
-                    const float* br = p.B + (int64_t)cj * p.K;
+            for (int j0 = 0; j0 < LPR; j0 += UNR) {
+                Vec<VEC> x[UNR][ACC];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int cj = __shfl_sync(kFull, c, (j0 + u) * EPI + grp);
+                    const char* br = blane + (uint64_t)(uint32_t)max(cj, 0) * row_bytes;
 #pragma unroll
                     for (int a = 0; a < ACC; ++a) {
-                        if (fvalid[a]) {
-                            Vec<VEC> x;
-                            x.load(br + (a * LPR + sub) * VEC);
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) d = fmaf(areg[a][v], x.v[v], d);
-                        }
+                        for (int v = 0; v < VEC; ++v) x[u][a].v[v] = 0.0f;
+                        if (fvalid[a]) x[u][a].load(reinterpret_cast<const float*>(br) + a * LPR * VEC);
                     }
-                    for (int tl = 1; tl < ntiles; ++tl) {  // K > TW: remaining tiles from L1/L2
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    float s = 0.0f;
+#pragma unroll
+                    for (int a = 0; a < ACC; ++a)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) s = fmaf(areg[a][v], x[u][a].v[v], s);
+                    d[j0 + u] = s;
+                }
+            }
+            if (ntiles > 1) {  // K > TW: remaining feature tiles (A row from L1)
+#pragma unroll 1
+                for (int j = 0; j < LPR; ++j) {
+                    const int cj = __shfl_sync(kFull, c, j * EPI + grp);
+                    const float* br = p.B + (uint64_t)(uint32_t)max(cj, 0) * (uint32_t)p.K;
+                    float s = 0.0f;
+                    for (int tl = 1; tl < ntiles; ++tl) {
 #pragma unroll
                         for (int a = 0; a < ACC; ++a) {
                             const int f = tl * TW + (a * LPR + sub) * VEC;
@@ -221,18 +217,28 @@ __global__ void __launch_bounds__(kCtaThreads) sddmm_kernel(const __grid_constan
                                 x.load(br + f);
                                 y.load(arow + f);
 #pragma unroll
-                                for (int v = 0; v < VEC; ++v) d = fmaf(y.v[v], x.v[v], d);
+                                for (int v = 0; v < VEC; ++v) s = fmaf(y.v[v], x.v[v], s);
                             }
                         }
                     }
-                }
 #pragma unroll
-                for (int o = 1; o < LPR; o <<= 1) d += __shfl_xor_sync(kFull, d, o);
-                // lane L owns edge L of the chunk = iteration L / EPI, group L % EPI
-                const float got = __shfl_sync(kFull, d, (lane % EPI) * LPR);
-                if (lane / EPI == j) mine = got;
+                    for (int jj = 0; jj < LPR; ++jj)
+                        if (jj == j) d[jj] += s;
+                }
             }
-            if (idx < e1) st_stream(p.out + idx, mine);
+            // halving exchange: after the step with offset o each lane keeps the half of its
+            // partials whose edge index has bit o equal to the lane's own bit o
+#pragma unroll
+            for (int o = LPR >> 1, n = LPR; o > 0; o >>= 1, n >>= 1) {
+                const bool upper = (sub & o) != 0;
+#pragma unroll
+                for (int i = 0; i < (n >> 1); ++i) {
+                    const float send = upper ? d[i] : d[i + (n >> 1)];
+                    const float keep = upper ? d[i + (n >> 1)] : d[i];
+                    d[i] = keep + __shfl_xor_sync(kFull, send, o);
+                }
+            }
+            if (base + my_pos < e1) st_stream(p.out + base + my_pos, d[0]);
         }
     });
 }

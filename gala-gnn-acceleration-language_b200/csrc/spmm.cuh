@@ -30,9 +30,7 @@ struct SpmmParams {
     const float* __restrict__ col_scale;  // nullable
     int accumulate;
     int relu;
-    const int* __restrict__ hub_rows;
-    int n_hub;
-    int hub_threshold;
+    TaskParams t;
     // MODE_GAT
     const float* __restrict__ aL;
     const float* __restrict__ aR;
@@ -44,12 +42,15 @@ struct SpmmParams {
 
 // Gather the feature rows of the (up to) 32 edges a warp holds one-per-lane and
 // accumulate them.  All loads of a batch are issued before the first FMA that
-// consumes them (UNR x ACC independent 16-byte loads in flight per lane); FULL
-// chunks carry no per-edge validity checks.
-template <int VEC, int LPR, int ACC, bool FULL>
-__device__ __forceinline__ void gather_chunk(const float* __restrict__ X, int K, int tile_base, int sub,
-                                             int grp, int c, float w, bool weighted,
-                                             const bool (&fvalid)[ACC], float (&acc)[ACC][VEC]) {
+// consumes them (UNR x ACC independent 16-byte loads in flight per lane).
+//   FULL : every lane of the chunk holds a valid edge (no per-edge checks)
+//   EXACT: K is a multiple of the tile width (no per-lane feature predicates)
+// xlane = X + tile_base + sub*VEC (the lane's first feature); the row address is one
+// IMAD.WIDE.U32: xlane + col * row_bytes.
+template <int VEC, int LPR, int ACC, bool FULL, bool EXACT>
+__device__ __forceinline__ void gather_chunk(const char* __restrict__ xlane, uint32_t row_bytes, int grp,
+                                             int c, float w, bool weighted, const bool (&fvalid)[ACC],
+                                             float (&acc)[ACC][VEC]) {
     constexpr int EPI = 32 / LPR;
     constexpr int UNR_ = 32 / (ACC * VEC) < 1 ? 1 : 32 / (ACC * VEC);
     constexpr int UNR = UNR_ > LPR ? LPR : (UNR_ > 16 ? 16 : UNR_);
@@ -65,13 +66,17 @@ __device__ __forceinline__ void gather_chunk(const float* __restrict__ X, int K,
         Vec<VEC> x[UNR][ACC];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const int cc = FULL ? cj[u] : max(cj[u], 0);
-            const float* xr = X + (int64_t)cc * K + tile_base + sub * VEC;
+            const uint32_t cc = (uint32_t)(FULL ? cj[u] : max(cj[u], 0));
+            const char* xr = xlane + (uint64_t)cc * row_bytes;
 #pragma unroll
             for (int a = 0; a < ACC; ++a) {
+                if (EXACT) {
+                    x[u][a].load(reinterpret_cast<const float*>(xr) + a * LPR * VEC);
+                } else {
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) x[u][a].v[v] = 0.0f;
-                if (fvalid[a]) x[u][a].load(xr + a * LPR * VEC);
+                    for (int v = 0; v < VEC; ++v) x[u][a].v[v] = 0.0f;
+                    if (fvalid[a]) x[u][a].load(reinterpret_cast<const float*>(xr) + a * LPR * VEC);
+                }
             }
         }
 #pragma unroll
@@ -87,7 +92,7 @@ __device__ __forceinline__ void gather_chunk(const float* __restrict__ X, int K,
     }
 }
 
-template <int VEC, int LPR, int ACC, int MODE>
+template <int VEC, int LPR, int ACC, int MODE, bool EXACT>
 __global__ void __launch_bounds__(kCtaThreads)
 spmm_kernel(const __grid_constant__ SpmmParams p) {
     constexpr int TW = VEC * LPR * ACC;  // features covered by one warp pass
@@ -98,22 +103,14 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
     const int sub = lane % LPR;
     const int grp = lane / LPR;
     const int tile_base = blockIdx.y * TW;
-    const bool hub_cta = (int)blockIdx.x < p.n_hub;
-
-    int row, lo, hi;
-    if (hub_cta) {
-        row = __ldg(p.hub_rows + blockIdx.x);
-        int deg = row_degree(g, row);
-        int per = ((deg + kWarpsPerCta * 32 - 1) / (kWarpsPerCta * 32)) * 32;
-        lo = warp * per;
-        hi = min(deg, lo + per);
-    } else {
-        row = ((int)blockIdx.x - p.n_hub) * kWarpsPerCta + warp;
-        if (row >= g.nrows) return;
-        if (p.n_hub > 0 && row_degree(g, row) > p.hub_threshold) return;
-        lo = 0;
-        hi = 0x7fffffff;
-    }
+    const RowTask task = row_task(g, p.t);
+    if (!task.valid) return;
+    const bool hub_cta = task.hub;
+    const int row = task.row, lo = task.lo, hi = task.hi;
+    const uint32_t row_bytes = (uint32_t)p.K * 4u;
+    // the lane's first feature; lanes past K (non-EXACT shapes) point at the tile start
+    const char* xlane = reinterpret_cast<const char*>(
+        p.X + tile_base + ((EXACT || tile_base + sub * VEC < p.K) ? sub * VEC : 0));
 
     bool fvalid[ACC];
 #pragma unroll
@@ -157,9 +154,9 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
             const float w = w_nxt;
             if (base + 32 < e1) fetch(base + 32 + lane, e1, c_nxt, w_nxt);
             if (base + 32 <= e1)
-                gather_chunk<VEC, LPR, ACC, true>(p.X, p.K, tile_base, sub, grp, c, w, weighted, fvalid, acc);
+                gather_chunk<VEC, LPR, ACC, true, EXACT>(xlane, row_bytes, grp, c, w, weighted, fvalid, acc);
             else
-                gather_chunk<VEC, LPR, ACC, false>(p.X, p.K, tile_base, sub, grp, c, w, weighted, fvalid, acc);
+                gather_chunk<VEC, LPR, ACC, false, EXACT>(xlane, row_bytes, grp, c, w, weighted, fvalid, acc);
         }
     });
 

@@ -71,12 +71,16 @@ typedef struct gala_graph {
 /*
  * Load-balance plan for power-law graphs: the list of "hub" rows (total degree
  * above `hub_threshold`) that are executed by a whole thread block instead of a
- * single warp.  Built once per graph, reused by every call.  All kernels accept
- * plan == NULL (pure warp-per-row).
+ * single warp, and the remaining rows in degree-descending order (so the warps of
+ * a block carry rows of equal length and long rows are scheduled first).  Built
+ * once per graph on the device, reused by every call.  All kernels accept
+ * plan == NULL (pure warp-per-row in natural row order).
  */
 typedef struct gala_plan {
-    const int32_t *hub_rows; /* device, [n_hub] ascending row ids                   */
+    const int32_t *hub_rows;  /* device, [n_hub]: rows run by a whole CTA              */
+    const int32_t *row_order; /* device, [n_ordered]: all other rows, longest first    */
     int32_t n_hub;
+    int32_t n_ordered;        /* == nrows - n_hub                                      */
     int32_t hub_threshold;
 } gala_plan_t;
 
