@@ -1,0 +1,222 @@
+// gala_b200_torch.h -- libtorch shim: re-creates, on top of the C-ABI in
+// include/gala_b200.h, the host wrappers that GALA's code generator emits as text into
+// every gala.cu (reference src/codegen/cuda.h:441-952).  Header-only; a generated program
+// includes it after its globals (`int global_nrows; int global_ra; int global_rb;`,
+// src/codegen/common.h:1694-1705) and links libgala_b200.so.
+//
+//   reference (text pasted into gala.cu)                      here
+//   ---------------------------------------------------------------------------------------
+//   <kernel>_call(input_dense, offset, cols, vals[, bounds,   GALA_B200_DEFINE_AGGREGATE(name, weighted,
+//       segments])                 cuda.h:441-499, 213-276        nsamples) stamps the exact emitted name
+//   edge_sddvv                     cuda.h:773-807             edge_sddvv
+//   edge_sddmm                     cuda.h:808-845             edge_sddmm
+//   node_spmv_backward_of_sddmm_{nln,eaggr}  :565-600,737-772 same names
+//   inplace_softmax_sddvv[_mult]   cuda.h:601-656             same names
+//   aggregate_edge_mul[_dir]       cuda.h:870-952             same names
+//
+// Semantics kept: fresh output tensors with requires_grad(true) on the input's device,
+// in-place ops return value_graph, `bounds` is a CPU int tensor, errors abort the program
+// (the reference exit()s; here TORCH_CHECK throws).  Changed: one launch per call on the
+// current torch stream instead of 1-3 fresh never-destroyed streams per segment.
+#pragma once
+#include <c10/cuda/CUDAStream.h>
+#include <torch/torch.h>
+
+#include <unordered_map>
+
+#include "gala_b200.h"
+
+extern int global_nrows;
+extern int global_ra;
+extern int global_rb;
+
+namespace gala_b200 {
+
+inline void check(int rc, const char* what) {
+    TORCH_CHECK(rc == 0, what, ": ", gala_b200_error_string(rc), " (", rc, ")");
+}
+
+inline gala_stream_t stream() { return (gala_stream_t)c10::cuda::getCurrentCUDAStream().stream(); }
+
+struct PlanEntry {
+    torch::Tensor workspace;
+    gala_plan_t plan;
+};
+
+inline gala_graph_t make_graph(const torch::Tensor& offset_graph, const torch::Tensor& columns_graph,
+                               const torch::Tensor& bounds, int segments, int64_t nrows) {
+    gala_graph_t g;
+    g.offsets = offset_graph.data_ptr<int>();
+    g.cols = columns_graph.data_ptr<int>();
+    g.bounds = (bounds.defined() && bounds.numel() > 0) ? bounds.data_ptr<int>() : nullptr;  // CPU tensor
+    g.nrows = (int32_t)nrows;
+    g.ncols = (int32_t)nrows;
+    g.segments = segments;
+    g.nvals = columns_graph.numel();
+    return g;
+}
+
+// One plan per graph (keyed by the row-pointer array), built on first use.
+inline const gala_plan_t* plan_for(const gala_graph_t& g, const torch::Tensor& like) {
+    static std::unordered_map<const void*, PlanEntry> cache;
+    auto it = cache.find(g.offsets);
+    if (it != cache.end() && it->second.plan.n_hub + it->second.plan.n_ordered == g.nrows) return &it->second.plan;
+    PlanEntry e;
+    size_t bytes = gala_plan_workspace_bytes(&g);
+    e.workspace = torch::empty({(int64_t)bytes}, torch::TensorOptions().dtype(torch::kUInt8).device(like.device()));
+    check(gala_plan_build(&g, 2048, e.workspace.data_ptr(), bytes, &e.plan, stream()), "gala_plan_build");
+    cache[g.offsets] = e;
+    return &cache[g.offsets].plan;
+}
+
+inline torch::TensorOptions out_options(const torch::Tensor& like) {
+    return torch::TensorOptions().dtype(torch::kFloat).requires_grad(true).device(like.device());
+}
+
+// aggregate_node_mul_sum*_call: Y = A @ X.  nsamples > 0 selects the sampled flavour
+// (cuda.h:313-320) with global_ra / global_rb.
+inline torch::Tensor aggregate(const torch::Tensor& input_dense, const torch::Tensor& offset_graph,
+                               const torch::Tensor& columns_graph, const torch::Tensor& value_graph,
+                               const torch::Tensor& bounds, int segments, bool weighted, int nsamples) {
+    // cuda.h:451 uses global_nrows; the cuSPARSE flavour (cuda.h:217) derives it from the row pointers
+    const int64_t nrows = global_nrows > 0 ? global_nrows : offset_graph.numel() - 1;
+    const int64_t dcols = input_dense.numel() / nrows;
+    auto X = input_dense.contiguous();
+    auto Y = torch::empty({nrows, dcols}, out_options(input_dense));
+    gala_graph_t g = make_graph(offset_graph, columns_graph, bounds, segments > 0 ? segments : 1, nrows);
+    const float* vals = weighted ? value_graph.data_ptr<float>() : nullptr;
+    if (nsamples > 0) {
+        check(gala_spmm_sampled_f32(&g, vals, X.data_ptr<float>(), (int)dcols, Y.data_ptr<float>(), nsamples,
+                                    global_ra, global_rb, 0, stream()), "gala_spmm_sampled_f32");
+    } else {
+        check(gala_spmm_f32(&g, vals, X.data_ptr<float>(), (int)dcols, Y.data_ptr<float>(), nullptr,
+                            plan_for(g, input_dense), stream()), "gala_spmm_f32");
+    }
+    return Y;
+}
+
+// Fused GAT layer: what the retargeted generator emits for edge_sddvv -> LeakyReLU ->
+// non_lnr_op_softmax -> aggregate_node_mul_sum (common.h:622-675,735-810,835-927).
+inline torch::Tensor gat_forward(const torch::Tensor& res, const torch::Tensor& attenL, const torch::Tensor& attenR,
+                                 const torch::Tensor& offset_graph, const torch::Tensor& columns_graph,
+                                 const torch::Tensor& bounds, int segments, float slope, bool relu,
+                                 torch::Tensor* alpha_out = nullptr) {
+    const int64_t nrows = global_nrows;
+    const int64_t dcols = res.numel() / nrows;
+    auto X = res.contiguous();
+    auto aL = attenL.contiguous();
+    auto aR = attenR.contiguous();
+    auto Y = torch::empty({nrows, dcols}, out_options(res));
+    gala_graph_t g = make_graph(offset_graph, columns_graph, bounds, segments, nrows);
+    float* alpha = nullptr;
+    if (alpha_out) {
+        *alpha_out = torch::empty({columns_graph.numel()}, out_options(res));
+        alpha = alpha_out->data_ptr<float>();
+    }
+    check(gala_gat_forward_f32(&g, aL.data_ptr<float>(), aR.data_ptr<float>(), X.data_ptr<float>(), (int)dcols,
+                               slope, Y.data_ptr<float>(), alpha, relu ? 1 : 0, plan_for(g, res), stream()),
+          "gala_gat_forward_f32");
+    return Y;
+}
+
+}  // namespace gala_b200
+
+// Stamps out one emitted aggregation wrapper under its generated name, e.g.
+//   GALA_B200_DEFINE_AGGREGATE_TILED(aggregate_node_mul_sum_coarse2_call, true, 0)
+#define GALA_B200_DEFINE_AGGREGATE_TILED(NAME, WEIGHTED, NSAMPLES)                                          \
+    inline torch::Tensor NAME(torch::Tensor input_dense, torch::Tensor offset_graph,                       \
+                              torch::Tensor columns_graph, torch::Tensor value_graph, torch::Tensor bounds, \
+                              int segments) {                                                              \
+        return gala_b200::aggregate(input_dense, offset_graph, columns_graph, value_graph, bounds, segments, \
+                                    WEIGHTED, NSAMPLES);                                                   \
+    }
+#define GALA_B200_DEFINE_AGGREGATE(NAME, WEIGHTED, NSAMPLES)                                                \
+    inline torch::Tensor NAME(torch::Tensor input_dense, torch::Tensor offset_graph,                       \
+                              torch::Tensor columns_graph, torch::Tensor value_graph) {                    \
+        return gala_b200::aggregate(input_dense, offset_graph, columns_graph, value_graph, torch::Tensor(), 0, \
+                                    WEIGHTED, NSAMPLES);                                                   \
+    }
+
+// ---- fixed emitted names ---------------------------------------------------------------------
+inline torch::Tensor node_spmv_backward_of_sddmm_nln(torch::Tensor offset_graph, torch::Tensor columns_graph,
+                                                     torch::Tensor value_graph, torch::Tensor bounds, int nrows,
+                                                     int segments) {
+    auto vals = value_graph.contiguous();
+    auto out = torch::empty({nrows, 1}, gala_b200::out_options(value_graph));
+    gala_graph_t g = gala_b200::make_graph(offset_graph, columns_graph, bounds, segments, nrows);
+    gala_b200::check(gala_edge_rowsum_f32(&g, vals.data_ptr<float>(), out.data_ptr<float>(), 1e-12f,
+                                          gala_b200::plan_for(g, value_graph), gala_b200::stream()),
+                     "gala_edge_rowsum_f32");
+    return out;
+}
+
+inline torch::Tensor node_spmv_backward_of_sddmm_eaggr(torch::Tensor offset_graph, torch::Tensor columns_graph,
+                                                       torch::Tensor value_graph, torch::Tensor bounds, int nrows,
+                                                       int segments) {
+    return node_spmv_backward_of_sddmm_nln(offset_graph, columns_graph, value_graph, bounds, nrows, segments);
+}
+
+inline torch::Tensor inplace_softmax_sddvv(torch::Tensor row_val, torch::Tensor offset_graph,
+                                           torch::Tensor columns_graph, torch::Tensor value_graph,
+                                           torch::Tensor bounds, int nrows, int segments) {
+    auto rv = row_val.contiguous();
+    gala_graph_t g = gala_b200::make_graph(offset_graph, columns_graph, bounds, segments, nrows);
+    gala_b200::check(gala_edge_scale_rows_f32(&g, value_graph.data_ptr<float>(), rv.data_ptr<float>(),
+                                              gala_b200::plan_for(g, value_graph), gala_b200::stream()),
+                     "gala_edge_scale_rows_f32");
+    return value_graph;
+}
+
+inline torch::Tensor inplace_softmax_sddvv_mult(torch::Tensor row_val, torch::Tensor offset_graph,
+                                                torch::Tensor columns_graph, torch::Tensor value_graph,
+                                                torch::Tensor bounds, int nrows, int segments) {
+    return inplace_softmax_sddvv(row_val, offset_graph, columns_graph, value_graph, bounds, nrows, segments);
+}
+
+inline torch::Tensor gala_b200_sddvv(torch::Tensor in1, torch::Tensor in2, torch::Tensor offset_graph,
+                                     torch::Tensor columns_graph, torch::Tensor bounds, int nrows, int segments,
+                                     int op) {
+    auto a = in1.contiguous();
+    auto b = in2.contiguous();
+    auto out = torch::empty({columns_graph.numel()}, gala_b200::out_options(in1));
+    gala_graph_t g = gala_b200::make_graph(offset_graph, columns_graph, bounds, segments, nrows);
+    gala_b200::check(gala_sddvv_f32(&g, a.data_ptr<float>(), b.data_ptr<float>(), out.data_ptr<float>(), op, 1.0f,
+                                    gala_b200::plan_for(g, in1), gala_b200::stream()),
+                     "gala_sddvv_f32");
+    return out;
+}
+
+inline torch::Tensor edge_sddvv(torch::Tensor input_dense1, torch::Tensor input_dense2, torch::Tensor offset_graph,
+                                torch::Tensor columns_graph, torch::Tensor value_graph, torch::Tensor bounds,
+                                int nrows, int segments) {
+    return gala_b200_sddvv(input_dense1, input_dense2, offset_graph, columns_graph, bounds, nrows, segments,
+                           GALA_SDDVV_ADD);
+}
+
+inline torch::Tensor edge_sddmm(torch::Tensor input_dense1, torch::Tensor input_dense2, torch::Tensor offset_graph,
+                                torch::Tensor columns_graph, torch::Tensor value_graph, torch::Tensor bounds,
+                                int nrows, int segments) {
+    auto a = input_dense1.contiguous();
+    auto b = input_dense2.contiguous();
+    const int64_t dcols = a.numel() / nrows;
+    auto out = torch::empty({columns_graph.numel()}, gala_b200::out_options(input_dense1));
+    gala_graph_t g = gala_b200::make_graph(offset_graph, columns_graph, bounds, segments, nrows);
+    gala_b200::check(gala_sddmm_f32(&g, a.data_ptr<float>(), b.data_ptr<float>(), (int)dcols, out.data_ptr<float>(),
+                                    gala_b200::plan_for(g, input_dense1), gala_b200::stream()),
+                     "gala_sddmm_f32");
+    return out;
+}
+
+inline torch::Tensor aggregate_edge_mul(torch::Tensor input_dense1, torch::Tensor input_dense2,
+                                        torch::Tensor offset_graph, torch::Tensor columns_graph,
+                                        torch::Tensor value_graph, torch::Tensor bounds, int segments) {
+    return gala_b200_sddvv(input_dense1, input_dense2, offset_graph, columns_graph, bounds, global_nrows, segments,
+                           GALA_SDDVV_MUL);
+}
+
+inline torch::Tensor aggregate_edge_mul_dir(torch::Tensor input_dense1, torch::Tensor input_dense2,
+                                            torch::Tensor offset_graph, torch::Tensor columns_graph,
+                                            torch::Tensor value_graph) {
+    return gala_b200_sddvv(input_dense1, input_dense2, offset_graph, columns_graph, torch::Tensor(), global_nrows, 1,
+                           GALA_SDDVV_MUL);
+}

@@ -1,0 +1,159 @@
+// shim_selftest.cpp -- exercises host/gala_b200_torch.h exactly the way a generated gala.cu
+// does (same globals, same call spelling) and checks every wrapper against dense torch math
+// on the GPU.  Built by host/Makefile, run on the B200 box by tests/test_shim_gpu.py.
+#include <torch/torch.h>
+
+#include <cstdio>
+#include <random>
+#include <vector>
+
+int global_nrows;
+int global_ra;
+int global_rb;
+std::vector<int> global_segments;
+std::vector<torch::Tensor> global_offset_graph, global_columns_graph, global_value_graph, global_bounds;
+
+#include "gala_b200_torch.h"
+
+// the two aggregation wrappers of the checked-in sample program (codegen/gala.cu:225-390), tiled flavour
+GALA_B200_DEFINE_AGGREGATE_TILED(aggregate_node_mul_sum_coarse2_call, true, 0)
+GALA_B200_DEFINE_AGGREGATE_TILED(aggregate_node_mul_sum_direct_coarse2_call, false, 0)
+GALA_B200_DEFINE_AGGREGATE(aggregate_node_mul_sum_call, true, 0)
+GALA_B200_DEFINE_AGGREGATE_TILED(aggregate_node_mul_sum_sample20_call, false, 20)
+
+static int failures = 0;
+static void expect_close(const char* what, const torch::Tensor& got, const torch::Tensor& want, double tol) {
+    double err = ((got.to(torch::kDouble) - want.to(torch::kDouble)).norm() /
+                  want.to(torch::kDouble).norm().clamp_min(1e-30)).item<double>();
+    std::printf("%-44s rel err %.3e %s\n", what, err, err < tol ? "ok" : "FAIL");
+    if (!(err < tol)) ++failures;
+}
+
+int main() {
+    if (!torch::cuda::is_available()) {
+        std::printf("no CUDA device\n");
+        return 2;
+    }
+    const int N = 1500, K = 32, S = 3, T = 500;
+    std::mt19937 rng(7);
+    // symmetric random graph with self loops, a few heavy rows
+    std::vector<std::vector<int>> adj(N);
+    auto add = [&](int u, int v) { adj[u].push_back(v); };
+    for (int i = 0; i < N; ++i) add(i, i);
+    for (int e = 0; e < 40000; ++e) {
+        int u = (int)(std::pow(rng() / 4294967296.0, 3.0) * N), v = rng() % N;
+        if (u == v) continue;
+        add(u, v);
+        add(v, u);
+    }
+    std::vector<int> off(S * (N + 1), 0), cols, bounds(2 * S);
+    std::vector<float> vals;
+    std::vector<int64_t> coo_r, coo_c;
+    for (auto& r : adj) {
+        std::sort(r.begin(), r.end());
+        r.erase(std::unique(r.begin(), r.end()), r.end());
+    }
+    std::uniform_real_distribution<float> U(0.1f, 1.0f);
+    std::vector<float> coo_v;
+    for (int s = 0; s < S; ++s) {   // column-tiled layout of src/ops/tiling.h:222-283
+        bounds[2 * s] = (int)cols.size();
+        int base = (int)cols.size();
+        for (int i = 0; i < N; ++i) {
+            off[s * (N + 1) + i] = (int)cols.size() - base;
+            for (int c : adj[i])
+                if (c >= s * T && c < (s + 1) * T) {
+                    cols.push_back(c);
+                    float w = U(rng);
+                    vals.push_back(w);
+                    coo_r.push_back(i);
+                    coo_c.push_back(c);
+                    coo_v.push_back(w);
+                }
+        }
+        off[s * (N + 1) + N] = (int)cols.size() - base;
+        bounds[2 * s + 1] = (int)cols.size();
+    }
+    const int64_t E = (int64_t)cols.size();
+    auto dev = torch::Device(torch::kCUDA, 0);
+    auto oi = torch::TensorOptions().dtype(torch::kInt);
+    auto of = torch::TensorOptions().dtype(torch::kFloat);
+    global_nrows = N;
+    global_ra = 5;
+    global_rb = 7;
+    torch::Tensor t_off = torch::from_blob(off.data(), {(int64_t)off.size()}, oi).clone().to(dev);
+    torch::Tensor t_col = torch::from_blob(cols.data(), {E}, oi).clone().to(dev);
+    torch::Tensor t_val = torch::from_blob(vals.data(), {E}, of).clone().to(dev);
+    torch::Tensor t_bnd = torch::from_blob(bounds.data(), {2 * S}, oi).clone();   // stays on the CPU
+    global_offset_graph.push_back(t_off);
+    global_columns_graph.push_back(t_col);
+    global_value_graph.push_back(t_val);
+    global_bounds.push_back(t_bnd);
+    global_segments.push_back(S);
+
+    auto ol = torch::TensorOptions().dtype(torch::kLong);
+    torch::Tensor r64 = torch::from_blob(coo_r.data(), {E}, ol).clone().to(dev);
+    torch::Tensor c64 = torch::from_blob(coo_c.data(), {E}, ol).clone().to(dev);
+    torch::Tensor v32 = torch::from_blob(coo_v.data(), {E}, of).clone().to(dev);
+    torch::Tensor A_w = torch::zeros({N, N}, of.device(dev).dtype(torch::kDouble));
+    A_w.index_put_({r64, c64}, v32.to(torch::kDouble));
+    torch::Tensor A_1 = (A_w != 0).to(torch::kDouble);
+
+    torch::manual_seed(0);
+    torch::Tensor X = torch::rand({N, K}, of.device(dev)) - 0.5;
+    torch::Tensor Xd = X.to(torch::kDouble);
+
+    expect_close("aggregate_node_mul_sum_coarse2_call",
+                 aggregate_node_mul_sum_coarse2_call(X, t_off, t_col, t_val, t_bnd, S), A_w.mm(Xd), 1e-5);
+    expect_close("aggregate_node_mul_sum_direct_coarse2_call",
+                 aggregate_node_mul_sum_direct_coarse2_call(X, t_off, t_col, t_val, t_bnd, S), A_1.mm(Xd), 1e-5);
+    torch::Tensor ones = torch::ones({N, 1}, of.device(dev));
+    torch::Tensor deg = aggregate_node_mul_sum_direct_coarse2_call(ones, t_off, t_col, t_val, t_bnd, S);
+    expect_close("degrees via ones (codegen/gala.cu:437)", deg, A_1.sum(1, true), 1e-7);
+
+    torch::Tensor aL = torch::randn({N, 1}, of.device(dev)), aR = torch::randn({N, 1}, of.device(dev));
+    torch::Tensor att = edge_sddvv(aL, aR, t_off, t_col, t_val, t_bnd, N, S);
+    torch::Tensor att_want = aL.index({r64, 0}) + aR.index({c64, 0});
+    expect_close("edge_sddvv", att, att_want, 1e-7);
+    att = torch::leaky_relu(att, 0.2);
+    // body of non_lnr_op_softmax_AutoGrad::forward (common.h:760-773)
+    torch::Tensor val_exp = torch::clamp(torch::exp(att), 0.0, 1e12);
+    torch::Tensor row_sum = node_spmv_backward_of_sddmm_nln(t_off, t_col, val_exp, t_bnd, global_nrows, S);
+    torch::Tensor rs_want = torch::zeros({N}, of.device(dev).dtype(torch::kDouble)).index_add_(0, r64, val_exp.to(torch::kDouble));
+    expect_close("node_spmv_backward_of_sddmm_nln", row_sum.flatten(), rs_want, 1e-5);
+    row_sum = torch::reciprocal(row_sum);
+    val_exp = inplace_softmax_sddvv(row_sum, t_off, t_col, val_exp, t_bnd, global_nrows, S);
+    torch::Tensor alpha_want = torch::exp(att.to(torch::kDouble)) / rs_want.index({r64});
+    expect_close("inplace_softmax_sddvv (softmax)", val_exp, alpha_want, 1e-5);
+    torch::Tensor A_att = torch::zeros({N, N}, of.device(dev).dtype(torch::kDouble));
+    A_att.index_put_({r64, c64}, alpha_want);
+    expect_close("weighted aggregate with attention",
+                 aggregate_node_mul_sum_coarse2_call(X, t_off, t_col, val_exp, t_bnd, S), A_att.mm(Xd), 1e-5);
+    torch::Tensor alpha;
+    torch::Tensor fused = gala_b200::gat_forward(X, aL, aR, t_off, t_col, t_bnd, S, 0.2f, false, &alpha);
+    expect_close("gala_b200::gat_forward (fused layer)", fused, A_att.mm(Xd), 1e-5);
+    expect_close("gala_b200::gat_forward alpha", alpha, alpha_want, 1e-5);
+
+    torch::Tensor dZ = torch::rand({N, K}, of.device(dev)) - 0.5;
+    torch::Tensor dd = edge_sddmm(dZ, X, t_off, t_col, t_val, t_bnd, global_nrows, S);
+    torch::Tensor dd_want = (dZ.to(torch::kDouble).index({r64}) * Xd.index({c64})).sum(1);
+    expect_close("edge_sddmm", dd, dd_want, 1e-5);
+
+    torch::Tensor norm = torch::pow(deg, -0.5);
+    torch::Tensor ev = aggregate_edge_mul(norm, norm, t_off, t_col, t_val, t_bnd, S);
+    expect_close("aggregate_edge_mul", ev, norm.index({r64, 0}) * norm.index({c64, 0}), 1e-6);
+
+    torch::Tensor ys = aggregate_node_mul_sum_sample20_call(X, t_off, t_col, t_val, t_bnd, S);
+    // reference semantics (cuda.h:313-320): per row AND per segment, 20 picks j=(5*ji+7)%deg
+    torch::Tensor want = torch::zeros({N, K}, of.dtype(torch::kDouble));
+    torch::Tensor Xc = Xd.cpu();
+    for (int s = 0; s < S; ++s)
+        for (int i = 0; i < N; ++i) {
+            int b = off[s * (N + 1) + i], d = off[s * (N + 1) + i + 1] - b;
+            if (d <= 0) continue;
+            for (int ji = 0; ji < 20; ++ji) want[i] += Xc[cols[bounds[2 * s] + b + (5 * ji + 7) % d]];
+        }
+    expect_close("sampled aggregate (global_ra/rb = 5/7)", ys, want.to(dev), 1e-5);
+
+    std::printf(failures ? "SHIM SELFTEST FAILED (%d)\n" : "SHIM SELFTEST OK\n", failures);
+    return failures ? 1 : 0;
+}
