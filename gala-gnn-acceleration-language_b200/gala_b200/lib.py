@@ -17,6 +17,9 @@ EXPORTS = [
     "gala_plan_build", "gala_spmm_f32", "gala_spmm_sampled_f32", "gala_edge_rowsum_f32",
     "gala_edge_scale_rows_f32", "gala_sddvv_f32", "gala_sddmm_f32", "gala_edge_softmax_fwd_f32",
     "gala_edge_softmax_bwd_f32", "gala_gat_forward_f32",
+    "gala_csr_from_coo_workspace_bytes", "gala_csr_from_coo", "gala_csr_transpose",
+    "gala_col_tile_segments", "gala_col_tile_workspace_bytes", "gala_col_tile", "gala_sample_ab",
+    "gala_mask_subgraph_workspace_bytes", "gala_mask_subgraph",
 ]
 
 
@@ -73,6 +76,22 @@ def load():
         "gala_edge_softmax_bwd_f32": [G, vp, vp, vp, P, vp],
         "gala_gat_forward_f32": [G, vp, vp, vp, i32, f32, vp, vp, i32, P, vp],
     }
+    i64, sz = C.c_int64, C.c_size_t
+    sigs.update({
+        "gala_csr_from_coo": [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp],
+        "gala_csr_transpose": [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp],
+        "gala_col_tile": [i32, i32, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp],
+        "gala_sample_ab": [i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
+        "gala_mask_subgraph": [i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int64), vp, vp, sz, vp],
+    })
+    lib.gala_csr_from_coo_workspace_bytes.restype = sz
+    lib.gala_csr_from_coo_workspace_bytes.argtypes = [i32, i32, i64]
+    lib.gala_col_tile_segments.restype = i32
+    lib.gala_col_tile_segments.argtypes = [i32, i32]
+    lib.gala_col_tile_workspace_bytes.restype = sz
+    lib.gala_col_tile_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.gala_mask_subgraph_workspace_bytes.restype = sz
+    lib.gala_mask_subgraph_workspace_bytes.argtypes = [i32]
     for name, args in sigs.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

@@ -174,6 +174,59 @@ int gala_gat_forward_f32(const gala_graph_t *g, const float *aL, const float *aR
                          int32_t K, float slope, float *Y, float *alpha_out, int32_t relu,
                          const gala_plan_t *plan, gala_stream_t stream);
 
+/* ---- format construction on the device ---------- */
+/* All integer outputs are bit-exact against the reference functions named below.       */
+
+/* Replaces CSRCMatrix::build, CSR branch (src/formats/csrc_matrix.h:148-282; count /    */
+/* prefix / place / per-row sort, src/utils/mtx_sort.h:52-64,165-174,114-137,683-722):   */
+/* COO (row_ids, col_ids[, vals]) in any order, duplicates kept -> offsets[nrows+1],     */
+/* ids[nvals] sorted by (row, col), out_vals travelling with their edge (stable among    */
+/* duplicates; the reference's order among duplicates is unspecified).  vals/out_vals    */
+/* may be NULL (the pipeline sets every value to 1 afterwards, tests/common.h:363).      */
+size_t gala_csr_from_coo_workspace_bytes(int32_t nrows, int32_t ncols, int64_t nvals);
+int gala_csr_from_coo(int32_t nrows, int32_t ncols, int64_t nvals, const int32_t *row_ids,
+                      const int32_t *col_ids, const float *vals, int32_t *offsets, int32_t *ids,
+                      float *out_vals, void *workspace, size_t workspace_bytes,
+                      gala_stream_t stream);
+
+/* Replaces buildTranspose (tests/common.h:107-123) + get_sids (csrc_matrix.h:399-411). */
+/* Workspace: gala_csr_from_coo_workspace_bytes(ncols, nrows, nvals).                   */
+int gala_csr_transpose(int32_t nrows, int32_t ncols, int64_t nvals, const int32_t *offsets,
+                       const int32_t *ids, const float *vals, int32_t *t_offsets, int32_t *t_ids,
+                       float *t_vals, void *workspace, size_t workspace_bytes,
+                       gala_stream_t stream);
+
+/* Replaces static_ord_col_breakpoints (src/ops/tiling.h:1594-1608) +                   */
+/* ord_col_tiling_torch (:222-283).  segments = ceil(ncols / cols_per_partition);       */
+/* out_offsets[segments*(nrows+1)], out_cols/out_vals[nvals] on the device,             */
+/* bounds_host[2*segments] on the HOST (the call synchronises the stream once).         */
+/* Requires column-sorted rows, as the reference does (tiling.h:273-276).               */
+int32_t gala_col_tile_segments(int32_t ncols, int32_t cols_per_partition);
+size_t gala_col_tile_workspace_bytes(int32_t nrows, int32_t ncols, int32_t cols_per_partition);
+int gala_col_tile(int32_t nrows, int32_t ncols, int64_t nvals, const int32_t *offsets,
+                  const int32_t *ids, const float *vals, int32_t cols_per_partition,
+                  int32_t *out_offsets, int32_t *out_cols, float *out_vals, int32_t *bounds_host,
+                  void *workspace, size_t workspace_bytes, gala_stream_t stream);
+
+/* Replaces inplace_sample_graph_ab (src/ops/tiling.h:454-508): per row keep            */
+/* sample_size edges at the sorted positions (ra*ji+rb) % deg; new_offsets[i] =         */
+/* i*sample_size.  sample_size <= 128.  *status_dev (device int) is set to 1 if a row   */
+/* has no edge (`% 0` in the reference).                                                */
+int gala_sample_ab(int32_t nrows, const int32_t *offsets, const int32_t *ids, const float *vals,
+                   int32_t sample_size, int32_t ra, int32_t rb, int32_t *new_offsets,
+                   int32_t *new_ids, float *new_vals, int32_t *status_dev, gala_stream_t stream);
+
+/* One layer of getMaskSubgraphs (tests/common.h:20-105): forward sub-graph = rows with  */
+/* mask > 0 kept whole (new_ids/new_vals sized for nvals), *new_nvals_host = its edge    */
+/* count (the call synchronises once); next_mask (nullable) = one-hop growth of the      */
+/* mask (maxAgg gSpMM into a ZEROED buffer; the reference leaves it uninitialised).      */
+/* The backward graph is gala_csr_transpose of the result.                               */
+size_t gala_mask_subgraph_workspace_bytes(int32_t nrows);
+int gala_mask_subgraph(int32_t nrows, const int32_t *offsets, const int32_t *ids, const float *vals,
+                       const uint8_t *mask, int32_t *new_offsets, int32_t *new_ids, float *new_vals,
+                       int64_t *new_nvals_host, uint8_t *next_mask, void *workspace,
+                       size_t workspace_bytes, gala_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
