@@ -63,8 +63,9 @@ def test_csr_build_and_transpose_match_oracle(orc, n, e, seed):
     gto, gti, _ = formats.buildTranspose(n, n, off, ids)
     assert eq(gto, to) and eq(gti, ti)
     # transpose of a symmetric duplicate-free graph is itself
-    o2, i2, _ = formats.buildTranspose(n, n, dev(offset0), dev(ids0))
-    assert eq(o2, offset0) and eq(i2, ids0)
+    offset_s, ids_s = make_csr(n, e, seed)
+    o2, i2, _ = formats.buildTranspose(n, n, dev(offset_s), dev(ids_s))
+    assert eq(o2, offset_s) and eq(i2, ids_s)
 
 
 @pytest.mark.parametrize("T", [1, 7, 64, 1000, 100000])
