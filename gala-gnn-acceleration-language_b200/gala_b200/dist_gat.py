@@ -1,0 +1,115 @@
+"""1-D row-partitioned execution over the GPUs of one node.
+
+The reference is single-GPU (`device(torch::kCUDA, 0)` everywhere, src/codegen/cuda.h:226,462);
+this layer is new.  Rows (output nodes) are split into P contiguous blocks balanced by nnz;
+rank p holds the CSR slab of its rows with column ids remapped into the padded all-gather
+layout, so that one `all_gather_into_tensor` of the hidden-width features per layer is the
+only exchange.  Attention needs no extra exchange: aR is recomputed from the gathered
+features (an N x K GEMV), aL only for the rank's own rows.
+
+Host-side logic (partition, remap, padded layout) is plain torch and runs on CPU tensors
+too -- tests/test_dist_cpu.py drives it with the gloo backend, world_size 2.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+def partition_rows_by_nnz(offset, world):
+    """Row boundaries [r_0=0, ..., r_P=N] such that every block holds ~E/P edges
+    (prefix-sum split on the row pointers; cf. nnz_ord_row_tile_info,
+    reference src/ops/tiling.h:1656-1708)."""
+    n = offset.numel() - 1
+    e = int(offset[-1])
+    targets = torch.arange(1, world, dtype=torch.int64, device=offset.device) * e // world
+    cuts = torch.searchsorted(offset.to(torch.int64), targets, right=False).clamp_(0, n)
+    b = torch.cat([torch.zeros(1, dtype=torch.int64, device=offset.device), cuts,
+                   torch.full((1,), n, dtype=torch.int64, device=offset.device)])
+    return torch.cummax(b, 0).values.tolist()
+
+
+class RowPartition:
+    """Rank `rank`'s slab of a CSR graph in the padded all-gather layout.
+
+    Gathered buffers have shape [world * max_rows, K]; row j of rank q sits at
+    q * max_rows + (j - bounds[q]).  `cols` are remapped into that layout once here."""
+
+    def __init__(self, offset, ids, n, rank, world):
+        self.n, self.rank, self.world = n, rank, world
+        self.bounds = partition_rows_by_nnz(offset, world)
+        self.row_lo, self.row_hi = self.bounds[rank], self.bounds[rank + 1]
+        self.rows = self.row_hi - self.row_lo
+        self.max_rows = max(self.bounds[q + 1] - self.bounds[q] for q in range(world))
+        e_lo, e_hi = int(offset[self.row_lo]), int(offset[self.row_hi])
+        self.local_nvals = e_hi - e_lo
+        self.offset = (offset[self.row_lo:self.row_hi + 1] - e_lo).to(torch.int32).contiguous()
+        bt = torch.tensor(self.bounds, dtype=torch.int64, device=ids.device)
+        cols = ids[e_lo:e_hi].to(torch.int64)
+        owner = torch.searchsorted(bt, cols, right=True) - 1
+        self.cols = (owner * self.max_rows + (cols - bt[owner])).to(torch.int32).contiguous()
+        self.padded_n = world * self.max_rows
+
+    def pad(self, x_local):
+        """[rows, K] -> [max_rows, K] (zero rows at the end)."""
+        if x_local.shape[0] == self.max_rows:
+            return x_local.contiguous()
+        out = x_local.new_zeros((self.max_rows,) + tuple(x_local.shape[1:]))
+        out[:self.rows] = x_local
+        return out
+
+    def all_gather(self, x_local):
+        """Every rank's rows, padded layout: [world * max_rows, K]."""
+        send = self.pad(x_local)
+        out = send.new_empty((self.padded_n,) + tuple(send.shape[1:]))
+        dist.all_gather_into_tensor(out, send)
+        return out
+
+    def local_slice(self, gathered):
+        lo = self.rank * self.max_rows
+        return gathered[lo:lo + self.rows]
+
+    def unpad(self, gathered):
+        """Padded layout -> natural node order [n, K] (used by tests / final gathers)."""
+        parts = [gathered[q * self.max_rows:q * self.max_rows + self.bounds[q + 1] - self.bounds[q]]
+                 for q in range(self.world)]
+        return torch.cat(parts, 0)
+
+
+def gat2_forward_partitioned(model, part, X_local, aggregate, hook=None):
+    """The 2-layer GAT forward of gat_model.GAT2 on a row partition.
+    aggregate(aL_local, aR_all, feats_all, relu) -> [rows, K] runs the fused GAT kernel on
+    the rank's slab (or, in the CPU tests, the oracle)."""
+    run = hook if hook is not None else (lambda name, fn: fn())
+    res_loc = F.linear(X_local, *model.fc0)
+    res_all = part.all_gather(res_loc)
+    aL = F.linear(res_loc, *model.efc0).reshape(-1)
+    aR = F.linear(res_all, *model.efc1).reshape(-1)
+    y_loc = run("gat_layer1", lambda: aggregate(aL, aR, res_all, True))
+    y_all = part.all_gather(y_loc)
+    t_all = F.linear(y_all, *model.fc1)
+    aL = F.linear(part.local_slice(t_all), *model.efc2).reshape(-1)
+    aR = F.linear(t_all, *model.efc3).reshape(-1)
+    agg = run("gat_layer2", lambda: aggregate(aL, aR, y_all, False))
+    return F.linear(agg, *model.fc1)
+
+
+class PartitionedGAT:
+    """GPU runner: slab graph + plan + fused kernel, NCCL all-gather between layers."""
+
+    launches_per_step = 2
+
+    def __init__(self, model, offset, ids, n, rank, world, device):
+        from . import ops
+
+        self.model, self.ops = model, ops
+        self.part = RowPartition(offset, ids, n, rank, world)
+        self.row_lo, self.row_hi = self.part.row_lo, self.part.row_hi
+        self.local_nvals = self.part.local_nvals
+        self.graph = ops.TiledGraph(self.part.offset, self.part.cols, self.part.rows,
+                                    ncols=self.part.padded_n).build_plan()
+
+    def _aggregate(self, aL, aR, feats, relu):
+        return self.ops.gat_forward(self.graph, aL.contiguous(), aR.contiguous(), feats, self.model.slope, relu=relu)
+
+    def forward(self, X_local, hook=None):
+        return gat2_forward_partitioned(self.model, self.part, X_local, self._aggregate, hook)
