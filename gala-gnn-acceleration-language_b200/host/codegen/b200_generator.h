@@ -1,0 +1,104 @@
+// b200_generator.h -- the retargeted code generator: GALA's CUDAGenerator
+// (reference src/codegen/cuda.h) with the three edits INTEGRATION.md section 3 describes.
+// Everything else (model emission, autograd classes, data prep, H2D transfer, main) is
+// inherited unchanged from the reference, so generated programs differ from the reference's
+// only in that the kernel / launch-tree text is replaced by calls into libgala_b200.so.
+//
+// Compiled against the reference tree (-I/root/reference); no reference source is copied.
+#pragma once
+#include <unordered_set>
+
+#include "src/codegen/cuda.h"
+
+class B200Generator : public CUDAGenerator {
+public:
+    B200Generator(GALAContext* context, std::string& outputPath, const std::string& galaB200Root)
+        : CUDAGenerator(context, outputPath), root_(galaB200Root) {}
+
+    // replaces CUDAGenerator::initCMake (cuda.h:18-56): no icpx, sm_100a, link libgala_b200
+    void initCMake() override {
+        std::string cm =
+            "cmake_minimum_required(VERSION 3.18 FATAL_ERROR)\n"
+            "project(gala_cuda LANGUAGES CUDA CXX)\n"
+            "set(CMAKE_CUDA_ARCHITECTURES 100a)\n"
+            "find_package(Torch REQUIRED)\n"
+            "find_package(OpenMP REQUIRED)\n"
+            "include_directories(${CMAKE_CUDA_TOOLKIT_INCLUDE_DIRECTORIES} " + root_ + "/include " + root_ +
+            "/gala-gnn-acceleration-language_b200/host)\n"
+            "link_directories(" + root_ + "/gala-gnn-acceleration-language_b200)\n"
+            "link_libraries(\"${TORCH_LIBRARIES}\" cudart gala_b200 OpenMP::OpenMP_CXX)\n"
+            "add_compile_options(-Xcompiler -fopenmp -O3)\n"
+            "add_compile_definitions(GALA_TORCH GN_1 PT_0 ST_0 A_ALLOC)\n"
+            "add_executable(gala_model gala.cu)\n"
+            "target_compile_features(gala_model PRIVATE cxx_std_17)";
+        cmakeCode.addCode(cm);
+    }
+
+    // replaces CUDAGenerator::initKernels (cuda.h:957-1050) + generateCudaCodeForCNode (:170-955)
+    void initKernels(std::vector<CIRNode*>& program) override {
+        std::string imports =
+            "#include <cuda_runtime_api.h>\n"
+            "#include <torch/script.h>\n"
+            "#include <cmath>\n#include <iostream>\n#include <parallel/algorithm>\n#include <vector>\n"
+            "#include <bits/stdc++.h>\n#include <omp.h>\n#include <stdlib.h>\n#include <torch/torch.h>\n"
+            "#include \"../src/formats/csrc_matrix.h\"\n"
+            "#include \"../src/formats/dense_matrix.h\"\n"
+            "#include \"../src/ops/aggregators.h\"\n"
+            "#include \"../src/ops/tiling.h\"\n"
+            "#include \"../src/utils/mtx_io.h\"\n"
+            "#include \"../tests/common.h\"\n";
+        importCode.addCode(imports);
+
+        std::string prelude =
+            "\n#define CUDA_CHECK(func)\\\n"
+            "  do {\\\n"
+            "    cudaError_t status = (func);\\\n"
+            "    if (status != cudaSuccess) {\\\n"
+            "      printf(\"CUDA API failed at line %d with error: %s (%d)\\n\", __LINE__,\\\n"
+            "             cudaGetErrorString(status), status);\\\n"
+            "      exit(EXIT_FAILURE);\\\n"
+            "    }\\\n"
+            "  } while (0)\n"
+            "// sparse kernels: libgala_b200.so through the libtorch shim (INTEGRATION.md)\n"
+            "#include \"gala_b200_torch.h\"\n";
+        if (GALAFEContext::print_memory) {
+            prelude +=
+                "int printMemoryUsage() {\n  size_t freeMem, totalMem;\n  cudaMemGetInfo(&freeMem, &totalMem);\n"
+                "  return (int)((totalMem - freeMem) / (1024 * 1024));\n}\n";
+        }
+        kernelCode.addCode(prelude);
+
+        std::unordered_set<std::string> seen;
+        auto visit = [&](CIRNode* node) {
+            auto cNode = dynamic_cast<ComputeNode*>(node);
+            if (!cNode) return;
+            std::string name = getKernelName(cNode);
+            if (seen.insert(name).second) emitBinding(cNode, name);
+        };
+        for (CIRNode* node : program) {
+            if (dynamic_cast<ComputeNode*>(node)) {
+                visit(node);
+            } else if (auto loop = dynamic_cast<TrainingLoopNode*>(node)) {
+                for (int ix = 0; ix < loop->getLoopNodeNum(); ix++) visit(loop->getNode(ix));
+            }
+        }
+    }
+
+private:
+    std::string root_;
+
+    // One line per aggregation flavour instead of kernel text + launch tree; the edge ops
+    // (softmax / edge-sum / edge-mul nodes) need nothing: the shim defines their fixed names.
+    void emitBinding(ComputeNode* cNode, const std::string& name) {
+        if (cNode->getOpType() != AGGREGATE_NODE) return;
+        bool weighted = cNode->getInput(1)->getDataInfo()->getWeighted();
+        bool colTile = hasDOpt(cNode->getInput(1), COL_TILE_DOPT);
+        int nsamples = 0;
+        for (auto opt : *cNode->getOpts())
+            if (opt.first == SAMPLE_COPT || opt.first == SAMPLE_DYNAMIC_COPT) nsamples = (int)opt.second;
+        std::string line = std::string(colTile ? "GALA_B200_DEFINE_AGGREGATE_TILED(" : "GALA_B200_DEFINE_AGGREGATE(") +
+                           name + "_call, " + (weighted ? "true" : "false") + ", " + std::to_string(nsamples) + ")\n";
+        kernelCallCode.addCode(line);
+        cNode->setKernelName("gather_forward");
+    }
+};
