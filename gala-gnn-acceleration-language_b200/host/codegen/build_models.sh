@@ -21,6 +21,8 @@ build_one() {
   "$HERE/gala_b200_codegen" "$model" Reddit 602 41 "$tile" "$mode" "$dir/" "$REPO" $flag > "$dir/codegen.log" 2>&1
   # instrumentation of the GENERATED text (identical for both generators)
   sed -i 's|    if (epoch >= skip_cache_warmup) {|    if (epoch == 1) { std::cout << "CHECK " << std::setprecision(9) << prediction.abs().sum().item<float>() << " " << d_loss.item<float>() << std::endl; }\n    if (epoch >= skip_cache_warmup) {|' "$dir/gala.cu"
+  # the generated program never seeds libtorch: weights differ from run to run.  Seed it.
+  sed -i 's|auto net = std::make_shared<GALAGNN>|torch::manual_seed(0); auto net = std::make_shared<GALAGNN>|' "$dir/gala.cu"
   local extra="-lcusparse"
   [ "$kind" = "b200" ] && extra="-I$REPO/include -I$REPO/gala-gnn-acceleration-language_b200/host -L$REPO/gala-gnn-acceleration-language_b200 -lgala_b200 -Xlinker -rpath -Xlinker $REPO/gala-gnn-acceleration-language_b200"
   (cd "$dir" && nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -O3 -w -Xcompiler -fopenmp \
