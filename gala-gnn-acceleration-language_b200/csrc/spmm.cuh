@@ -92,8 +92,19 @@ __device__ __forceinline__ void gather_chunk(const char* __restrict__ xlane, uin
     }
 }
 
+// Minimum resident CTAs per SM the register allocator must allow.  Decides how many of
+// the UNR gathers ptxas keeps in flight (it serialises them when squeezed below ~64
+// registers); tuned on B200, see profiles/r01_variants.txt.
+#ifndef GALA_SPMM_MINB
+#define GALA_SPMM_MINB 5
+#endif
+#if GALA_SPMM_MINB > 0
+#define GALA_SPMM_BOUNDS __launch_bounds__(kCtaThreads, GALA_SPMM_MINB)
+#else
+#define GALA_SPMM_BOUNDS __launch_bounds__(kCtaThreads)
+#endif
 template <int VEC, int LPR, int ACC, int MODE, bool EXACT>
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void GALA_SPMM_BOUNDS
 spmm_kernel(const __grid_constant__ SpmmParams p) {
     constexpr int TW = VEC * LPR * ACC;  // features covered by one warp pass
     constexpr int EPI = 32 / LPR;        // edges in flight per load instruction

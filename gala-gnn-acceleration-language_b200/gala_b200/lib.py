@@ -10,7 +10,8 @@ import os
 import torch
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "libgala_b200.so")
+# GALA_B200_LIB selects an alternative build of the same library (kernel-variant experiments)
+LIB_PATH = os.environ.get("GALA_B200_LIB") or os.path.join(_PKG_ROOT, "libgala_b200.so")
 
 EXPORTS = [
     "gala_b200_abi_version", "gala_b200_error_string", "gala_plan_workspace_bytes",

@@ -1,0 +1,43 @@
+"""Times the gather kernels for every library build under variants/ (one subprocess per build).
+   python profiles/variant_bench.py            -> table on stdout"""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "gala-gnn-acceleration-language_b200")
+
+CHILD = r'''
+import sys, json, torch
+sys.path.insert(0, %r)
+from gala_b200 import ops, synth
+n, e, f, K, c = synth.SHAPES["reddit"]
+dev = "cuda:0"
+offset, ids = synth.powerlaw_csr_torch(n, e, seed=0, device=dev)
+g = ops.TiledGraph(offset, ids, n).build_plan()
+gen = torch.Generator(device=dev); gen.manual_seed(3)
+X = torch.rand(n, K, generator=gen, device=dev) - 0.5
+a = torch.randn(n, generator=gen, device=dev)
+w = torch.rand(g.nvals, generator=gen, device=dev)
+Y = torch.empty(n, K, device=dev); ev = torch.empty(g.nvals, device=dev)
+def t(fn, reps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    s, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps): fn()
+    e_.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e_) / reps
+print(json.dumps({"gat": t(lambda: ops.gat_forward(g, a, a, X, out=Y)),
+                  "spmm": t(lambda: ops.spmm(g, X, out=Y)),
+                  "spmm_w": t(lambda: ops.spmm(g, X, vals=w, out=Y)),
+                  "sddmm": t(lambda: ops.sddmm(g, X, X, out=ev))}))
+''' % PKG
+
+for lib in sorted(glob.glob(os.path.join(PKG, "variants", "*.so"))) + [os.path.join(PKG, "libgala_b200.so")]:
+    env = dict(os.environ, GALA_B200_LIB=lib)
+    r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
+    line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
+    print(os.path.basename(lib), line, flush=True)
