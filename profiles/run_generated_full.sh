@@ -9,6 +9,6 @@ python $CG/make_npy_dataset.py $D 232965 114615892 602 41
 for m in ${1:-gat_inference gcn_inference}; do
   for k in ref b200; do
     echo "== $m $k"
-    (cd $CG/_models/${m}_$k/build && /usr/bin/time -f "wall %e s" ./gala_model 2>&1 | tail -3)
+    (cd $CG/_models/${m}_$k/build && ( time ./gala_model ) 2>&1 | tail -7)
   done
 done
