@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--nodes", type=int, default=None, help="override graph size (debug)")
     ap.add_argument("--edges", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernels", action="store_true", help="also report the kernel sweep (SpMM/SDDMM GB/s)")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel sweep (SpMM/SDDMM GB/s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -367,7 +367,7 @@ def main():
                     "h2d_bytes_per_step": int(X_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4)},
             "roofline": roofline, "kernel_ms": {k: round(v, 4) for k, v in kern_ms.items()}}
 
-    if args.kernels and world == 1:
+    if not args.no_kernels and world == 1:
         line["kernels"] = kernel_sweep(g, n, nvals, hidden, peak, dev)
 
     if world == 1 and not args.no_cpu_baseline:
@@ -415,6 +415,11 @@ def kernel_sweep(g, n, nvals, K, peak, dev):
     rp = 4 * (n + 1)
     rec("spmm_k32_unweighted", time_op(lambda: ops.spmm(g, X, out=Y)), rp + 4 * nvals + 8 * n * K)
     rec("spmm_k32_weighted", time_op(lambda: ops.spmm(g, X, vals=w, out=Y)), rp + 8 * nvals + 8 * n * K)
+    nrm = torch.rand(n, generator=gen, device=dev) + 0.1
+    # GCN layer body of the generated model (norm*res -> aggregate -> norm*res -> relu, codegen/gala.cu:441-450)
+    # as ONE launch with the fused row/col scale + ReLU epilogue
+    rec("gcn_layer_aggregate_fused_k32", time_op(lambda: ops.spmm(g, X, out=Y, row_scale=nrm, col_scale=nrm, relu=True)),
+        rp + 4 * nvals + 8 * n * K + 8 * n)
     rec("sddmm_k32", time_op(lambda: ops.sddmm(g, Z, X, out=ev)), rp + 4 * nvals + 8 * n * K + 4 * nvals)
     rec("sddvv_add", time_op(lambda: ops.sddvv(g, a, a, "add", out=ev)), rp + 4 * nvals + 8 * n + 4 * nvals)
     rec("edge_softmax_fwd", time_op(lambda: ops.edge_softmax_fwd(g, w, out=ev)), rp + 8 * nvals)

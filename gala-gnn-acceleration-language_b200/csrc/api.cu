@@ -311,9 +311,11 @@ int gala_edge_rowsum_f32(const gala_graph_t* g, const float* vals, float* out, f
     if (!out || (g->nvals > 0 && !vals)) return GALA_ERR_NULL_POINTER;
     p.a = vals;
     p.out = out;
+    const bool v4 = aligned(vals, 16);
     // reference: `local_C = 1e-12` once per segment, then C += local_C (cuda.h:512-522)
     p.seed = (float)g->segments * seed;
-    edge_rowsum_kernel<<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    if (v4) edge_rowsum_kernel<true><<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    else edge_rowsum_kernel<false><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     return last_error();
 }
 
@@ -326,7 +328,9 @@ int gala_edge_scale_rows_f32(const gala_graph_t* g, float* vals, const float* ro
     if (!vals || !rowval) return GALA_ERR_NULL_POINTER;
     p.a = rowval;
     p.out = vals;
-    edge_scale_kernel<<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    const bool v4 = aligned(vals, 16);
+    if (v4) edge_scale_kernel<true><<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    else edge_scale_kernel<false><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     return last_error();
 }
 
@@ -343,7 +347,9 @@ int gala_sddvv_f32(const gala_graph_t* g, const float* A, const float* B, float*
     p.out = out;
     p.op = op;
     p.slope = leaky_slope;
-    sddvv_kernel<<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    const bool v4 = aligned(g->cols, 16) && aligned(out, 16);
+    if (v4) sddvv_kernel<true><<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    else sddvv_kernel<false><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     return last_error();
 }
 
@@ -357,8 +363,10 @@ int gala_edge_softmax_fwd_f32(const gala_graph_t* g, const float* x, float* alph
     p.a = x;
     p.out = alpha;
     p.out2 = recip;
+    const bool v4 = aligned(x, 16) && aligned(alpha, 16);
     p.seed = (float)g->segments * 1e-12f;
-    edge_softmax_fwd_kernel<<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    if (v4) edge_softmax_fwd_kernel<true><<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    else edge_softmax_fwd_kernel<false><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     return last_error();
 }
 
@@ -373,7 +381,9 @@ int gala_edge_softmax_bwd_f32(const gala_graph_t* g, const float* alpha, const f
     p.b = dalpha;
     p.out = out;
     p.seed = (float)g->segments * 1e-12f;
-    edge_softmax_bwd_kernel<<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    const bool v4 = aligned(alpha, 16) && aligned(dalpha, 16) && aligned(out, 16);
+    if (v4) edge_softmax_bwd_kernel<true><<<grid, kCtaThreads, 0, S(stream)>>>(p);
+    else edge_softmax_bwd_kernel<false><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     return last_error();
 }
 

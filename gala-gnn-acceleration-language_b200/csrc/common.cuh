@@ -102,6 +102,29 @@ __device__ __forceinline__ void for_each_chunk(const GraphDev& g, int row, int l
     }
 }
 
+// Visit the edges [e0, e1) of one row with a whole warp: 128-bit accesses over the 16-byte
+// aligned body (4 edges per lane per step, 4 steps unrolled = 2 KB in flight per warp),
+// scalar accesses on the ragged head and tail.  VEC4 = false keeps everything scalar
+// (edge arrays that are not 16-byte aligned).
+template <bool VEC4, class FS, class FV>
+__device__ __forceinline__ void warp_edges(int e0, int e1, int lane, FS&& scalar, FV&& vec4) {
+    if (!VEC4) {
+#pragma unroll 4
+        for (int e = e0 + lane; e < e1; e += 32) scalar(e);
+        return;
+    }
+    const int a0 = min((e0 + 3) & ~3, e1);
+    const int a1 = max(a0, e1 & ~3);
+    if (e0 + lane < a0) scalar(e0 + lane);
+#pragma unroll 4
+    for (int e = a0 + lane * 4; e < a1; e += 128) vec4(e);
+    if (a1 + lane < e1) scalar(a1 + lane);
+}
+
+__device__ __forceinline__ float4 ld_stream4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ int4 ld_stream4(const int* p) { return __ldcs(reinterpret_cast<const int4*>(p)); }
+__device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
 __device__ __forceinline__ int row_degree(const GraphDev& g, int row) {
     int d = 0;
 #pragma unroll 1

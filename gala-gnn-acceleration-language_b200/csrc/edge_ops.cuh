@@ -35,14 +35,18 @@ struct EdgeParams {
 };
 
 // ---- K3: out[row] = seed + sum vals -------------------------------------------------
+template <bool V4>
 __global__ void __launch_bounds__(kCtaThreads) edge_rowsum_kernel(const __grid_constant__ EdgeParams p) {
     RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
     float s = 0.0f;
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
-#pragma unroll 4
-        for (int e = e0 + lane; e < e1; e += 32) s += ld_stream(p.a + e);
+        warp_edges<V4>(e0, e1, lane, [&](int e) { s += ld_stream(p.a + e); },
+                       [&](int e) {
+                           float4 v = ld_stream4(p.a + e);
+                           s += (v.x + v.y) + (v.z + v.w);
+                       });
     });
     s = warp_sum(s);
     if (t.hub) s = cta_sum_ordered(s);
@@ -50,18 +54,24 @@ __global__ void __launch_bounds__(kCtaThreads) edge_rowsum_kernel(const __grid_c
 }
 
 // ---- K4: vals[e] *= rowval[row] -------------------------------------------------------
+template <bool V4>
 __global__ void __launch_bounds__(kCtaThreads) edge_scale_kernel(const __grid_constant__ EdgeParams p) {
     RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
     const float r = __ldg(p.a + t.row);
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
-#pragma unroll 4
-        for (int e = e0 + lane; e < e1; e += 32) p.out[e] = p.out[e] * r;
+        warp_edges<V4>(e0, e1, lane, [&](int e) { p.out[e] = p.out[e] * r; },
+                       [&](int e) {
+                           float4 v = *reinterpret_cast<const float4*>(p.out + e);
+                           v.x *= r; v.y *= r; v.z *= r; v.w *= r;
+                           *reinterpret_cast<float4*>(p.out + e) = v;
+                       });
     });
 }
 
 // ---- K5 / K7: out[e] = A[row] (+|*) B[col[e]]  (optional fused LeakyReLU) ---------------
+template <bool V4>
 __global__ void __launch_bounds__(kCtaThreads) sddvv_kernel(const __grid_constant__ EdgeParams p) {
     RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
@@ -69,26 +79,35 @@ __global__ void __launch_bounds__(kCtaThreads) sddvv_kernel(const __grid_constan
     const float ar = __ldg(p.a + t.row);
     const bool mul = p.op == GALA_SDDVV_MUL;
     const bool act = p.slope != 1.0f;
+    auto f = [&](float bv) {
+        float r = mul ? ar * bv : ar + bv;
+        return act ? leaky(r, p.slope) : r;
+    };
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
-#pragma unroll 4
-        for (int e = e0 + lane; e < e1; e += 32) {
-            float bv = __ldg(p.b + ld_stream(p.g.cols + e));
-            float r = mul ? ar * bv : ar + bv;
-            if (act) r = leaky(r, p.slope);
-            st_stream(p.out + e, r);
-        }
+        warp_edges<V4>(e0, e1, lane, [&](int e) { st_stream(p.out + e, f(__ldg(p.b + ld_stream(p.g.cols + e)))); },
+                       [&](int e) {
+                           int4 c = ld_stream4(p.g.cols + e);
+                           float4 o;
+                           o.x = __ldg(p.b + c.x); o.y = __ldg(p.b + c.y); o.z = __ldg(p.b + c.z); o.w = __ldg(p.b + c.w);
+                           o.x = f(o.x); o.y = f(o.y); o.z = f(o.z); o.w = f(o.w);
+                           st_stream4(p.out + e, o);
+                       });
     });
 }
 
 // ---- edge-softmax forward: alpha = clamp(exp(x)) / (seed + sum_row clamp(exp(x))) --------
+template <bool V4>
 __global__ void __launch_bounds__(kCtaThreads) edge_softmax_fwd_kernel(const __grid_constant__ EdgeParams p) {
     RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
     float s = 0.0f;
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
-#pragma unroll 4
-        for (int e = e0 + lane; e < e1; e += 32) s += softmax_num(p.a[e]);
+        warp_edges<V4>(e0, e1, lane, [&](int e) { s += softmax_num(p.a[e]); },
+                       [&](int e) {
+                           float4 v = *reinterpret_cast<const float4*>(p.a + e);
+                           s += (softmax_num(v.x) + softmax_num(v.y)) + (softmax_num(v.z) + softmax_num(v.w));
+                       });
     });
     s = warp_sum(s);
     if (t.hub) s = cta_sum_ordered(s);
@@ -96,31 +115,48 @@ __global__ void __launch_bounds__(kCtaThreads) edge_softmax_fwd_kernel(const __g
     if (p.out2 && threadIdx.x == (t.hub ? 0 : (threadIdx.x & ~31))) p.out2[t.row] = r;
     // second pass: the row was just read, so it is served from L1/L2
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
-#pragma unroll 4
-        for (int e = e0 + lane; e < e1; e += 32) p.out[e] = softmax_num(p.a[e]) * r;
+        warp_edges<V4>(e0, e1, lane, [&](int e) { p.out[e] = softmax_num(p.a[e]) * r; },
+                       [&](int e) {
+                           float4 v = *reinterpret_cast<const float4*>(p.a + e);
+                           v.x = softmax_num(v.x) * r; v.y = softmax_num(v.y) * r;
+                           v.z = softmax_num(v.z) * r; v.w = softmax_num(v.w) * r;
+                           *reinterpret_cast<float4*>(p.out + e) = v;
+                       });
     });
 }
 
 // ---- edge-softmax backward: out = a*da - a * (seed + sum_row a*da) -----------------------
+template <bool V4>
 __global__ void __launch_bounds__(kCtaThreads) edge_softmax_bwd_kernel(const __grid_constant__ EdgeParams p) {
     RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
     float s = 0.0f;
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
-#pragma unroll 4
-        for (int e = e0 + lane; e < e1; e += 32) s += p.a[e] * p.b[e];
+        warp_edges<V4>(e0, e1, lane, [&](int e) { s += p.a[e] * p.b[e]; },
+                       [&](int e) {
+                           float4 a = *reinterpret_cast<const float4*>(p.a + e);
+                           float4 b = *reinterpret_cast<const float4*>(p.b + e);
+                           s += (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w);
+                       });
     });
     s = warp_sum(s);
     if (t.hub) s = cta_sum_ordered(s);
     const float tot = s + p.seed;
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
-#pragma unroll 4
-        for (int e = e0 + lane; e < e1; e += 32) {
-            float al = p.a[e];
-            float sds = al * p.b[e];
-            p.out[e] = sds - al * tot;
-        }
+        warp_edges<V4>(e0, e1, lane,
+                       [&](int e) {
+                           float al = p.a[e];
+                           p.out[e] = al * p.b[e] - al * tot;
+                       },
+                       [&](int e) {
+                           float4 a = *reinterpret_cast<const float4*>(p.a + e);
+                           float4 b = *reinterpret_cast<const float4*>(p.b + e);
+                           float4 o;
+                           o.x = a.x * b.x - a.x * tot; o.y = a.y * b.y - a.y * tot;
+                           o.z = a.z * b.z - a.z * tot; o.w = a.w * b.w - a.w * tot;
+                           *reinterpret_cast<float4*>(p.out + e) = o;
+                       });
     });
 }
 
