@@ -261,6 +261,40 @@ int gala_gat_forward_f32(const gala_graph_t* g, const float* aL, const float* aR
     return launch_spmm<MODE_GAT>(p, S(stream));
 }
 
+int gala_gat_forward_dot_f32(const gala_graph_t* g, const float* aL, const float* wR, float bR, const float* X,
+                             int32_t K, float slope, float* Y, float* alpha_out, int32_t relu,
+                             const gala_plan_t* plan, gala_stream_t stream) {
+    if (int rc = check_graph(g)) return rc;
+    if (K <= 0 || K > 32 || K % 4 != 0) return GALA_ERR_UNSUPPORTED;   // one 8-lane pass must hold the row
+    if (g->nrows > 0 && (!aL || !wR || !X || !Y)) return GALA_ERR_NULL_POINTER;
+    if (!aligned(X, 16) || !aligned(Y, 16)) return GALA_ERR_UNSUPPORTED;
+    if (g->nrows == 0) return GALA_OK;
+    SpmmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.g = make_dev(g);
+    p.X = X;
+    p.Y = Y;
+    p.K = K;
+    p.relu = relu;
+    p.aL = aL;
+    p.wR = wR;
+    p.bR = bR;
+    p.slope = slope;
+    p.alpha_out = alpha_out;
+    p.seed_total = (float)g->segments * 1e-12f;
+    HubView h = hub_of(plan, g);
+    p.t = task_of(h);
+    dim3 grid(p.t.n_hub + (p.t.n_ordered + kWarpsPerCta - 1) / kWarpsPerCta, 1);
+    cudaStream_t st = S(stream);
+    const int units = K / 4;
+    if (units <= 1) spmm_kernel<4, 1, 1, MODE_GAT_DOT, false><<<grid, kCtaThreads, 0, st>>>(p);
+    else if (units <= 2) spmm_kernel<4, 2, 1, MODE_GAT_DOT, false><<<grid, kCtaThreads, 0, st>>>(p);
+    else if (units <= 4) spmm_kernel<4, 4, 1, MODE_GAT_DOT, false><<<grid, kCtaThreads, 0, st>>>(p);
+    else if (K == 32) spmm_kernel<4, 8, 1, MODE_GAT_DOT, true><<<grid, kCtaThreads, 0, st>>>(p);
+    else spmm_kernel<4, 8, 1, MODE_GAT_DOT, false><<<grid, kCtaThreads, 0, st>>>(p);
+    return last_error();
+}
+
 int gala_spmm_sampled_f32(const gala_graph_t* g, const float* vals, const float* X, int32_t K, float* Y,
                           int32_t nsamples, int32_t ra, int32_t rb, int32_t accumulate, gala_stream_t stream) {
     if (int rc = check_graph(g)) return rc;

@@ -18,7 +18,10 @@
 
 namespace gala {
 
-enum { MODE_PLAIN = 0, MODE_GAT = 1 };
+// MODE_GAT_DOT: like MODE_GAT, but aR[col] = dot(X[col,:], wR) + bR is recomputed from the
+// gathered feature row itself, which removes the second random gather per edge.
+enum { MODE_PLAIN = 0, MODE_GAT = 1, MODE_GAT_DOT = 2 };
+#define GALA_IS_GAT(M) ((M) == MODE_GAT || (M) == MODE_GAT_DOT)
 
 struct SpmmParams {
     GraphDev g;
@@ -37,6 +40,8 @@ struct SpmmParams {
     float slope;
     float* __restrict__ alpha_out;        // nullable
     float seed_total;                     // S * 1e-12f
+    const float* __restrict__ wR;         // MODE_GAT_DOT: aR[j] = dot(X[j,:], wR) + bR
+    float bR;
 };
 
 
@@ -92,14 +97,74 @@ __device__ __forceinline__ void gather_chunk(const char* __restrict__ xlane, uin
     }
 }
 
+
+// MODE_GAT_DOT chunk: gather the 32 rows (LPR loads per lane, all in flight), form each
+// edge's dot product with wR on the LPR lanes that hold the row, reduce the LPR partials of
+// the LPR edges of a group with a halving exchange (LPR-1 shuffles; lane `sub` ends up with
+// edge `sub` of its group), evaluate the softmax numerator ONCE per edge on that lane, then
+// broadcast it back as the weight of the row that is already sitting in registers.
+// Requires ACC == 1 and a batch that covers all LPR sub-iterations (LPR * VEC <= 32).
+template <int VEC, int LPR, bool FULL>
+__device__ __forceinline__ void gather_chunk_dot(const char* __restrict__ xlane, uint32_t row_bytes, int sub, int grp,
+                                                 int c, int base, int e1, const float (&wreg)[VEC], float aL_row,
+                                                 float bR, float slope, float* __restrict__ alpha_out, float& rs,
+                                                 float (&acc)[1][VEC]) {
+    constexpr int EPI = 32 / LPR;
+    int cj[LPR];
+    Vec<VEC> x[LPR];
+#pragma unroll
+    for (int u = 0; u < LPR; ++u) cj[u] = __shfl_sync(kFull, c, u * EPI + grp);
+#pragma unroll
+    for (int u = 0; u < LPR; ++u) {
+        const uint32_t cc = (uint32_t)(FULL ? cj[u] : max(cj[u], 0));
+        x[u].load(reinterpret_cast<const float*>(xlane + (uint64_t)cc * row_bytes));
+    }
+    float d[LPR];
+#pragma unroll
+    for (int u = 0; u < LPR; ++u) {
+        float t = 0.0f;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) t = fmaf(x[u].v[v], wreg[v], t);
+        d[u] = t;
+    }
+#pragma unroll
+    for (int o = LPR >> 1, n = LPR; o > 0; o >>= 1, n >>= 1) {
+        const bool upper = (sub & o) != 0;
+#pragma unroll
+        for (int i = 0; i < (n >> 1); ++i) {
+            const float send = upper ? d[i] : d[i + (n >> 1)];
+            const float keep = upper ? d[i + (n >> 1)] : d[i];
+            d[i] = keep + __shfl_xor_sync(kFull, send, o);
+        }
+    }
+    // this lane now owns chunk position sub*EPI + grp
+    const int pos = base + sub * EPI + grp;
+    float e = 0.0f;
+    if (FULL || pos < e1) {
+        e = softmax_num(leaky(aL_row + (d[0] + bR), slope));
+        rs += e;
+        if (alpha_out) alpha_out[pos] = e;
+    }
+#pragma unroll
+    for (int u = 0; u < LPR; ++u) {
+        const float wj = __shfl_sync(kFull, e, grp * LPR + u);   // 0 for invalid edges
+        const bool ok = FULL || cj[u] >= 0;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[0][v] = fmaf(wj, ok ? x[u].v[v] : 0.0f, acc[0][v]);
+    }
+}
+
 // Minimum resident CTAs per SM the register allocator must allow.  Decides how many of
 // the UNR gathers ptxas keeps in flight (it serialises them when squeezed below ~64
 // registers); tuned on B200, see profiles/r01_variants.txt.
 #ifndef GALA_SPMM_MINB
 #define GALA_SPMM_MINB 5
 #endif
+#ifndef GALA_GATDOT_MINB
+#define GALA_GATDOT_MINB 3   // the dot mode keeps 8 rows + 8 partial dots live
+#endif
 #if GALA_SPMM_MINB > 0
-#define GALA_SPMM_BOUNDS __launch_bounds__(kCtaThreads, GALA_SPMM_MINB)
+#define GALA_SPMM_BOUNDS __launch_bounds__(kCtaThreads, (MODE == MODE_GAT_DOT ? GALA_GATDOT_MINB : GALA_SPMM_MINB))
 #else
 #define GALA_SPMM_BOUNDS __launch_bounds__(kCtaThreads)
 #endif
@@ -133,10 +198,18 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[a][v] = 0.0f;
 
-    const bool weighted = MODE == MODE_GAT || p.vals != nullptr || p.col_scale != nullptr;
+    const bool weighted = GALA_IS_GAT(MODE) || p.vals != nullptr || p.col_scale != nullptr;
     float aL_row = 0.0f, rs = 0.0f;
-    if (MODE == MODE_GAT) aL_row = __ldg(p.aL + row);
-    const bool write_alpha = MODE == MODE_GAT && p.alpha_out != nullptr && blockIdx.y == 0;
+    if (GALA_IS_GAT(MODE)) aL_row = __ldg(p.aL + row);
+    const bool write_alpha = GALA_IS_GAT(MODE) && p.alpha_out != nullptr && blockIdx.y == 0;
+    float wreg[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) wreg[v] = 0.0f;
+    if (MODE == MODE_GAT_DOT) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (sub * VEC + v < p.K) wreg[v] = __ldg(p.wR + sub * VEC + v);
+    }
 
     // one edge per lane: column index and the weight the edge contributes with
     auto fetch = [&](int idx, int e1, int& c, float& w) {
@@ -144,7 +217,9 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
         w = 0.0f;
         if (idx < e1) {
             c = ld_stream(g.cols + idx);
-            if (MODE == MODE_GAT) {
+            if (MODE == MODE_GAT_DOT) {
+                // weight comes from the gathered row (gather_chunk_dot)
+            } else if (MODE == MODE_GAT) {
                 float e = softmax_num(leaky(aL_row + __ldg(p.aR + c), p.slope));
                 rs += e;
                 if (write_alpha) p.alpha_out[idx] = e;
@@ -164,7 +239,15 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
             const int c = c_nxt;
             const float w = w_nxt;
             if (base + 32 < e1) fetch(base + 32 + lane, e1, c_nxt, w_nxt);
-            if (base + 32 <= e1)
+            if constexpr (MODE == MODE_GAT_DOT) {
+                float* ao = write_alpha ? p.alpha_out : nullptr;
+                if (base + 32 <= e1)
+                    gather_chunk_dot<VEC, LPR, true>(xlane, row_bytes, sub, grp, c, base, e1, wreg, aL_row, p.bR,
+                                                     p.slope, ao, rs, acc);
+                else
+                    gather_chunk_dot<VEC, LPR, false>(xlane, row_bytes, sub, grp, c, base, e1, wreg, aL_row, p.bR,
+                                                      p.slope, ao, rs, acc);
+            } else if (base + 32 <= e1)
                 gather_chunk<VEC, LPR, ACC, true, EXACT>(xlane, row_bytes, grp, c, w, weighted, fvalid, acc);
             else
                 gather_chunk<VEC, LPR, ACC, false, EXACT>(xlane, row_bytes, grp, c, w, weighted, fvalid, acc);
@@ -178,12 +261,12 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
         for (int a = 0; a < ACC; ++a)
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[a][v] += __shfl_xor_sync(kFull, acc[a][v], o);
-    if (MODE == MODE_GAT) rs = warp_sum(rs);
+    if (GALA_IS_GAT(MODE)) rs = warp_sum(rs);
 
     float scale = p.row_scale ? __ldg(p.row_scale + row) : 1.0f;
 
     if (!hub_cta) {
-        if (MODE == MODE_GAT) scale = 1.0f / (rs + p.seed_total);
+        if (GALA_IS_GAT(MODE)) scale = 1.0f / (rs + p.seed_total);
         if (grp == 0) {
 #pragma unroll
             for (int a = 0; a < ACC; ++a) {
@@ -202,6 +285,7 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
             }
         }
         if (write_alpha) {
+            __syncwarp();   // MODE_GAT_DOT: the numerators were stored by other lanes of this warp
             for_each_chunk(g, row, lo, hi, [&](int e0, int e1) {
                 for (int e = e0 + lane; e < e1; e += 32) p.alpha_out[e] *= scale;
             });
@@ -218,9 +302,9 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) part[warp * TW + (a * LPR + sub) * VEC + v] = acc[a][v];
     }
-    if (MODE == MODE_GAT && lane == 0) part_rs[warp] = rs;
+    if (GALA_IS_GAT(MODE) && lane == 0) part_rs[warp] = rs;
     __syncthreads();
-    if (MODE == MODE_GAT) {
+    if (GALA_IS_GAT(MODE)) {
         float t = 0.0f;
 #pragma unroll
         for (int w = 0; w < kWarpsPerCta; ++w) t += part_rs[w];

@@ -93,6 +93,20 @@ def gat2_forward_partitioned(model, part, X_local, aggregate, hook=None):
     return F.linear(agg, *model.fc1)
 
 
+def gat2_forward_partitioned_dot(model, part, X_local, aggregate_dot, hook=None):
+    """Same forward with the right-hand attention term recomputed inside the kernel
+    (ops.gat_forward_dot): nothing but the hidden features is exchanged or re-derived."""
+    run = hook if hook is not None else (lambda name, fn: fn())
+    res_loc = F.linear(X_local, *model.fc0)
+    aL = F.linear(res_loc, *model.efc0).reshape(-1)
+    res_all = part.all_gather(res_loc)
+    y_loc = run("gat_layer1", lambda: aggregate_dot(aL, model.wR1, model.bR1, res_all, True))
+    aL = torch.addmv(torch.full((y_loc.shape[0],), model.bL2, device=y_loc.device), y_loc, model.wL2)
+    y_all = part.all_gather(y_loc)
+    agg = run("gat_layer2", lambda: aggregate_dot(aL, model.wR2, model.bR2, y_all, False))
+    return F.linear(agg, *model.fc1)
+
+
 class PartitionedGAT:
     """GPU runner: slab graph + plan + fused kernel, NCCL all-gather between layers."""
 
@@ -111,5 +125,10 @@ class PartitionedGAT:
     def _aggregate(self, aL, aR, feats, relu):
         return self.ops.gat_forward(self.graph, aL.contiguous(), aR.contiguous(), feats, self.model.slope, relu=relu)
 
-    def forward(self, X_local, hook=None):
+    def _aggregate_dot(self, aL, wR, bR, feats, relu):
+        return self.ops.gat_forward_dot(self.graph, aL.contiguous(), wR, bR, feats, self.model.slope, relu=relu)
+
+    def forward(self, X_local, hook=None, dot=True):
+        if dot:
+            return gat2_forward_partitioned_dot(self.model, self.part, X_local, self._aggregate_dot, hook)
         return gat2_forward_partitioned(self.model, self.part, X_local, self._aggregate, hook)

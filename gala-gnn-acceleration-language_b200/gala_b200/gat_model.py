@@ -39,14 +39,38 @@ class GAT2:
         self.efc2 = _linear_init(gen, 1, classes, device)
         self.efc3 = _linear_init(gen, 1, classes, device)
         self.slope = 0.2
+        self.fold()
+
+    def fold(self):
+        """Attention projections as linear functions of the AGGREGATED features, so that the
+        fused kernel can recompute aR[col] from the row it gathers (ops.gat_forward_dot):
+          layer 1: aR = efc1(res)                      -> wR1 = efc1.w,        bR1 = efc1.b
+          layer 2: aL/aR = efc2/efc3(fc1(res))         -> w = efc.w @ fc1.W,   b = efc.w @ fc1.b + efc.b
+        Scalars are read back once here, never inside a step."""
+        W1, b1 = self.fc1
+        self.wR1 = self.efc1[0].reshape(-1).contiguous()
+        self.bR1 = float(self.efc1[1])
+        self.wL2 = (self.efc2[0] @ W1).reshape(-1).contiguous()
+        self.bL2 = float(self.efc2[0] @ b1 + self.efc2[1])
+        self.wR2 = (self.efc3[0] @ W1).reshape(-1).contiguous()
+        self.bR2 = float(self.efc3[0] @ b1 + self.efc3[1])
 
     def attention_inputs(self, t, wl, wr):
         return F.linear(t, *wl).reshape(-1), F.linear(t, *wr).reshape(-1)
 
-    def forward(self, g, X, hook=None):
+    def forward(self, g, X, hook=None, dot=True):
         """g: TiledGraph (rows = output nodes, cols index X's rows).  `hook(name, fn)`
-        lets the benchmark time the sparse kernels individually."""
+        lets the benchmark time the sparse kernels individually.  dot=True recomputes the
+        right-hand attention term inside the kernel (gala_gat_forward_dot_f32); dot=False
+        materialises aL/aR exactly as the generated program does (gala_gat_forward_f32)."""
         run = hook if hook is not None else (lambda name, fn: fn())
+        if dot:
+            res = F.linear(X, *self.fc0)
+            aL = F.linear(res, *self.efc0).reshape(-1)
+            res = run("gat_layer1", lambda: ops.gat_forward_dot(g, aL, self.wR1, self.bR1, res, self.slope, relu=True))
+            aL = torch.addmv(torch.full((res.shape[0],), self.bL2, device=res.device), res, self.wL2)
+            agg = run("gat_layer2", lambda: ops.gat_forward_dot(g, aL, self.wR2, self.bR2, res, self.slope, relu=False))
+            return F.linear(agg, *self.fc1)
         res = F.linear(X, *self.fc0)
         aL, aR = self.attention_inputs(res, self.efc0, self.efc1)
         res = run("gat_layer1", lambda: ops.gat_forward(g, aL, aR, res, self.slope, relu=True))

@@ -152,3 +152,21 @@ def gat_forward(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None):
                                             _l.ptr(X), K, slope, _l.ptr(out), _l.ptr(alpha_out),
                                             int(relu), g._p(), _l.stream_ptr()))
     return out
+
+
+def gat_forward_dot(g, aL, wR, bR, X, slope=0.2, relu=False, out=None, alpha_out=None):
+    """Fused GAT layer with aR[j] = dot(X[j,:], wR) + bR recomputed inside the kernel from the
+    gathered rows (one random gather per edge instead of two).  Falls back to gat_forward with a
+    materialised aR when the shape is outside the kernel's range (K % 4 != 0 or K > 32)."""
+    X = _f32(X)
+    K = X.shape[1]
+    wR = _f32(wR).reshape(-1)
+    if K % 4 != 0 or K > 32 or X.data_ptr() % 16 != 0:
+        aR = (X @ wR + bR).contiguous()
+        return gat_forward(g, aL, aR, X, slope, relu, out, alpha_out)
+    if out is None:
+        out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
+    _l.check(_l.load().gala_gat_forward_dot_f32(C.byref(g.c), _l.ptr(_f32(aL)), _l.ptr(wR), float(bR),
+                                                _l.ptr(X), K, slope, _l.ptr(out), _l.ptr(alpha_out),
+                                                int(relu), g._p(), _l.stream_ptr()))
+    return out

@@ -174,6 +174,16 @@ int gala_gat_forward_f32(const gala_graph_t *g, const float *aL, const float *aR
                          int32_t K, float slope, float *Y, float *alpha_out, int32_t relu,
                          const gala_plan_t *plan, gala_stream_t stream);
 
+/* Same layer when the right-hand attention term is a linear function of the aggregated    */
+/* features, aR[j] = dot(X[j,:], wR) + bR -- which is how the generated GAT computes it      */
+/* (attenR = efc(res), common.h:1185-1281; with the layer-2 FFN-recompute rewrite wR = W1^T  */
+/* w and bR = w.b1 + b, middle-end.h:324-375).  The kernel recomputes aR from the row it has */
+/* just gathered, so the second random gather per edge disappears.  K % 4 == 0, K <= 32,     */
+/* X and Y 16-byte aligned; otherwise GALA_ERR_UNSUPPORTED (use gala_gat_forward_f32).        */
+int gala_gat_forward_dot_f32(const gala_graph_t *g, const float *aL, const float *wR, float bR,
+                             const float *X, int32_t K, float slope, float *Y, float *alpha_out,
+                             int32_t relu, const gala_plan_t *plan, gala_stream_t stream);
+
 /* ---- format construction on the device ---------- */
 /* All integer outputs are bit-exact against the reference functions named below.       */
 

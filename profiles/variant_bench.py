@@ -31,6 +31,7 @@ def t(fn, reps=20):
     e_.record(); torch.cuda.synchronize()
     return s.elapsed_time(e_) / reps
 print(json.dumps({"gat": t(lambda: ops.gat_forward(g, a, a, X, out=Y)),
+                  "gat_dot": t(lambda: ops.gat_forward_dot(g, a, X[0].contiguous(), 0.1, X, out=Y)),
                   "spmm": t(lambda: ops.spmm(g, X, out=Y)),
                   "spmm_w": t(lambda: ops.spmm(g, X, vals=w, out=Y)),
                   "sddmm": t(lambda: ops.sddmm(g, X, X, out=ev))}))

@@ -196,6 +196,46 @@ def test_gat_fused_forward_matches_composition(orc, case, K):
     assert rel_err(got_Y, unfused) < FP32_TOL
 
 
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("K", [4, 8, 12, 16, 32])
+def test_gat_dot_variant_matches_composition(orc, case, K):
+    """gala_gat_forward_dot_f32: aR recomputed from the gathered rows, aR[j] = X[j,:].wR + bR."""
+    n, e, seed, T, empty, thr = case
+    t = graph_case(orc, n, e, seed, T, empty)
+    g = to_gpu_graph(t, thr)
+    rng = np.random.default_rng(seed + K)
+    aL = rng.normal(size=n).astype(np.float32)
+    wR = rng.normal(size=K).astype(np.float32)
+    bR = 0.3
+    X = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    aR = (X.astype(np.float64) @ wR.astype(np.float64) + bR).astype(np.float32)
+    want_Y, want_alpha = orc.gat_forward(t, aL, aR, X)
+    alpha = torch.empty(t.nvals, device=DEV)
+    got = ops.gat_forward_dot(g, dev(aL), dev(wR), bR, dev(X), alpha_out=alpha, relu=True).cpu().numpy()
+    assert rel_err(got, np.maximum(want_Y, 0)) < FP32_TOL
+    assert rel_err(alpha.cpu().numpy(), want_alpha) < FP32_TOL
+    # a shape outside the kernel's range takes the documented fallback (materialised aR)
+    if K == 12:
+        X2 = rng.uniform(-0.5, 0.5, (n, 41)).astype(np.float32)
+        w2 = rng.normal(size=41).astype(np.float32)
+        aR2 = (X2.astype(np.float64) @ w2.astype(np.float64) + bR).astype(np.float32)
+        want2, _ = orc.gat_forward(t, aL, aR2, X2)
+        got2 = ops.gat_forward_dot(g, dev(aL), dev(w2), bR, dev(X2)).cpu().numpy()
+        assert rel_err(got2, want2) < FP32_TOL
+
+
+def test_gat_model_dot_and_materialised_paths_agree(orc):
+    from gala_b200.gat_model import GAT2
+    n = 3000
+    t = graph_case(orc, n, 200000, 11)
+    g = to_gpu_graph(t, 256)
+    model = GAT2(64, 32, 41, DEV, seed=3)
+    X = torch.rand(n, 64, device=DEV) - 0.5
+    a = model.forward(g, X, dot=True)
+    b = model.forward(g, X, dot=False)
+    assert float((a - b).double().norm() / b.double().norm()) < FP32_TOL
+
+
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_golden_fixtures_on_gpu(orc, name):
     """The reference's own outputs (tests/golden) reproduced by the CUDA path."""
