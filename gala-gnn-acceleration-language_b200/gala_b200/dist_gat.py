@@ -93,6 +93,20 @@ def gat2_forward_partitioned(model, part, X_local, aggregate, hook=None):
     return F.linear(agg, *model.fc1)
 
 
+def gat2_forward_partitioned_folded(model, part, X_local, aggregate, hook=None):
+    """Folded attention projections (gat_model mode="folded"): one [K,2] matmul per layer on the
+    gathered features gives aR for every column and aL for the rank's own rows."""
+    run = hook if hook is not None else (lambda name, fn: fn())
+    res_loc = F.linear(X_local, *model.fc0)
+    res_all = part.all_gather(res_loc)
+    a = F.linear(res_all, model.W_att1, model.b_att1).t().contiguous()
+    y_loc = run("gat_layer1", lambda: aggregate(part.local_slice(a[0]), a[1], res_all, True))
+    y_all = part.all_gather(y_loc)
+    a = F.linear(y_all, model.W_att2, model.b_att2).t().contiguous()
+    agg = run("gat_layer2", lambda: aggregate(part.local_slice(a[0]), a[1], y_all, False))
+    return F.linear(agg, *model.fc1)
+
+
 def gat2_forward_partitioned_dot(model, part, X_local, aggregate_dot, hook=None):
     """Same forward with the right-hand attention term recomputed inside the kernel
     (ops.gat_forward_dot): nothing but the hidden features is exchanged or re-derived."""
@@ -128,7 +142,9 @@ class PartitionedGAT:
     def _aggregate_dot(self, aL, wR, bR, feats, relu):
         return self.ops.gat_forward_dot(self.graph, aL.contiguous(), wR, bR, feats, self.model.slope, relu=relu)
 
-    def forward(self, X_local, hook=None, dot=True):
-        if dot:
+    def forward(self, X_local, hook=None, mode="folded"):
+        if mode == "dot":
             return gat2_forward_partitioned_dot(self.model, self.part, X_local, self._aggregate_dot, hook)
+        if mode == "folded":
+            return gat2_forward_partitioned_folded(self.model, self.part, X_local, self._aggregate, hook)
         return gat2_forward_partitioned(self.model, self.part, X_local, self._aggregate, hook)

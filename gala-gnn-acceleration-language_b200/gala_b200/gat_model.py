@@ -54,24 +54,36 @@ class GAT2:
         self.bL2 = float(self.efc2[0] @ b1 + self.efc2[1])
         self.wR2 = (self.efc3[0] @ W1).reshape(-1).contiguous()
         self.bR2 = float(self.efc3[0] @ b1 + self.efc3[1])
+        # both projections of a layer as one [2, K] weight
+        self.W_att1 = torch.cat([self.efc0[0], self.efc1[0]], 0).contiguous()
+        self.b_att1 = torch.cat([self.efc0[1], self.efc1[1]], 0).contiguous()
+        self.W_att2 = torch.stack([self.wL2, self.wR2], 0).contiguous()
+        self.b_att2 = torch.tensor([self.bL2, self.bR2], device=W1.device)
 
     def attention_inputs(self, t, wl, wr):
         return F.linear(t, *wl).reshape(-1), F.linear(t, *wr).reshape(-1)
 
-    def forward(self, g, X, hook=None, dot=True):
-        """g: TiledGraph (rows = output nodes, cols index X's rows).  `hook(name, fn)`
-        lets the benchmark time the sparse kernels individually.  dot=True recomputes the
-        right-hand attention term inside the kernel (gala_gat_forward_dot_f32); dot=False
-        materialises aL/aR exactly as the generated program does (gala_gat_forward_f32)."""
+    def forward(self, g, X, hook=None, mode="folded"):
+        """g: TiledGraph (rows = output nodes, cols index X's rows).  `hook(name, fn)` lets the
+        benchmark time the sparse kernels individually.
+          mode="literal": the op sequence of the generated program, one Linear per projection
+          mode="folded" : same math with the attention projections folded (one [K,2] matmul
+                          per layer; layer 2 never materialises fc1(res) for the logits)
+          mode="dot"    : aR recomputed inside the kernel (gala_gat_forward_dot_f32)"""
         run = hook if hook is not None else (lambda name, fn: fn())
-        if dot:
-            res = F.linear(X, *self.fc0)
+        res = F.linear(X, *self.fc0)
+        if mode == "dot":
             aL = F.linear(res, *self.efc0).reshape(-1)
             res = run("gat_layer1", lambda: ops.gat_forward_dot(g, aL, self.wR1, self.bR1, res, self.slope, relu=True))
             aL = torch.addmv(torch.full((res.shape[0],), self.bL2, device=res.device), res, self.wL2)
             agg = run("gat_layer2", lambda: ops.gat_forward_dot(g, aL, self.wR2, self.bR2, res, self.slope, relu=False))
             return F.linear(agg, *self.fc1)
-        res = F.linear(X, *self.fc0)
+        if mode == "folded":
+            a = F.linear(res, self.W_att1, self.b_att1).t().contiguous()      # [2, N]: aL, aR
+            res = run("gat_layer1", lambda: ops.gat_forward(g, a[0], a[1], res, self.slope, relu=True))
+            a = F.linear(res, self.W_att2, self.b_att2).t().contiguous()
+            agg = run("gat_layer2", lambda: ops.gat_forward(g, a[0], a[1], res, self.slope, relu=False))
+            return F.linear(agg, *self.fc1)
         aL, aR = self.attention_inputs(res, self.efc0, self.efc1)
         res = run("gat_layer1", lambda: ops.gat_forward(g, aL, aR, res, self.slope, relu=True))
         t = F.linear(res, *self.fc1)

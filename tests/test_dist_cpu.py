@@ -33,6 +33,10 @@ def _oracle_aggregate(orc, part):
     return agg
 
 
+def rank_mode(rank):
+    return "folded"     # both ranks must take the same collective sequence
+
+
 def _worker(rank, world, port, n, e, feats, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -43,7 +47,8 @@ def _worker(rank, world, port, n, e, feats, out_path):
     model = GAT2(feats, 8, 5, "cpu", seed=1)
     X = torch.rand(n, feats, generator=torch.Generator().manual_seed(2)) - 0.5
     part = dist_gat.RowPartition(offset, ids, n, rank, world)
-    out_loc = dist_gat.gat2_forward_partitioned(model, part, X[part.row_lo:part.row_hi], _oracle_aggregate(orc, part))
+    fwd = dist_gat.gat2_forward_partitioned if rank_mode(rank) == 'literal' else dist_gat.gat2_forward_partitioned_folded
+    out_loc = fwd(model, part, X[part.row_lo:part.row_hi], _oracle_aggregate(orc, part))
     gathered = part.unpad(part.all_gather(out_loc))
     if rank == 0:
         np.save(out_path, gathered.numpy())
