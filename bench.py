@@ -238,6 +238,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from gala_b200 import ops
     from gala_b200.gat_model import GAT2
@@ -353,7 +354,7 @@ def main():
                 "note": "X (N*K*4 = 29.8 MB) is L2-resident; the 4*E*K gather bytes are served by L2/L1, not HBM "
                         "(SURVEY.md section 7), so frac against the compulsory-byte model is L2/LSU-limited"}
     tfile = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tfile):
+    if world == 1 and os.path.exists(tfile):
         try:
             roofline["traffic"] = json.load(open(tfile)).get("gat_fused_k32_bytes_per_launch")
         except (ValueError, OSError):
