@@ -377,9 +377,18 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
 
-    if rank != 0:
+    def finish():
+        """Leave without tearing NCCL down: destroy_process_group() after a captured collective can
+        wait forever on the watchdog; every rank has passed the final barrier, so just exit."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     # ---- roofline of the dominant kernel (fused GAT layer, inference: alpha not stored)
@@ -426,8 +435,7 @@ def main():
         info["unit"] = "ms"
         line["cpu_baseline"] = info
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def time_op(fn, reps=10, warm=3):
