@@ -182,7 +182,27 @@ def cpu_arm(n, e, feats, offset, ids, X_cpu, model, reps, warm, frac=None):
 
 
 # ------------------------------------------------------------------------------- main
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything that libraries print on fd 1 (NCCL's version banner, ...) goes to stderr; the ONE
+    JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -224,12 +244,12 @@ def main():
                            max(args.steps, 1), args.warmup)
         info["value"] = ms
         info["unit"] = "ms"
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms",
+        emit({"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                           "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                           "data": "synthetic", "config": config, "cpu_baseline": info,
                           "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}))
+                          "gpu_launches": 0})
         return
 
     if not torch.cuda.is_available():
@@ -434,7 +454,7 @@ def main():
         info["value"] = round(ms, 2)
         info["unit"] = "ms"
         line["cpu_baseline"] = info
-    print(json.dumps(line))
+    emit(line)
     finish()
 
 

@@ -117,3 +117,39 @@ def test_sddmm_with_ones_is_row_sum(reddit):
     rowsum = A.double().sum(1)
     rows = torch.repeat_interleave(torch.arange(n, device=DEV), (offset[1:] - offset[:-1]).long())
     assert float((out.double() - rowsum[rows]).abs().max()) < 1e-5
+
+
+@pytest.fixture(scope="module")
+def products():
+    n, e, feats, hidden, classes = synth.SHAPES["products"]
+    offset, ids = synth.powerlaw_csr_torch(n, e, seed=1, device=DEV)
+    return n, e, feats, offset, ids, ops.TiledGraph(offset, ids, n).build_plan()
+
+
+def test_products_shape_spmm_k100_and_sampled(products):
+    """BASELINE configs[2]/[3]: ogbn-products shape (2.45 M nodes, 123.7 M edges, 100 feats):
+    GIN/SAGE aggregate at the input width K = 100; gala_inference_sample uses sample(20)."""
+    n, e, K, offset, ids, g = products
+    assert abs(g.nvals - e) <= 1
+    deg = (offset[1:] - offset[:-1]).float()
+    y = ops.spmm(g, torch.ones(n, K, device=DEV))
+    assert torch.equal(y, deg[:, None].expand(n, K))                  # exact degrees in every column
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(5)
+    X = torch.rand(n, K, generator=gen, device=DEV) - 0.5
+    y = ops.spmm(g, X)
+    rows = torch.cat([torch.topk(deg, 4).indices, torch.randint(0, n, (128,), generator=gen, device=DEV)])
+    for r in rows.tolist():
+        b, en = int(offset[r]), int(offset[r + 1])
+        want = X[ids[b:en].long()].double().sum(0)
+        assert float((y[r].double() - want).norm() / want.norm().clamp_min(1e-30)) < 1e-5
+    # SAGE mean = row_scale fused: (1/deg) * sum
+    ym = ops.spmm(g, X, row_scale=1.0 / deg)
+    assert float((ym - y / deg[:, None]).abs().max()) < 1e-5
+    # sampled kernel (s=20, ra=5, rb=7) against an index-exact torch recomputation of sampled rows
+    ys = ops.spmm_sampled(g, X, 20, 5, 7)
+    for r in rows[:64].tolist():
+        b, d = int(offset[r]), int(offset[r + 1] - offset[r])
+        j = (5 * torch.arange(20, device=DEV) + 7) % d
+        want = X[ids[b + j].long()].double().sum(0)
+        assert float((ys[r].double() - want).norm() / want.norm().clamp_min(1e-30)) < 1e-5
