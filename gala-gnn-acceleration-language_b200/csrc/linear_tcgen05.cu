@@ -1,0 +1,308 @@
+// linear_tcgen05.cu -- the dense feature transform Y = X * W^T + b of the generated models
+// (torch::nn::Linear, reference src/codegen/common.h:1185-1281) on the 5th-generation tensor
+// cores: tcgen05.mma kind::tf32 with the accumulator in TMEM, error-compensated to fp32 accuracy
+// ("3xTF32": x = hi + lo with hi = the 19 significant bits the tensor core keeps,
+//  X*W ~= Xhi*Whi + Xhi*Wlo + Xlo*Whi; the dropped Xlo*Wlo term is 2^-22 relative).
+//
+// Why a hand-written kernel: [233K x 602] * [602 x 32] is 9 GFLOP over 561 MB of X -- 86 us at
+// the HBM roofline, out of reach of the fp32 SIMT pipes (cuBLAS' fp32 path takes ~240 us on
+// B200) and plain TF32 misses the 1e-5 parity bound.  The tensor pipe makes it HBM-bound.
+//
+// Shape of the kernel (one CTA = 128 rows of X, all N <= 64 output columns):
+//   warps 0-3  producers: coalesced 128-byte row loads (X's row pitch K*4 is not a multiple of
+//              16 bytes for K = 602, so TMA cannot describe it), hi/lo split in registers,
+//              stores into the 128B-swizzled K-major layout UMMA expects; later the epilogue
+//              (tcgen05.ld: one accumulator row per thread, bias / ReLU / attention projections).
+//   warp 4     one elected thread issues 3 x 4 tcgen05.mma per 32-wide K chunk and commits to
+//              the stage's "empty" mbarrier; TMEM allocation / release.
+//   2-stage shared-memory ring (A hi/lo 2 x 16 KB + B hi/lo 2 x NPAD*128 B per stage), several
+//   CTAs per SM so that one CTA's epilogue overlaps another's loads.
+#include <cstring>
+
+#include "common.cuh"
+
+using namespace gala;
+
+namespace {
+
+constexpr int kBM = 128;          // rows per CTA = UMMA_M
+constexpr int kBK = 32;           // fp32 per K chunk = one 128-byte swizzle row
+constexpr int kStages = 2;
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 160;     // 4 producer/epilogue warps + 1 MMA warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 in [0,14), LBO >> 4 in [16,30) (unused for swizzled K-major), SBO >> 4 in
+// [32,46) = 1024 B between 8-row groups, version 1 in [46,48), layout type 2 (128B) in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// byte offset of element (row r, 4-byte column c) inside a [rows x 32 fp32] K-major SW128 tile
+__device__ __forceinline__ uint32_t sw128(int r, int c) {
+    return (uint32_t)(r * 128 + ((((c >> 2) ^ (r & 7)) << 4) | ((c & 3) << 2)));
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);   // exactly representable in tf32
+    lo = x - hi;                                              // exact in fp32; tf32 keeps its top bits
+}
+
+struct LinearParams {
+    const float* __restrict__ X;      // [M, K]
+    const float* __restrict__ W;      // [N, K]
+    const float* __restrict__ bias;   // [N] or nullptr
+    float* __restrict__ Y;            // [M, N]
+    const float* __restrict__ att_w;  // [2, N] or nullptr
+    float att_b0, att_b1;
+    float* __restrict__ att_out;      // [2, M]
+    int64_t M;
+    int K, N, relu;
+};
+
+template <int NPAD>
+__global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid_constant__ LinearParams p) {
+    constexpr uint32_t kABytes = kBM * 128;            // one A tile (hi or lo)
+    constexpr uint32_t kBBytes = NPAD * 128;           // one B tile (hi or lo)
+    constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+    constexpr uint32_t kTmemCols = NPAD <= 32 ? 32 : 64;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * kBM;
+    const int nchunks = (p.K + kBK - 1) / kBK;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], kProducerThreads);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {   // TMEM allocation is warp-collective
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp < 4) {
+        // ---------------- producers: 4 warps x 32 rows of the tile each, one row per step -------------
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int s = ch % kStages;
+            const uint32_t ph = (uint32_t)((ch / kStages) & 1);
+            if (ch >= kStages) mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* a_hi = smem + (size_t)s * kStageBytes;
+            uint8_t* a_lo = a_hi + kABytes;
+            uint8_t* b_hi = a_lo + kABytes;
+            uint8_t* b_lo = b_hi + kBBytes;
+            const int k = ch * kBK + lane;
+            const bool kok = k < p.K;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int64_t r = row0 + warp * 32 + i;
+                v[i] = (kok && r < p.M) ? __ldg(p.X + r * p.K + k) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float hi, lo;
+                split_tf32(v[i], hi, lo);
+                const uint32_t off = sw128(warp * 32 + i, lane);
+                *reinterpret_cast<float*>(a_hi + off) = hi;
+                *reinterpret_cast<float*>(a_lo + off) = lo;
+            }
+            // W tile: NPAD rows shared among the 4 warps (rows >= N are zero)
+#pragma unroll
+            for (int i = 0; i < NPAD / 4; ++i) {
+                const int n = warp * (NPAD / 4) + i;
+                float w = (kok && n < p.N) ? __ldg(p.W + (int64_t)n * p.K + k) : 0.0f;
+                float hi, lo;
+                split_tf32(w, hi, lo);
+                const uint32_t off = sw128(n, lane);
+                *reinterpret_cast<float*>(b_hi + off) = hi;
+                *reinterpret_cast<float*>(b_lo + off) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
+            mbar_arrive(&full_bar[s]);
+        }
+        // ---------------- epilogue: thread t owns accumulator row t (TMEM lane t) ----------------------
+        mbar_wait(&acc_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t r = row0 + tid;
+        float acc[NPAD];
+#pragma unroll
+        for (int c0 = 0; c0 < NPAD; c0 += 16) {
+            uint32_t u[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                  "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(u[j]);
+        }
+        if (r < p.M) {
+            float a0 = p.att_b0, a1 = p.att_b1;
+#pragma unroll
+            for (int n = 0; n < NPAD; ++n) {
+                if (n < p.N) {
+                    float y = acc[n] + (p.bias ? __ldg(p.bias + n) : 0.0f);
+                    if (p.att_w) {   // projections of the (pre-activation) output row: aL = y.wl + bl, aR = y.wr + br
+                        a0 = fmaf(y, __ldg(p.att_w + n), a0);
+                        a1 = fmaf(y, __ldg(p.att_w + p.N + n), a1);
+                    }
+                    if (p.relu) y = fmaxf(y, 0.0f);
+                    acc[n] = y;
+                }
+            }
+            float* yrow = p.Y + r * p.N;
+            if ((p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(yrow) & 15) == 0) {
+#pragma unroll
+                for (int n = 0; n < NPAD; n += 4)
+                    if (n < p.N) *reinterpret_cast<float4*>(yrow + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+            } else {
+#pragma unroll
+                for (int n = 0; n < NPAD; ++n)
+                    if (n < p.N) yrow[n] = acc[n];
+            }
+            if (p.att_w) {
+                p.att_out[r] = a0;
+                p.att_out[p.M + r] = a1;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else if (lane == 0) {
+        // ---------------- MMA issuer (one thread) ---------------------------------------------------
+        constexpr uint32_t idesc = make_idesc(NPAD);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int s = ch % kStages;
+            const uint32_t ph = (uint32_t)((ch / kStages) & 1);
+            mbar_wait(&full_bar[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes);
+            const uint32_t a_lo = a_hi + kABytes;
+            const uint32_t b_hi = a_lo + kABytes;
+            const uint32_t b_lo = b_hi + kBBytes;
+#pragma unroll
+            for (int k8 = 0; k8 < kBK / 8; ++k8) {   // UMMA_K = 8 tf32 = 32 bytes along the swizzled row
+                const uint32_t ko = (uint32_t)k8 * 32;
+                umma_tf32(tmem_base, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, (ch | k8) != 0);
+                umma_tf32(tmem_base, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                umma_tf32(tmem_base, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+            }
+            umma_commit(&empty_bar[s]);            // frees the stage when these MMAs have read it
+        }
+        umma_commit(&acc_bar);                     // accumulator complete
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+template <int NPAD>
+int launch_linear(const LinearParams& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)kStages * (2 * kBM * 128 + 2 * NPAD * 128) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const unsigned grid = (unsigned)((p.M + kBM - 1) / kBM);
+    linear_tf32x3_kernel<NPAD><<<grid, kThreads, smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GALA_OK : (int)e;
+}
+
+}  // namespace
+
+extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float* W, const float* bias, int32_t N, float* Y,
+                               int32_t relu, const float* att_w, const float* att_b, float* att_out,
+                               gala_stream_t stream) {
+    if (M < 0 || K <= 0 || N <= 0) return GALA_ERR_BAD_SHAPE;
+    if (N > 64) return GALA_ERR_UNSUPPORTED;   // one CTA holds every output column (GNN hidden / class widths)
+    if (M == 0) return GALA_OK;
+    if (!X || !W || !Y || (att_w && (!att_b || !att_out))) return GALA_ERR_NULL_POINTER;
+    LinearParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.X = X;
+    p.W = W;
+    p.bias = bias;
+    p.Y = Y;
+    p.att_w = att_w;
+    p.att_out = att_out;
+    p.M = M;
+    p.K = K;
+    p.N = N;
+    p.relu = relu;
+    if (att_w) {   // att_b is a HOST pointer to two floats
+        p.att_b0 = att_b[0];
+        p.att_b1 = att_b[1];
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (N <= 16) return launch_linear<16>(p, st);
+    if (N <= 32) return launch_linear<32>(p, st);
+    if (N <= 48) return launch_linear<48>(p, st);
+    return launch_linear<64>(p, st);
+}

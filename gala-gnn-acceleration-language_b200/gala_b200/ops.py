@@ -170,3 +170,24 @@ def gat_forward_dot(g, aL, wR, bR, X, slope=0.2, relu=False, out=None, alpha_out
                                                 _l.ptr(X), K, slope, _l.ptr(out), _l.ptr(alpha_out),
                                                 int(relu), g._p(), _l.stream_ptr()))
     return out
+
+
+def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None):
+    """Y = X @ W.T + bias on the tensor cores (tcgen05 kind::tf32, 3xTF32 error compensation).
+    With att_w [2,N] / att_b (two floats) also returns att [2,M] = the two attention
+    projections of the pre-activation output rows (fused epilogue)."""
+    X, W = _f32(X), _f32(W)
+    M, K = X.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and N <= 64
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=X.device)
+    att = None
+    ab = None
+    if att_w is not None:
+        att = torch.empty((2, M), dtype=torch.float32, device=X.device)
+        ab = (C.c_float * 2)(float(att_b[0]), float(att_b[1]))
+    _l.check(_l.load().gala_linear_f32(_l.ptr(X), M, K, _l.ptr(W), _l.ptr(bias), N, _l.ptr(out), int(relu),
+                                       _l.ptr(_f32(att_w)) if att_w is not None else None, ab,
+                                       _l.ptr(att), _l.stream_ptr()))
+    return (out, att) if att_w is not None else out

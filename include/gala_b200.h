@@ -184,6 +184,18 @@ int gala_gat_forward_dot_f32(const gala_graph_t *g, const float *aL, const float
                              const float *X, int32_t K, float slope, float *Y, float *alpha_out,
                              int32_t relu, const gala_plan_t *plan, gala_stream_t stream);
 
+/* ---- dense feature transform on the tensor cores -------- */
+/* Replaces torch::nn::Linear of the generated model (common.h:1185-1281; cuBLAS fp32 SIMT   */
+/* through libtorch): Y[M,N] = X[M,K] * W[N,K]^T + bias, optional ReLU.  tcgen05.mma         */
+/* kind::tf32 with the accumulator in TMEM, error-compensated (3xTF32) so that the result     */
+/* stays within the fp32 parity bound.  N <= 64 (hidden / class widths of the GNN layers).    */
+/* Optional fused attention projections of a GAT layer (attenL/attenR = Linear(h,1)(res),      */
+/* frontend.y:987-994): att_out[0:M] = Y_pre_relu . att_w[0,:] + att_b[0], att_out[M:2M] the   */
+/* same with row 1.  att_w device [2,N], att_b HOST [2], att_out device [2,M]; all nullable.   */
+int gala_linear_f32(const float *X, int64_t M, int32_t K, const float *W, const float *bias,
+                    int32_t N, float *Y, int32_t relu, const float *att_w, const float *att_b,
+                    float *att_out, gala_stream_t stream);
+
 /* ---- format construction on the device ---------- */
 /* All integer outputs are bit-exact against the reference functions named below.       */
 

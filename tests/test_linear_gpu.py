@@ -1,0 +1,48 @@
+"""GPU parity: the tcgen05 (3xTF32) dense transform against an fp64 reference and against the
+fp32 path the reference uses (torch.nn.functional.linear with TF32 off = cuBLAS fp32)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gala_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 32, 32), (128, 64, 32), (1000, 602, 32), (5000, 100, 32), (777, 32, 41),
+                                   (300, 1433, 32), (4096, 602, 16), (130, 7, 8), (1, 5, 64), (233000, 602, 32)])
+def test_linear_matches_fp64_and_torch_fp32(M, K, N):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(M + K + N)
+    X = torch.rand(M, K, generator=gen, device=DEV) - 0.5
+    W = (torch.rand(N, K, generator=gen, device=DEV) - 0.5) * 0.2
+    b = torch.rand(N, generator=gen, device=DEV) - 0.5
+    want64 = X.double() @ W.double().t() + b.double()
+    got = ops.linear(X, W, b)
+    ref32 = F.linear(X, W, b)
+    err = float((got.double() - want64).norm() / want64.norm())
+    err_ref = float((ref32.double() - want64).norm() / want64.norm())
+    assert err < 1e-5                       # north_star fp32 bound
+    assert err <= max(4 * err_ref, 5e-7)    # as accurate as the fp32 SIMT path it replaces
+    got_relu = ops.linear(X, W, b, relu=True)
+    assert torch.equal(got_relu, torch.relu(got))
+    got_nb = ops.linear(X, W)
+    assert float((got_nb.double() - (want64 - b.double())).norm() / want64.norm()) < 1e-5
+
+
+def test_linear_fused_attention_projections():
+    M, K, N = 3000, 602, 32
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(0)
+    X = torch.rand(M, K, generator=gen, device=DEV) - 0.5
+    W = (torch.rand(N, K, generator=gen, device=DEV) - 0.5) * 0.2
+    b = torch.rand(N, generator=gen, device=DEV) - 0.5
+    aw = torch.rand(2, N, generator=gen, device=DEV) - 0.5
+    ab = [0.25, -0.5]
+    y, att = ops.linear(X, W, b, relu=False, att_w=aw, att_b=ab)
+    y64 = X.double() @ W.double().t() + b.double()
+    want = y64 @ aw.double().t() + torch.tensor(ab, device=DEV, dtype=torch.float64)
+    assert float((att.double().t() - want).norm() / want.norm()) < 1e-5
+    assert float((y.double() - y64).norm() / y64.norm()) < 1e-5
