@@ -113,7 +113,13 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
     constexpr uint32_t kABytes = kBM * 128;            // one A tile (hi or lo)
     constexpr uint32_t kBBytes = NPAD * 128;           // one B tile (hi or lo)
     constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
-    constexpr uint32_t kTmemCols = NPAD <= 32 ? 32 : 64;
+    // The tensor core truncates when it aligns addends into the fp32 accumulator, so one long
+    // accumulation chain drifts (4e-6 relative after 228 MMAs, measured).  The hi*hi products are
+    // therefore spread round-robin over kMain accumulators, the small correction terms go to their
+    // own accumulator, and the epilogue adds the kMain + 1 partials with IEEE fp32 adds.
+    constexpr int kMain = NPAD == 64 ? 3 : 4;
+    constexpr uint32_t kAccCols = (kMain + 1) * NPAD;
+    constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : 256;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_bar;
@@ -144,7 +150,25 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
 
     if (warp < 4) {
         // ---------------- producers: 4 warps x 32 rows of the tile each, one row per step -------------
-        for (int ch = 0; ch < nchunks; ++ch) {
+        // Software-pipelined: the 32 + NPAD/4 global loads of chunk ch+1 are issued before chunk ch is
+        // split and stored, so every producer warp keeps two chunks (8 KB) of HBM requests in flight.
+        constexpr int kWRows = NPAD / 4;
+        float va[32], wa[kWRows], vb[32], wb[kWRows];
+        auto load_chunk = [&](int ch, float (&v)[32], float (&w)[kWRows]) {
+            const int k = ch * kBK + lane;
+            const bool kok = k < p.K;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int64_t r = row0 + warp * 32 + i;
+                v[i] = (kok && r < p.M) ? __ldg(p.X + r * p.K + k) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < kWRows; ++i) {
+                const int n = warp * kWRows + i;   // rows >= N are zero
+                w[i] = (kok && n < p.N) ? __ldg(p.W + (int64_t)n * p.K + k) : 0.0f;
+            }
+        };
+        auto store_chunk = [&](int ch, const float (&v)[32], const float (&w)[kWRows]) {
             const int s = ch % kStages;
             const uint32_t ph = (uint32_t)((ch / kStages) & 1);
             if (ch >= kStages) mbar_wait(&empty_bar[s], ph ^ 1);
@@ -152,14 +176,6 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
             uint8_t* a_lo = a_hi + kABytes;
             uint8_t* b_hi = a_lo + kABytes;
             uint8_t* b_lo = b_hi + kBBytes;
-            const int k = ch * kBK + lane;
-            const bool kok = k < p.K;
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int64_t r = row0 + warp * 32 + i;
-                v[i] = (kok && r < p.M) ? __ldg(p.X + r * p.K + k) : 0.0f;
-            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 float hi, lo;
@@ -168,19 +184,25 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
                 *reinterpret_cast<float*>(a_hi + off) = hi;
                 *reinterpret_cast<float*>(a_lo + off) = lo;
             }
-            // W tile: NPAD rows shared among the 4 warps (rows >= N are zero)
 #pragma unroll
-            for (int i = 0; i < NPAD / 4; ++i) {
-                const int n = warp * (NPAD / 4) + i;
-                float w = (kok && n < p.N) ? __ldg(p.W + (int64_t)n * p.K + k) : 0.0f;
+            for (int i = 0; i < kWRows; ++i) {
                 float hi, lo;
-                split_tf32(w, hi, lo);
-                const uint32_t off = sw128(n, lane);
+                split_tf32(w[i], hi, lo);
+                const uint32_t off = sw128(warp * kWRows + i, lane);
                 *reinterpret_cast<float*>(b_hi + off) = hi;
                 *reinterpret_cast<float*>(b_lo + off) = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
             mbar_arrive(&full_bar[s]);
+        };
+        load_chunk(0, va, wa);
+        for (int ch = 0; ch < nchunks; ch += 2) {
+            if (ch + 1 < nchunks) load_chunk(ch + 1, vb, wb);
+            store_chunk(ch, va, wa);
+            if (ch + 1 < nchunks) {
+                if (ch + 2 < nchunks) load_chunk(ch + 2, va, wa);
+                store_chunk(ch + 1, vb, wb);
+            }
         }
         // ---------------- epilogue: thread t owns accumulator row t (TMEM lane t) ----------------------
         mbar_wait(&acc_bar, 0);
@@ -188,7 +210,11 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
         const int64_t r = row0 + tid;
         float acc[NPAD];
 #pragma unroll
-        for (int c0 = 0; c0 < NPAD; c0 += 16) {
+        for (int n = 0; n < NPAD; ++n) acc[n] = 0.0f;
+#pragma unroll
+        for (int c0 = 0; c0 < (int)kAccCols; c0 += 16) {
+            // main accumulator a is written only if the tile has more than a K chunks
+            if (c0 / NPAD < kMain && c0 / NPAD >= nchunks) continue;
             uint32_t u[16];
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
             asm volatile(
@@ -198,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(u[j]);
+            for (int j = 0; j < 16; ++j) acc[(c0 + j) % NPAD] += __uint_as_float(u[j]);
         }
         if (r < p.M) {
             float a0 = p.att_b0, a1 = p.att_b1;
@@ -242,12 +268,14 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
             const uint32_t a_lo = a_hi + kABytes;
             const uint32_t b_hi = a_lo + kABytes;
             const uint32_t b_lo = b_hi + kBBytes;
+            const uint32_t d_main = tmem_base + (uint32_t)((ch % kMain) * NPAD);
+            const uint32_t d_corr = tmem_base + (uint32_t)(kMain * NPAD);
 #pragma unroll
             for (int k8 = 0; k8 < kBK / 8; ++k8) {   // UMMA_K = 8 tf32 = 32 bytes along the swizzled row
                 const uint32_t ko = (uint32_t)k8 * 32;
-                umma_tf32(tmem_base, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, (ch | k8) != 0);
-                umma_tf32(tmem_base, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
-                umma_tf32(tmem_base, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                umma_tf32(d_main, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, (ch >= kMain) | (k8 != 0));
+                umma_tf32(d_corr, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, (ch | k8) != 0);
+                umma_tf32(d_corr, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
             }
             umma_commit(&empty_bar[s]);            // frees the stage when these MMAs have read it
         }
