@@ -212,6 +212,8 @@ def main():
     ap.add_argument("--edges", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
+    ap.add_argument("--dense", default="tcgen05", choices=["tcgen05", "torch"],
+                    help="layer-1 feature transform: hand-written tcgen05 3xTF32 kernel or cuBLAS fp32 via torch")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel sweep (SpMM/SDDMM GB/s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -283,9 +285,11 @@ def main():
     else:
         g = ops.TiledGraph(offset, ids, n).build_plan()
         X_in = X
-        step_fn = lambda hook=None: model.forward(g, X_in, hook)   # noqa: E731
-        launches_per_step = 2
+        step_fn = lambda hook=None: model.forward(g, X_in, hook, dense=args.dense)   # noqa: E731
+        launches_per_step = 3 if args.dense == "tcgen05" else 2
         config["parallelism"] = "single GPU"
+        config["dense"] = ("layer-1 X*W + attention projections: gala_linear_f32 (tcgen05 kind::tf32, 3xTF32)"
+                           if args.dense == "tcgen05" else "cuBLAS fp32 through torch")
         config["hub_rows"] = int(g.plan.n_hub)
         config["hub_threshold"] = int(g.plan.hub_threshold)
 
@@ -376,7 +380,7 @@ def main():
 
     def e2e_step():
         X_stage.copy_(X_host, non_blocking=True)
-        o = (runner.forward(X_stage) if world > 1 else model.forward(g, X_stage))
+        o = (runner.forward(X_stage) if world > 1 else model.forward(g, X_stage, dense=args.dense))
         out_host.copy_(o, non_blocking=True)
 
     for _ in range(2):

@@ -154,43 +154,60 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
         // split and stored, so every producer warp keeps two chunks (8 KB) of HBM requests in flight.
         constexpr int kWRows = NPAD / 4;
         float va[32], wa[kWRows], vb[32], wb[kWRows];
+        // Addressing is hoisted so that the steady state costs one IMAD + LDG per element on the load
+        // side and LOP3 + FADD + 2 STS (immediate offsets) on the store side.
+        const int64_t wrow0 = row0 + warp * 32;
+        const char* xlane = reinterpret_cast<const char*>(p.X + wrow0 * p.K + lane);
+        const char* wlane = reinterpret_cast<const char*>(p.W + (int64_t)(warp * kWRows) * p.K + lane);
+        const uint32_t pitch = (uint32_t)p.K * 4u;
+        const bool rows_full = wrow0 + 32 <= p.M;
+        const bool wrows_full = warp * kWRows + kWRows <= p.N;
+        uint32_t sw[8];   // swizzled 16-byte chunk of this lane's column for row-in-atom j
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sw[j] = (uint32_t)((((lane >> 2) ^ j) << 4) | ((lane & 3) << 2));
         auto load_chunk = [&](int ch, float (&v)[32], float (&w)[kWRows]) {
-            const int k = ch * kBK + lane;
-            const bool kok = k < p.K;
+            const bool kok = ch * kBK + lane < p.K;
+            const char* xc = xlane + ch * (kBK * 4);
+            const char* wc = wlane + ch * (kBK * 4);
+            if (rows_full && kok) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int64_t r = row0 + warp * 32 + i;
-                v[i] = (kok && r < p.M) ? __ldg(p.X + r * p.K + k) : 0.0f;
+                for (int i = 0; i < 32; ++i) v[i] = __ldg(reinterpret_cast<const float*>(xc + (uint64_t)i * pitch));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    v[i] = (kok && wrow0 + i < p.M) ? __ldg(reinterpret_cast<const float*>(xc + (uint64_t)i * pitch)) : 0.0f;
             }
+            if (wrows_full && kok) {
 #pragma unroll
-            for (int i = 0; i < kWRows; ++i) {
-                const int n = warp * kWRows + i;   // rows >= N are zero
-                w[i] = (kok && n < p.N) ? __ldg(p.W + (int64_t)n * p.K + k) : 0.0f;
+                for (int i = 0; i < kWRows; ++i) w[i] = __ldg(reinterpret_cast<const float*>(wc + (uint64_t)i * pitch));
+            } else {
+#pragma unroll
+                for (int i = 0; i < kWRows; ++i)   // rows >= N are zero
+                    w[i] = (kok && warp * kWRows + i < p.N) ? __ldg(reinterpret_cast<const float*>(wc + (uint64_t)i * pitch)) : 0.0f;
             }
         };
         auto store_chunk = [&](int ch, const float (&v)[32], const float (&w)[kWRows]) {
             const int s = ch % kStages;
             const uint32_t ph = (uint32_t)((ch / kStages) & 1);
             if (ch >= kStages) mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* a_hi = smem + (size_t)s * kStageBytes;
+            uint8_t* a_hi = smem + (size_t)s * kStageBytes + warp * 4096;
             uint8_t* a_lo = a_hi + kABytes;
-            uint8_t* b_hi = a_lo + kABytes;
+            uint8_t* b_hi = smem + (size_t)s * kStageBytes + 2 * kABytes + warp * (kWRows * 128);
             uint8_t* b_lo = b_hi + kBBytes;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 float hi, lo;
                 split_tf32(v[i], hi, lo);
-                const uint32_t off = sw128(warp * 32 + i, lane);
-                *reinterpret_cast<float*>(a_hi + off) = hi;
-                *reinterpret_cast<float*>(a_lo + off) = lo;
+                *reinterpret_cast<float*>(a_hi + i * 128 + sw[i & 7]) = hi;
+                *reinterpret_cast<float*>(a_lo + i * 128 + sw[i & 7]) = lo;
             }
 #pragma unroll
-            for (int i = 0; i < kWRows; ++i) {
+            for (int i = 0; i < kWRows; ++i) {   // warp * kWRows is a multiple of 4; row-in-atom = (warp*kWRows + i) & 7
                 float hi, lo;
                 split_tf32(w[i], hi, lo);
-                const uint32_t off = sw128(warp * kWRows + i, lane);
-                *reinterpret_cast<float*>(b_hi + off) = hi;
-                *reinterpret_cast<float*>(b_lo + off) = lo;
+                const uint32_t o = (uint32_t)(i * 128) + sw[(warp * kWRows + i) & 7];
+                *reinterpret_cast<float*>(b_hi + o) = hi;
+                *reinterpret_cast<float*>(b_lo + o) = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
             mbar_arrive(&full_bar[s]);

@@ -57,21 +57,30 @@ class GAT2:
         # both projections of a layer as one [2, K] weight
         self.W_att1 = torch.cat([self.efc0[0], self.efc1[0]], 0).contiguous()
         self.b_att1 = torch.cat([self.efc0[1], self.efc1[1]], 0).contiguous()
+        self.b_att1_host = [float(self.efc0[1]), float(self.efc1[1])]
         self.W_att2 = torch.stack([self.wL2, self.wR2], 0).contiguous()
         self.b_att2 = torch.tensor([self.bL2, self.bR2], device=W1.device)
 
     def attention_inputs(self, t, wl, wr):
         return F.linear(t, *wl).reshape(-1), F.linear(t, *wr).reshape(-1)
 
-    def forward(self, g, X, hook=None, mode="folded"):
+    def forward(self, g, X, hook=None, mode="folded", dense="tcgen05"):
         """g: TiledGraph (rows = output nodes, cols index X's rows).  `hook(name, fn)` lets the
         benchmark time the sparse kernels individually.
           mode="literal": the op sequence of the generated program, one Linear per projection
           mode="folded" : same math with the attention projections folded (one [K,2] matmul
                           per layer; layer 2 never materialises fc1(res) for the logits)
-          mode="dot"    : aR recomputed inside the kernel (gala_gat_forward_dot_f32)"""
+          mode="dot"    : aR recomputed inside the kernel (gala_gat_forward_dot_f32)
+        dense="tcgen05" runs the layer-1 transform (and, in folded mode, its two attention
+        projections, fused in the epilogue) on the tensor cores (gala_linear_f32); "torch" = cuBLAS."""
         run = hook if hook is not None else (lambda name, fn: fn())
-        res = F.linear(X, *self.fc0)
+        if dense == "tcgen05" and mode == "folded":
+            res, a = run("linear1", lambda: ops.linear(X, self.fc0[0], self.fc0[1], att_w=self.W_att1, att_b=self.b_att1_host))
+            res = run("gat_layer1", lambda: ops.gat_forward(g, a[0], a[1], res, self.slope, relu=True))
+            a = F.linear(res, self.W_att2, self.b_att2).t().contiguous()
+            agg = run("gat_layer2", lambda: ops.gat_forward(g, a[0], a[1], res, self.slope, relu=False))
+            return F.linear(agg, *self.fc1)
+        res = ops.linear(X, *self.fc0) if dense == "tcgen05" else F.linear(X, *self.fc0)
         if mode == "dot":
             aL = F.linear(res, *self.efc0).reshape(-1)
             res = run("gat_layer1", lambda: ops.gat_forward_dot(g, aL, self.wR1, self.bR1, res, self.slope, relu=True))

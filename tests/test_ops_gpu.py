@@ -231,10 +231,11 @@ def test_gat_model_dot_and_materialised_paths_agree(orc):
     g = to_gpu_graph(t, 256)
     model = GAT2(64, 32, 41, DEV, seed=3)
     X = torch.rand(n, 64, device=DEV) - 0.5
-    b = model.forward(g, X, mode="literal")
-    for mode in ("folded", "dot"):
-        a = model.forward(g, X, mode=mode)
-        assert float((a - b).double().norm() / b.double().norm()) < FP32_TOL
+    b = model.forward(g, X, mode="literal", dense="torch")
+    for mode in ("folded", "dot", "literal"):
+        for dense in ("torch", "tcgen05"):
+            a = model.forward(g, X, mode=mode, dense=dense)
+            assert float((a - b).double().norm() / b.double().norm()) < FP32_TOL
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
