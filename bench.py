@@ -502,6 +502,15 @@ def kernel_sweep(g, n, nvals, K, peak, dev):
     # as ONE launch with the fused row/col scale + ReLU epilogue
     rec("gcn_layer_aggregate_fused_k32", time_op(lambda: ops.spmm(g, X, out=Y, row_scale=nrm, col_scale=nrm, relu=True)),
         rp + 4 * nvals + 8 * n * K + 8 * n)
+    # 2-layer GCN forward as generated (codegen/gala.cu:422-459) with every norm*res pass in an epilogue
+    from gala_b200.gcn_model import GCN2
+    feats = 602
+    gcn = GCN2(feats, K, 41, dev).prepare(g)
+    Xf = torch.rand(n, feats, generator=gen, device=dev) - 0.5
+    ms = time_op(lambda: gcn.forward(g, Xf))
+    res["gcn_2layer_forward"] = {"ms": round(ms, 4), "layer_ms": round(ms / 2, 4),
+                                 "launches": "linear(tcgen05)+2 aggregations+cuBLAS classifier"}
+    del Xf
     rec("sddmm_k32", time_op(lambda: ops.sddmm(g, Z, X, out=ev)), rp + 4 * nvals + 8 * n * K + 4 * nvals)
     rec("sddvv_add", time_op(lambda: ops.sddvv(g, a, a, "add", out=ev)), rp + 4 * nvals + 8 * n + 4 * nvals)
     rec("edge_softmax_fwd", time_op(lambda: ops.edge_softmax_fwd(g, w, out=ev)), rp + 8 * nvals)

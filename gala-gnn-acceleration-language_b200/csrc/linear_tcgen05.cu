@@ -101,6 +101,7 @@ struct LinearParams {
     const float* __restrict__ W;      // [N, K]
     const float* __restrict__ bias;   // [N] or nullptr
     float* __restrict__ Y;            // [M, N]
+    const float* __restrict__ row_scale;  // [M] or nullptr: Y[r,:] *= row_scale[r] (before ReLU)
     const float* __restrict__ att_w;  // [2, N] or nullptr
     float att_b0, att_b1;
     float* __restrict__ att_out;      // [2, M]
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
         }
         if (r < p.M) {
             float a0 = p.att_b0, a1 = p.att_b1;
+            const float rscale = p.row_scale ? __ldg(p.row_scale + r) : 1.0f;
 #pragma unroll
             for (int n = 0; n < NPAD; ++n) {
                 if (n < p.N) {
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
                         a0 = fmaf(y, __ldg(p.att_w + n), a0);
                         a1 = fmaf(y, __ldg(p.att_w + p.N + n), a1);
                     }
+                    y *= rscale;
                     if (p.relu) y = fmaxf(y, 0.0f);
                     acc[n] = y;
                 }
@@ -323,8 +326,8 @@ int launch_linear(const LinearParams& p, cudaStream_t st) {
 }  // namespace
 
 extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float* W, const float* bias, int32_t N, float* Y,
-                               int32_t relu, const float* att_w, const float* att_b, float* att_out,
-                               gala_stream_t stream) {
+                               const float* row_scale, int32_t relu, const float* att_w, const float* att_b,
+                               float* att_out, gala_stream_t stream) {
     if (M < 0 || K <= 0 || N <= 0) return GALA_ERR_BAD_SHAPE;
     if (N > 64) return GALA_ERR_UNSUPPORTED;   // one CTA holds every output column (GNN hidden / class widths)
     if (M == 0) return GALA_OK;
@@ -335,6 +338,7 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
     p.W = W;
     p.bias = bias;
     p.Y = Y;
+    p.row_scale = row_scale;
     p.att_w = att_w;
     p.att_out = att_out;
     p.M = M;

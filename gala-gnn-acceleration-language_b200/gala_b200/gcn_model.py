@@ -1,0 +1,55 @@
+"""The 2-layer GCN forward as GALA generates it (reference codegen/gala.cu:422-459, emitted by
+src/codegen/common.h:1128-1180; after complexityOperatorReordering the transform runs first):
+
+    deg = A @ 1; norm = deg^-0.5                       (training-invariant, computed once)
+    layer 1: res = fc0(X); res = norm*res; res = A@res; res = norm*res; res = relu(res)
+    layer 2: res = norm*res; res = A@res; res = norm*res; out = fc1(res)
+
+Here every `norm*res` pass is folded into a kernel epilogue: the transform scales its rows
+(gala_linear_f32 row_scale), layer 1's aggregation applies norm^2 before the ReLU
+(norm * relu(norm * x) == relu(norm^2 * x) for norm > 0, which also pre-scales layer 2's input),
+layer 2's aggregation applies norm.  Four launches instead of eleven."""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .gat_model import _linear_init
+
+
+class GCN2:
+    def __init__(self, in_feats, hidden, classes, device, seed=0):
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        self.fc0 = _linear_init(gen, hidden, in_feats, device)
+        self.fc1 = _linear_init(gen, classes, hidden, device)
+        self.norm = None
+
+    def prepare(self, g):
+        """Invariant code: degrees through the aggregation kernel itself (A @ ones, K = 1)."""
+        ones = torch.ones(g.ncols, 1, device=g.device)
+        deg = ops.spmm(g, ones).reshape(-1)
+        self.norm = torch.pow(deg, -0.5).contiguous()
+        self.norm2 = (self.norm * self.norm).contiguous()
+        return self
+
+    def forward_literal(self, g, X):
+        """Op-by-op, as emitted (ATen elementwise passes between the kernels)."""
+        n = self.norm[:, None]
+        res = F.linear(X, *self.fc0)
+        res = n * res
+        res = ops.spmm(g, res)
+        res = torch.relu(n * res)
+        res = n * res
+        res = ops.spmm(g, res)
+        res = n * res
+        return F.linear(res, *self.fc1)
+
+    def forward(self, g, X, hook=None, dense="tcgen05"):
+        run = hook if hook is not None else (lambda name, fn: fn())
+        if dense == "tcgen05":
+            res = run("linear1", lambda: ops.linear(X, self.fc0[0], self.fc0[1], row_scale=self.norm))
+        else:
+            res = self.norm[:, None] * F.linear(X, *self.fc0)
+        res = run("gcn_aggregate1", lambda: ops.spmm(g, res, row_scale=self.norm2, relu=True))
+        res = run("gcn_aggregate2", lambda: ops.spmm(g, res, row_scale=self.norm))
+        return F.linear(res, *self.fc1)

@@ -172,7 +172,7 @@ def gat_forward_dot(g, aL, wR, bR, X, slope=0.2, relu=False, out=None, alpha_out
     return out
 
 
-def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None):
+def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None, row_scale=None):
     """Y = X @ W.T + bias on the tensor cores (tcgen05 kind::tf32, 3xTF32 error compensation).
     With att_w [2,N] / att_b (two floats) also returns att [2,M] = the two attention
     projections of the pre-activation output rows (fused epilogue)."""
@@ -187,7 +187,8 @@ def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None):
     if att_w is not None:
         att = torch.empty((2, M), dtype=torch.float32, device=X.device)
         ab = (C.c_float * 2)(float(att_b[0]), float(att_b[1]))
-    _l.check(_l.load().gala_linear_f32(_l.ptr(X), M, K, _l.ptr(W), _l.ptr(bias), N, _l.ptr(out), int(relu),
+    _l.check(_l.load().gala_linear_f32(_l.ptr(X), M, K, _l.ptr(W), _l.ptr(bias), N, _l.ptr(out),
+                                       _l.ptr(row_scale), int(relu),
                                        _l.ptr(_f32(att_w)) if att_w is not None else None, ab,
                                        _l.ptr(att), _l.stream_ptr()))
     return (out, att) if att_w is not None else out

@@ -192,9 +192,11 @@ int gala_gat_forward_dot_f32(const gala_graph_t *g, const float *aL, const float
 /* Optional fused attention projections of a GAT layer (attenL/attenR = Linear(h,1)(res),      */
 /* frontend.y:987-994): att_out[0:M] = Y_pre_relu . att_w[0,:] + att_b[0], att_out[M:2M] the   */
 /* same with row 1.  att_w device [2,N], att_b HOST [2], att_out device [2,M]; all nullable.   */
+/* row_scale (device [M], nullable) multiplies output row r before the ReLU: the `norm * res`   */
+/* pass that follows the transform in the generated GCN (codegen/gala.cu:441-443).              */
 int gala_linear_f32(const float *X, int64_t M, int32_t K, const float *W, const float *bias,
-                    int32_t N, float *Y, int32_t relu, const float *att_w, const float *att_b,
-                    float *att_out, gala_stream_t stream);
+                    int32_t N, float *Y, const float *row_scale, int32_t relu, const float *att_w,
+                    const float *att_b, float *att_out, gala_stream_t stream);
 
 /* ---- format construction on the device ---------- */
 /* All integer outputs are bit-exact against the reference functions named below.       */

@@ -46,3 +46,14 @@ def test_linear_fused_attention_projections():
     want = y64 @ aw.double().t() + torch.tensor(ab, device=DEV, dtype=torch.float64)
     assert float((att.double().t() - want).norm() / want.norm()) < 1e-5
     assert float((y.double() - y64).norm() / y64.norm()) < 1e-5
+
+
+def test_linear_row_scale_epilogue():
+    M, K, N = 2000, 100, 32
+    X = torch.rand(M, K, device=DEV) - 0.5
+    W = torch.rand(N, K, device=DEV) - 0.5
+    b = torch.rand(N, device=DEV)
+    rs = torch.rand(M, device=DEV) + 0.1
+    got = ops.linear(X, W, b, row_scale=rs, relu=True)
+    want = torch.relu(rs[:, None].double() * (X.double() @ W.double().t() + b.double()))
+    assert float((got.double() - want).norm() / want.norm()) < 1e-5

@@ -238,6 +238,30 @@ def test_gat_model_dot_and_materialised_paths_agree(orc):
             assert float((a - b).double().norm() / b.double().norm()) < FP32_TOL
 
 
+def test_gcn_model_fused_matches_literal_and_oracle(orc):
+    """2-layer GCN as generated (codegen/gala.cu:422-459): fused epilogues == op-by-op == oracle."""
+    from gala_b200.gcn_model import GCN2
+    n = 3000
+    t = graph_case(orc, n, 200000, 12, 700)
+    g = to_gpu_graph(t, 256)
+    model = GCN2(100, 32, 47, DEV, seed=4).prepare(g)
+    X = torch.rand(n, 100, device=DEV) - 0.5
+    lit = model.forward_literal(g, X)
+    for dense in ("torch", "tcgen05"):
+        fused = model.forward(g, X, dense=dense)
+        assert float((fused - lit).double().norm() / lit.double().norm()) < FP32_TOL
+    # oracle composition on the host
+    import torch.nn.functional as F
+    Xc = X.cpu()
+    deg = orc.spmm(t, np.ones((n, 1), np.float32), weighted=False).ravel()
+    norm = (deg ** -0.5).astype(np.float32)
+    res = F.linear(Xc, *[w.cpu() for w in model.fc0]).numpy() * norm[:, None]
+    res = np.maximum(orc.spmm(t, res, weighted=False) * norm[:, None], 0) * norm[:, None]
+    res = orc.spmm(t, res.astype(np.float32), weighted=False) * norm[:, None]
+    want = F.linear(torch.from_numpy(res.astype(np.float32)), *[w.cpu() for w in model.fc1]).numpy()
+    assert rel_err(lit.cpu().numpy(), want) < FP32_TOL
+
+
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_golden_fixtures_on_gpu(orc, name):
     """The reference's own outputs (tests/golden) reproduced by the CUDA path."""
