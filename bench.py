@@ -285,11 +285,13 @@ def main():
     else:
         g = ops.TiledGraph(offset, ids, n).build_plan()
         X_in = X
-        step_fn = lambda hook=None: model.forward(g, X_in, hook, dense=args.dense)   # noqa: E731
+        mode = "fused" if args.dense == "tcgen05" else "folded"
+        step_fn = lambda hook=None: model.forward(g, X_in, hook, mode=mode, dense=args.dense)   # noqa: E731
         launches_per_step = 3 if args.dense == "tcgen05" else 2
         config["parallelism"] = "single GPU"
-        config["dense"] = ("layer-1 X*W + attention projections: gala_linear_f32 (tcgen05 kind::tf32, 3xTF32)"
-                           if args.dense == "tcgen05" else "cuBLAS fp32 through torch")
+        config["dense"] = ("whole step = 3 launches of this repo's kernels: gala_linear_f32 (tcgen05 kind::tf32, 3xTF32; "
+                           "+ layer-1 attention projections) and 2 x gala_gat_forward_ex_f32 (layer-2 projections / "
+                           "classifier in the epilogue)" if args.dense == "tcgen05" else "cuBLAS fp32 through torch")
         config["hub_rows"] = int(g.plan.n_hub)
         config["hub_threshold"] = int(g.plan.hub_threshold)
 
@@ -380,7 +382,7 @@ def main():
 
     def e2e_step():
         X_stage.copy_(X_host, non_blocking=True)
-        o = (runner.forward(X_stage) if world > 1 else model.forward(g, X_stage, dense=args.dense))
+        o = (runner.forward(X_stage) if world > 1 else model.forward(g, X_stage, mode=mode, dense=args.dense))
         out_host.copy_(o, non_blocking=True)
 
     for _ in range(2):

@@ -123,8 +123,8 @@ Shape pick_shape(int K, bool a16, bool a8) {
 template <int MODE>
 int launch_spmm(const SpmmParams& p, cudaStream_t st) {
     if (p.g.nrows == 0 || p.K == 0) return GALA_OK;
-    const bool a16 = aligned(p.X, 16) && aligned(p.Y, 16);
-    const bool a8 = aligned(p.X, 8) && aligned(p.Y, 8);
+    const bool a16 = aligned(p.X, 16) && (!p.Y || aligned(p.Y, 16));
+    const bool a8 = aligned(p.X, 8) && (!p.Y || aligned(p.Y, 8));
     Shape sh = pick_shape(p.K, a16, a8);
     const int tw = sh.vec * sh.lpr * sh.acc;
     dim3 grid(p.t.n_hub + (p.t.n_ordered + kWarpsPerCta - 1) / kWarpsPerCta, (p.K + tw - 1) / tw);
@@ -258,6 +258,50 @@ int gala_gat_forward_f32(const gala_graph_t* g, const float* aL, const float* aR
     p.seed_total = (float)g->segments * 1e-12f;
     HubView h = hub_of(plan, g);
     p.t = task_of(h);
+    return launch_spmm<MODE_GAT>(p, S(stream));
+}
+
+int gala_gat_forward_ex_f32(const gala_graph_t* g, const float* aL, const float* aR, const float* X, int32_t K,
+                            float slope, float* Y, float* alpha_out, int32_t relu, const gala_dense_epilogue_t* ep,
+                            const gala_plan_t* plan, gala_stream_t stream) {
+    if (int rc = check_graph(g)) return rc;
+    if (K <= 0) return GALA_ERR_BAD_SHAPE;
+    const bool has_ep = ep && (ep->att_w || ep->cls_wT);
+    if (g->nrows > 0 && (!aL || !aR || !X || (!Y && !(has_ep && ep->cls_wT)))) return GALA_ERR_NULL_POINTER;
+    if (!aligned(X, 4) || !aligned(Y, 4)) return GALA_ERR_MISALIGNED;
+    SpmmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.g = make_dev(g);
+    p.X = X;
+    p.Y = Y;
+    p.K = K;
+    p.relu = relu;
+    p.aL = aL;
+    p.aR = aR;
+    p.slope = slope;
+    p.alpha_out = alpha_out;
+    p.seed_total = (float)g->segments * 1e-12f;
+    if (has_ep) {
+        if (K > kRowBufMax) return GALA_ERR_UNSUPPORTED;
+        if (ep->att_w && !ep->att_out) return GALA_ERR_NULL_POINTER;
+        if (ep->cls_wT && (!ep->cls_out || ep->cls_n <= 0)) return GALA_ERR_NULL_POINTER;
+        p.att_w = ep->att_w;
+        p.att_b0 = ep->att_b[0];
+        p.att_b1 = ep->att_b[1];
+        p.att_out = ep->att_out;
+        p.cls_wT = ep->cls_wT;
+        p.cls_b = ep->cls_b;
+        p.cls_out = ep->cls_out;
+        p.cls_n = ep->cls_n;
+    }
+    HubView h = hub_of(plan, g);
+    p.t = task_of(h);
+    if (has_ep) {   // the dense epilogue needs the whole row in one warp pass: check the tiling the dispatcher picks
+        const bool a16 = aligned(X, 16) && (!Y || aligned(Y, 16));
+        const bool a8 = aligned(X, 8) && (!Y || aligned(Y, 8));
+        Shape sh = pick_shape(K, a16, a8);
+        if (sh.vec * sh.lpr * sh.acc < K) return GALA_ERR_UNSUPPORTED;
+    }
     return launch_spmm<MODE_GAT>(p, S(stream));
 }
 

@@ -42,6 +42,14 @@ struct SpmmParams {
     float seed_total;                     // S * 1e-12f
     const float* __restrict__ wR;         // MODE_GAT_DOT: aR[j] = dot(X[j,:], wR) + bR
     float bR;
+    // fused dense epilogue on the finished output row y (K <= 128, one feature tile):
+    const float* __restrict__ att_w;      // [2, K]: att_out[row] = y.att_w[0] + att_b0, att_out[nrows+row] = y.att_w[1] + att_b1
+    float att_b0, att_b1;
+    float* __restrict__ att_out;
+    const float* __restrict__ cls_wT;     // [K, cls_n] (transposed Linear weight): cls_out[row,:] = y @ cls_wT + cls_b
+    const float* __restrict__ cls_b;      // [cls_n] or nullptr
+    float* __restrict__ cls_out;          // [nrows, cls_n]
+    int cls_n;
 };
 
 
@@ -151,6 +159,37 @@ __device__ __forceinline__ void gather_chunk_dot(const char* __restrict__ xlane,
         const bool ok = FULL || cj[u] >= 0;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[0][v] = fmaf(wj, ok ? x[u].v[v] : 0.0f, acc[0][v]);
+    }
+}
+
+
+constexpr int kRowBufMax = 128;   // widest output row the fused dense epilogue handles
+
+// Dense epilogue of one finished output row held in shared memory (K floats): the next layer's two
+// attention projections and / or the classifier transform, computed by the warp that owns the row.
+__device__ __forceinline__ void row_dense_epilogue(const SpmmParams& p, const float* __restrict__ rowbuf, int row,
+                                                   int lane) {
+    if (p.att_w) {
+        float a0 = 0.0f, a1 = 0.0f;
+        for (int f = lane; f < p.K; f += 32) {
+            const float y = rowbuf[f];
+            a0 = fmaf(y, __ldg(p.att_w + f), a0);
+            a1 = fmaf(y, __ldg(p.att_w + p.K + f), a1);
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        if (lane == 0) {
+            p.att_out[row] = a0 + p.att_b0;
+            p.att_out[p.g.nrows + row] = a1 + p.att_b1;
+        }
+    }
+    if (p.cls_wT) {
+        for (int n = lane; n < p.cls_n; n += 32) {
+            float o = p.cls_b ? __ldg(p.cls_b + n) : 0.0f;
+#pragma unroll 8
+            for (int f = 0; f < p.K; ++f) o = fmaf(rowbuf[f], __ldg(p.cls_wT + f * p.cls_n + n), o);
+            p.cls_out[(int64_t)row * p.cls_n + n] = o;
+        }
     }
 }
 
@@ -265,13 +304,17 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
 
     float scale = p.row_scale ? __ldg(p.row_scale + row) : 1.0f;
 
+    __shared__ float rowbuf[kWarpsPerCta][kRowBufMax];
+    const bool dense_ep = p.att_w != nullptr || p.cls_wT != nullptr;   // host guarantees K <= kRowBufMax, one tile
+
     if (!hub_cta) {
         if (GALA_IS_GAT(MODE)) scale = 1.0f / (rs + p.seed_total);
         if (grp == 0) {
 #pragma unroll
             for (int a = 0; a < ACC; ++a) {
                 if (!fvalid[a]) continue;
-                float* y = p.Y + (int64_t)row * p.K + tile_base + (a * LPR + sub) * VEC;
+                const int f0 = tile_base + (a * LPR + sub) * VEC;
+                float* y = p.Y + (int64_t)row * p.K + f0;
                 Vec<VEC> o;
                 if (p.accumulate) o.load_rw(y);
 #pragma unroll
@@ -280,9 +323,14 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
                     if (p.accumulate) t += o.v[v];
                     if (p.relu) t = fmaxf(t, 0.0f);
                     o.v[v] = t;
+                    if (dense_ep) rowbuf[warp][f0 + v] = t;
                 }
-                o.store(y);
+                if (p.Y) o.store(y);
             }
+        }
+        if (dense_ep) {
+            __syncwarp();
+            row_dense_epilogue(p, rowbuf[warp], row, lane);
         }
         if (write_alpha) {
             __syncwarp();   // MODE_GAT_DOT: the numerators were stored by other lanes of this warp
@@ -319,7 +367,12 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
         t *= scale;
         if (p.accumulate) t += *y;
         if (p.relu) t = fmaxf(t, 0.0f);
-        *y = t;
+        if (p.Y) *y = t;
+        if (dense_ep) rowbuf[0][f] = t;
+    }
+    if (dense_ep) {
+        __syncthreads();
+        if (warp == 0) row_dense_epilogue(p, rowbuf[0], row, lane);
     }
     if (write_alpha) {
         for_each_chunk(g, row, lo, hi, [&](int e0, int e1) {

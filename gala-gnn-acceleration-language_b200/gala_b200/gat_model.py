@@ -60,6 +60,8 @@ class GAT2:
         self.b_att1_host = [float(self.efc0[1]), float(self.efc1[1])]
         self.W_att2 = torch.stack([self.wL2, self.wR2], 0).contiguous()
         self.b_att2 = torch.tensor([self.bL2, self.bR2], device=W1.device)
+        self.b_att2_host = [self.bL2, self.bR2]
+        self.fc1_wT = W1.t().contiguous()
 
     def attention_inputs(self, t, wl, wr):
         return F.linear(t, *wl).reshape(-1), F.linear(t, *wr).reshape(-1)
@@ -70,10 +72,21 @@ class GAT2:
           mode="literal": the op sequence of the generated program, one Linear per projection
           mode="folded" : same math with the attention projections folded (one [K,2] matmul
                           per layer; layer 2 never materialises fc1(res) for the logits)
+          mode="fused"  : folded projections AND the dense ops that follow each aggregation computed in
+                          the kernels' epilogues (gala_linear_f32 + 2 x gala_gat_forward_ex_f32)
           mode="dot"    : aR recomputed inside the kernel (gala_gat_forward_dot_f32)
         dense="tcgen05" runs the layer-1 transform (and, in folded mode, its two attention
         projections, fused in the epilogue) on the tensor cores (gala_linear_f32); "torch" = cuBLAS."""
         run = hook if hook is not None else (lambda name, fn: fn())
+        if mode == "fused":
+            # three launches, no library kernel: tcgen05 transform (+ layer-1 projections), fused GAT layer
+            # (+ layer-2 projections of its own output rows), fused GAT layer (+ classifier on its rows)
+            res, a = run("linear1", lambda: ops.linear(X, self.fc0[0], self.fc0[1], att_w=self.W_att1, att_b=self.b_att1_host))
+            res, a2, _ = run("gat_layer1", lambda: ops.gat_forward_ex(g, a[0], a[1], res, self.slope, relu=True,
+                                                                      att_w=self.W_att2, att_b=self.b_att2_host))
+            _, _, out = run("gat_layer2", lambda: ops.gat_forward_ex(g, a2[0], a2[1], res, self.slope, relu=False,
+                                                                     cls_wT=self.fc1_wT, cls_b=self.fc1[1], want_y=False))
+            return out
         if dense == "tcgen05" and mode == "folded":
             res, a = run("linear1", lambda: ops.linear(X, self.fc0[0], self.fc0[1], att_w=self.W_att1, att_b=self.b_att1_host))
             res = run("gat_layer1", lambda: ops.gat_forward(g, a[0], a[1], res, self.slope, relu=True))

@@ -192,3 +192,33 @@ def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None, row_sc
                                        _l.ptr(_f32(att_w)) if att_w is not None else None, ab,
                                        _l.ptr(att), _l.stream_ptr()))
     return (out, att) if att_w is not None else out
+
+
+def gat_forward_ex(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None, att_w=None, att_b=None,
+                   cls_wT=None, cls_b=None, want_y=True):
+    """Fused GAT layer + dense epilogue on every finished output row: the next layer's two attention
+    projections (att_w [2,K], att_b two floats -> att [2, nrows]) and / or the transform that follows
+    the aggregation (cls_wT [K,C] = Linear weight transposed -> [nrows, C]).  Returns (Y, att, cls)."""
+    X = _f32(X)
+    K = X.shape[1]
+    dev = X.device
+    if want_y and out is None:
+        out = torch.empty((g.nrows, K), dtype=torch.float32, device=dev)
+    ep = _l.GalaDenseEpilogue()
+    att = cls = None
+    if att_w is not None:
+        att = torch.empty((2, g.nrows), dtype=torch.float32, device=dev)
+        ep.att_w = _f32(att_w).data_ptr()
+        ep.att_b[0], ep.att_b[1] = float(att_b[0]), float(att_b[1])
+        ep.att_out = att.data_ptr()
+    if cls_wT is not None:
+        cls_wT = _f32(cls_wT)
+        cls = torch.empty((g.nrows, cls_wT.shape[1]), dtype=torch.float32, device=dev)
+        ep.cls_wT = cls_wT.data_ptr()
+        ep.cls_b = cls_b.data_ptr() if cls_b is not None else None
+        ep.cls_out = cls.data_ptr()
+        ep.cls_n = cls_wT.shape[1]
+    _l.check(_l.load().gala_gat_forward_ex_f32(C.byref(g.c), _l.ptr(_f32(aL)), _l.ptr(_f32(aR)), _l.ptr(X), K,
+                                               slope, _l.ptr(out) if want_y else None, _l.ptr(alpha_out),
+                                               int(relu), C.byref(ep), g._p(), _l.stream_ptr()))
+    return out, att, cls

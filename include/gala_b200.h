@@ -174,6 +174,27 @@ int gala_gat_forward_f32(const gala_graph_t *g, const float *aL, const float *aR
                          int32_t K, float slope, float *Y, float *alpha_out, int32_t relu,
                          const gala_plan_t *plan, gala_stream_t stream);
 
+/* The same kernel with a fused dense epilogue on each finished output row y (K <= 128):    */
+/*   att_w  [2,K] device, att_b[2]: att_out[row] = y.att_w[0] + att_b[0] and                 */
+/*          att_out[nrows+row] = y.att_w[1] + att_b[1] -- the NEXT layer's attenL/attenR      */
+/*          projections (Linear(h,1), frontend.y:987-994), att_out device [2*nrows];          */
+/*   cls_wT [K,cls_n] device (the Linear weight transposed), cls_b [cls_n] nullable:          */
+/*          cls_out[row,:] = y @ cls_wT + cls_b -- the classifier / FFN that follows the      */
+/*          aggregation (FFN-recompute rewrite, middle-end.h:324-375).  Y may be NULL then.   */
+typedef struct gala_dense_epilogue {
+    const float *att_w;
+    float att_b[2];
+    float *att_out;
+    const float *cls_wT;
+    const float *cls_b;
+    float *cls_out;
+    int32_t cls_n;
+} gala_dense_epilogue_t;
+int gala_gat_forward_ex_f32(const gala_graph_t *g, const float *aL, const float *aR, const float *X,
+                            int32_t K, float slope, float *Y, float *alpha_out, int32_t relu,
+                            const gala_dense_epilogue_t *ep, const gala_plan_t *plan,
+                            gala_stream_t stream);
+
 /* Same layer when the right-hand attention term is a linear function of the aggregated    */
 /* features, aR[j] = dot(X[j,:], wR) + bR -- which is how the generated GAT computes it      */
 /* (attenR = efc(res), common.h:1185-1281; with the layer-2 FFN-recompute rewrite wR = W1^T  */

@@ -232,10 +232,36 @@ def test_gat_model_dot_and_materialised_paths_agree(orc):
     model = GAT2(64, 32, 41, DEV, seed=3)
     X = torch.rand(n, 64, device=DEV) - 0.5
     b = model.forward(g, X, mode="literal", dense="torch")
-    for mode in ("folded", "dot", "literal"):
+    for mode in ("folded", "dot", "literal", "fused"):
         for dense in ("torch", "tcgen05"):
             a = model.forward(g, X, mode=mode, dense=dense)
             assert float((a - b).double().norm() / b.double().norm()) < FP32_TOL
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("K,C", [(32, 41), (8, 3), (64, 64), (100, 47), (128, 7)])
+def test_gat_dense_epilogue(orc, case, K, C):
+    """gala_gat_forward_ex_f32: next-layer attention projections + classifier fused on the output rows."""
+    n, e, seed, T, empty, thr = case
+    t = graph_case(orc, n, e, seed, T, empty)
+    g = to_gpu_graph(t, thr)
+    rng = np.random.default_rng(seed + K + C)
+    aL, aR = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)
+    X = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    att_w = rng.normal(size=(2, K)).astype(np.float32)
+    att_b = [0.1, -0.2]
+    Wc = rng.normal(size=(C, K)).astype(np.float32)
+    bc = rng.normal(size=C).astype(np.float32)
+    want_Y, _ = orc.gat_forward(t, aL, aR, X)
+    want_Y = np.maximum(want_Y, 0)
+    y, att, cls = ops.gat_forward_ex(g, dev(aL), dev(aR), dev(X), relu=True, att_w=dev(att_w), att_b=att_b,
+                                     cls_wT=dev(np.ascontiguousarray(Wc.T)), cls_b=dev(bc))
+    assert rel_err(y.cpu().numpy(), want_Y) < FP32_TOL
+    assert rel_err(att.cpu().numpy().T, want_Y.astype(np.float64) @ att_w.T.astype(np.float64) + np.array(att_b)) < FP32_TOL
+    assert rel_err(cls.cpu().numpy(), want_Y.astype(np.float64) @ Wc.T.astype(np.float64) + bc) < FP32_TOL
+    _, _, cls2 = ops.gat_forward_ex(g, dev(aL), dev(aR), dev(X), relu=True, cls_wT=dev(np.ascontiguousarray(Wc.T)),
+                                    cls_b=dev(bc), want_y=False)
+    assert torch.equal(cls2, cls)
 
 
 def test_gcn_model_fused_matches_literal_and_oracle(orc):
