@@ -212,6 +212,8 @@ def main():
     ap.add_argument("--edges", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
+    ap.add_argument("--mode", default="folded", choices=["folded", "fused", "literal", "dot"],
+                    help="how the dense ops around the fused GAT kernel run (gala_b200/gat_model.py)")
     ap.add_argument("--dense", default="tcgen05", choices=["tcgen05", "torch"],
                     help="layer-1 feature transform: hand-written tcgen05 3xTF32 kernel or cuBLAS fp32 via torch")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel sweep (SpMM/SDDMM GB/s)")
@@ -285,13 +287,13 @@ def main():
     else:
         g = ops.TiledGraph(offset, ids, n).build_plan()
         X_in = X
-        mode = "fused" if args.dense == "tcgen05" else "folded"
+        mode = args.mode
         step_fn = lambda hook=None: model.forward(g, X_in, hook, mode=mode, dense=args.dense)   # noqa: E731
-        launches_per_step = 3 if args.dense == "tcgen05" else 2
+        launches_per_step = 3 if (args.dense == "tcgen05" and mode in ("folded", "fused")) else 2
         config["parallelism"] = "single GPU"
-        config["dense"] = ("whole step = 3 launches of this repo's kernels: gala_linear_f32 (tcgen05 kind::tf32, 3xTF32; "
-                           "+ layer-1 attention projections) and 2 x gala_gat_forward_ex_f32 (layer-2 projections / "
-                           "classifier in the epilogue)" if args.dense == "tcgen05" else "cuBLAS fp32 through torch")
+        config["dense"] = ("layer-1 X*W + attention projections: gala_linear_f32 (tcgen05 kind::tf32, 3xTF32)"
+                           if args.dense == "tcgen05" else "cuBLAS fp32 through torch")
+        config["mode"] = mode
         config["hub_rows"] = int(g.plan.n_hub)
         config["hub_threshold"] = int(g.plan.hub_threshold)
 
