@@ -17,6 +17,7 @@
 //              the stage's "empty" mbarrier; TMEM allocation / release.
 //   2-stage shared-memory ring (A hi/lo 2 x 16 KB + B hi/lo 2 x NPAD*128 B per stage), several
 //   CTAs per SM so that one CTA's epilogue overlaps another's loads.
+#include <algorithm>
 #include <cstring>
 
 #include "common.cuh"
@@ -308,6 +309,259 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: persistent, warp-specialised (one CTA per SM).
+//   warps 0-7   producers: 16 rows each, one 8-byte load per lane per row = 256 contiguous bytes of a
+//               row per instruction (two 32-float swizzle atoms), next super-stage prefetched in
+//               registers while the current one is split and stored;
+//   warp  8     MMA issuer (one thread), 2 shared-memory super-stages, 2 TMEM accumulator sets;
+//   warps 9-12  epilogue of tile i while the producers / tensor core already work on tile i+1.
+// Requires even K and 8-byte aligned X / W (the 4-byte kernel above covers the rest).
+constexpr int kV2Producers = 8;
+constexpr int kV2Threads = (kV2Producers + 1 + 4) * 32;   // 416
+
+template <int NPAD>
+__global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const __grid_constant__ LinearParams p) {
+    constexpr int kSK = 64;                                  // floats of K per super-stage (2 atoms)
+    constexpr uint32_t kAtomA = kBM * 128;                   // 16 KB: [128 rows x 32 fp32]
+    constexpr uint32_t kAtomB = NPAD * 128;
+    constexpr uint32_t kStageBytes = 4 * kAtomA + 4 * kAtomB;   // A hi[2] lo[2], B hi[2] lo[2]
+    constexpr int kMain = NPAD == 64 ? 3 : 4;
+    constexpr uint32_t kAccCols = (kMain + 1) * NPAD;
+    constexpr uint32_t kTmemCols = 2 * kAccCols <= 256 ? 256 : 512;
+    constexpr int kWRows = NPAD / kV2Producers;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], accf_bar[2], acce_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nss = (p.K + kSK - 1) / kSK;
+    const int64_t ntiles = (p.M + kBM - 1) / kBM;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full_bar[s], kV2Producers * 32);
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&accf_bar[s], 1);
+            mbar_init(&acce_bar[s], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kV2Producers) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp < kV2Producers) {
+        // ------------------------------- producers ------------------------------------------------
+        const uint32_t pitch = (uint32_t)p.K * 4u;
+        const int atom = lane >> 4, col = (2 * lane) & 31;
+        uint32_t swa[8], swb[kWRows];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            swa[j] = (uint32_t)atom * kAtomA + (uint32_t)(((((col >> 2) ^ j)) << 4) | ((col & 3) << 2));
+#pragma unroll
+        for (int i = 0; i < kWRows; ++i) {
+            const int n = warp * kWRows + i;
+            swb[i] = (uint32_t)atom * kAtomB + (uint32_t)(n * 128) + (uint32_t)(((((col >> 2) ^ (n & 7))) << 4) | ((col & 3) << 2));
+        }
+        const char* wlane = reinterpret_cast<const char*>(p.W + (int64_t)(warp * kWRows) * p.K + 2 * lane);
+        const bool wrows_full = warp * kWRows + kWRows <= p.N;
+        float2 va[16], vb[16], wa[kWRows], wb[kWRows];
+        const float2 zero2 = make_float2(0.0f, 0.0f);
+
+        auto load_ss = [&](const char* xlane, bool rows_full, int64_t wrow0, int ss, float2 (&v)[16], float2 (&w)[kWRows]) {
+            const bool kok = ss * kSK + 2 * lane < p.K;   // K even: the pair is in or out together
+            const char* xc = xlane + ss * (kSK * 4);
+            const char* wc = wlane + ss * (kSK * 4);
+            if (rows_full && kok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __ldg(reinterpret_cast<const float2*>(xc + (uint64_t)i * pitch));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    v[i] = (kok && wrow0 + i < p.M) ? __ldg(reinterpret_cast<const float2*>(xc + (uint64_t)i * pitch)) : zero2;
+            }
+#pragma unroll
+            for (int i = 0; i < kWRows; ++i)
+                w[i] = (kok && (wrows_full || warp * kWRows + i < p.N))
+                           ? __ldg(reinterpret_cast<const float2*>(wc + (uint64_t)i * pitch)) : zero2;
+        };
+        auto store_ss = [&](uint32_t g, const float2 (&v)[16], const float2 (&w)[kWRows]) {
+            const uint32_t s = g & 1;
+            if (g >= 2) mbar_wait(&empty_bar[s], ((g >> 1) & 1) ^ 1);
+            uint8_t* a_hi = smem + (size_t)s * kStageBytes + warp * (16 * 128);
+            uint8_t* a_lo = a_hi + 2 * kAtomA;
+            uint8_t* b_hi = smem + (size_t)s * kStageBytes + 4 * kAtomA;
+            uint8_t* b_lo = b_hi + 2 * kAtomB;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float2 hi, lo;
+                split_tf32(v[i].x, hi.x, lo.x);
+                split_tf32(v[i].y, hi.y, lo.y);
+                *reinterpret_cast<float2*>(a_hi + i * 128 + swa[i & 7]) = hi;
+                *reinterpret_cast<float2*>(a_lo + i * 128 + swa[i & 7]) = lo;
+            }
+#pragma unroll
+            for (int i = 0; i < kWRows; ++i) {
+                float2 hi, lo;
+                split_tf32(w[i].x, hi.x, lo.x);
+                split_tf32(w[i].y, hi.y, lo.y);
+                *reinterpret_cast<float2*>(b_hi + swb[i]) = hi;
+                *reinterpret_cast<float2*>(b_lo + swb[i]) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full_bar[s]);
+        };
+
+        uint32_t g = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t wrow0 = tile * kBM + warp * 16;
+            const char* xlane = reinterpret_cast<const char*>(p.X + wrow0 * p.K + 2 * lane);
+            const bool rows_full = wrow0 + 16 <= p.M;
+            load_ss(xlane, rows_full, wrow0, 0, va, wa);
+            for (int ss = 0; ss < nss; ss += 2) {
+                if (ss + 1 < nss) load_ss(xlane, rows_full, wrow0, ss + 1, vb, wb);
+                store_ss(g++, va, wa);
+                if (ss + 1 < nss) {
+                    if (ss + 2 < nss) load_ss(xlane, rows_full, wrow0, ss + 2, va, wa);
+                    store_ss(g++, vb, wb);
+                }
+            }
+        }
+    } else if (warp == kV2Producers) {
+        // ------------------------------- MMA issuer -----------------------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(NPAD);
+            uint32_t g = 0, it = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const uint32_t aset = it & 1;
+                if (it >= 2) mbar_wait(&acce_bar[aset], ((it >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc0 = tmem_base + aset * kAccCols;
+                for (int ss = 0; ss < nss; ++ss, ++g) {
+                    const uint32_t s = g & 1;
+                    mbar_wait(&full_bar[s], (g >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes);
+                    const uint32_t a_lo = a_hi + 2 * kAtomA;
+                    const uint32_t b_hi = a_hi + 4 * kAtomA;
+                    const uint32_t b_lo = b_hi + 2 * kAtomB;
+                    const uint32_t d_main = acc0 + (uint32_t)((ss % kMain) * NPAD);
+                    const uint32_t d_corr = acc0 + (uint32_t)(kMain * NPAD);
+                    const int natoms = (p.K - ss * kSK) > 32 ? 2 : 1;
+                    for (int at = 0; at < natoms; ++at) {
+#pragma unroll
+                        for (int k8 = 0; k8 < 4; ++k8) {
+                            const uint32_t ao = (uint32_t)at * kAtomA + (uint32_t)k8 * 32;
+                            const uint32_t bo = (uint32_t)at * kAtomB + (uint32_t)k8 * 32;
+                            const uint32_t first = (uint32_t)((at | k8) == 0);
+                            umma_tf32(d_main, make_desc(a_hi + ao), make_desc(b_hi + bo), idesc, !(first && ss < kMain));
+                            umma_tf32(d_corr, make_desc(a_hi + ao), make_desc(b_lo + bo), idesc, !(first && ss == 0));
+                            umma_tf32(d_corr, make_desc(a_lo + ao), make_desc(b_hi + bo), idesc, 1);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&accf_bar[aset]);
+            }
+        }
+    } else {
+        // ------------------------------- epilogue warps -------------------------------------------
+        const int q = warp & 3;                  // TMEM lane quarter this warp may read
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t aset = it & 1;
+            mbar_wait(&accf_bar[aset], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t r = tile * kBM + q * 32 + lane;
+            float acc[NPAD];
+#pragma unroll
+            for (int n = 0; n < NPAD; ++n) acc[n] = 0.0f;
+#pragma unroll
+            for (int c0 = 0; c0 < (int)kAccCols; c0 += 16) {
+                if (c0 / NPAD < kMain && c0 / NPAD >= nss) continue;   // accumulator never written
+                uint32_t u[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + aset * kAccCols + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                      "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[(c0 + j) % NPAD] += __uint_as_float(u[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acce_bar[aset]);        // the accumulator set may be overwritten
+            if (r < p.M) {
+                float a0 = p.att_b0, a1 = p.att_b1;
+                const float rscale = p.row_scale ? __ldg(p.row_scale + r) : 1.0f;
+#pragma unroll
+                for (int n = 0; n < NPAD; ++n) {
+                    if (n < p.N) {
+                        float y = acc[n] + (p.bias ? __ldg(p.bias + n) : 0.0f);
+                        if (p.att_w) {
+                            a0 = fmaf(y, __ldg(p.att_w + n), a0);
+                            a1 = fmaf(y, __ldg(p.att_w + p.N + n), a1);
+                        }
+                        y *= rscale;
+                        if (p.relu) y = fmaxf(y, 0.0f);
+                        acc[n] = y;
+                    }
+                }
+                float* yrow = p.Y + r * p.N;
+                if ((p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(yrow) & 15) == 0) {
+#pragma unroll
+                    for (int n = 0; n < NPAD; n += 4)
+                        if (n < p.N) *reinterpret_cast<float4*>(yrow + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+                } else {
+#pragma unroll
+                    for (int n = 0; n < NPAD; ++n)
+                        if (n < p.N) yrow[n] = acc[n];
+                }
+                if (p.att_w) {
+                    p.att_out[r] = a0;
+                    p.att_out[p.M + r] = a1;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kV2Producers) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+template <int NPAD>
+int launch_linear_v2(const LinearParams& p, cudaStream_t st) {
+    constexpr size_t smem = 2 * (size_t)(4 * kBM * 128 + 4 * NPAD * 128) + 1024;
+    static bool configured = false;
+    static int sms = 0;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_v2_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    const int64_t ntiles = (p.M + kBM - 1) / kBM;
+    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, sms > 0 ? sms : 148);
+    linear_tf32x3_v2_kernel<NPAD><<<grid, kV2Threads, smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GALA_OK : (int)e;
+}
+
 template <int NPAD>
 int launch_linear(const LinearParams& p, cudaStream_t st) {
     constexpr size_t smem = (size_t)kStages * (2 * kBM * 128 + 2 * NPAD * 128) + 1024;
@@ -350,6 +604,14 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
         p.att_b1 = att_b[1];
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool v2 = (K % 2 == 0) && (reinterpret_cast<uintptr_t>(X) % 8 == 0) && (reinterpret_cast<uintptr_t>(W) % 8 == 0) &&
+                    M >= 4 * kBM;
+    if (v2) {
+        if (N <= 16) return launch_linear_v2<16>(p, st);
+        if (N <= 32) return launch_linear_v2<32>(p, st);
+        if (N <= 48) return launch_linear_v2<48>(p, st);
+        return launch_linear_v2<64>(p, st);
+    }
     if (N <= 16) return launch_linear<16>(p, st);
     if (N <= 32) return launch_linear<32>(p, st);
     if (N <= 48) return launch_linear<48>(p, st);
