@@ -145,6 +145,6 @@ class PartitionedGAT:
     def forward(self, X_local, hook=None, mode="folded"):
         if mode == "dot":
             return gat2_forward_partitioned_dot(self.model, self.part, X_local, self._aggregate_dot, hook)
-        if mode == "folded":
+        if mode in ("folded", "fused"):   # the row-partitioned runner has no separate fused variant
             return gat2_forward_partitioned_folded(self.model, self.part, X_local, self._aggregate, hook)
         return gat2_forward_partitioned(self.model, self.part, X_local, self._aggregate, hook)
