@@ -267,7 +267,9 @@ int gala_gat_forward_ex_f32(const gala_graph_t* g, const float* aL, const float*
     if (int rc = check_graph(g)) return rc;
     if (K <= 0) return GALA_ERR_BAD_SHAPE;
     const bool has_ep = ep && (ep->att_w || ep->cls_wT);
-    if (g->nrows > 0 && (!aL || !aR || !X || (!Y && !(has_ep && ep->cls_wT)))) return GALA_ERR_NULL_POINTER;
+    const bool multi = ep && ep->multi_out && ep->multi_out->count > 0;
+    if (g->nrows > 0 && (!aL || !aR || !X || (!Y && !(has_ep && ep->cls_wT) && !multi))) return GALA_ERR_NULL_POINTER;
+    if (multi && ep->multi_out->count > kMaxPeers) return GALA_ERR_UNSUPPORTED;
     if (!aligned(X, 4) || !aligned(Y, 4)) return GALA_ERR_MISALIGNED;
     SpmmParams p;
     std::memset(&p, 0, sizeof(p));
@@ -293,6 +295,11 @@ int gala_gat_forward_ex_f32(const gala_graph_t* g, const float* aL, const float*
         p.cls_b = ep->cls_b;
         p.cls_out = ep->cls_out;
         p.cls_n = ep->cls_n;
+    }
+    if (multi) {
+        p.mo.count = ep->multi_out->count;
+        p.mo.mc_base = ep->multi_out->multicast_base;
+        for (int q = 0; q < p.mo.count; ++q) p.mo.base[q] = ep->multi_out->base[q];
     }
     HubView h = hub_of(plan, g);
     p.t = task_of(h);

@@ -135,6 +135,40 @@ __device__ __forceinline__ int row_degree(const GraphDev& g, int row) {
     return d;
 }
 
+// ---- output rows pushed to several GPUs (fused "compute + all-gather") ------------------------
+// count == 0: plain local output.  Otherwise the row is stored either once through an NVLS
+// multicast address (multimem.st: the NVSwitch replicates it into every GPU's buffer, the local
+// one included) or, without multicast support, to each of the `count` peer-mapped bases.
+constexpr int kMaxPeers = 8;
+struct MultiOut {
+    float* base[kMaxPeers];
+    float* mc_base;
+    int count;
+};
+
+template <int VEC>
+__device__ __forceinline__ void multimem_store(float* p, const float (&v)[VEC]) {
+    if constexpr (VEC == 4)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+                     "f"(v[2]), "f"(v[3])
+                     : "memory");
+    else if constexpr (VEC == 2)
+        asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+    else
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory");
+}
+
+// store VEC consecutive floats of an output row at element offset `off` of every destination
+template <int VEC>
+__device__ __forceinline__ void multi_store(const MultiOut& mo, int64_t off, const Vec<VEC>& o) {
+    if (mo.mc_base) {
+        multimem_store<VEC>(mo.mc_base + off, o.v);
+    } else {
+#pragma unroll 1
+        for (int q = 0; q < mo.count; ++q) o.store(mo.base[q] + off);
+    }
+}
+
 // ---- row -> warp / CTA assignment shared by every row-structured kernel -----------
 // blockIdx.x <  n_hub : hub row hub_rows[blockIdx.x], its edge list split over the 8 warps
 // blockIdx.x >= n_hub : 8 rows per CTA, one per warp, taken from row_order (degree-

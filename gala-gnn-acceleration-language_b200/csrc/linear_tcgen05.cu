@@ -108,6 +108,7 @@ struct LinearParams {
     float* __restrict__ att_out;      // [2, M]
     int64_t M;
     int K, N, relu;
+    MultiOut mo;                      // count > 0: output rows pushed to every GPU instead of Y
 };
 
 template <int NPAD>
@@ -262,7 +263,15 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
                 }
             }
             float* yrow = p.Y + r * p.N;
-            if ((p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(yrow) & 15) == 0) {
+            if (p.mo.count > 0) {
+#pragma unroll
+                for (int n = 0; n < NPAD; n += 4)
+                    if (n < p.N) {
+                        Vec<4> o;
+                        o.v[0] = acc[n]; o.v[1] = acc[n + 1]; o.v[2] = acc[n + 2]; o.v[3] = acc[n + 3];
+                        multi_store<4>(p.mo, r * p.N + n, o);
+                    }
+            } else if ((p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(yrow) & 15) == 0) {
 #pragma unroll
                 for (int n = 0; n < NPAD; n += 4)
                     if (n < p.N) *reinterpret_cast<float4*>(yrow + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
@@ -518,7 +527,15 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
                     }
                 }
                 float* yrow = p.Y + r * p.N;
-                if ((p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(yrow) & 15) == 0) {
+                if (p.mo.count > 0) {   // host guarantees N % 4 == 0 and 16-byte aligned bases
+#pragma unroll
+                    for (int n = 0; n < NPAD; n += 4)
+                        if (n < p.N) {
+                            Vec<4> o;
+                            o.v[0] = acc[n]; o.v[1] = acc[n + 1]; o.v[2] = acc[n + 2]; o.v[3] = acc[n + 3];
+                            multi_store<4>(p.mo, r * p.N + n, o);
+                        }
+                } else if ((p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(yrow) & 15) == 0) {
 #pragma unroll
                     for (int n = 0; n < NPAD; n += 4)
                         if (n < p.N) *reinterpret_cast<float4*>(yrow + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
@@ -581,11 +598,13 @@ int launch_linear(const LinearParams& p, cudaStream_t st) {
 
 extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float* W, const float* bias, int32_t N, float* Y,
                                const float* row_scale, int32_t relu, const float* att_w, const float* att_b,
-                               float* att_out, gala_stream_t stream) {
+                               float* att_out, const gala_multi_out_t* multi_out, gala_stream_t stream) {
     if (M < 0 || K <= 0 || N <= 0) return GALA_ERR_BAD_SHAPE;
     if (N > 64) return GALA_ERR_UNSUPPORTED;   // one CTA holds every output column (GNN hidden / class widths)
     if (M == 0) return GALA_OK;
-    if (!X || !W || !Y || (att_w && (!att_b || !att_out))) return GALA_ERR_NULL_POINTER;
+    const bool multi = multi_out && multi_out->count > 0;
+    if (!X || !W || (!Y && !multi) || (att_w && (!att_b || !att_out))) return GALA_ERR_NULL_POINTER;
+    if (multi && (multi_out->count > kMaxPeers || (N & 3) != 0)) return GALA_ERR_UNSUPPORTED;
     LinearParams p;
     std::memset(&p, 0, sizeof(p));
     p.X = X;
@@ -595,6 +614,11 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
     p.row_scale = row_scale;
     p.att_w = att_w;
     p.att_out = att_out;
+    if (multi) {
+        p.mo.count = multi_out->count;
+        p.mo.mc_base = multi_out->multicast_base;
+        for (int q = 0; q < multi_out->count; ++q) p.mo.base[q] = multi_out->base[q];
+    }
     p.M = M;
     p.K = K;
     p.N = N;

@@ -50,6 +50,7 @@ struct SpmmParams {
     const float* __restrict__ cls_b;      // [cls_n] or nullptr
     float* __restrict__ cls_out;          // [nrows, cls_n]
     int cls_n;
+    MultiOut mo;                          // count > 0: Y rows go to every GPU (Y itself unused)
 };
 
 
@@ -325,7 +326,8 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
                     o.v[v] = t;
                     if (dense_ep) rowbuf[warp][f0 + v] = t;
                 }
-                if (p.Y) o.store(y);
+                if (p.mo.count > 0) multi_store<VEC>(p.mo, (int64_t)row * p.K + f0, o);
+                else if (p.Y) o.store(y);
             }
         }
         if (dense_ep) {
@@ -367,7 +369,13 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
         t *= scale;
         if (p.accumulate) t += *y;
         if (p.relu) t = fmaxf(t, 0.0f);
-        if (p.Y) *y = t;
+        if (p.mo.count > 0) {
+            Vec<1> o1;
+            o1.v[0] = t;
+            multi_store<1>(p.mo, (int64_t)row * p.K + tile_base + f, o1);
+        } else if (p.Y) {
+            *y = t;
+        }
         if (dense_ep) rowbuf[0][f] = t;
     }
     if (dense_ep) {

@@ -121,12 +121,45 @@ def gat2_forward_partitioned_dot(model, part, X_local, aggregate_dot, hook=None)
     return F.linear(agg, *model.fc1)
 
 
+class PeerExchange:
+    """Symmetric (peer-mapped) gathered buffers: every rank's kernels push their output rows
+    straight into all GPUs' copies while they compute (NVLS multicast store when the fabric
+    supports it, per-peer stores otherwise); a device-side barrier replaces the all-gather."""
+
+    def __init__(self, part, widths, device):
+        import torch.distributed._symmetric_memory as symm
+
+        self.part = part
+        self.bufs, self.hdls, self.mos = [], [], []
+        for K in widths:
+            buf = symm.empty((part.padded_n, K), dtype=torch.float32, device=device)
+            buf.zero_()   # padding rows are never written
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            off = part.rank * part.max_rows * K * 4
+            mc = None
+            try:
+                if hdl.has_multicast_support and hdl.multicast_ptr:
+                    mc = hdl.multicast_ptr + off
+            except Exception:
+                mc = None
+            from . import ops
+            self.bufs.append(buf)
+            self.hdls.append(hdl)
+            self.mos.append(ops.make_multi_out([p + off for p in hdl.buffer_ptrs], mc))
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def barrier(self, i):
+        self.hdls[i].barrier(channel=i)
+
+
 class PartitionedGAT:
-    """GPU runner: slab graph + plan + fused kernel, NCCL all-gather between layers."""
+    """GPU runner: slab graph + plan + fused kernel.  exchange="p2p": kernels push their rows to every
+    GPU (PeerExchange); exchange="nccl": all_gather_into_tensor between layers."""
 
-    launches_per_step = 2
+    launches_per_step = 3
 
-    def __init__(self, model, offset, ids, n, rank, world, device):
+    def __init__(self, model, offset, ids, n, rank, world, device, exchange="p2p"):
         from . import ops
 
         self.model, self.ops = model, ops
@@ -135,6 +168,35 @@ class PartitionedGAT:
         self.local_nvals = self.part.local_nvals
         self.graph = ops.TiledGraph(self.part.offset, self.part.cols, self.part.rows,
                                     ncols=self.part.padded_n).build_plan()
+        self.px = None
+        self.exchange = "nccl"
+        if exchange == "p2p":
+            try:
+                hidden = model.fc0[0].shape[0]
+                self.px = PeerExchange(self.part, [hidden, hidden], device)
+                self.exchange = "p2p-multicast" if self.px.mos[0].multicast_base else "p2p"
+            except Exception as ex:   # no symmetric memory on this system: NCCL all-gather instead
+                import sys
+                sys.stderr.write(f"gala_b200.dist_gat: peer exchange unavailable ({type(ex).__name__}: {ex}); using NCCL\n")
+                self.px = None
+
+    def forward_p2p(self, X_local, hook=None):
+        """Folded-projection forward with the two exchanges fused into the producing kernels."""
+        run = hook if hook is not None else (lambda name, fn: fn())
+        m, px, part, ops = self.model, self.px, self.part, self.ops
+        run("linear1", lambda: ops.linear(X_local, m.fc0[0], m.fc0[1], multi_out=px.mos[0]))
+        px.barrier(0)
+        res_all = px.bufs[0]
+        a = F.linear(res_all, m.W_att1, m.b_att1).t().contiguous()
+        run("gat_layer1", lambda: ops.gat_forward_ex(self.graph, part.local_slice(a[0]).contiguous(), a[1], res_all,
+                                                     m.slope, relu=True, multi_out=px.mos[1]))
+        px.barrier(1)
+        y_all = px.bufs[1]
+        a = F.linear(y_all, m.W_att2, m.b_att2).t().contiguous()
+        _, _, out = run("gat_layer2", lambda: ops.gat_forward_ex(self.graph, part.local_slice(a[0]).contiguous(), a[1],
+                                                                 y_all, m.slope, relu=False, cls_wT=m.fc1_wT,
+                                                                 cls_b=m.fc1[1], want_y=False))
+        return out
 
     def _aggregate(self, aL, aR, feats, relu):
         return self.ops.gat_forward(self.graph, aL.contiguous(), aR.contiguous(), feats, self.model.slope, relu=relu)
@@ -143,6 +205,8 @@ class PartitionedGAT:
         return self.ops.gat_forward_dot(self.graph, aL.contiguous(), wR, bR, feats, self.model.slope, relu=relu)
 
     def forward(self, X_local, hook=None, mode="folded"):
+        if self.px is not None and mode in ("folded", "fused"):
+            return self.forward_p2p(X_local, hook)
         if mode == "dot":
             return gat2_forward_partitioned_dot(self.model, self.part, X_local, self._aggregate_dot, hook)
         if mode in ("folded", "fused"):   # the row-partitioned runner has no separate fused variant

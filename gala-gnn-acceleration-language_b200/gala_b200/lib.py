@@ -41,10 +41,14 @@ class GalaEpilogue(C.Structure):
                 ("relu", C.c_int32)]
 
 
+class GalaMultiOut(C.Structure):
+    _fields_ = [("base", C.c_void_p * 8), ("multicast_base", C.c_void_p), ("count", C.c_int32)]
+
+
 class GalaDenseEpilogue(C.Structure):
     _fields_ = [("att_w", C.c_void_p), ("att_b", C.c_float * 2), ("att_out", C.c_void_p),
                 ("cls_wT", C.c_void_p), ("cls_b", C.c_void_p), ("cls_out", C.c_void_p),
-                ("cls_n", C.c_int32)]
+                ("cls_n", C.c_int32), ("multi_out", C.POINTER(GalaMultiOut))]
 
 
 class GalaError(RuntimeError):
@@ -88,7 +92,8 @@ def load():
     }
     i64, sz = C.c_int64, C.c_size_t
     sigs.update({
-        "gala_linear_f32": [vp, i64, i32, vp, vp, i32, vp, vp, i32, vp, C.POINTER(C.c_float), vp, vp],
+        "gala_linear_f32": [vp, i64, i32, vp, vp, i32, vp, vp, i32, vp, C.POINTER(C.c_float), vp,
+                            C.POINTER(GalaMultiOut), vp],
         "gala_csr_from_coo": [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp],
         "gala_csr_transpose": [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp],
         "gala_col_tile": [i32, i32, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp],

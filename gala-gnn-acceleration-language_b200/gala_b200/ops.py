@@ -172,7 +172,17 @@ def gat_forward_dot(g, aL, wR, bR, X, slope=0.2, relu=False, out=None, alpha_out
     return out
 
 
-def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None, row_scale=None):
+def make_multi_out(bases, multicast_base=None):
+    """bases: per-GPU addresses (ints) of this rank's slab inside every peer-mapped gathered buffer."""
+    mo = _l.GalaMultiOut()
+    for q, b in enumerate(bases):
+        mo.base[q] = int(b)
+    mo.multicast_base = int(multicast_base) if multicast_base else None
+    mo.count = len(bases)
+    return mo
+
+
+def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None, row_scale=None, multi_out=None):
     """Y = X @ W.T + bias on the tensor cores (tcgen05 kind::tf32, 3xTF32 error compensation).
     With att_w [2,N] / att_b (two floats) also returns att [2,M] = the two attention
     projections of the pre-activation output rows (fused epilogue)."""
@@ -180,31 +190,37 @@ def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None, row_sc
     M, K = X.shape
     N = W.shape[0]
     assert W.shape[1] == K and N <= 64
-    if out is None:
+    if out is None and multi_out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=X.device)
     att = None
     ab = None
     if att_w is not None:
         att = torch.empty((2, M), dtype=torch.float32, device=X.device)
         ab = (C.c_float * 2)(float(att_b[0]), float(att_b[1]))
-    _l.check(_l.load().gala_linear_f32(_l.ptr(X), M, K, _l.ptr(W), _l.ptr(bias), N, _l.ptr(out),
+    _l.check(_l.load().gala_linear_f32(_l.ptr(X), M, K, _l.ptr(W), _l.ptr(bias), N,
+                                       _l.ptr(out) if out is not None else None,
                                        _l.ptr(row_scale), int(relu),
                                        _l.ptr(_f32(att_w)) if att_w is not None else None, ab,
-                                       _l.ptr(att), _l.stream_ptr()))
+                                       _l.ptr(att), C.byref(multi_out) if multi_out is not None else None,
+                                       _l.stream_ptr()))
     return (out, att) if att_w is not None else out
 
 
 def gat_forward_ex(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None, att_w=None, att_b=None,
-                   cls_wT=None, cls_b=None, want_y=True):
+                   cls_wT=None, cls_b=None, want_y=True, multi_out=None):
     """Fused GAT layer + dense epilogue on every finished output row: the next layer's two attention
     projections (att_w [2,K], att_b two floats -> att [2, nrows]) and / or the transform that follows
     the aggregation (cls_wT [K,C] = Linear weight transposed -> [nrows, C]).  Returns (Y, att, cls)."""
     X = _f32(X)
     K = X.shape[1]
     dev = X.device
+    if multi_out is not None:
+        want_y = False
     if want_y and out is None:
         out = torch.empty((g.nrows, K), dtype=torch.float32, device=dev)
     ep = _l.GalaDenseEpilogue()
+    if multi_out is not None:
+        ep.multi_out = C.pointer(multi_out)
     att = cls = None
     if att_w is not None:
         att = torch.empty((2, g.nrows), dtype=torch.float32, device=dev)

@@ -181,6 +181,17 @@ int gala_gat_forward_f32(const gala_graph_t *g, const float *aL, const float *aR
 /*   cls_wT [K,cls_n] device (the Linear weight transposed), cls_b [cls_n] nullable:          */
 /*          cls_out[row,:] = y @ cls_wT + cls_b -- the classifier / FFN that follows the      */
 /*          aggregation (FFN-recompute rewrite, middle-end.h:324-375).  Y may be NULL then.   */
+/* Output rows pushed to every GPU of the node while they are produced (compute fused with  */
+/* the all-gather that would follow): base[q] = address, in GPU q's peer-mapped copy of the  */
+/* gathered buffer, where row 0 of THIS rank's slab lives; multicast_base = the same address */
+/* in the NVLS multicast mapping (one multimem.st, replicated by the NVSwitch) or NULL.      */
+/* The caller synchronises the GPUs (a barrier on the stream) before anyone reads the rows.  */
+typedef struct gala_multi_out {
+    float *base[8];
+    float *multicast_base;
+    int32_t count;
+} gala_multi_out_t;
+
 typedef struct gala_dense_epilogue {
     const float *att_w;
     float att_b[2];
@@ -189,6 +200,7 @@ typedef struct gala_dense_epilogue {
     const float *cls_b;
     float *cls_out;
     int32_t cls_n;
+    const gala_multi_out_t *multi_out; /* nullable: Y rows go to every GPU instead of Y */
 } gala_dense_epilogue_t;
 int gala_gat_forward_ex_f32(const gala_graph_t *g, const float *aL, const float *aR, const float *X,
                             int32_t K, float slope, float *Y, float *alpha_out, int32_t relu,
@@ -215,9 +227,11 @@ int gala_gat_forward_dot_f32(const gala_graph_t *g, const float *aL, const float
 /* same with row 1.  att_w device [2,N], att_b HOST [2], att_out device [2,M]; all nullable.   */
 /* row_scale (device [M], nullable) multiplies output row r before the ReLU: the `norm * res`   */
 /* pass that follows the transform in the generated GCN (codegen/gala.cu:441-443).              */
+/* multi_out (nullable): push the output rows to every GPU instead of Y (N % 4 == 0).          */
 int gala_linear_f32(const float *X, int64_t M, int32_t K, const float *W, const float *bias,
                     int32_t N, float *Y, const float *row_scale, int32_t relu, const float *att_w,
-                    const float *att_b, float *att_out, gala_stream_t stream);
+                    const float *att_b, float *att_out, const struct gala_multi_out *multi_out,
+                    gala_stream_t stream);
 
 /* ---- format construction on the device ---------- */
 /* All integer outputs are bit-exact against the reference functions named below.       */
