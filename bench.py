@@ -212,6 +212,8 @@ def main():
     ap.add_argument("--edges", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU feature exchange: fused into the kernels over peer memory, or NCCL all-gather")
     ap.add_argument("--mode", default="folded", choices=["folded", "fused", "literal", "dot"],
                     help="how the dense ops around the fused GAT kernel run (gala_b200/gat_model.py)")
     ap.add_argument("--dense", default="tcgen05", choices=["tcgen05", "torch"],
@@ -279,11 +281,15 @@ def main():
     if world > 1:
         from gala_b200 import dist_gat
 
-        runner = dist_gat.PartitionedGAT(model, offset, ids, n, rank, world, dev)
+        runner = dist_gat.PartitionedGAT(model, offset, ids, n, rank, world, dev, exchange=args.exchange)
         X_in = X[runner.row_lo:runner.row_hi].contiguous()
         step_fn = lambda hook=None: runner.forward(X_in, hook)   # noqa: E731
         launches_per_step = runner.launches_per_step
-        config["parallelism"] = f"1D row partition over {world} GPUs (nnz-balanced), NCCL all-gather of hidden features"
+        config["parallelism"] = (f"1D row partition over {world} GPUs (nnz-balanced); exchange of hidden features: "
+                                 + {"p2p-multicast": "fused into the producing kernels (multimem.st through NVLS multicast "
+                                                     "into every GPU's buffer + device barrier)",
+                                    "p2p": "fused into the producing kernels (peer stores over NVLink + device barrier)",
+                                    "nccl": "NCCL all_gather_into_tensor"}[runner.exchange])
     else:
         g = ops.TiledGraph(offset, ids, n).build_plan()
         X_in = X
