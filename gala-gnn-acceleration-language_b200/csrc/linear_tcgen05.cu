@@ -343,6 +343,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], accf_bar[2], acce_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    // epilogue staging: each epilogue warp transposes its 32 rows through shared memory so that a
+    // row leaves as one contiguous store (full 128-byte NVLink / HBM writes instead of 16-byte pieces)
+    __shared__ __align__(16) float stage_out[4][32][NPAD + 4];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nss = (p.K + kSK - 1) / kSK;
@@ -510,8 +513,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acce_bar[aset]);        // the accumulator set may be overwritten
+            float a0 = p.att_b0, a1 = p.att_b1;
             if (r < p.M) {
-                float a0 = p.att_b0, a1 = p.att_b1;
                 const float rscale = p.row_scale ? __ldg(p.row_scale + r) : 1.0f;
 #pragma unroll
                 for (int n = 0; n < NPAD; ++n) {
@@ -526,28 +529,37 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
                         acc[n] = y;
                     }
                 }
-                float* yrow = p.Y + r * p.N;
-                if (p.mo.count > 0) {   // host guarantees N % 4 == 0 and 16-byte aligned bases
-#pragma unroll
-                    for (int n = 0; n < NPAD; n += 4)
-                        if (n < p.N) {
-                            Vec<4> o;
-                            o.v[0] = acc[n]; o.v[1] = acc[n + 1]; o.v[2] = acc[n + 2]; o.v[3] = acc[n + 3];
-                            multi_store<4>(p.mo, r * p.N + n, o);
-                        }
-                } else if ((p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(yrow) & 15) == 0) {
-#pragma unroll
-                    for (int n = 0; n < NPAD; n += 4)
-                        if (n < p.N) *reinterpret_cast<float4*>(yrow + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
-                } else {
-#pragma unroll
-                    for (int n = 0; n < NPAD; ++n)
-                        if (n < p.N) yrow[n] = acc[n];
-                }
                 if (p.att_w) {
                     p.att_out[r] = a0;
                     p.att_out[p.M + r] = a1;
                 }
+            }
+            if ((p.N & 3) == 0 && (p.mo.count > 0 || (reinterpret_cast<uintptr_t>(p.Y) & 15) == 0)) {
+                // transpose through shared memory: lane l holds row l -> a group of N/4 lanes stores one row
+                float (*st)[NPAD + 4] = stage_out[q];
+#pragma unroll
+                for (int n = 0; n < NPAD; n += 4)
+                    if (n < p.N) *reinterpret_cast<float4*>(&st[lane][n]) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+                __syncwarp();
+                const int vec_per_row = p.N >> 2;
+                const int64_t tile_row0 = tile * kBM + q * 32;
+                for (int idx = lane; idx < 32 * vec_per_row; idx += 32) {
+                    const int rr = idx / vec_per_row, cv = idx - rr * vec_per_row;
+                    const int64_t row = tile_row0 + rr;
+                    if (row < p.M) {
+                        const float4 v = *reinterpret_cast<const float4*>(&st[rr][cv * 4]);
+                        Vec<4> o;
+                        o.v[0] = v.x; o.v[1] = v.y; o.v[2] = v.z; o.v[3] = v.w;
+                        if (p.mo.count > 0) multi_store<4>(p.mo, row * p.N + cv * 4, o);
+                        else o.store(p.Y + row * p.N + cv * 4);
+                    }
+                }
+                __syncwarp();
+            } else if (r < p.M) {
+                float* yrow = p.Y + r * p.N;
+#pragma unroll
+                for (int n = 0; n < NPAD; ++n)
+                    if (n < p.N) yrow[n] = acc[n];
             }
         }
     }
@@ -634,7 +646,7 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
         if (N <= 16) return launch_linear_v2<16>(p, st);
         if (N <= 32) return launch_linear_v2<32>(p, st);
         if (N <= 48) return launch_linear_v2<48>(p, st);
-        return launch_linear_v2<64>(p, st);
+        // N in (48, 64]: the persistent variant would need 229 KB of shared memory; use the 2-CTA/SM kernel
     }
     if (N <= 16) return launch_linear<16>(p, st);
     if (N <= 32) return launch_linear<32>(p, st);
