@@ -331,7 +331,7 @@ constexpr int kV2Rows = kBM / kV2Producers;
 constexpr int kV2Threads = (kV2Producers + 1 + 4) * 32;   // 672
 
 template <int NPAD>
-__global__ void __maxnreg__(96) linear_tf32x3_v2_kernel(const __grid_constant__ LinearParams p) {
+__global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const __grid_constant__ LinearParams p) {
     constexpr int kSK = 64;                                  // floats of K per super-stage (2 atoms)
     constexpr uint32_t kAtomA = kBM * 128;                   // 16 KB: [128 rows x 32 fp32]
     constexpr uint32_t kAtomB = NPAD * 128;
