@@ -320,15 +320,14 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
 
 // ---------------------------------------------------------------------------------------------
 // v2: persistent, warp-specialised (one CTA per SM).
-//   warps 0-15  producers: 8 rows each, one 8-byte load per lane per row = 256 contiguous bytes of a
-//               row per instruction (two 32-float swizzle atoms); a 3-deep register pipeline keeps
-//               ~2.5 super-stages (80 KB per SM) of HBM requests in flight;
-//   warp  16    MMA issuer (one thread), 2 shared-memory super-stages, 2 TMEM accumulator sets;
-//   warps 17-20 epilogue of tile i while the producers / tensor core already work on tile i+1.
+//   warps 0-7   producers: 16 rows each, one 8-byte load per lane per row = 256 contiguous bytes of a
+//               row per instruction (two 32-float swizzle atoms), next super-stage prefetched in
+//               registers while the current one is split and stored;
+//   warp  8     MMA issuer (one thread), 2 shared-memory super-stages, 2 TMEM accumulator sets;
+//   warps 9-12  epilogue of tile i while the producers / tensor core already work on tile i+1.
 // Requires even K and 8-byte aligned X / W (the 4-byte kernel above covers the rest).
-constexpr int kV2Producers = 16;                          // producer warps, 8 rows of the tile each
-constexpr int kV2Rows = kBM / kV2Producers;
-constexpr int kV2Threads = (kV2Producers + 1 + 4) * 32;   // 672
+constexpr int kV2Producers = 8;
+constexpr int kV2Threads = (kV2Producers + 1 + 4) * 32;   // 416
 
 template <int NPAD>
 __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const __grid_constant__ LinearParams p) {
@@ -376,10 +375,10 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
         // ------------------------------- producers ------------------------------------------------
         const uint32_t pitch = (uint32_t)p.K * 4u;
         const int atom = lane >> 4, col = (2 * lane) & 31;
-        uint32_t swa[kV2Rows], swb[kWRows];
+        uint32_t swa[8], swb[kWRows];
 #pragma unroll
-        for (int j = 0; j < kV2Rows; ++j)   // warp * kV2Rows is a multiple of 8: row-in-atom = j
-            swa[j] = (uint32_t)atom * kAtomA + (uint32_t)(j * 128) + (uint32_t)(((((col >> 2) ^ (j & 7))) << 4) | ((col & 3) << 2));
+        for (int j = 0; j < 8; ++j)
+            swa[j] = (uint32_t)atom * kAtomA + (uint32_t)(((((col >> 2) ^ j)) << 4) | ((col & 3) << 2));
 #pragma unroll
         for (int i = 0; i < kWRows; ++i) {
             const int n = warp * kWRows + i;
@@ -387,40 +386,40 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
         }
         const char* wlane = reinterpret_cast<const char*>(p.W + (int64_t)(warp * kWRows) * p.K + 2 * lane);
         const bool wrows_full = warp * kWRows + kWRows <= p.N;
-        float2 va[kV2Rows], vb[kV2Rows], vc[kV2Rows], wa[kWRows], wb[kWRows], wc[kWRows];
+        float2 va[16], vb[16], wa[kWRows], wb[kWRows];
         const float2 zero2 = make_float2(0.0f, 0.0f);
 
-        auto load_ss = [&](const char* xlane, bool rows_full, int64_t wrow0, int ss, float2 (&v)[kV2Rows], float2 (&w)[kWRows]) {
+        auto load_ss = [&](const char* xlane, bool rows_full, int64_t wrow0, int ss, float2 (&v)[16], float2 (&w)[kWRows]) {
             const bool kok = ss * kSK + 2 * lane < p.K;   // K even: the pair is in or out together
             const char* xc = xlane + ss * (kSK * 4);
-            const char* wcp = wlane + ss * (kSK * 4);
+            const char* wc = wlane + ss * (kSK * 4);
             if (rows_full && kok) {
 #pragma unroll
-                for (int i = 0; i < kV2Rows; ++i) v[i] = __ldg(reinterpret_cast<const float2*>(xc + (uint64_t)i * pitch));
+                for (int i = 0; i < 16; ++i) v[i] = __ldg(reinterpret_cast<const float2*>(xc + (uint64_t)i * pitch));
             } else {
 #pragma unroll
-                for (int i = 0; i < kV2Rows; ++i)
+                for (int i = 0; i < 16; ++i)
                     v[i] = (kok && wrow0 + i < p.M) ? __ldg(reinterpret_cast<const float2*>(xc + (uint64_t)i * pitch)) : zero2;
             }
 #pragma unroll
             for (int i = 0; i < kWRows; ++i)
                 w[i] = (kok && (wrows_full || warp * kWRows + i < p.N))
-                           ? __ldg(reinterpret_cast<const float2*>(wcp + (uint64_t)i * pitch)) : zero2;
+                           ? __ldg(reinterpret_cast<const float2*>(wc + (uint64_t)i * pitch)) : zero2;
         };
-        auto store_ss = [&](uint32_t g, const float2 (&v)[kV2Rows], const float2 (&w)[kWRows]) {
+        auto store_ss = [&](uint32_t g, const float2 (&v)[16], const float2 (&w)[kWRows]) {
             const uint32_t s = g & 1;
             if (g >= 2) mbar_wait(&empty_bar[s], ((g >> 1) & 1) ^ 1);
-            uint8_t* a_hi = smem + (size_t)s * kStageBytes + warp * (kV2Rows * 128);
+            uint8_t* a_hi = smem + (size_t)s * kStageBytes + warp * (16 * 128);
             uint8_t* a_lo = a_hi + 2 * kAtomA;
             uint8_t* b_hi = smem + (size_t)s * kStageBytes + 4 * kAtomA;
             uint8_t* b_lo = b_hi + 2 * kAtomB;
 #pragma unroll
-            for (int i = 0; i < kV2Rows; ++i) {
+            for (int i = 0; i < 16; ++i) {
                 float2 hi, lo;
                 split_tf32(v[i].x, hi.x, lo.x);
                 split_tf32(v[i].y, hi.y, lo.y);
-                *reinterpret_cast<float2*>(a_hi + swa[i]) = hi;
-                *reinterpret_cast<float2*>(a_lo + swa[i]) = lo;
+                *reinterpret_cast<float2*>(a_hi + i * 128 + swa[i & 7]) = hi;
+                *reinterpret_cast<float2*>(a_lo + i * 128 + swa[i & 7]) = lo;
             }
 #pragma unroll
             for (int i = 0; i < kWRows; ++i) {
@@ -436,21 +435,16 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
 
         uint32_t g = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t wrow0 = tile * kBM + warp * kV2Rows;
+            const int64_t wrow0 = tile * kBM + warp * 16;
             const char* xlane = reinterpret_cast<const char*>(p.X + wrow0 * p.K + 2 * lane);
-            const bool rows_full = wrow0 + kV2Rows <= p.M;
+            const bool rows_full = wrow0 + 16 <= p.M;
             load_ss(xlane, rows_full, wrow0, 0, va, wa);
-            if (nss > 1) load_ss(xlane, rows_full, wrow0, 1, vb, wb);
-            for (int ss = 0; ss < nss; ss += 3) {   // three register buffers rotate: A, B, C
-                if (ss + 2 < nss) load_ss(xlane, rows_full, wrow0, ss + 2, vc, wc);
+            for (int ss = 0; ss < nss; ss += 2) {
+                if (ss + 1 < nss) load_ss(xlane, rows_full, wrow0, ss + 1, vb, wb);
                 store_ss(g++, va, wa);
                 if (ss + 1 < nss) {
-                    if (ss + 3 < nss) load_ss(xlane, rows_full, wrow0, ss + 3, va, wa);
+                    if (ss + 2 < nss) load_ss(xlane, rows_full, wrow0, ss + 2, va, wa);
                     store_ss(g++, vb, wb);
-                }
-                if (ss + 2 < nss) {
-                    if (ss + 4 < nss) load_ss(xlane, rows_full, wrow0, ss + 4, vb, wb);
-                    store_ss(g++, vc, wc);
                 }
             }
         }
