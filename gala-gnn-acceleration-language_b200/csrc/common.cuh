@@ -29,12 +29,23 @@ __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 
+// Gathered feature rows: GALA_GATHER_CG = 1 reads them with ld.global.cg (L2 only, no L1
+// allocation) instead of ld.global.nc -- see profiles/r01_variants.txt for the measurement.
+#ifndef GALA_GATHER_CG
+#define GALA_GATHER_CG 0
+#endif
+#if GALA_GATHER_CG
+#define GALA_GATHER_LD(p) __ldcg(p)
+#else
+#define GALA_GATHER_LD(p) __ldg(p)
+#endif
+
 template <int VEC>
 struct Vec;
 template <>
 struct Vec<1> {
     float v[1];
-    __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void load(const float* p) { v[0] = GALA_GATHER_LD(p); }
     __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
     __device__ __forceinline__ void load_rw(const float* p) { v[0] = *p; }
 };
@@ -42,7 +53,7 @@ template <>
 struct Vec<2> {
     float v[2];
     __device__ __forceinline__ void load(const float* p) {
-        float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        float2 t = GALA_GATHER_LD(reinterpret_cast<const float2*>(p));
         v[0] = t.x; v[1] = t.y;
     }
     __device__ __forceinline__ void store(float* p) const {
@@ -57,7 +68,7 @@ template <>
 struct Vec<4> {
     float v[4];
     __device__ __forceinline__ void load(const float* p) {
-        float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        float4 t = GALA_GATHER_LD(reinterpret_cast<const float4*>(p));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
     __device__ __forceinline__ void store(float* p) const {
