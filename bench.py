@@ -295,7 +295,7 @@ def main():
         X_in = X
         mode = args.mode
         step_fn = lambda hook=None: model.forward(g, X_in, hook, mode=mode, dense=args.dense)   # noqa: E731
-        launches_per_step = 3 if (args.dense == "tcgen05" and mode in ("folded", "fused")) else 2
+        launches_per_step = {"folded": 5, "fused": 3}.get(mode, 2) if args.dense == "tcgen05" else 2
         config["parallelism"] = "single GPU"
         config["dense"] = ("layer-1 X*W + attention projections: gala_linear_f32 (tcgen05 kind::tf32, 3xTF32)"
                            if args.dense == "tcgen05" else "cuBLAS fp32 through torch")

@@ -238,3 +238,16 @@ def gat_forward_ex(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None
                                                slope, _l.ptr(out) if want_y else None, _l.ptr(alpha_out),
                                                int(relu), C.byref(ep), g._p(), _l.stream_ptr()))
     return out, att, cls
+
+
+def linear_small(X, W, bias=None, relu=False, transpose_out=False, out=None):
+    """Y = X @ W.T + bias for K <= 64, N <= 64 (exact fp32, one streaming pass, weights in
+    registers).  transpose_out=True returns [N, M] (e.g. the two attention projections)."""
+    X, W = _f32(X), _f32(W)
+    M, K = X.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty((N, M) if transpose_out else (M, N), dtype=torch.float32, device=X.device)
+    _l.check(_l.load().gala_linear_small_f32(_l.ptr(X), M, K, _l.ptr(W), _l.ptr(bias), N, _l.ptr(out), int(relu),
+                                             int(transpose_out), _l.stream_ptr()))
+    return out

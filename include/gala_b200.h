@@ -233,6 +233,14 @@ int gala_linear_f32(const float *X, int64_t M, int32_t K, const float *W, const 
                     const float *att_b, float *att_out, const struct gala_multi_out *multi_out,
                     gala_stream_t stream);
 
+/* The narrow transforms that follow an aggregation (classifier Linear(h, classes), the two    */
+/* Linear(h,1) attention projections; common.h:1185-1281): K <= 64, N <= 64, exact fp32 FMA,   */
+/* weights in registers, one streaming pass.  transpose_out != 0 writes Y as [N, M] (each      */
+/* projection a contiguous vector).                                                            */
+int gala_linear_small_f32(const float *X, int64_t M, int32_t K, const float *W, const float *bias,
+                          int32_t N, float *Y, int32_t relu, int32_t transpose_out,
+                          gala_stream_t stream);
+
 /* ---- format construction on the device ---------- */
 /* All integer outputs are bit-exact against the reference functions named below.       */
 

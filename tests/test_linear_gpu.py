@@ -57,3 +57,16 @@ def test_linear_row_scale_epilogue():
     got = ops.linear(X, W, b, row_scale=rs, relu=True)
     want = torch.relu(rs[:, None].double() * (X.double() @ W.double().t() + b.double()))
     assert float((got.double() - want).norm() / want.norm()) < 1e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 32, 41), (233, 32, 2), (5000, 64, 64), (77, 7, 3), (4096, 47, 33), (1, 1, 1)])
+def test_linear_small_matches_fp64(M, K, N):
+    X = torch.rand(M, K, device=DEV) - 0.5
+    W = torch.rand(N, K, device=DEV) - 0.5
+    b = torch.rand(N, device=DEV)
+    want = X.double() @ W.double().t() + b.double()
+    got = ops.linear_small(X, W, b)
+    assert float((got.double() - want).norm() / want.norm()) < 1e-6
+    got_t = ops.linear_small(X, W, b, transpose_out=True)
+    assert torch.equal(got_t.t().contiguous(), got)
+    assert torch.equal(ops.linear_small(X, W, b, relu=True), torch.relu(got))
