@@ -29,37 +29,98 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const __grid_constant
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // W -> shared memory with coalesced loads (row stride K+1: the per-lane column reads below are
+    // conflict-free), then each lane keeps its one or two output columns in registers.
+    __shared__ float sW[64 * 65];
+    for (int i = threadIdx.x; i < p.N * p.K; i += blockDim.x) sW[(i / p.K) * (p.K + 1) + (i % p.K)] = __ldg(p.W + i);
+    __syncthreads();
     float w0[KP], w1[KP];
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
-        w0[k] = (lane < p.N && k < p.K) ? __ldg(p.W + (int64_t)lane * p.K + k) : 0.0f;
-        w1[k] = (lane + 32 < p.N && k < p.K) ? __ldg(p.W + (int64_t)(lane + 32) * p.K + k) : 0.0f;
+        w0[k] = (lane < p.N && k < p.K) ? sW[lane * (p.K + 1) + k] : 0.0f;
+        w1[k] = (lane + 32 < p.N && k < p.K) ? sW[(lane + 32) * (p.K + 1) + k] : 0.0f;
     }
     const float b0 = (p.bias && lane < p.N) ? __ldg(p.bias + lane) : 0.0f;
     const float b1 = (p.bias && lane + 32 < p.N) ? __ldg(p.bias + lane + 32) : 0.0f;
     const bool two = p.N > 32;
-    for (int64_t row = warp_global; row < p.M; row += nwarps) {
-        const float* xr = p.X + row * p.K;
-        float x0 = lane < p.K ? ld_stream(xr + lane) : 0.0f;
-        float x1 = 0.0f;
-        if (KP > 32) x1 = lane + 32 < p.K ? ld_stream(xr + lane + 32) : 0.0f;
-        float o0 = b0, o1 = b1;
+    constexpr int R = 4;   // rows per warp iteration: R independent loads in flight, R independent FMA chains
+    for (int64_t row0 = warp_global * R; row0 < p.M; row0 += nwarps * R) {
+        float x0[R], x1[R], o0[R], o1[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r;
+            const float* xr = p.X + row * p.K;
+            x0[r] = (row < p.M && lane < p.K) ? ld_stream(xr + lane) : 0.0f;
+            x1[r] = 0.0f;
+            if (KP > 32) x1[r] = (row < p.M && lane + 32 < p.K) ? ld_stream(xr + lane + 32) : 0.0f;
+            o0[r] = b0;
+            o1[r] = b1;
+        }
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
-            const float xk = __shfl_sync(kFull, k < 32 ? x0 : x1, k & 31);
-            o0 = fmaf(xk, w0[k], o0);
-            if (two) o1 = fmaf(xk, w1[k], o1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float xk = __shfl_sync(kFull, k < 32 ? x0[r] : x1[r], k & 31);
+                o0[r] = fmaf(xk, w0[k], o0[r]);
+                if (two) o1[r] = fmaf(xk, w1[k], o1[r]);
+            }
         }
-        if (p.relu) {
-            o0 = fmaxf(o0, 0.0f);
-            o1 = fmaxf(o1, 0.0f);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r;
+            if (row >= p.M) break;
+            float a = o0[r], c = o1[r];
+            if (p.relu) {
+                a = fmaxf(a, 0.0f);
+                c = fmaxf(c, 0.0f);
+            }
+            if (p.transpose_out) {   // Y laid out [N, M]: attention projections as two contiguous vectors
+                if (lane < p.N) p.Y[(int64_t)lane * p.M + row] = a;
+                if (lane + 32 < p.N) p.Y[(int64_t)(lane + 32) * p.M + row] = c;
+            } else {
+                if (lane < p.N) st_stream(p.Y + row * p.N + lane, a);
+                if (lane + 32 < p.N) st_stream(p.Y + row * p.N + lane + 32, c);
+            }
         }
-        if (p.transpose_out) {   // Y laid out [N, M]: attention projections as two contiguous vectors
-            if (lane < p.N) p.Y[(int64_t)lane * p.M + row] = o0;
-            if (lane + 32 < p.N) p.Y[(int64_t)(lane + 32) * p.M + row] = o1;
-        } else {
-            if (lane < p.N) st_stream(p.Y + row * p.N + lane, o0);
-            if (lane + 32 < p.N) st_stream(p.Y + row * p.N + lane + 32, o1);
+    }
+}
+
+// N <= 4 (the attention projections): lane l multiplies its input element with W[n, l] and the
+// warp reduces -- 5 shuffles per output instead of one broadcast shuffle per input element.
+template <int NT>
+__global__ void __launch_bounds__(256) linear_tiny_kernel(const __grid_constant__ SmallParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float w0[NT], w1[NT], b[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        w0[n] = (n < p.N && lane < p.K) ? __ldg(p.W + n * p.K + lane) : 0.0f;
+        w1[n] = (n < p.N && lane + 32 < p.K) ? __ldg(p.W + n * p.K + lane + 32) : 0.0f;
+        b[n] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+    }
+    constexpr int R = 8;
+    for (int64_t row0 = warp_global * R; row0 < p.M; row0 += nwarps * R) {
+        float x0[R], x1[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r;
+            const float* xr = p.X + row * p.K;
+            x0[r] = (row < p.M && lane < p.K) ? ld_stream(xr + lane) : 0.0f;
+            x1[r] = (row < p.M && lane + 32 < p.K) ? ld_stream(xr + lane + 32) : 0.0f;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                float s = warp_sum(fmaf(x0[r], w0[n], x1[r] * w1[n])) + b[n];
+                if (p.relu) s = fmaxf(s, 0.0f);
+                if (lane == 0 && n < p.N && row < p.M) {
+                    if (p.transpose_out) p.Y[(int64_t)n * p.M + row] = s;
+                    else p.Y[row * p.N + n] = s;
+                }
+            }
         }
     }
 }
@@ -84,9 +145,11 @@ extern "C" int gala_linear_small_f32(const float* X, int64_t M, int32_t K, const
     p.relu = relu;
     p.transpose_out = transpose_out;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int64_t warps_needed = M;
-    const unsigned grid = (unsigned)std::min<int64_t>((warps_needed + 7) / 8, 148 * 8);
-    if (K <= 32) linear_small_kernel<32><<<grid, 256, 0, st>>>(p);
+    const int64_t warps_needed = (M + 3) / 4;
+    const unsigned grid = (unsigned)std::min<int64_t>((warps_needed + 7) / 8, 148 * 2);   // persistent: weights are loaded once per CTA
+    if (N <= 2) linear_tiny_kernel<2><<<(unsigned)std::min<int64_t>((M + 63) / 64, 148 * 8), 256, 0, st>>>(p);
+    else if (N <= 4) linear_tiny_kernel<4><<<(unsigned)std::min<int64_t>((M + 63) / 64, 148 * 8), 256, 0, st>>>(p);
+    else if (K <= 32) linear_small_kernel<32><<<grid, 256, 0, st>>>(p);
     else linear_small_kernel<64><<<grid, 256, 0, st>>>(p);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GALA_OK : (int)e;
