@@ -212,6 +212,10 @@ int gala_plan_build(const gala_graph_t* g, int32_t hub_threshold, void* workspac
     return GALA_OK;
 }
 
+// Feature matrices larger than this do not stay resident in the 126 MB L2 while the whole
+// column range is gathered from; column-tiled graphs are then executed segment by segment.
+constexpr int64_t kL2ResidentBytes = 96ll << 20;
+
 int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int32_t K, float* Y,
                   const gala_epilogue_t* ep, const gala_plan_t* plan, gala_stream_t stream) {
     if (int rc = check_graph(g)) return rc;
@@ -225,15 +229,38 @@ int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int3
     p.X = X;
     p.Y = Y;
     p.K = K;
+    int schedule = 0;
     if (ep) {
         p.row_scale = ep->row_scale;
         p.col_scale = ep->col_scale;
         p.accumulate = ep->accumulate;
         p.relu = ep->relu;
+        schedule = ep->schedule;
     }
     HubView h = hub_of(plan, g);
     p.t = task_of(h);
-    return launch_spmm<MODE_PLAIN>(p, S(stream));
+    // Segment-major schedule: one launch per column segment, accumulating into Y, so that the slice of
+    // X a segment gathers from stays in L2 (GALA's col_tile idea sized for a 126 MB L2).  The reference
+    // also launches per segment, but concurrently on separate streams (cuda.h:470-476).
+    bool seg_major = g->segments > 1 &&
+                     (schedule == GALA_SCHEDULE_SEGMENT_MAJOR ||
+                      (schedule == GALA_SCHEDULE_AUTO && (int64_t)g->ncols * K * 4 > kL2ResidentBytes));
+    if (p.accumulate && p.row_scale) seg_major = false;   // Y_old must not be scaled: keep the single launch
+    if (!seg_major) return launch_spmm<MODE_PLAIN>(p, S(stream));
+    const float* row_scale = p.row_scale;
+    const int relu = p.relu;
+    for (int s = 0; s < g->segments; ++s) {
+        const bool last = s == g->segments - 1;
+        p.g.offsets = g->offsets + (int64_t)s * (g->nrows + 1);
+        p.g.S = 1;
+        p.g.seg_base[0] = g->bounds[2 * s];
+        p.accumulate = (s > 0) || (ep && ep->accumulate);
+        p.row_scale = last ? row_scale : nullptr;
+        p.relu = last ? relu : 0;
+        p.scale_after = last ? 1 : 0;
+        if (int rc = launch_spmm<MODE_PLAIN>(p, S(stream))) return rc;
+    }
+    return GALA_OK;
 }
 
 int gala_gat_forward_f32(const gala_graph_t* g, const float* aL, const float* aR, const float* X, int32_t K,

@@ -33,6 +33,7 @@ struct SpmmParams {
     const float* __restrict__ col_scale;  // nullable
     int accumulate;
     int relu;
+    int scale_after;                      // 1: Y = act(row_scale * (sum + Y_old)) -- last pass of a segment-major run
     TaskParams t;
     // MODE_GAT
     const float* __restrict__ aL;
@@ -320,8 +321,9 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
                 if (p.accumulate) o.load_rw(y);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
-                    float t = acc[a][v] * scale;
+                    float t = p.scale_after ? acc[a][v] : acc[a][v] * scale;
                     if (p.accumulate) t += o.v[v];
+                    if (p.scale_after) t *= scale;
                     if (p.relu) t = fmaxf(t, 0.0f);
                     o.v[v] = t;
                     if (dense_ep) rowbuf[warp][f0 + v] = t;
@@ -366,8 +368,9 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
 #pragma unroll
         for (int w = 0; w < kWarpsPerCta; ++w) t += part[w * TW + f];
         float* y = p.Y + (int64_t)row * p.K + tile_base + f;
-        t *= scale;
+        if (!p.scale_after) t *= scale;
         if (p.accumulate) t += *y;
+        if (p.scale_after) t *= scale;
         if (p.relu) t = fmaxf(t, 0.0f);
         if (p.mo.count > 0) {
             Vec<1> o1;

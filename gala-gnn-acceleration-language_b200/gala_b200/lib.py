@@ -38,7 +38,7 @@ class GalaPlan(C.Structure):
 
 class GalaEpilogue(C.Structure):
     _fields_ = [("row_scale", C.c_void_p), ("col_scale", C.c_void_p), ("accumulate", C.c_int32),
-                ("relu", C.c_int32)]
+                ("relu", C.c_int32), ("schedule", C.c_int32)]
 
 
 class GalaMultiOut(C.Structure):

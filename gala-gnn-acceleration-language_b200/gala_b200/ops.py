@@ -67,8 +67,12 @@ def _f32(t):
     return t.contiguous()
 
 
-def spmm(g, X, vals=None, out=None, row_scale=None, col_scale=None, accumulate=False, relu=False):
-    """Y = A @ X (optionally weighted / scaled / accumulated / ReLU'd) in one launch."""
+SCHEDULES = {"auto": 0, "row_major": 1, "segment_major": 2}
+
+
+def spmm(g, X, vals=None, out=None, row_scale=None, col_scale=None, accumulate=False, relu=False, schedule="auto"):
+    """Y = A @ X (optionally weighted / scaled / accumulated / ReLU'd).  One launch, or -- for
+    column-tiled graphs whose feature matrix exceeds the L2 -- one launch per column segment."""
     X = _f32(X)
     K = X.shape[1] if X.dim() == 2 else 1
     if out is None:
@@ -76,7 +80,7 @@ def spmm(g, X, vals=None, out=None, row_scale=None, col_scale=None, accumulate=F
         assert not accumulate, "accumulate needs a caller-provided output"
     ep = _l.GalaEpilogue(row_scale=row_scale.data_ptr() if row_scale is not None else None,
                          col_scale=col_scale.data_ptr() if col_scale is not None else None,
-                         accumulate=int(accumulate), relu=int(relu))
+                         accumulate=int(accumulate), relu=int(relu), schedule=SCHEDULES[schedule])
     _l.check(_l.load().gala_spmm_f32(C.byref(g.c), _l.ptr(vals), _l.ptr(X), K, _l.ptr(out),
                                      C.byref(ep), g._p(), _l.stream_ptr()))
     return out

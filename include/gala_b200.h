@@ -95,7 +95,15 @@ typedef struct gala_epilogue {
     int32_t accumulate;     /* 0: Y is overwritten; 1: Y += (reference semantics
                                of the per-segment `C = C + ...`, cuda.h:309-351)  */
     int32_t relu;           /* apply max(.,0) last                                 */
+    int32_t schedule;       /* column-tiled graphs: GALA_SCHEDULE_AUTO picks
+                               segment-major (one launch per column segment, so the
+                               slice of X a segment gathers from stays in L2) when
+                               ncols*K*4 exceeds the L2, row-major (one launch)
+                               otherwise; or force either                            */
 } gala_epilogue_t;
+#define GALA_SCHEDULE_AUTO 0
+#define GALA_SCHEDULE_ROW_MAJOR 1
+#define GALA_SCHEDULE_SEGMENT_MAJOR 2
 
 int gala_b200_abi_version(void);
 const char *gala_b200_error_string(int code);

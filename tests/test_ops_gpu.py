@@ -64,6 +64,30 @@ def test_spmm_matches_oracle(orc, case, K, weighted):
     assert np.all(np.abs(got - exact) <= 1e-5 * mag + 1e-30)
 
 
+@pytest.mark.parametrize("case", [CASES[3], CASES[4], CASES[5]])
+@pytest.mark.parametrize("K", [1, 32, 100])
+def test_spmm_segment_major_schedule(orc, case, K):
+    """One launch per column segment (the schedule used when X exceeds the L2) == single launch == oracle,
+    including the fused row/col scale + ReLU epilogue and user-level accumulation."""
+    n, e, seed, T, empty, thr = case
+    t = graph_case(orc, n, e, seed, T, empty)
+    g = to_gpu_graph(t, thr)
+    rng = np.random.default_rng(seed + K)
+    X = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    norm = rng.uniform(0.1, 1.0, n).astype(np.float32)
+    want = orc.spmm(t, X, weighted=True)
+    a = ops.spmm(g, dev(X), vals=dev(t.vals), schedule="segment_major").cpu().numpy()
+    b = ops.spmm(g, dev(X), vals=dev(t.vals), schedule="row_major").cpu().numpy()
+    assert rel_err(a, want) < FP32_TOL and rel_err(b, want) < FP32_TOL
+    want2 = np.maximum(norm[:, None] * orc.spmm(t, norm[:, None] * X, weighted=False), 0)
+    a2 = ops.spmm(g, dev(X), row_scale=dev(norm), col_scale=dev(norm), relu=True, schedule="segment_major").cpu().numpy()
+    assert rel_err(a2, want2) < FP32_TOL
+    Y0 = rng.uniform(-1, 1, (n, K)).astype(np.float32)
+    out = dev(Y0.copy())
+    ops.spmm(g, dev(X), vals=dev(t.vals), out=out, accumulate=True, schedule="segment_major")
+    assert rel_err(out.cpu().numpy(), Y0 + want) < FP32_TOL
+
+
 def test_spmm_degrees_are_exact(orc):
     """SpMM(A, ones) = degrees: small integers, exact in fp32 whatever the order
     (the generated GCN computes its normalisation this way, codegen/gala.cu:437)."""
