@@ -244,7 +244,10 @@ int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int3
     // also launches per segment, but concurrently on separate streams (cuda.h:470-476).
     bool seg_major = g->segments > 1 &&
                      (schedule == GALA_SCHEDULE_SEGMENT_MAJOR ||
-                      (schedule == GALA_SCHEDULE_AUTO && (int64_t)g->ncols * K * 4 > kL2ResidentBytes));
+                      (schedule == GALA_SCHEDULE_AUTO && (int64_t)g->ncols * K * 4 > kL2ResidentBytes &&
+                       g->nvals / std::max<int64_t>(1, (int64_t)g->nrows * g->segments) >= 128));
+    // (measured, profiles/r01_tiling_*.txt: segment-major only pays when every row still has >= ~100 edges per
+    //  segment -- Reddit shape at K = 602: 21.2 -> 19.1 ms; on the Products shape, mean degree 50, it loses)
     if (p.accumulate && p.row_scale) seg_major = false;   // Y_old must not be scaled: keep the single launch
     if (!seg_major) return launch_spmm<MODE_PLAIN>(p, S(stream));
     const float* row_scale = p.row_scale;
