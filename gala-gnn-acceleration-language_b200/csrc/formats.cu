@@ -378,6 +378,66 @@ __global__ void mask_next_kernel(const int* __restrict__ offsets, const int* __r
     if (lane == 0) next[row] = (unsigned char)m;
 }
 
+// ----------------------------------------------------------------------------- reordering
+// rowReorderToAdj (src/ops/reordering.h:940-1013): key = (perm[row] << 32) | perm[col]
+__global__ void pack_permuted_kernel(const int* __restrict__ offsets, const int* __restrict__ ids, const int* __restrict__ perm,
+                                     int nrows, uint64_t* __restrict__ keys) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= nrows) return;
+    const uint64_t hi = (uint64_t)(uint32_t)perm[row] << 32;
+    for (int e = offsets[row] + lane; e < offsets[row + 1]; e += 32) keys[e] = hi | (uint32_t)perm[ids[e]];
+}
+
+// The reference sorts each row's (column, value) PAIRS (reordering.h:1000), so duplicate edges end up ordered by
+// value; the radix sort above is stable in the source order.  One thread per run of equal (row, column) keys
+// re-orders that run's values (runs are rare and short).
+__global__ void sort_duplicate_runs_kernel(const uint64_t* __restrict__ keys, float* __restrict__ vals, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e + 1 < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[e];
+        if (keys[e + 1] != k || (e > 0 && keys[e - 1] == k)) continue;   // not the head of a run
+        int64_t end = e + 2;
+        while (end < n && keys[end] == k) ++end;
+        for (int64_t i = e + 1; i < end; ++i) {   // insertion sort, ascending (std::pair operator<)
+            const float v = vals[i];
+            int64_t j = i;
+            while (j > e && v < vals[j - 1]) {
+                vals[j] = vals[j - 1];
+                --j;
+            }
+            vals[j] = v;
+        }
+    }
+}
+
+// rowPermuteDenseTo (reordering.h:244-283): Y[perm[i], :] = X[i, :];  rowPermuteDenseFrom (:207-236): Y[i, :] = X[perm[i], :]
+template <typename V>
+__global__ void permute_rows_kernel(const V* __restrict__ X, const int* __restrict__ perm, V* __restrict__ Y, int nrows,
+                                    int kv, int from) {
+    const int64_t total = (int64_t)nrows * kv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / kv), c = (int)(i - (int64_t)r * kv);
+        const int p = perm[r];
+        const int64_t src = from ? (int64_t)p * kv + c : i;
+        const int64_t dst = from ? i : (int64_t)p * kv + c;
+        Y[dst] = X[src];
+    }
+}
+
+// degree-descending order: key = (~degree << 32) | row  -> ascending sort puts the widest rows first, ties by row id
+__global__ void degree_keys_kernel(const int* __restrict__ offsets, int nrows, uint64_t* __restrict__ keys) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x)
+        keys[r] = ((uint64_t)(0x7fffffffu - (uint32_t)(offsets[r + 1] - offsets[r])) << 32) | (uint32_t)r;
+}
+__global__ void invert_order_kernel(const uint64_t* __restrict__ keys, int nrows, int* __restrict__ perm,
+                                    int* __restrict__ order) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nrows; k += gridDim.x * blockDim.x) {
+        const int r = (int)(uint32_t)keys[k];
+        perm[r] = k;
+        if (order) order[k] = r;
+    }
+}
+
 int csr_from_keys(SortBuffers& b, int32_t nrows, int32_t ncols, int64_t nvals, bool has_val, int32_t* offsets, int32_t* ids,
                   float* out_vals, cudaStream_t st) {
     uint64_t* ks;
@@ -444,6 +504,72 @@ int gala_csr_transpose(int32_t nrows, int32_t ncols, int64_t nvals, const int32_
     }
     // rows of the transpose = columns of the source, and vice versa
     return csr_from_keys(b, ncols, nrows, nvals, has_val, t_offsets, t_ids, t_vals, st);
+}
+
+int gala_csr_reorder(int32_t nrows, int64_t nvals, const int32_t* offsets, const int32_t* ids, const float* vals,
+                     const int32_t* perm, int32_t* new_offsets, int32_t* new_ids, float* new_vals, void* workspace,
+                     size_t workspace_bytes, gala_stream_t stream) {
+    if (nrows < 0 || nvals < 0) return GALA_ERR_BAD_SHAPE;
+    if (nvals > 0x7fffffffLL) return GALA_ERR_UNSUPPORTED;
+    if (!new_offsets || (nrows > 0 && (!offsets || !perm)) || (nvals > 0 && (!ids || !new_ids || !workspace))) return GALA_ERR_NULL_POINTER;
+    if (nvals > 0 && workspace_bytes < gala_csr_from_coo_workspace_bytes(nrows, nrows, nvals)) return GALA_ERR_WORKSPACE;
+    cudaStream_t st = S(stream);
+    if (nvals == 0) {
+        fill_int_kernel<<<grid_for(nrows + 1), 256, 0, st>>>(new_offsets, (int64_t)nrows + 1, 0);
+        return last_error();
+    }
+    SortBuffers b = carve(workspace, nvals);
+    pack_permuted_kernel<<<(unsigned)(((int64_t)nrows * 32 + 255) / 256), 256, 0, st>>>(offsets, ids, perm, nrows, b.ka);
+    const bool has_val = vals != nullptr && new_vals != nullptr;
+    if (has_val) {
+        cudaError_t e = cudaMemcpyAsync(b.va, vals, (size_t)nvals * 4, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    uint64_t* ks;
+    float* vs;
+    radix_sort_pairs(b, nvals, bits_for((uint32_t)nrows), bits_for((uint32_t)nrows), has_val, st, &ks, &vs);
+    if (has_val) sort_duplicate_runs_kernel<<<grid_for(nvals), 256, 0, st>>>(ks, vs, nvals);
+    unpack_sorted_kernel<<<grid_for(nvals), 256, 0, st>>>(ks, nvals, nrows, new_offsets, new_ids);
+    if (has_val) {
+        cudaError_t e = cudaMemcpyAsync(new_vals, vs, (size_t)nvals * 4, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return last_error();
+}
+
+int gala_permute_rows_f32(const float* X, const int32_t* perm, float* Y, int32_t nrows, int32_t K, int32_t from,
+                          gala_stream_t stream) {
+    if (nrows < 0 || K < 0) return GALA_ERR_BAD_SHAPE;
+    if (nrows == 0 || K == 0) return GALA_OK;
+    if (!X || !perm || !Y) return GALA_ERR_NULL_POINTER;
+    if (X == Y) return GALA_ERR_UNSUPPORTED;   // out of place only
+    cudaStream_t st = S(stream);
+    const bool v4 = K % 4 == 0 && (reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) % 16 == 0;
+    if (v4)
+        permute_rows_kernel<float4><<<grid_for((int64_t)nrows * (K / 4)), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(X), perm, reinterpret_cast<float4*>(Y), nrows, K / 4, from != 0);
+    else
+        permute_rows_kernel<float><<<grid_for((int64_t)nrows * K), 256, 0, st>>>(X, perm, Y, nrows, K, from != 0);
+    return last_error();
+}
+
+size_t gala_degree_order_workspace_bytes(int32_t nrows) { return sort_ws_bytes(std::max<int64_t>(nrows, 1)); }
+
+int gala_degree_order(int32_t nrows, const int32_t* offsets, int32_t* perm, int32_t* order, void* workspace,
+                      size_t workspace_bytes, gala_stream_t stream) {
+    if (nrows < 0) return GALA_ERR_BAD_SHAPE;
+    if (nrows == 0) return GALA_OK;
+    if (!offsets || !perm || !workspace) return GALA_ERR_NULL_POINTER;
+    if (workspace_bytes < gala_degree_order_workspace_bytes(nrows)) return GALA_ERR_WORKSPACE;
+    cudaStream_t st = S(stream);
+    SortBuffers b = carve(workspace, nrows);
+    degree_keys_kernel<<<grid_for(nrows), 256, 0, st>>>(offsets, nrows, b.ka);
+    uint64_t* ks;
+    float* vs;
+    // the row id in the low word is already ascending: only the degree word needs sorting (stable)
+    radix_sort_pairs(b, nrows, 0, 32, false, st, &ks, &vs);
+    invert_order_kernel<<<grid_for(nrows), 256, 0, st>>>(ks, nrows, perm, order);
+    return last_error();
 }
 
 int32_t gala_col_tile_segments(int32_t ncols, int32_t cols_per_partition) {

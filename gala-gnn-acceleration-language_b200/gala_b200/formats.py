@@ -101,3 +101,60 @@ def getMaskSubgraphs(nrows, ncols, offsets, ids, vals, mask, layers):
         res.append((no, ni, nv, to, ti, tv))
         cur = nxt
     return res
+
+
+def rowReorderToAdj(nrows, offsets, ids, vals, perm):
+    """reordering.h:940-1013: relabel node i as perm[i] (rows and columns), rows column-sorted."""
+    lib = _l.load()
+    E = int(ids.numel())
+    dev = ids.device
+    no = torch.empty(nrows + 1, dtype=torch.int32, device=dev)
+    ni = torch.empty(E, dtype=torch.int32, device=dev)
+    nv = torch.empty(E, dtype=torch.float32, device=dev) if vals is not None else None
+    nb = lib.gala_csr_from_coo_workspace_bytes(nrows, nrows, E)
+    ws = _ws(nb, dev)
+    _l.check(lib.gala_csr_reorder(nrows, E, _l.ptr(offsets), _l.ptr(ids), _l.ptr(vals), _l.ptr(perm),
+                                  _l.ptr(no), _l.ptr(ni), _l.ptr(nv), _l.ptr(ws), nb, _l.stream_ptr()))
+    return no, ni, nv
+
+
+def _permute_rows(X, perm, from_):
+    lib = _l.load()
+    n, K = X.shape
+    Y = torch.empty_like(X)
+    _l.check(lib.gala_permute_rows_f32(_l.ptr(X), _l.ptr(perm), _l.ptr(Y), n, K, from_, _l.stream_ptr()))
+    return Y
+
+
+def rowPermuteDenseTo(X, perm):
+    """reordering.h:244-283: Y[perm[i]] = X[i] (returned; the reference overwrites in place)."""
+    return _permute_rows(X, perm, 0)
+
+
+def rowPermuteDenseFrom(X, perm):
+    """reordering.h:207-236: Y[i] = X[perm[i]]."""
+    return _permute_rows(X, perm, 1)
+
+
+def getAcendingOrder(nrows, device):
+    """reordering.h:1085-1093 (identity; the spelling is the reference's)."""
+    return torch.arange(nrows, dtype=torch.int32, device=device)
+
+
+def getDecendingOrder(nrows, device):
+    """reordering.h:1095-1103: ret[nrows-1-i] = i."""
+    return torch.arange(nrows - 1, -1, -1, dtype=torch.int32, device=device)
+
+
+def degree_order(nrows, offsets):
+    """Nodes by descending degree (ties by id): (perm, order), perm in the "to" form the two
+    functions above take.  Not in the reference (its rabbit order is commented out)."""
+    lib = _l.load()
+    dev = offsets.device
+    perm = torch.empty(nrows, dtype=torch.int32, device=dev)
+    order = torch.empty(nrows, dtype=torch.int32, device=dev)
+    nb = lib.gala_degree_order_workspace_bytes(nrows)
+    ws = _ws(nb, dev)
+    _l.check(lib.gala_degree_order(nrows, _l.ptr(offsets), _l.ptr(perm), _l.ptr(order), _l.ptr(ws), nb,
+                                   _l.stream_ptr()))
+    return perm, order

@@ -22,6 +22,7 @@ EXPORTS = [
     "gala_csr_from_coo_workspace_bytes", "gala_csr_from_coo", "gala_csr_transpose",
     "gala_col_tile_segments", "gala_col_tile_workspace_bytes", "gala_col_tile", "gala_sample_ab",
     "gala_mask_subgraph_workspace_bytes", "gala_mask_subgraph",
+    "gala_csr_reorder", "gala_permute_rows_f32", "gala_degree_order_workspace_bytes", "gala_degree_order",
 ]
 
 
@@ -100,7 +101,12 @@ def load():
         "gala_col_tile": [i32, i32, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp],
         "gala_sample_ab": [i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
         "gala_mask_subgraph": [i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int64), vp, vp, sz, vp],
+        "gala_csr_reorder": [i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp],
+        "gala_permute_rows_f32": [vp, vp, vp, i32, i32, i32, vp],
+        "gala_degree_order": [i32, vp, vp, vp, vp, sz, vp],
     })
+    lib.gala_degree_order_workspace_bytes.restype = sz
+    lib.gala_degree_order_workspace_bytes.argtypes = [i32]
     lib.gala_csr_from_coo_workspace_bytes.restype = sz
     lib.gala_csr_from_coo_workspace_bytes.argtypes = [i32, i32, i64]
     lib.gala_col_tile_segments.restype = i32

@@ -271,6 +271,27 @@ int gala_csr_transpose(int32_t nrows, int32_t ncols, int64_t nvals, const int32_
                        float *t_vals, void *workspace, size_t workspace_bytes,
                        gala_stream_t stream);
 
+/* Replaces rowReorderToAdj (src/ops/reordering.h:940-1013): perm[i] = new index of   */
+/* node i; row perm[i] of the result holds (perm[col], val) of row i, sorted by (column, */
+/* value).  Square graphs (the permutation relabels rows and columns).  perm must be a   */
+/* permutation of [0, nrows).  Workspace: gala_csr_from_coo_workspace_bytes(n, n, nvals). */
+int gala_csr_reorder(int32_t nrows, int64_t nvals, const int32_t *offsets, const int32_t *ids,
+                     const float *vals, const int32_t *perm, int32_t *new_offsets, int32_t *new_ids,
+                     float *new_vals, void *workspace, size_t workspace_bytes, gala_stream_t stream);
+
+/* Replaces rowPermuteDenseTo (reordering.h:244-283; from = 0: Y[perm[i],:] = X[i,:])    */
+/* and rowPermuteDenseFrom (:207-236; from = 1: Y[i,:] = X[perm[i],:]).  Out of place.   */
+int gala_permute_rows_f32(const float *X, const int32_t *perm, float *Y, int32_t nrows, int32_t K,
+                          int32_t from, gala_stream_t stream);
+
+/* A permutation generator for the above (the reference ships only the identity and the  */
+/* reversal, getAcendingOrder / getDecendingOrder reordering.h:1085-1103; its rabbit     */
+/* order is commented out): nodes by DESCENDING degree, ties by node id.                 */
+/* perm[i] = new index of node i ("to" form); order[k] (nullable) = node at new index k. */
+size_t gala_degree_order_workspace_bytes(int32_t nrows);
+int gala_degree_order(int32_t nrows, const int32_t *offsets, int32_t *perm, int32_t *order,
+                      void *workspace, size_t workspace_bytes, gala_stream_t stream);
+
 /* Replaces static_ord_col_breakpoints (src/ops/tiling.h:1594-1608) +                   */
 /* ord_col_tiling_torch (:222-283).  segments = ceil(ncols / cols_per_partition);       */
 /* out_offsets[segments*(nrows+1)], out_cols/out_vals[nvals] on the device,             */

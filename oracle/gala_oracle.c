@@ -514,6 +514,71 @@ ORC_API void orc_mask_next(int nrows, const int *offset, const int *ids, const u
 }
 
 /* ------------------------------------------------------------------------- */
+/* Reordering (src/ops/reordering.h).                                         */
+/* ------------------------------------------------------------------------- */
+typedef struct { int id; float v; } orc_idval_t;
+static int orc_idval_cmp(const void *a, const void *b) {   /* std::pair<int,float> operator< */
+    const orc_idval_t *x = (const orc_idval_t *)a, *y = (const orc_idval_t *)b;
+    if (x->id != y->id) return x->id < y->id ? -1 : 1;
+    return x->v < y->v ? -1 : (y->v < x->v ? 1 : 0);
+}
+
+/* rowReorderToAdj, reordering.h:940-1013: perm[i] = new index of node i; new row  */
+/* perm[i] holds (perm[col], val) of old row i sorted as pairs.                   */
+ORC_API void orc_csr_reorder(int nrows, const int *offset, const int *ids, const float *vals,
+                             const int *perm, int *new_offset, int *new_ids, float *new_vals) {
+    new_offset[0] = 0;
+    for (int i = 0; i < nrows; i++) new_offset[perm[i] + 1] = offset[i + 1] - offset[i];
+    for (int i = 0; i < nrows; i++) new_offset[i + 1] += new_offset[i];
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int i = 0; i < nrows; i++) {
+        int n = offset[i + 1] - offset[i], base = new_offset[perm[i]];
+        orc_idval_t *t = (orc_idval_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(orc_idval_t));
+        for (int j = 0; j < n; j++) {
+            t[j].id = perm[ids[offset[i] + j]];
+            t[j].v = vals[offset[i] + j];
+        }
+        qsort(t, (size_t)n, sizeof(orc_idval_t), orc_idval_cmp);
+        for (int j = 0; j < n; j++) {
+            new_ids[base + j] = t[j].id;
+            new_vals[base + j] = t[j].v;
+        }
+        free(t);
+    }
+}
+
+/* rowPermuteDenseTo (reordering.h:244-283): Y[perm[i]] = X[i];                    */
+/* rowPermuteDenseFrom (:207-236): Y[i] = X[perm[i]].                              */
+ORC_API void orc_permute_rows(int nrows, int K, const float *X, const int *perm, int from, float *Y) {
+    for (int i = 0; i < nrows; i++) {
+        const float *src = X + (int64_t)(from ? perm[i] : i) * K;
+        float *dst = Y + (int64_t)(from ? i : perm[i]) * K;
+        memcpy(dst, src, (size_t)K * sizeof(float));
+    }
+}
+
+/* Descending-degree order, ties by node id (no reference counterpart; stated here */
+/* so that the GPU generator has an independent check): order[k] = node at new     */
+/* index k, perm[order[k]] = k.                                                   */
+ORC_API void orc_degree_order(int nrows, const int *offset, int *perm, int *order) {
+    /* counting sort over degrees, stable */
+    int maxd = 0;
+    for (int i = 0; i < nrows; i++) {
+        int d = offset[i + 1] - offset[i];
+        if (d > maxd) maxd = d;
+    }
+    int64_t *start = (int64_t *)calloc((size_t)maxd + 2, sizeof(int64_t));
+    for (int i = 0; i < nrows; i++) start[maxd - (offset[i + 1] - offset[i]) + 1]++;
+    for (int d = 0; d <= maxd; d++) start[d + 1] += start[d];
+    for (int i = 0; i < nrows; i++) {
+        int k = (int)start[maxd - (offset[i + 1] - offset[i])]++;
+        order[k] = i;
+        perm[i] = k;
+    }
+    free(start);
+}
+
+/* ------------------------------------------------------------------------- */
 /* Fused GAT layer forward as the generated model composes it                */
 /* (src/codegen/common.h:622-675, 735-810, 835-927):  */
 /*   e = aL[row] + aR[col]  -> LeakyReLU(0.2) -> edge-softmax -> Y = alpha X */

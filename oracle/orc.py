@@ -384,3 +384,44 @@ def ref_mask_subgraphs(nrows, ncols, offset, ids, vals, mask, layers):
                     bi[pos:pos + n].copy(), bv[pos:pos + n].copy()))
         pos += n
     return res
+
+
+def csr_reorder(nrows, offset, ids, vals, perm):
+    offset, ids, vals, perm = _c(offset, np.int32), _c(ids, np.int32), _c(vals, np.float32), _c(perm, np.int32)
+    E = ids.shape[0]
+    no, ni, nv = np.zeros(nrows + 1, np.int32), np.zeros(E, np.int32), np.zeros(E, np.float32)
+    lib().orc_csr_reorder(C.c_int(nrows), offset.ctypes, ids.ctypes, vals.ctypes, perm.ctypes,
+                          no.ctypes, ni.ctypes, nv.ctypes)
+    return no, ni, nv
+
+
+def permute_rows(X, perm, from_=False):
+    X, perm = _c(X, np.float32), _c(perm, np.int32)
+    Y = np.zeros_like(X)
+    lib().orc_permute_rows(C.c_int(X.shape[0]), C.c_int(X.shape[1]), X.ctypes, perm.ctypes,
+                           C.c_int(int(from_)), Y.ctypes)
+    return Y
+
+
+def degree_order(nrows, offset):
+    offset = _c(offset, np.int32)
+    perm, order = np.zeros(nrows, np.int32), np.zeros(nrows, np.int32)
+    lib().orc_degree_order(C.c_int(nrows), offset.ctypes, perm.ctypes, order.ctypes)
+    return perm, order
+
+
+def ref_row_reorder_to_adj(nrows, offset, ids, vals, perm):
+    offset, ids, vals, perm = _c(offset, np.int32), _c(ids, np.int32), _c(vals, np.float32), _c(perm, np.int32)
+    E = ids.shape[0]
+    no, ni, nv = np.zeros(nrows + 1, np.int32), np.zeros(E, np.int32), np.zeros(E, np.float32)
+    ref().ref_row_reorder_to_adj(C.c_int(nrows), offset.ctypes, ids.ctypes, vals.ctypes, perm.ctypes,
+                                 no.ctypes, ni.ctypes, nv.ctypes)
+    return no, ni, nv
+
+
+def ref_row_permute_dense(X, perm, from_=False):
+    X = np.array(X, dtype=np.float32, order="C", copy=True)
+    perm = _c(perm, np.int32)
+    ref().ref_row_permute_dense(C.c_int(X.shape[0]), C.c_int(X.shape[1]), X.ctypes, perm.ctypes,
+                                C.c_int(int(from_)))
+    return X

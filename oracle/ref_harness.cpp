@@ -28,6 +28,7 @@
 #include "src/formats/dense_matrix.h"
 #include "src/ops/aggregators.h"
 #include "src/ops/tiling.h"
+#include "src/ops/reordering.h"
 #include "tests/common.h"
 
 typedef int ind1_t;
@@ -188,6 +189,33 @@ int ref_mask_subgraphs(int nrows, int ncols, const int *offset, const int *ids, 
         pos += nv;
     }
     return 0;
+}
+
+// rowReorderToAdj (src/ops/reordering.h:940-1013).  It free()s the matrix' previous arrays, so it
+// is handed malloc'd copies.
+void ref_row_reorder_to_adj(int nrows, const int *offset, const int *ids, const float *vals,
+                            const int *perm, int *new_offset, int *new_ids, float *new_vals) {
+    int64_t nvals = offset[nrows];
+    int *o = dup(offset, (size_t)nrows + 1);
+    int *c = dup(ids, (size_t)nvals);
+    float *v = dup(vals, (size_t)nvals);
+    SM *A = view_csr(nrows, nrows, o, c, v);
+    rowReorderToAdj(A, const_cast<int *>(perm));
+    std::memcpy(new_offset, A->offset_ptr(), ((size_t)nrows + 1) * sizeof(int));
+    std::memcpy(new_ids, A->ids_ptr(), (size_t)nvals * sizeof(int));
+    std::memcpy(new_vals, A->vals_ptr(), (size_t)nvals * sizeof(float));
+}
+
+// rowPermuteDenseTo (:244-283, PR_0 flavour) / rowPermuteDenseFrom (:207-236); both work in place.
+void ref_row_permute_dense(int nrows, int K, float *X, const int *perm, int from) {
+    DM Xm;
+    Xm.import_mtx(nrows, K, (int)((int64_t)nrows * K), X);
+    DM *p = &Xm;
+    if (from)
+        rowPermuteDenseFrom(p, const_cast<int *>(perm));
+    else
+        rowPermuteDenseTo(p, const_cast<int *>(perm));
+    Xm.import_mtx((float *)nullptr);
 }
 
 }  // extern "C"

@@ -8,7 +8,8 @@ Reference entry points exercised (file:line relative to /root/reference):
   CSRCMatrix::build src/formats/csrc_matrix.h:148-376, buildTranspose tests/common.h:107-123,
   gSpMM<wsumAgg> src/ops/aggregators.h:55-127, static_ord_col_breakpoints +
   ord_col_tiling_torch src/ops/tiling.h:1594-1608,222-283, inplace_sample_graph_ab
-  src/ops/tiling.h:454-508, getMaskSubgraphs tests/common.h:20-105 (1 layer).
+  src/ops/tiling.h:454-508, getMaskSubgraphs tests/common.h:20-105 (1 layer), rowReorderToAdj / rowPermuteDenseTo /
+  rowPermuteDenseFrom src/ops/reordering.h:940-1013,244-283,207-236.
 """
 import os
 import sys
@@ -43,12 +44,17 @@ def case(name, n, e, seed, K, T, dup=False):
     s_off, s_ids, s_vals = orc.ref_sample_ab(n, n, offset, ids, w, 20, 5, 7)
     mask = (rng.random(n) < 0.1).astype(np.uint8)
     (m_fo, m_fi, m_fv, m_bo, m_bi, m_bv), = orc.ref_mask_subgraphs(n, n, offset, ids, vals, mask, 1)
+    perm = rng.permutation(n).astype(np.int32)                      # drawn last: earlier vectors unchanged
+    r_off, r_ids, r_vals = orc.ref_row_reorder_to_adj(n, offset, ids, w, perm)
+    X_to = orc.ref_row_permute_dense(X, perm, False)
+    X_from = orc.ref_row_permute_dense(X, perm, True)
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"), n=n, K=K, T=T, coo_src=src, coo_dst=dst, offset=offset,
         ids=ids, t_offset=t_off, t_ids=t_ids, w=w, X=X, Y_w=Y_w, Y_1=Y_1, breakpoints=bp,
         tile_offsets=tiled.offsets, tile_cols=tiled.cols, tile_vals=tiled.vals,
         tile_bounds=tiled.bounds, s_offset=s_off, s_ids=s_ids, s_vals=s_vals, mask=mask,
-        m_fwd_offset=m_fo, m_fwd_ids=m_fi, m_bwd_offset=m_bo, m_bwd_ids=m_bi)
+        m_fwd_offset=m_fo, m_fwd_ids=m_fi, m_bwd_offset=m_bo, m_bwd_ids=m_bi,
+        perm=perm, r_offset=r_off, r_ids=r_ids, r_vals=r_vals, X_to=X_to, X_from=X_from)
     print(name, "n", n, "E", ids.shape[0], "segments", tiled.S)
 
 

@@ -113,6 +113,41 @@ def test_mask_subgraphs_two_layers_match_oracle(orc):
     assert got[1][1].numel() > got[0][1].numel()     # the mask grows by one hop
 
 
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_reorder_on_gpu(name):
+    """The reference's own rowReorderToAdj / rowPermuteDense{To,From} outputs."""
+    g = golden(name)
+    n = int(g["n"])
+    perm = dev(g["perm"])
+    ro, ri, rv = formats.rowReorderToAdj(n, dev(g["offset"]), dev(g["ids"]), dev(g["w"]), perm)
+    assert eq(ro, g["r_offset"]) and eq(ri, g["r_ids"]) and eq(rv, g["r_vals"])
+    assert eq(formats.rowPermuteDenseTo(dev(g["X"]), perm), g["X_to"])
+    assert eq(formats.rowPermuteDenseFrom(dev(g["X"]), perm), g["X_from"])
+
+
+@pytest.mark.parametrize("n,e,K", [(1, 1, 3), (300, 5000, 7), (20000, 600000, 32)])
+def test_reorder_matches_oracle_and_commutes_with_spmm(orc, n, e, K):
+    offset, ids = make_csr(n, e, 9, empty_rows=min(n // 10, 30))
+    rng = np.random.default_rng(n)
+    w = rng.uniform(-1, 1, ids.shape[0]).astype(np.float32)
+    X = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    perm, order = formats.degree_order(n, dev(offset))
+    operm, oorder = orc.degree_order(n, offset)
+    assert eq(perm, operm) and eq(order, oorder)
+    want = orc.csr_reorder(n, offset, ids, w, operm)
+    ro, ri, rv = formats.rowReorderToAdj(n, dev(offset), dev(ids), dev(w), perm)
+    assert eq(ro, want[0]) and eq(ri, want[1]) and eq(rv, want[2])
+    assert np.all(np.diff(np.diff(want[0])) <= 0)                       # degrees now descend
+    Xp = formats.rowPermuteDenseTo(dev(X), perm)
+    assert eq(Xp, orc.permute_rows(X, operm, False))
+    assert eq(formats.rowPermuteDenseFrom(Xp, perm), X)                 # from undoes to
+    # P A P^T (P X) = P (A X): aggregation on the relabelled graph is the relabelled aggregation
+    y = ops.spmm(ops.TiledGraph(dev(offset), dev(ids), n).build_plan(), dev(X), vals=dev(w))
+    yp = ops.spmm(ops.TiledGraph(ro, ri, n).build_plan(), Xp, vals=rv)
+    back = formats.rowPermuteDenseFrom(yp, perm)
+    assert float((back - y).abs().max()) <= 1e-5 * max(1.0, float(y.abs().max()))
+
+
 def test_csr_build_at_reddit_scale_properties():
     """Full BASELINE size: sortedness, row-pointer consistency, idempotence, involution."""
     n, e, *_ = synth.SHAPES["reddit"]
@@ -131,3 +166,32 @@ def test_csr_build_at_reddit_scale_properties():
     a = ops.spmm(tg.build_plan(), X)
     b = ops.spmm(ops.TiledGraph(offset, ids, n).build_plan(), X)
     assert float((a - b).double().norm() / b.double().norm()) < 1e-6
+
+
+def test_npy_ingest_builds_the_reference_csr_on_the_device(orc, tmp_path):
+    """readSM_npy32 / readDM_npy (tests/common.h:331-389) replaced by mmap -> pinned -> device -> GPU build."""
+    from gala_b200 import ingest
+    n, f, c = 3000, 19, 5
+    offset, ids = make_csr(n, 50000, 4)
+    rows = np.repeat(np.arange(n, dtype=np.uint32), np.diff(offset))
+    rng = np.random.default_rng(0)
+    p = rng.permutation(rows.shape[0])                       # the file need not be sorted
+    np.save(tmp_path / "Adj_src.npy", np.concatenate([np.array([n, n], np.uint32), rows[p]]))
+    np.save(tmp_path / "Adj_dst.npy", ids[p].astype(np.uint32))
+    feat = rng.uniform(-0.5, 0.5, (n, f)).astype(np.float32)
+    lab = rng.integers(0, c, (n, 1)).astype(np.int64)
+    lab[:c, 0] = np.arange(c)
+    np.save(tmp_path / "Feat.npy", feat)
+    np.save(tmp_path / "Lab.npy", lab)
+    for name in ("TnMsk", "VlMsk", "TsMsk"):
+        np.save(tmp_path / (name + ".npy"), (rng.random((n, 1)) < 0.3).astype(np.int32))
+    old = ingest.CHUNK_BYTES
+    ingest.CHUNK_BYTES = 4096 * 4                            # force several staging rounds
+    try:
+        d = ingest.load_dataset(str(tmp_path) + "/", DEV)
+    finally:
+        ingest.CHUNK_BYTES = old
+    oo, oi, _ = orc.csr_build(n, rows[p].astype(np.int32), ids[p].astype(np.int32))
+    assert d["nrows"] == n and eq(d["offsets"], oo) and eq(d["ids"], oi) and bool((d["vals"] == 1).all())
+    assert eq(d["input_emb"], feat) and eq(d["labels"], lab) and d["classes"] == c
+    assert d["train_mask"].dtype == torch.bool and d["train_mask"].shape == (n, 1)

@@ -75,6 +75,26 @@ def test_mask_subgraph_matches_reference_golden(orc, name):
     assert np.array_equal(bo, g["m_bwd_offset"]) and np.array_equal(bi, g["m_bwd_ids"])
 
 
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_reorder_matches_reference_golden(orc, name):
+    """rowReorderToAdj / rowPermuteDenseTo / rowPermuteDenseFrom (src/ops/reordering.h)."""
+    g = golden(name)
+    n = int(g["n"])
+    ro, ri, rv = orc.csr_reorder(n, g["offset"], g["ids"], g["w"], g["perm"])
+    assert np.array_equal(ro, g["r_offset"]) and np.array_equal(ri, g["r_ids"])
+    assert np.array_equal(rv, g["r_vals"])          # small_dup: duplicate edges ordered by value
+    assert np.array_equal(orc.permute_rows(g["X"], g["perm"], False), g["X_to"])
+    assert np.array_equal(orc.permute_rows(g["X"], g["perm"], True), g["X_from"])
+
+
+def test_degree_order_is_stable_descending(orc):
+    offset, ids = make_csr(500, 6000, 3, empty_rows=20)
+    perm, order = orc.degree_order(500, offset)
+    deg = np.diff(offset)
+    assert np.array_equal(order, np.argsort(-deg, kind="stable"))
+    assert np.array_equal(perm[order], np.arange(500))
+
+
 def test_sampled_spmm_equals_spmm_on_sampled_graph(orc):
     """K1s (sampling inside the kernel, cuda.h:313-320) and inplace_sample_graph_ab
     (tiling.h:454-508) pick the same multiset of edges per row."""
