@@ -502,6 +502,28 @@ int gala_edge_softmax_bwd_f32(const gala_graph_t* g, const float* alpha, const f
     return last_error();
 }
 
+int gala_gat_backward_att_f32(const gala_graph_t* g, const float* alpha, const float* dalpha, const float* aL,
+                              const float* aR, float slope, float* d_att, const gala_plan_t* plan,
+                              gala_stream_t stream) {
+    GatBwdParams q;
+    dim3 grid;
+    if (int rc = edge_common(g, plan, q.e, grid)) return rc;
+    if (g->nrows == 0) return GALA_OK;
+    if (!d_att || !aL || (g->nvals > 0 && (!alpha || !dalpha || !aR))) return GALA_ERR_NULL_POINTER;
+    q.e.a = alpha;
+    q.e.b = dalpha;
+    q.e.out = d_att;
+    q.e.seed = (float)g->segments * 1e-12f;
+    q.e.slope = slope;
+    q.aL = aL;
+    q.aR = aR;
+    // the 128-bit body also reads the column ids as int4: the segment bases must keep 16-byte phase
+    bool v4 = aligned(alpha, 16) && aligned(dalpha, 16) && aligned(g->cols, 16);
+    if (v4) gat_bwd_att_kernel<true><<<grid, kCtaThreads, 0, S(stream)>>>(q);
+    else gat_bwd_att_kernel<false><<<grid, kCtaThreads, 0, S(stream)>>>(q);
+    return last_error();
+}
+
 int gala_sddmm_f32(const gala_graph_t* g, const float* A, const float* B, int32_t K, float* out,
                    const gala_plan_t* plan, gala_stream_t stream) {
     if (int rc = check_graph(g)) return rc;

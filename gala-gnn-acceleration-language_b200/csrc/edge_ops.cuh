@@ -160,6 +160,57 @@ __global__ void __launch_bounds__(kCtaThreads) edge_softmax_bwd_kernel(const __g
     });
 }
 
+// ---- GAT attention backward, edge side in one kernel ----------------------------------------
+// What autograd runs for one GAT layer between d(alpha) and d(attenL)/d(attenR) in the generated
+// program (common.h:791-799 softmax backward, LeakyReLU backward, common.h:630-675 edge-sum backward):
+//   sds = alpha*dalpha;  ds = sds - alpha*(seed + sum_row sds);  de = ds * (aL[row]+aR[col] > 0 ? 1 : slope)
+//   out[row] = seed + sum_row de            (the reference returns this row sum for BOTH attenL and attenR)
+// e.a = alpha, e.b = dalpha, e.out = d_att; nothing of size E is written.
+struct GatBwdParams {
+    EdgeParams e;
+    const float* __restrict__ aL;
+    const float* __restrict__ aR;
+};
+
+template <bool V4>
+__global__ void __launch_bounds__(kCtaThreads) gat_bwd_att_kernel(const __grid_constant__ GatBwdParams q) {
+    const EdgeParams& p = q.e;
+    RowTask t = row_task(p.g, p.t);
+    if (!t.valid) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.0f;
+    for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
+        warp_edges<V4>(e0, e1, lane, [&](int e) { s += p.a[e] * p.b[e]; },
+                       [&](int e) {
+                           float4 a = *reinterpret_cast<const float4*>(p.a + e);
+                           float4 b = *reinterpret_cast<const float4*>(p.b + e);
+                           s += (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w);
+                       });
+    });
+    s = warp_sum(s);
+    if (t.hub) s = cta_sum_ordered(s);
+    const float tot = s + p.seed;
+    const float al = __ldg(q.aL + t.row);
+    const float slope = p.slope;
+    float r = 0.0f;
+    auto one = [&](float a, float b, int c) {
+        const float ds = a * b - a * tot;
+        return (al + __ldg(q.aR + c)) > 0.0f ? ds : ds * slope;
+    };
+    for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
+        warp_edges<V4>(e0, e1, lane, [&](int e) { r += one(p.a[e], p.b[e], ld_stream(p.g.cols + e)); },
+                       [&](int e) {
+                           float4 a = *reinterpret_cast<const float4*>(p.a + e);
+                           float4 b = *reinterpret_cast<const float4*>(p.b + e);
+                           int4 c = *reinterpret_cast<const int4*>(p.g.cols + e);
+                           r += (one(a.x, b.x, c.x) + one(a.y, b.y, c.y)) + (one(a.z, b.z, c.z) + one(a.w, b.w, c.w));
+                       });
+    });
+    r = warp_sum(r);
+    if (t.hub) r = cta_sum_ordered(r);
+    if (threadIdx.x == (t.hub ? 0 : (threadIdx.x & ~31))) p.out[t.row] = r + p.seed;
+}
+
 // ---- K6: out[e] = dot(A[row,:], B[col[e],:]) -----------------------------------------------
 // LPR lanes cover one feature row; the A row lives in registers (ACC*VEC per lane) when
 // K <= VEC*LPR*ACC, further feature tiles are re-read from L1.  Each lane keeps one partial

@@ -146,6 +146,17 @@ def edge_softmax_bwd(g, alpha, dalpha, out=None):
     return out
 
 
+def gat_backward_att(g, alpha, dalpha, aL, aR, slope=0.2, out=None):
+    """d(attenL) = d(attenR) of one GAT layer from d(alpha): softmax backward + LeakyReLU backward +
+    row sum in one kernel (gala_gat_backward_att_f32)."""
+    if out is None:
+        out = torch.empty((g.nrows, 1), dtype=torch.float32, device=alpha.device)
+    _l.check(_l.load().gala_gat_backward_att_f32(C.byref(g.c), _l.ptr(_f32(alpha)), _l.ptr(_f32(dalpha)),
+                                                 _l.ptr(_f32(aL)), _l.ptr(_f32(aR)), slope, _l.ptr(out),
+                                                 g._p(), _l.stream_ptr()))
+    return out
+
+
 def gat_forward(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None):
     """Fused SDDVV + LeakyReLU + edge-softmax + weighted SpMM (one pass over the edges)."""
     X = _f32(X)

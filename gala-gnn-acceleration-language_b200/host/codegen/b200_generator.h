@@ -6,6 +6,9 @@
 //
 // Compiled against the reference tree (-I/root/reference); no reference source is copied.
 #pragma once
+#include <fstream>
+#include <regex>
+#include <sstream>
 #include <unordered_set>
 
 #include "src/codegen/cuda.h"
@@ -82,6 +85,52 @@ public:
                 for (int ix = 0; ix < loop->getLoopNodeNum(); ix++) visit(loop->getNode(ix));
             }
         }
+    }
+
+    // Peephole over the emitted forward() text, run after writeCode(): a GAT layer whose four nodes
+    // (aggregate_edge_sum -> LeakyReLU -> non_lnr_op_softmax -> aggregate_node_mul_sum*, emitted by
+    // common.h:622-675, 1176-1184, 735-810, 835-927) all address the same graph slot becomes ONE call of
+    // gala_b200::gat_layer_AutoGrad (gala_b200_torch.h): fused forward kernel, same gradients.  Layers
+    // whose nodes use different slots (training sub-graphs, tests/common.h:20-105) are left as emitted.
+    // Returns the number of layers fused.
+    static int fuseGatLayers(const std::string& path) {
+        std::ifstream in(path);
+        if (!in) return 0;
+        std::stringstream buf;
+        buf << in.rdbuf();
+        std::string text = buf.str();
+        in.close();
+        const std::regex layer(
+            R"(attn = aggregate_edge_sum_AutoGrad::apply\((\w+), (\w+), (\d+)\);\s*)"
+            R"((torch::nn::LeakyReLU leaky_relu\(torch::nn::LeakyReLUOptions\(\)\.negative_slope\(([0-9.]+)\)\);\s*)?)"
+            R"(attn = leaky_relu->forward\(attn\);\s*)"
+            R"(attn = non_lnr_op_softmax_AutoGrad::apply\(attn, (\d+)\);\s*)"
+            R"(if \(ep % mod_v == 0\) \{\s*res = \w+_AutoGrad::apply\(res, attn, (\d+)\);\s*\} else \{\s*)"
+            R"(res = \w+_AutoGrad::apply\(res, attn, (\d+)\);\s*\})");
+        std::string out, slope = "0.2";
+        int fused = 0;
+        auto it = std::sregex_iterator(text.begin(), text.end(), layer);
+        size_t pos = 0;
+        for (; it != std::sregex_iterator(); ++it) {
+            const std::smatch& m = *it;
+            out += text.substr(pos, m.position() - pos);
+            pos = m.position() + m.length();
+            if (m[5].matched) slope = m[5].str();
+            const bool same = m[3] == m[6] && m[3] == m[7] && m[3] == m[8];
+            if (!same) {
+                out += m.str();
+                continue;
+            }
+            out += "res = gala_b200::gat_layer_AutoGrad::apply(res, " + m[1].str() + ", " + m[2].str() + ", " + m[3].str() +
+                   ", " + slope + ");   // fused: edge_sddvv + LeakyReLU + softmax + aggregate";
+            ++fused;
+        }
+        out += text.substr(pos);
+        if (fused) {
+            std::ofstream o(path);
+            o << out;
+        }
+        return fused;
     }
 
 private:

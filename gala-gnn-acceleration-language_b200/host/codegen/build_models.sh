@@ -5,7 +5,11 @@
 # Authoring container only (needs /root/reference + nvcc); the binaries land in _models/
 # (git-ignored, shipped to the GPU box).  One line is added to every generated main loop so
 # that the two programs can be compared: it prints a checksum of the first forward pass.
-#   usage: build_models.sh "<model:mode:col_tile> ..."     e.g.  "gat:inference:370000 gcn:inference:37000"
+#   usage: build_models.sh "<model:mode:col_tile[:dataset:feats:labels[:flags]]> ..."
+#          e.g.  "gat:inference:370000 gcn:inference:37000 sage:train:10000000:Products:100:47"
+#          flags: codegen options joined by '+', e.g. --sample+20 (aggrFn.sample) or --graph-sample+20 (G.sample);
+#          a program with flags is named <model>_<mode>_<flag words>, e.g. gcn_inference_sample20
+#   KINDS="b200" (or "ref") builds only that generator's programs;  JOBS=<n> bounds the number of concurrent nvcc runs (default 4; each takes ~5 min and ~3 GB)
 set -e
 HERE=$(cd "$(dirname "$0")" && pwd)
 REPO=$(cd "$HERE/../../.." && pwd)
@@ -14,11 +18,15 @@ TORCH=$(python -c "import torch,os;print(os.path.dirname(torch.__file__))")
 make -s -C "$HERE"
 SPECS=${1:-"gat:inference:370000 gcn:inference:37000"}
 build_one() {
-  local model=$1 mode=$2 tile=$3 kind=$4
-  local dir="$HERE/_models/${model}_${mode}_${kind}/build"
+  local model=$1 mode=$2 tile=$3 kind=$4 dataset=${5:-Reddit} feats=${6:-602} labels=${7:-41} flags=${8:-}
+  local name="${model}_${mode}"
+  [ "$dataset" != "Reddit" ] && name="${name}_$(echo "$dataset" | tr 'A-Z' 'a-z')"
+  [ -n "$flags" ] && name="${name}_$(echo "$flags" | tr -d '+-')"
+  local dir="$HERE/_models/${name}_${kind}/build"
   mkdir -p "$dir"
+  echo "$dataset $feats $labels" > "$dir/../spec.txt"
   local flag=""; [ "$kind" = "ref" ] && flag="--reference"
-  "$HERE/gala_b200_codegen" "$model" Reddit 602 41 "$tile" "$mode" "$dir/" "$REPO" $flag > "$dir/codegen.log" 2>&1
+  "$HERE/gala_b200_codegen" "$model" "$dataset" "$feats" "$labels" "$tile" "$mode" "$dir/" "$REPO" $flag ${flags//+/ } > "$dir/codegen.log" 2>&1
   # instrumentation of the GENERATED text (identical for both generators)
   sed -i 's|    if (epoch >= skip_cache_warmup) {|    if (epoch == 1) { std::cout << "CHECK " << std::setprecision(9) << prediction.abs().sum().item<float>() << " " << d_loss.item<float>() << std::endl; }\n    if (epoch >= skip_cache_warmup) {|' "$dir/gala.cu"
   # the generated program never seeds libtorch: weights differ from run to run.  Seed it.
@@ -31,9 +39,12 @@ build_one() {
       -L"$TORCH/lib" -Xlinker -rpath -Xlinker "$TORCH/lib" -Xlinker --no-as-needed \
       -ltorch -ltorch_cpu -ltorch_cuda -lc10 -lc10_cuda -lgomp $extra > build.log 2>&1 && echo "built $dir") || echo "FAILED $dir (see build.log)"
 }
+JOBS=${JOBS:-4}
 for spec in $SPECS; do
-  IFS=: read -r model mode tile <<< "$spec"
-  build_one "$model" "$mode" "$tile" b200 &
-  build_one "$model" "$mode" "$tile" ref &
+  IFS=: read -r model mode tile dataset feats labels flags <<< "$spec"
+  for kind in ${KINDS:-b200 ref}; do
+    while [ "$(jobs -rp | wc -l)" -ge "$JOBS" ]; do wait -n; done
+    build_one "$model" "$mode" "$tile" "$kind" "$dataset" "$feats" "$labels" "$flags" &
+  done
 done
 wait

@@ -11,7 +11,7 @@
 // reference is copied into the repository.
 //
 // usage: gala_b200_codegen <gcn|gat|gin|sage> <dataset> <feat> <labels> <col_tile> <inference|train>
-//                          <outdir> <gala_b200_root> [--reference] [--sample S] [--graph-sample S]
+//                          <outdir> <gala_b200_root> [--reference] [--no-fuse] [--sample S] [--graph-sample S]
 #include <cstring>
 #include <iostream>
 #include <map>
@@ -49,15 +49,17 @@ std::string GALAFEContext::opt_input = "";
 int main(int argc, char** argv) {
     if (argc < 9) {
         std::cerr << "usage: gala_b200_codegen <gcn|gat|gin|sage> <dataset> <feat> <labels> <col_tile> "
-                     "<inference|train> <outdir> <gala_b200_root> [--reference] [--sample S] [--graph-sample S]\n";
+                     "<inference|train> <outdir> <gala_b200_root> [--reference] [--no-fuse] [--sample S] [--graph-sample S]\n";
         return 2;
     }
     std::string model = argv[1], dataset = argv[2], mode = argv[6], outdir = argv[7], root = argv[8];
     int feat = atoi(argv[3]), labels = atoi(argv[4]), colTile = atoi(argv[5]);
     bool reference = false;
     int sample = 0, graphSample = 0;
+    bool noFuse = false;
     for (int i = 9; i < argc; i++) {
         if (!strcmp(argv[i], "--reference")) reference = true;
+        else if (!strcmp(argv[i], "--no-fuse")) noFuse = true;
         else if (!strcmp(argv[i], "--sample") && i + 1 < argc) sample = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--graph-sample") && i + 1 < argc) graphSample = atoi(argv[++i]);
     }
@@ -125,5 +127,9 @@ int main(int argc, char** argv) {
     gen->writeCode(GALAFEContext::program, GALAFEContext::dependencies, GALAFEContext::associations,
                    GALAFEContext::transforms);
     std::cout << "wrote " << outPath << "gala.cu (" << (reference ? "reference kernels" : "gala_b200 bindings") << ")\n";
+    if (!reference && !noFuse) {
+        int fused = B200Generator::fuseGatLayers(outPath + "gala.cu");
+        if (fused) std::cout << "fused " << fused << " GAT layer(s) into gala_b200::gat_layer_AutoGrad\n";
+    }
     return 0;
 }

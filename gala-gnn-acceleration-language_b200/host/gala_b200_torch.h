@@ -29,6 +29,10 @@
 extern int global_nrows;
 extern int global_ra;
 extern int global_rb;
+extern std::vector<int> global_segments;                      // common.h:1694-1705: slot 2g = forward graph g,
+extern std::vector<torch::Tensor> global_offset_graph;        // slot 2g+1 = its backward (transpose) graph
+extern std::vector<torch::Tensor> global_columns_graph;
+extern std::vector<torch::Tensor> global_bounds;
 
 namespace gala_b200 {
 
@@ -119,6 +123,21 @@ inline torch::Tensor gat_forward(const torch::Tensor& res, const torch::Tensor& 
     return Y;
 }
 
+// K6 (cuda.h:699-734, 808-845): out[e] = dot(A[row(e),:], B[col(e),:])
+inline torch::Tensor edge_sddmm_impl(const torch::Tensor& input_dense1, const torch::Tensor& input_dense2,
+                                     const torch::Tensor& offset_graph, const torch::Tensor& columns_graph,
+                                     const torch::Tensor& bounds, int nrows, int segments) {
+    auto a = input_dense1.contiguous();
+    auto b = input_dense2.contiguous();
+    const int64_t dcols = a.numel() / nrows;
+    auto out = torch::empty({columns_graph.numel()}, out_options(input_dense1));
+    gala_graph_t g = make_graph(offset_graph, columns_graph, bounds, segments, nrows);
+    check(gala_sddmm_f32(&g, a.data_ptr<float>(), b.data_ptr<float>(), (int)dcols, out.data_ptr<float>(),
+                         plan_for(g, input_dense1), stream()),
+          "gala_sddmm_f32");
+    return out;
+}
+
 }  // namespace gala_b200
 
 // Stamps out one emitted aggregation wrapper under its generated name, e.g.
@@ -196,15 +215,7 @@ inline torch::Tensor edge_sddvv(torch::Tensor input_dense1, torch::Tensor input_
 inline torch::Tensor edge_sddmm(torch::Tensor input_dense1, torch::Tensor input_dense2, torch::Tensor offset_graph,
                                 torch::Tensor columns_graph, torch::Tensor value_graph, torch::Tensor bounds,
                                 int nrows, int segments) {
-    auto a = input_dense1.contiguous();
-    auto b = input_dense2.contiguous();
-    const int64_t dcols = a.numel() / nrows;
-    auto out = torch::empty({columns_graph.numel()}, gala_b200::out_options(input_dense1));
-    gala_graph_t g = gala_b200::make_graph(offset_graph, columns_graph, bounds, segments, nrows);
-    gala_b200::check(gala_sddmm_f32(&g, a.data_ptr<float>(), b.data_ptr<float>(), (int)dcols, out.data_ptr<float>(),
-                                    gala_b200::plan_for(g, input_dense1), gala_b200::stream()),
-                     "gala_sddmm_f32");
-    return out;
+    return gala_b200::edge_sddmm_impl(input_dense1, input_dense2, offset_graph, columns_graph, bounds, nrows, segments);
 }
 
 inline torch::Tensor aggregate_edge_mul(torch::Tensor input_dense1, torch::Tensor input_dense2,
@@ -220,3 +231,52 @@ inline torch::Tensor aggregate_edge_mul_dir(torch::Tensor input_dense1, torch::T
     return gala_b200_sddvv(input_dense1, input_dense2, offset_graph, columns_graph, torch::Tensor(), global_nrows, 1,
                            GALA_SDDVV_MUL);
 }
+
+// ---- one GAT layer as ONE autograd node -------------------------------------------------------
+// The retargeted generator replaces the emitted sequence
+//     attn = aggregate_edge_sum_AutoGrad::apply(attenL, attenR, li);        (common.h:630-675)
+//     attn = leaky_relu->forward(attn);                                     (common.h:1176-1184)
+//     attn = non_lnr_op_softmax_AutoGrad::apply(attn, li);                  (common.h:735-810)
+//     res  = aggregate_node_mul_sum_*_AutoGrad::apply(res, attn, li);       (common.h:835-894)
+// by  res = gala_b200::gat_layer_AutoGrad::apply(res, attenL, attenR, li, slope)  whenever all four use
+// the same graph slot.  Forward: the fused kernel (alpha kept for the backward).  Backward: the same
+// values autograd would produce for the four nodes, graph slots as the emitted backward methods pick them:
+//   d res    = aggregate(dZ) over slot 2li+1 with alpha, bounds/segments of slot 2li   (common.h:876-889)
+//   d alpha  = edge_sddmm(dZ, res) over the same                                        (common.h:886-888)
+//   d attenL = d attenR = row sums of LeakyReLU'(.) * softmax-backward(d alpha) over slot 2li+1
+//              (common.h:791-799 and 654-670: one node_spmv result returned for both inputs)
+namespace gala_b200 {
+class gat_layer_AutoGrad : public torch::autograd::Function<gat_layer_AutoGrad> {
+public:
+    static torch::Tensor forward(torch::autograd::AutogradContext* ctx, torch::Tensor res, torch::Tensor attenL,
+                                 torch::Tensor attenR, int64_t li, double slope) {
+        ctx->saved_data["li"] = li;
+        ctx->saved_data["slope"] = slope;
+        torch::Tensor alpha;
+        torch::Tensor Y = gat_forward(res, attenL, attenR, global_offset_graph[2 * li], global_columns_graph[2 * li],
+                                      global_bounds[2 * li], global_segments[2 * li], (float)slope, false, &alpha);
+        ctx->save_for_backward({alpha, res, attenL, attenR});
+        return Y;
+    }
+
+    static torch::autograd::tensor_list backward(torch::autograd::AutogradContext* ctx,
+                                                 torch::autograd::tensor_list grad_outputs) {
+        torch::Tensor dZ = grad_outputs[0].contiguous();
+        auto saved = ctx->get_saved_variables();
+        torch::Tensor alpha = saved[0], X = saved[1].contiguous();
+        torch::Tensor aL = saved[2].contiguous(), aR = saved[3].contiguous();
+        const int64_t li = ctx->saved_data["li"].toInt();
+        const float slope = (float)ctx->saved_data["slope"].toDouble();
+        torch::Tensor off_b = global_offset_graph[2 * li + 1], col_b = global_columns_graph[2 * li + 1];
+        torch::Tensor dX = aggregate(dZ, off_b, col_b, alpha, global_bounds[2 * li], global_segments[2 * li], true, 0);
+        torch::Tensor dalpha = edge_sddmm_impl(dZ, X, off_b, col_b, global_bounds[2 * li], global_nrows,
+                                               global_segments[2 * li]);
+        gala_graph_t g = make_graph(off_b, col_b, global_bounds[2 * li + 1], global_segments[2 * li + 1], global_nrows);
+        torch::Tensor d_att = torch::empty({(int64_t)global_nrows, 1}, out_options(dZ));
+        check(gala_gat_backward_att_f32(&g, alpha.data_ptr<float>(), dalpha.data_ptr<float>(), aL.data_ptr<float>(),
+                                        aR.data_ptr<float>(), slope, d_att.data_ptr<float>(), plan_for(g, dZ), stream()),
+              "gala_gat_backward_att_f32");
+        return {dX, d_att, d_att, torch::Tensor(), torch::Tensor()};
+    }
+};
+}  // namespace gala_b200

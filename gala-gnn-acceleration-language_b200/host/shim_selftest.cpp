@@ -138,6 +138,34 @@ int main() {
     torch::Tensor dd_want = (dZ.to(torch::kDouble).index({r64}) * Xd.index({c64})).sum(1);
     expect_close("edge_sddmm", dd, dd_want, 1e-5);
 
+    // ---- gat_layer_AutoGrad: one node == the four emitted nodes, forward and backward ----------
+    // slot 1 = backward graph of slot 0; for undirected inputs the generated main pushes the same
+    // tensors twice (cuda.h:1129-1138)
+    global_offset_graph.push_back(t_off);
+    global_columns_graph.push_back(t_col);
+    global_value_graph.push_back(t_val);
+    global_bounds.push_back(t_bnd);
+    global_segments.push_back(S);
+    {
+        torch::Tensor Xg = X.clone().requires_grad_(true), aLg = aL.clone().requires_grad_(true),
+                      aRg = aR.clone().requires_grad_(true);
+        torch::Tensor Yf = gala_b200::gat_layer_AutoGrad::apply(Xg, aLg, aRg, 0, 0.2);
+        expect_close("gat_layer_AutoGrad forward", Yf, A_att.mm(Xd), 1e-5);
+        Yf.backward(dZ);
+        // what autograd evaluates for the emitted chain (common.h:654-670, 791-799, 876-889), op by op
+        torch::Tensor dX_w = aggregate_node_mul_sum_coarse2_call(dZ, t_off, t_col, alpha, t_bnd, S);
+        torch::Tensor da_w = edge_sddmm(dZ, X, t_off, t_col, alpha, t_bnd, global_nrows, S);
+        torch::Tensor sds = alpha * da_w;
+        torch::Tensor accum = node_spmv_backward_of_sddmm_nln(t_off, t_col, sds, t_bnd, global_nrows, S);
+        torch::Tensor sm = sds - inplace_softmax_sddvv_mult(accum, t_off, t_col, alpha.clone(), t_bnd, global_nrows, S);
+        torch::Tensor pre = edge_sddvv(aL, aR, t_off, t_col, t_val, t_bnd, N, S);
+        torch::Tensor de = torch::where(pre > 0, sm, sm * 0.2);
+        torch::Tensor datt_w = node_spmv_backward_of_sddmm_eaggr(t_off, t_col, de, t_bnd, global_nrows, S);
+        expect_close("gat_layer_AutoGrad d(res)", Xg.grad(), dX_w, 1e-6);
+        expect_close("gat_layer_AutoGrad d(attenL)", aLg.grad(), datt_w, 2e-4);   // cancelling row sums
+        expect_close("gat_layer_AutoGrad d(attenR)", aRg.grad(), datt_w, 2e-4);
+    }
+
     torch::Tensor norm = torch::pow(deg, -0.5);
     torch::Tensor ev = aggregate_edge_mul(norm, norm, t_off, t_col, t_val, t_bnd, S);
     expect_close("aggregate_edge_mul", ev, norm.index({r64, 0}) * norm.index({c64, 0}), 1e-6);

@@ -161,6 +161,16 @@ int gala_sddvv_f32(const gala_graph_t *g, const float *A, const float *B, float 
 int gala_sddmm_f32(const gala_graph_t *g, const float *A, const float *B, int32_t K, float *out,
                    const gala_plan_t *plan, gala_stream_t stream);
 
+/* The edge side of one GAT layer's backward as autograd runs it in the generated    */
+/* program, in one kernel and without E-sized temporaries: softmax backward            */
+/* (common.h:791-799), LeakyReLU backward, and the row sum the edge-sum backward         */
+/* returns for BOTH attention inputs (common.h:630-675, node_spmv_backward_of_sddmm_eaggr): */
+/*   ds = alpha*dalpha - alpha*(S*1e-12 + sum_row alpha*dalpha)                          */
+/*   d_att[i] = S*1e-12 + sum_{e in row i} ds[e] * (aL[i] + aR[col[e]] > 0 ? 1 : slope)  */
+int gala_gat_backward_att_f32(const gala_graph_t *g, const float *alpha, const float *dalpha,
+                              const float *aL, const float *aR, float slope, float *d_att,
+                              const gala_plan_t *plan, gala_stream_t stream);
+
 /* Replaces the 5-pass forward of non_lnr_op_softmax_AutoGrad (common.h:760-773): */
 /* alpha[e] = clamp(exp(x[e]),0,1e12) / (S*1e-12 + sum_row clamp(exp(x))).        */
 /* x and alpha may alias.  recip (nullable, [nrows]) receives 1/rowsum.           */

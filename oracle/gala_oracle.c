@@ -513,6 +513,27 @@ ORC_API void orc_mask_next(int nrows, const int *offset, const int *ids, const u
     orc_gspmm_max_u8(nrows, offset, ids, mask, next_mask);
 }
 
+/* Edge side of the GAT layer backward as the generated program's autograd graph     */
+/* evaluates it: non_lnr_op_softmax_AutoGrad::backward (common.h:791-799), LeakyReLU  */
+/* backward (x > 0 ? g : g*slope, ATen), aggregate_edge_sum_AutoGrad::backward         */
+/* (common.h:630-675: one row sum, returned for both attention inputs).  Composition   */
+/* of the restated kernels above; d_att[nrows].                                        */
+ORC_API void orc_gat_backward_att_tiled(int nrows, int S, const int *offsets, const int *cols,
+                                        const int *bounds, int64_t nvals, const float *alpha,
+                                        const float *dalpha, const float *aL, const float *aR,
+                                        float slope, float *d_att) {
+    size_t n = (size_t)(nvals > 0 ? nvals : 1);
+    float *ds = (float *)malloc(n * sizeof(float));
+    float *pre = (float *)malloc(n * sizeof(float));
+    orc_edge_softmax_bwd_tiled(nrows, S, offsets, bounds, nvals, alpha, dalpha, ds);
+    orc_sddvv_add_tiled(nrows, S, offsets, cols, bounds, aL, aR, pre);
+    for (int64_t e = 0; e < nvals; e++) ds[e] = pre[e] > 0.0f ? ds[e] : ds[e] * slope;
+    memset(d_att, 0, (size_t)nrows * sizeof(float));     /* the row-sum kernel accumulates (caller zeroes) */
+    orc_edge_rowsum_tiled(nrows, S, offsets, ds, bounds, d_att);
+    free(ds);
+    free(pre);
+}
+
 /* ------------------------------------------------------------------------- */
 /* Reordering (src/ops/reordering.h).                                         */
 /* ------------------------------------------------------------------------- */

@@ -191,6 +191,15 @@ def edge_softmax_bwd(g, alpha, dalpha):
     return out
 
 
+def gat_backward_att(g, alpha, dalpha, aL, aR, slope=0.2):
+    out = np.zeros(g.nrows, np.float32)
+    lib().orc_gat_backward_att_tiled(C.c_int(g.nrows), C.c_int(g.S), g.offsets.ctypes, g.cols.ctypes,
+                                     g.bounds.ctypes, C.c_int64(g.nvals), _c(alpha, np.float32).ctypes,
+                                     _c(dalpha, np.float32).ctypes, _c(aL, np.float32).ctypes,
+                                     _c(aR, np.float32).ctypes, C.c_float(slope), out.ctypes)
+    return out
+
+
 def gat_forward(g, aL, aR, X, slope=0.2):
     X = _c(X, np.float32)
     K = X.shape[1]

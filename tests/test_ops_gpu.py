@@ -172,6 +172,14 @@ def test_edge_kernels_match_oracle(orc, case):
     got_b = ops.edge_softmax_bwd(g, dev(want), dev(da)).cpu().numpy()
     want_b = orc.edge_softmax_bwd(t, want, da)
     assert rel_err(got_b, want_b) < FP32_TOL
+    # edge side of the GAT layer backward in one kernel (softmax bwd + LeakyReLU bwd + row sum)
+    aL = rng.normal(size=n).astype(np.float32)
+    aR = rng.normal(size=n).astype(np.float32)
+    got_g = ops.gat_backward_att(g, dev(want), dev(da), dev(aL), dev(aR), 0.2).cpu().numpy().ravel()
+    want_g = orc.gat_backward_att(t, want, da, aL, aR, 0.2)
+    mag = orc.edge_rowsum(t, np.abs(want_b))          # the row sums cancel: bound by the summed magnitudes
+    assert np.all(np.abs(got_g - want_g) <= 4e-6 * mag + 1e-10)
+    assert rel_err(got_g, want_g) < 20 * FP32_TOL
     # in place (x aliases alpha), as the generated code does with val_exp
     xi = dev(x.copy())
     ops.edge_softmax_fwd(g, xi, out=xi)
