@@ -121,6 +121,22 @@ def gat2_forward_partitioned_dot(model, part, X_local, aggregate_dot, hook=None)
     return F.linear(agg, *model.fc1)
 
 
+def gatn_forward_partitioned(model, part, X_local, aggregate, hook=None):
+    """L-layer GAT (gat_model.GATN) on a row partition, all-gather exchange: per hidden layer the rank
+    transforms its own rows and exchanges the hidden-width result; the last hidden output is exchanged
+    once more for the final aggregation.  aggregate(aL_local, aR_all, feats_all, relu) as above."""
+    run = hook if hook is not None else (lambda name, fn: fn())
+    res_loc = X_local
+    for i in range(model.L - 1):
+        t_all = part.all_gather(F.linear(res_loc, *model.fc[i]))
+        a = F.linear(t_all, model.W_att[i], model.b_att[i]).t().contiguous()
+        res_loc = run(f"gat_layer{i + 1}", lambda: aggregate(part.local_slice(a[0]), a[1], t_all, True))
+    y_all = part.all_gather(res_loc)
+    a = F.linear(y_all, model.W_att[-1], model.b_att[-1]).t().contiguous()
+    agg = run(f"gat_layer{model.L}", lambda: aggregate(part.local_slice(a[0]), a[1], y_all, False))
+    return F.linear(agg, *model.fc[-1])
+
+
 class PeerExchange:
     """Symmetric (peer-mapped) gathered buffers: every rank's kernels push their output rows
     straight into all GPUs' copies while they compute (NVLS multicast store when the fabric
@@ -212,3 +228,47 @@ class PartitionedGAT:
         if mode in ("folded", "fused"):   # the row-partitioned runner has no separate fused variant
             return gat2_forward_partitioned_folded(self.model, self.part, X_local, self._aggregate, hook)
         return gat2_forward_partitioned(self.model, self.part, X_local, self._aggregate, hook)
+
+
+class PartitionedGATN:
+    """L-layer runner (gat_model.GATN).  `part` is any object with RowPartition's interface, so that a
+    rank can build its slab without ever holding the whole graph."""
+
+    def __init__(self, model, part, device, exchange="p2p"):
+        from . import ops
+
+        self.model, self.ops, self.part = model, ops, part
+        self.graph = ops.TiledGraph(part.offset, part.cols, part.rows, ncols=part.padded_n).build_plan()
+        self.px = None
+        self.exchange = "nccl"
+        if exchange == "p2p":
+            self.px = PeerExchange(part, [model.dims[i + 1] for i in range(model.L - 1)] + [model.dims[-2]], device)
+            self.exchange = "p2p-multicast" if self.px.mos[0].multicast_base else "p2p"
+
+    def _aggregate(self, aL, aR, feats, relu):
+        return self.ops.gat_forward(self.graph, aL.contiguous(), aR.contiguous(), feats, self.model.slope, relu=relu)
+
+    def forward(self, X_local, hook=None):
+        m, px, part, ops = self.model, self.px, self.part, self.ops
+        if px is None:
+            return gatn_forward_partitioned(m, part, X_local, self._aggregate, hook)
+        run = hook if hook is not None else (lambda name, fn: fn())
+        res_loc = X_local
+        L = m.L
+        for i in range(L - 1):
+            # the transform pushes its rows to every GPU while it computes
+            run(f"linear{i + 1}", lambda: ops.linear(res_loc, m.fc[i][0], m.fc[i][1], multi_out=px.mos[i]))
+            px.barrier(i)
+            t_all = px.bufs[i]
+            a = F.linear(t_all, m.W_att[i], m.b_att[i]).t().contiguous()
+            last_hidden = i == L - 2
+            out = run(f"gat_layer{i + 1}", lambda: ops.gat_forward_ex(
+                self.graph, part.local_slice(a[0]).contiguous(), a[1], t_all, m.slope, relu=True,
+                multi_out=px.mos[L - 1] if last_hidden else None))
+            res_loc = out[0]
+        px.barrier(L - 1)
+        y_all = px.bufs[L - 1]
+        a = F.linear(y_all, m.W_att[-1], m.b_att[-1]).t().contiguous()
+        agg = run(f"gat_layer{L}", lambda: ops.gat_forward(self.graph, part.local_slice(a[0]).contiguous(), a[1], y_all,
+                                                           m.slope, relu=False))
+        return F.linear(agg, *m.fc[-1])

@@ -113,3 +113,61 @@ class GAT2:
         aL, aR = self.attention_inputs(t, self.efc2, self.efc3)
         agg = run("gat_layer2", lambda: ops.gat_forward(g, aL, aR, res, self.slope, relu=False))
         return F.linear(agg, *self.fc1)
+
+
+class GATN:
+    """L-layer GAT in the shape GALA emits for deeper programs (BASELINE.json configs[4]: 3 layers on the
+    Papers shape): hidden layers are  t = fc_i(res); res = relu(attention_i(t) @ t)  and the last layer uses
+    the FFN-recompute rewrite (middle-end.h:324-375) as GAT2 does: logits from fc_L(res), aggregation at the
+    hidden width, fc_L applied after it.  dims = [feats, hidden, ..., hidden, classes]."""
+
+    def __init__(self, dims, device, seed=0):
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        self.dims = list(dims)
+        self.L = len(dims) - 1
+        self.fc = [_linear_init(gen, dims[i + 1], dims[i], device) for i in range(self.L)]
+        self.efcL = [_linear_init(gen, 1, dims[i + 1], device) for i in range(self.L)]
+        self.efcR = [_linear_init(gen, 1, dims[i + 1], device) for i in range(self.L)]
+        self.slope = 0.2
+        # [2, width] attention projections per layer; the last one folded through fc_L
+        self.W_att, self.b_att = [], []
+        for i in range(self.L - 1):
+            self.W_att.append(torch.cat([self.efcL[i][0], self.efcR[i][0]], 0).contiguous())
+            self.b_att.append(torch.cat([self.efcL[i][1], self.efcR[i][1]], 0).contiguous())
+        W, b = self.fc[-1]
+        wl, wr = self.efcL[-1][0] @ W, self.efcR[-1][0] @ W
+        self.W_att.append(torch.cat([wl, wr], 0).contiguous())
+        self.b_att.append(torch.cat([self.efcL[-1][0] @ b + self.efcL[-1][1],
+                                     self.efcR[-1][0] @ b + self.efcR[-1][1]], 0).contiguous())
+
+    def forward_literal(self, g, X):
+        """Op by op (one Linear per projection, logits of the last layer from fc_L(res))."""
+        res = X
+        for i in range(self.L - 1):
+            t = F.linear(res, *self.fc[i])
+            aL = F.linear(t, *self.efcL[i]).reshape(-1)
+            aR = F.linear(t, *self.efcR[i]).reshape(-1)
+            res = ops.gat_forward(g, aL, aR, t, self.slope, relu=True)
+        t = F.linear(res, *self.fc[-1])
+        aL = F.linear(t, *self.efcL[-1]).reshape(-1)
+        aR = F.linear(t, *self.efcR[-1]).reshape(-1)
+        agg = ops.gat_forward(g, aL, aR, res, self.slope, relu=False)
+        return F.linear(agg, *self.fc[-1])
+
+    def forward(self, g, X, hook=None):
+        """Own kernels for the transforms (tcgen05 + folded projections in its epilogue)."""
+        run = hook if hook is not None else (lambda name, fn: fn())
+        res = X
+        for i in range(self.L - 1):
+            bh = [float(v) for v in self.b_att[i]] if not hasattr(self, "_bh") else self._bh[i]
+            t, a = run(f"linear{i + 1}", lambda: ops.linear(res, self.fc[i][0], self.fc[i][1], att_w=self.W_att[i], att_b=bh))
+            res = run(f"gat_layer{i + 1}", lambda: ops.gat_forward(g, a[0], a[1], t, self.slope, relu=True))
+        a = F.linear(res, self.W_att[-1], self.b_att[-1]).t().contiguous()
+        agg = run(f"gat_layer{self.L}", lambda: ops.gat_forward(g, a[0], a[1], res, self.slope, relu=False))
+        return F.linear(agg, *self.fc[-1])
+
+    def host_biases(self):
+        """Reads the folded biases back once (outside any timed step)."""
+        self._bh = [[float(v) for v in b] for b in self.b_att]
+        return self

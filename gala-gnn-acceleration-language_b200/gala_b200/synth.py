@@ -110,3 +110,28 @@ def powerlaw_csr_torch(n, n_edges, seed=0, gamma=0.85, shift=None, device="cuda"
     offset = torch.zeros(n + 1, dtype=torch.int32, device=device)
     offset[1:] = torch.cumsum(counts, 0).to(torch.int32)
     return offset, ids
+
+
+def powerlaw_multigraph_coo_torch(n, n_edges, seed=0, gamma=0.85, device="cuda", chunk=200_000_000):
+    """Papers-scale variant: directed power-law multigraph (both endpoints drawn from the same rank
+    distribution as above, node ids permuted; duplicates and self-loops kept, no symmetrisation -- at
+    1.6 G edges torch.unique would need ~3x the memory, and CSRCMatrix::build keeps duplicates anyway).
+    Returns unsorted (rows int32[E], cols int32[E]); deterministic in (n, n_edges, seed)."""
+    import torch
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    i = torch.arange(n, dtype=torch.float64, device=device)
+    w = (i + max(1.0, n / 500.0)) ** (-gamma)
+    cdf = torch.cumsum(w / w.sum(), 0)
+    del i, w
+    perm = torch.randperm(n, generator=gen, device=device, dtype=torch.int32)
+    rows = torch.empty(n_edges, dtype=torch.int32, device=device)
+    cols = torch.empty(n_edges, dtype=torch.int32, device=device)
+    for lo in range(0, n_edges, chunk):
+        m = min(chunk, n_edges - lo)
+        for dst in (rows, cols):
+            u = torch.searchsorted(cdf, torch.rand(m, generator=gen, device=device, dtype=torch.float64)).clamp_(max=n - 1)
+            dst[lo:lo + m] = perm[u]
+            del u
+    return rows, cols

@@ -1,0 +1,111 @@
+"""BASELINE.json configs[4]: 3-layer GAT, 1-D row-partitioned, on the ogbn-papers100M shape
+(111 059 956 nodes, 1 615 685 872 edges, 128 feats, hidden 32, 172 classes) at N = 1/2/4/8 B200.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \\
+           --master-port 29544 profiles/papers_partitioned_bench.py [scale]
+
+Every rank synthesises the same seeded COO, builds the CSR on its GPU (gala_csr_from_coo) and keeps the
+slab of its rows (nnz-balanced).  Phase 1 checks the partitioned forward against the single-GPU op-by-op
+forward on a small graph; phase 2 times the Papers-shape forward (CUDA events, max over ranks) with the
+exchange fused into the kernels (multimem / peer stores) and with NCCL all-gather."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gala-gnn-acceleration-language_b200"))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from gala_b200 import dist_gat, formats, ops, synth  # noqa: E402
+from gala_b200.gat_model import GATN  # noqa: E402
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = f"cuda:{local}"
+dist.init_process_group("nccl", device_id=torch.device(dev))
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+
+
+def say(*a):
+    if rank == 0:
+        print(*a, flush=True)
+
+
+def max_over_ranks(ms):
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+def timed(fn, steps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    return max_over_ranks(a.elapsed_time(b) / steps)
+
+
+def build(n, e, seed):
+    rows, cols = synth.powerlaw_multigraph_coo_torch(n, e, seed=seed, device=dev)
+    offset, ids, _ = formats.csr_build(n, n, rows, cols)
+    del rows, cols
+    torch.cuda.empty_cache()
+    return offset, ids
+
+
+# ---- phase 1: parity on a small graph --------------------------------------------------------------
+n, e, dims = 60000, 4_000_000, [64, 32, 32, 41]
+offset, ids = build(n, e, 3)
+model = GATN(dims, dev, seed=0).host_biases()
+X = torch.rand(n, dims[0], generator=torch.Generator(device=dev).manual_seed(1), device=dev) - 0.5
+want = model.forward_literal(ops.TiledGraph(offset, ids, n).build_plan(), X)
+worst = 0.0
+for exchange in (("nccl", "p2p") if world > 1 else ("nccl",)):
+    part = dist_gat.RowPartition(offset, ids, n, rank, world)
+    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange)
+    for _ in range(3):
+        out_loc = runner.forward(X[part.row_lo:part.row_hi].contiguous())
+    full = part.unpad(part.all_gather(out_loc))
+    err = float((full - want).double().norm() / want.double().norm())
+    worst = max(worst, err)
+    say(f"parity [{runner.exchange}] 3-layer GAT on {world} rank(s): rel err {err:.2e}")
+    del runner, part
+assert worst < 1e-5
+del offset, ids, X, want, full, out_loc
+torch.cuda.empty_cache()
+
+# ---- phase 2: Papers shape --------------------------------------------------------------------------
+n, e, feats, hidden, classes = synth.SHAPES["papers"]
+n, e = int(n * scale), int(e * scale)
+dims = [feats, hidden, hidden, classes]
+offset, ids = build(n, e, 0)
+part = dist_gat.RowPartition(offset, ids, n, rank, world)
+del ids
+torch.cuda.empty_cache()
+model = GATN(dims, dev, seed=0).host_biases()
+X_loc = torch.rand(part.rows, feats, device=dev) - 0.5
+say(f"papers shape x{scale}: n={n} E={e}; rank 0 holds rows [{part.row_lo},{part.row_hi}) nnz {part.local_nvals}")
+res = {"workload": f"3-layer GAT forward, papers100M shape x{scale}", "n_gpus": world, "nodes": n, "edges": e}
+for exchange in (("p2p", "nccl") if world > 1 else ("nccl",)):
+    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange)
+    ms = timed(lambda: runner.forward(X_loc))
+    res[f"ms_{runner.exchange}"] = round(ms, 3)
+    say(f"  [{runner.exchange}] forward {ms:.2f} ms (max over {world} ranks)")
+    del runner
+    torch.cuda.empty_cache()
+say(json.dumps(res))
+if rank == 0:
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"papers_partitioned_n{world}.json"), "w") as f:
+        json.dump(res, f)
+torch.cuda.synchronize()
+dist.barrier()
+os._exit(0)

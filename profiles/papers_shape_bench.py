@@ -38,21 +38,7 @@ def timed(fn, reps=3, warm=1):
 gen = torch.Generator(device=dev)
 gen.manual_seed(0)
 t0 = time.time()
-i = torch.arange(n, dtype=torch.float64, device=dev)
-w = (i + n / 500.0) ** (-0.85)
-cdf = torch.cumsum(w / w.sum(), 0)
-del i, w
-perm = torch.randperm(n, generator=gen, device=dev, dtype=torch.int32)
-rows = torch.empty(e_total, dtype=torch.int32, device=dev)
-cols = torch.empty(e_total, dtype=torch.int32, device=dev)
-CH = 200_000_000
-for lo in range(0, e_total, CH):
-    m = min(CH, e_total - lo)
-    for dst in (rows, cols):
-        u = torch.searchsorted(cdf, torch.rand(m, generator=gen, device=dev, dtype=torch.float64)).clamp_(max=n - 1)
-        dst[lo:lo + m] = perm[u]
-        del u
-del cdf, perm
+rows, cols = synth.powerlaw_multigraph_coo_torch(n, e_total, seed=0, device=dev)
 torch.cuda.synchronize()
 print(f"papers shape: n={n} E={e_total}  COO synthesised in {time.time() - t0:.1f} s", flush=True)
 

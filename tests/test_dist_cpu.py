@@ -102,3 +102,55 @@ def test_two_rank_gloo_forward_matches_single_process(orc, tmp_path):
     a2 = agg(F.linear(tt, *model.efc2).reshape(-1), F.linear(tt, *model.efc3).reshape(-1), y, False)
     want = F.linear(a2, *model.fc1).numpy()
     assert rel_err(got, want) < 1e-5
+
+
+def _worker_deep(rank, world, port, n, e, dims, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import orc
+    from gala_b200.gat_model import GATN
+
+    torch.set_num_threads(2)
+    offset, ids = synth.powerlaw_csr_torch(n, e, seed=5, device="cpu")
+    model = GATN(dims, "cpu", seed=4)
+    X = torch.rand(n, dims[0], generator=torch.Generator().manual_seed(6)) - 0.5
+    part = dist_gat.RowPartition(offset, ids, n, rank, world)
+    out_loc = dist_gat.gatn_forward_partitioned(model, part, X[part.row_lo:part.row_hi], _oracle_aggregate(orc, part))
+    gathered = part.unpad(part.all_gather(out_loc))
+    if rank == 0:
+        np.save(out_path, gathered.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_three_layer_gat_two_ranks_matches_dense_reference(orc, tmp_path):
+    """BASELINE.json configs[4] in miniature: 3-layer GAT, 1-D row partition, one exchange per layer --
+    against a dense fp64 evaluation of the same model."""
+    import torch.nn.functional as F
+    from gala_b200.gat_model import GATN
+
+    n, e, dims = 400, 5000, [10, 8, 8, 6]
+    out_path = str(tmp_path / "deep_out.npy")
+    mp.spawn(_worker_deep, args=(2, _free_port(), n, e, dims, out_path), nprocs=2, join=True)
+    got = np.load(out_path)
+    offset, ids = synth.powerlaw_csr_torch(n, e, seed=5, device="cpu")
+    model = GATN(dims, "cpu", seed=4)
+    X = (torch.rand(n, dims[0], generator=torch.Generator().manual_seed(6)) - 0.5).double()
+    A = torch.zeros(n, n, dtype=torch.bool)
+    rows = torch.repeat_interleave(torch.arange(n), (offset[1:] - offset[:-1]).long())
+    A[rows, ids.long()] = True
+
+    def lin(x, wb):
+        return F.linear(x, wb[0].double(), wb[1].double())
+
+    def attend(aL, aR, feats):
+        s = F.leaky_relu(aL[:, None] + aR[None, :], 0.2).exp().masked_fill(~A, 0.0)
+        return (s / s.sum(1, keepdim=True)) @ feats
+
+    res = X
+    for i in range(model.L - 1):
+        t = lin(res, model.fc[i])
+        res = torch.relu(attend(lin(t, model.efcL[i]).reshape(-1), lin(t, model.efcR[i]).reshape(-1), t))
+    t = lin(res, model.fc[-1])
+    want = lin(attend(lin(t, model.efcL[-1]).reshape(-1), lin(t, model.efcR[-1]).reshape(-1), res), model.fc[-1])
+    assert rel_err(got, want.float().numpy()) < 1e-5
