@@ -121,21 +121,40 @@ def gat2_forward_partitioned_dot(model, part, X_local, aggregate_dot, hook=None)
     return F.linear(agg, *model.fc1)
 
 
-def gatn_forward_partitioned(model, part, X_local, aggregate, hook=None):
-    """L-layer GAT (gat_model.GATN) on a row partition, all-gather exchange: per hidden layer the rank
-    transforms its own rows and exchanges the hidden-width result; the last hidden output is exchanged
-    once more for the final aggregation.  aggregate(aL_local, aR_all, feats_all, relu) as above."""
+def gatn_forward_partitioned(model, part, X_local, aggregate, hook=None, linear_att=None, aggregate_att=None):
+    """L-layer GAT (gat_model.GATN) on a row partition, all-gather exchange.  Per hidden layer the rank
+    transforms its OWN rows and projects them onto the two attention vectors; the hidden-width rows and the
+    one right-hand attention scalar per row are what is exchanged (nothing is recomputed on gathered rows).
+    The last hidden output is exchanged once more for the final aggregation.
+      aggregate(aL_local, aR_all, feats_all, relu) -> [rows, K]
+      linear_att(res_local, i) -> (t_local [rows, K], att [2, rows])          default: F.linear
+      aggregate_att(aL, aR_all, feats_all) -> (y_local, att_next [2, rows])    last hidden layer; default composes"""
     run = hook if hook is not None else (lambda name, fn: fn())
-    res_loc = X_local
-    for i in range(model.L - 1):
-        t_all = part.all_gather(F.linear(res_loc, *model.fc[i]))
-        a = F.linear(t_all, model.W_att[i], model.b_att[i]).t().contiguous()
-        res_loc = run(f"gat_layer{i + 1}", lambda: aggregate(part.local_slice(a[0]), a[1], t_all, True))
-    y_all = part.all_gather(res_loc)
-    a = F.linear(y_all, model.W_att[-1], model.b_att[-1]).t().contiguous()
-    agg = run(f"gat_layer{model.L}", lambda: aggregate(part.local_slice(a[0]), a[1], y_all, False))
-    return F.linear(agg, *model.fc[-1])
 
+    def gather_vec(v):
+        return part.all_gather(v.reshape(-1, 1)).reshape(-1)
+
+    def default_linear_att(res_loc, i):
+        t = F.linear(res_loc, *model.fc[i])
+        return t, F.linear(t, model.W_att[i], model.b_att[i]).t().contiguous()
+
+    def default_aggregate_att(aL, aR_all, feats_all):
+        y = aggregate(aL, aR_all, feats_all, True)
+        return y, F.linear(y, model.W_att[-1], model.b_att[-1]).t().contiguous()
+
+    linear_att = linear_att or default_linear_att
+    aggregate_att = aggregate_att or default_aggregate_att
+    res_loc, att = X_local, None
+    for i in range(model.L - 1):
+        t_loc, a = run(f"linear{i + 1}", lambda: linear_att(res_loc, i))
+        t_all, aR_all = part.all_gather(t_loc), gather_vec(a[1])
+        if i == model.L - 2:
+            res_loc, att = run(f"gat_layer{i + 1}", lambda: aggregate_att(a[0], aR_all, t_all))
+        else:
+            res_loc = run(f"gat_layer{i + 1}", lambda: aggregate(a[0], aR_all, t_all, True))
+    y_all, aR_all = part.all_gather(res_loc), gather_vec(att[1])
+    agg = run(f"gat_layer{model.L}", lambda: aggregate(att[0], aR_all, y_all, False))
+    return F.linear(agg, *model.fc[-1])
 
 class PeerExchange:
     """Symmetric (peer-mapped) gathered buffers: every rank's kernels push their output rows
@@ -248,27 +267,52 @@ class PartitionedGATN:
     def _aggregate(self, aL, aR, feats, relu):
         return self.ops.gat_forward(self.graph, aL.contiguous(), aR.contiguous(), feats, self.model.slope, relu=relu)
 
-    def forward(self, X_local, hook=None):
+    def forward(self, X_local, hook=None, mark=None):
+        """mark(name), if given, is called at every phase boundary (bench scripts record an event there)."""
         m, px, part, ops = self.model, self.px, self.part, self.ops
-        if px is None:
-            return gatn_forward_partitioned(m, part, X_local, self._aggregate, hook)
-        run = hook if hook is not None else (lambda name, fn: fn())
-        res_loc = X_local
+        mark = mark if mark is not None else (lambda name: None)
+        if not hasattr(m, "_bh"):
+            m.host_biases()
+        bh = m._bh
         L = m.L
+        if px is None:
+            def linear_att(res_loc, i):
+                return ops.linear(res_loc, m.fc[i][0], m.fc[i][1], att_w=m.W_att[i], att_b=bh[i])
+
+            def aggregate_att(aL, aR_all, feats_all):
+                y, att, _ = ops.gat_forward_ex(self.graph, aL, aR_all, feats_all, m.slope, relu=True,
+                                               att_w=m.W_att[-1], att_b=bh[-1])
+                return y, att
+            return gatn_forward_partitioned(m, part, X_local, self._aggregate, hook, linear_att, aggregate_att)
+        run = hook if hook is not None else (lambda name, fn: fn())
+
+        def gather_vec(v):
+            return part.all_gather(v.reshape(-1, 1)).reshape(-1)
+
+        res_loc, att = X_local, None
         for i in range(L - 1):
-            # the transform pushes its rows to every GPU while it computes
-            run(f"linear{i + 1}", lambda: ops.linear(res_loc, m.fc[i][0], m.fc[i][1], multi_out=px.mos[i]))
+            # the transform pushes its rows to every GPU while it computes and projects them onto the
+            # attention vectors; only the right-hand scalar per row goes through a (small) all-gather
+            _, a = run(f"linear{i + 1}", lambda: ops.linear(res_loc, m.fc[i][0], m.fc[i][1], att_w=m.W_att[i],
+                                                            att_b=bh[i], multi_out=px.mos[i]))
+            mark(f"linear{i + 1}+push")
+            aR_all = gather_vec(a[1])
             px.barrier(i)
-            t_all = px.bufs[i]
-            a = F.linear(t_all, m.W_att[i], m.b_att[i]).t().contiguous()
-            last_hidden = i == L - 2
-            out = run(f"gat_layer{i + 1}", lambda: ops.gat_forward_ex(
-                self.graph, part.local_slice(a[0]).contiguous(), a[1], t_all, m.slope, relu=True,
-                multi_out=px.mos[L - 1] if last_hidden else None))
-            res_loc = out[0]
+            mark(f"exchange{i + 1}")
+            if i == L - 2:
+                _, att, _ = run(f"gat_layer{i + 1}", lambda: ops.gat_forward_ex(
+                    self.graph, a[0], aR_all, px.bufs[i], m.slope, relu=True, att_w=m.W_att[-1], att_b=bh[-1],
+                    multi_out=px.mos[L - 1]))
+                mark(f"gat_layer{i + 1}+push")
+            else:
+                res_loc = run(f"gat_layer{i + 1}", lambda: ops.gat_forward(self.graph, a[0], aR_all, px.bufs[i],
+                                                                           m.slope, relu=True))
+                mark(f"gat_layer{i + 1}")
+        aR_all = gather_vec(att[1])
         px.barrier(L - 1)
-        y_all = px.bufs[L - 1]
-        a = F.linear(y_all, m.W_att[-1], m.b_att[-1]).t().contiguous()
-        agg = run(f"gat_layer{L}", lambda: ops.gat_forward(self.graph, part.local_slice(a[0]).contiguous(), a[1], y_all,
-                                                           m.slope, relu=False))
-        return F.linear(agg, *m.fc[-1])
+        mark(f"exchange{L}")
+        agg = run(f"gat_layer{L}", lambda: ops.gat_forward(self.graph, att[0], aR_all, px.bufs[L - 1], m.slope, relu=False))
+        mark(f"gat_layer{L}")
+        out = F.linear(agg, *m.fc[-1])
+        mark("classifier")
+        return out

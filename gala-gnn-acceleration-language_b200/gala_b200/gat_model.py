@@ -155,16 +155,29 @@ class GATN:
         agg = ops.gat_forward(g, aL, aR, res, self.slope, relu=False)
         return F.linear(agg, *self.fc[-1])
 
-    def forward(self, g, X, hook=None):
-        """Own kernels for the transforms (tcgen05 + folded projections in its epilogue)."""
+    def forward(self, g, X, hook=None, logits_chunk=None):
+        """Own kernels for the transforms (tcgen05 + folded projections in its epilogue).
+        logits_chunk = (rows, buffer): the classifier runs in row chunks into a re-used buffer (for
+        graphs whose [N, classes] logits do not fit next to the features on one GPU); returns None."""
         run = hook if hook is not None else (lambda name, fn: fn())
-        res = X
+        if not hasattr(self, "_bh"):
+            self.host_biases()
+        res, a_last = X, None
         for i in range(self.L - 1):
-            bh = [float(v) for v in self.b_att[i]] if not hasattr(self, "_bh") else self._bh[i]
-            t, a = run(f"linear{i + 1}", lambda: ops.linear(res, self.fc[i][0], self.fc[i][1], att_w=self.W_att[i], att_b=bh))
-            res = run(f"gat_layer{i + 1}", lambda: ops.gat_forward(g, a[0], a[1], t, self.slope, relu=True))
-        a = F.linear(res, self.W_att[-1], self.b_att[-1]).t().contiguous()
-        agg = run(f"gat_layer{self.L}", lambda: ops.gat_forward(g, a[0], a[1], res, self.slope, relu=False))
+            t, a = run(f"linear{i + 1}", lambda: ops.linear(res, self.fc[i][0], self.fc[i][1], att_w=self.W_att[i],
+                                                            att_b=self._bh[i]))
+            if i == self.L - 2:     # the last hidden layer also projects its rows for the final layer's logits
+                res, a_last, _ = run(f"gat_layer{i + 1}", lambda: ops.gat_forward_ex(
+                    g, a[0], a[1], t, self.slope, relu=True, att_w=self.W_att[-1], att_b=self._bh[-1]))
+            else:
+                res = run(f"gat_layer{i + 1}", lambda: ops.gat_forward(g, a[0], a[1], t, self.slope, relu=True))
+        agg = run(f"gat_layer{self.L}", lambda: ops.gat_forward(g, a_last[0], a_last[1], res, self.slope, relu=False))
+        if logits_chunk is not None:
+            rows, buf = logits_chunk
+            for lo in range(0, agg.shape[0], rows):
+                hi = min(agg.shape[0], lo + rows)
+                torch.addmm(self.fc[-1][1], agg[lo:hi], self.fc[-1][0].t(), out=buf[:hi - lo])
+            return None
         return F.linear(agg, *self.fc[-1])
 
     def host_biases(self):

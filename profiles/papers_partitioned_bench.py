@@ -94,13 +94,46 @@ model = GATN(dims, dev, seed=0).host_biases()
 X_loc = torch.rand(part.rows, feats, device=dev) - 0.5
 say(f"papers shape x{scale}: n={n} E={e}; rank 0 holds rows [{part.row_lo},{part.row_hi}) nnz {part.local_nvals}")
 res = {"workload": f"3-layer GAT forward, papers100M shape x{scale}", "n_gpus": world, "nodes": n, "edges": e}
-for exchange in (("p2p", "nccl") if world > 1 else ("nccl",)):
+for exchange in (("p2p", "nccl") if world > 1 else ()):
     runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange)
     ms = timed(lambda: runner.forward(X_loc))
     res[f"ms_{runner.exchange}"] = round(ms, 3)
     say(f"  [{runner.exchange}] forward {ms:.2f} ms (max over {world} ranks)")
+    if runner.px is not None:      # one more step with an event at every phase boundary (rank 0's view)
+        marks = []
+
+        def mark(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+        dist.barrier()
+        mark("start")
+        runner.forward(X_loc, mark=mark)
+        torch.cuda.synchronize()
+        res["phases_ms_rank0"] = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 2) for i in range(1, len(marks))}
+        say("  phases (rank 0):", res["phases_ms_rank0"])
     del runner
     torch.cuda.empty_cache()
+if world == 1:
+    g1 = ops.TiledGraph(part.offset, part.cols, part.rows, ncols=part.padded_n).build_plan()
+    # [N, 172] logits = 71 GiB do not fit next to the 53 GiB of features on one GPU: the classifier writes
+    # 8 M-row chunks into one re-used buffer (same bytes computed and written, not retained)
+    sink = (8_000_000, torch.empty(8_000_000, classes, device=dev))
+    ms = timed(lambda: model.forward(g1, X_loc, logits_chunk=sink))
+    res["ms_single_gpu_model"] = round(ms, 3)
+    phases = {}
+
+    def hook(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        phases[name] = round(a.elapsed_time(b), 2)
+        return out
+    model.forward(g1, X_loc, hook=hook, logits_chunk=sink)
+    res["phases_ms"] = phases
+    say(f"  single-GPU GATN.forward {ms:.2f} ms; kernels: {phases}")
 say(json.dumps(res))
 if rank == 0:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
