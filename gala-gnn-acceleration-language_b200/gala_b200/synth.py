@@ -116,22 +116,25 @@ def powerlaw_multigraph_coo_torch(n, n_edges, seed=0, gamma=0.85, device="cuda",
     """Papers-scale variant: directed power-law multigraph (both endpoints drawn from the same rank
     distribution as above, node ids permuted; duplicates and self-loops kept, no symmetrisation -- at
     1.6 G edges torch.unique would need ~3x the memory, and CSRCMatrix::build keeps duplicates anyway).
+    Ranks are drawn by inverting the continuous CDF of (i + shift)^-gamma in closed form: element-wise
+    fp64 math only, so every GPU of a partitioned run synthesises bit-identical edges (a cumsum-based
+    CDF is not reproducible: the device scan combines its partial sums in a timing-dependent order).
     Returns unsorted (rows int32[E], cols int32[E]); deterministic in (n, n_edges, seed)."""
     import torch
 
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
-    i = torch.arange(n, dtype=torch.float64, device=device)
-    w = (i + max(1.0, n / 500.0)) ** (-gamma)
-    cdf = torch.cumsum(w / w.sum(), 0)
-    del i, w
+    shift = max(1.0, n / 500.0)
+    p = 1.0 - gamma
+    lo_c, hi_c = shift ** p, (n + shift) ** p
     perm = torch.randperm(n, generator=gen, device=device, dtype=torch.int32)
     rows = torch.empty(n_edges, dtype=torch.int32, device=device)
     cols = torch.empty(n_edges, dtype=torch.int32, device=device)
     for lo in range(0, n_edges, chunk):
         m = min(chunk, n_edges - lo)
         for dst in (rows, cols):
-            u = torch.searchsorted(cdf, torch.rand(m, generator=gen, device=device, dtype=torch.float64)).clamp_(max=n - 1)
-            dst[lo:lo + m] = perm[u]
-            del u
+            u = torch.rand(m, generator=gen, device=device, dtype=torch.float64)
+            i = ((u * (hi_c - lo_c) + lo_c) ** (1.0 / p) - shift).floor_().clamp_(0, n - 1).long()
+            dst[lo:lo + m] = perm[i]
+            del u, i
     return rows, cols

@@ -58,6 +58,12 @@ def build(n, e, seed):
     offset, ids, _ = formats.csr_build(n, n, rows, cols)
     del rows, cols
     torch.cuda.empty_cache()
+    # every rank must hold the same graph (bit-identical synthesis): compare a checksum across ranks
+    chk = torch.stack([offset.long().sum(), (ids.long() * 31 % 1000003).sum()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "ranks synthesised different graphs"
     return offset, ids
 
 
