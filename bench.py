@@ -441,6 +441,18 @@ def main():
                 "no_reuse_gather_gbs": round(gather_bytes / (kms * 1e-3) / 1e9, 1),
                 "note": "X (N*K*4 = 29.8 MB) is L2-resident; the 4*E*K gather bytes are served by L2/L1, not HBM "
                         "(SURVEY.md section 7), so frac against the compulsory-byte model is L2/LSU-limited"}
+    if world == 1:
+        # what the gather is actually bounded by: the L2->SM read bandwidth, measured here with the library's
+        # probe on a buffer the size of X (L2-resident), next to the same probe on a 2 GiB buffer (HBM)
+        try:
+            l2 = ops.probe_read_gbs(int(n * hidden * 4) // 16 * 16, 400, dev)
+            hbm = ops.probe_read_gbs(2 << 30, 4, dev)
+            roofline["l2"] = {"measured_read_gbs": round(l2, 1), "probe_bytes": int(n * hidden * 4),
+                              "gather_gbs": roofline["no_reuse_gather_gbs"],
+                              "frac": round(roofline["no_reuse_gather_gbs"] / l2, 4),
+                              "hbm_probe_read_gbs": round(hbm, 1)}
+        except Exception as ex:   # measurement aid only
+            roofline["l2"] = {"error": f"{type(ex).__name__}: {ex}"}
     tfile = os.path.join(ROOT, "profiles", "traffic.json")
     if world == 1 and os.path.exists(tfile):
         try:

@@ -14,7 +14,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("GALA_B200_LIB") or os.path.join(_PKG_ROOT, "libgala_b200.so")
 
 EXPORTS = [
-    "gala_b200_abi_version", "gala_b200_error_string", "gala_plan_workspace_bytes",
+    "gala_b200_abi_version", "gala_b200_error_string", "gala_b200_probe_read", "gala_plan_workspace_bytes",
     "gala_plan_build", "gala_spmm_f32", "gala_spmm_sampled_f32", "gala_edge_rowsum_f32",
     "gala_edge_scale_rows_f32", "gala_sddvv_f32", "gala_sddmm_f32", "gala_edge_softmax_fwd_f32",
     "gala_edge_softmax_bwd_f32", "gala_gat_forward_f32", "gala_gat_forward_dot_f32", "gala_linear_f32",
@@ -102,6 +102,7 @@ def load():
         "gala_col_tile": [i32, i32, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp],
         "gala_sample_ab": [i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
         "gala_mask_subgraph": [i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int64), vp, vp, sz, vp],
+        "gala_b200_probe_read": [vp, sz, i32, vp, vp],
         "gala_csr_reorder": [i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp],
         "gala_permute_rows_f32": [vp, vp, vp, i32, i32, i32, vp],
         "gala_degree_order": [i32, vp, vp, vp, vp, sz, vp],

@@ -266,3 +266,20 @@ def linear_small(X, W, bias=None, relu=False, transpose_out=False, out=None):
     _l.check(_l.load().gala_linear_small_f32(_l.ptr(X), M, K, _l.ptr(W), _l.ptr(bias), N, _l.ptr(out), int(relu),
                                              int(transpose_out), _l.stream_ptr()))
     return out
+
+
+def probe_read_gbs(nbytes, repeats, device="cuda:0"):
+    """Measured read bandwidth (GB/s) of a `nbytes` buffer streamed `repeats` times by every SM
+    (gala_b200_probe_read): L2->SM bandwidth when the buffer fits the L2, HBM bandwidth when it does not."""
+    buf = torch.empty(nbytes // 4, dtype=torch.float32, device=device).normal_()
+    sink = torch.zeros(4, dtype=torch.int32, device=device)
+    lib = _l.load()
+    for _ in range(2):
+        _l.check(lib.gala_b200_probe_read(_l.ptr(buf), nbytes, repeats, _l.ptr(sink), _l.stream_ptr()))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    _l.check(lib.gala_b200_probe_read(_l.ptr(buf), nbytes, repeats, _l.ptr(sink), _l.stream_ptr()))
+    b.record()
+    torch.cuda.synchronize()
+    return nbytes * repeats / (a.elapsed_time(b) * 1e-3) / 1e9

@@ -108,6 +108,13 @@ typedef struct gala_epilogue {
 int gala_b200_abi_version(void);
 const char *gala_b200_error_string(int code);
 
+/* Measurement utility (no reference counterpart): every SM streams `bytes` of `buf`   */
+/* `repeats` times with 128-bit ld.global.cg loads.  A buffer that fits the L2 gives   */
+/* the L2->SM read bandwidth the gather kernels are bounded by, a large one the HBM    */
+/* read bandwidth.  *sink (device, 16 bytes) receives a value that depends on the data. */
+int gala_b200_probe_read(const void *buf, size_t bytes, int32_t repeats, void *sink,
+                         gala_stream_t stream);
+
 /* ---- plan ------------------------------------------------------------------ */
 /* Bytes of device workspace gala_plan_build needs for this graph.               */
 size_t gala_plan_workspace_bytes(const gala_graph_t *g);

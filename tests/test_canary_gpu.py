@@ -59,6 +59,7 @@ def test_outputs_stay_in_bounds(orc, n, e, T, thr, K):
     ops.edge_softmax_fwd(g, w, out=ar.out((E,)), recip=ar.out((n,)))
     ops.edge_softmax_bwd(g, w, w, out=ar.out((E,), align16=False))
     ops.gat_forward(g, a, a, X, out=ar.out((n, K)), alpha_out=ar.out((E,)))
+    ops.gat_backward_att(g, w, w, a, a, 0.2, out=ar.out((n, 1)))
     if K % 4 == 0 and K <= 32:
         ops.gat_forward_dot(g, a, X[0].contiguous(), 0.1, X, out=ar.out((n, K)), alpha_out=ar.out((E,)))
     torch.cuda.synchronize()
@@ -87,3 +88,45 @@ def test_format_outputs_are_fully_written_and_bounded(orc):
     assert int(off[-1]) == ids.shape[0] and int(idd.min()) >= 0 and int(idd.max()) < n
     tg = formats.ord_col_tiling(n, n, off, idd, torch.ones(idd.numel(), device=DEV), 100)
     assert int(tg.cols.min()) >= 0 and int(tg.cols.max()) < n and int(tg.bounds[-1]) == idd.numel()
+
+
+def test_reorder_outputs_stay_in_bounds_and_errors_are_reported():
+    import ctypes as C
+    from gala_b200 import lib as _l
+
+    n = 777
+    offset, ids = make_csr(n, 9001, 5, empty_rows=4)
+    E = ids.shape[0]
+    off, col = torch.from_numpy(offset).to(DEV), torch.from_numpy(ids).to(DEV)
+    w = torch.rand(E, device=DEV)
+    X = torch.rand(n, 7, device=DEV)
+    lib = _l.load()
+    ar = Arena()
+    perm = ar.out((n,), torch.int32)
+    order = ar.out((n,), torch.int32)
+    ws = torch.empty(lib.gala_degree_order_workspace_bytes(n), dtype=torch.uint8, device=DEV)
+    _l.check(lib.gala_degree_order(n, _l.ptr(off), _l.ptr(perm), _l.ptr(order), _l.ptr(ws), ws.numel(), _l.stream_ptr()))
+    no, ni, nv = ar.out((n + 1,), torch.int32), ar.out((E,), torch.int32), ar.out((E,))
+    nb = lib.gala_csr_from_coo_workspace_bytes(n, n, E)
+    ws2 = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    _l.check(lib.gala_csr_reorder(n, E, _l.ptr(off), _l.ptr(col), _l.ptr(w), _l.ptr(perm.contiguous()), _l.ptr(no),
+                                  _l.ptr(ni), _l.ptr(nv), _l.ptr(ws2), nb, _l.stream_ptr()))
+    Y = ar.out((n, 7))
+    _l.check(lib.gala_permute_rows_f32(_l.ptr(X), _l.ptr(perm.contiguous()), _l.ptr(Y), n, 7, 0, _l.stream_ptr()))
+    torch.cuda.synchronize()
+    ar.check()
+    assert sorted(perm.tolist()) == list(range(n)) and int(no[-1]) == E
+    # error convention: negative GALA_ERR_* codes, nothing launched
+    assert lib.gala_csr_reorder(n, E, _l.ptr(off), _l.ptr(col), None, None, _l.ptr(no), _l.ptr(ni), None, _l.ptr(ws2), nb,
+                                _l.stream_ptr()) == -1                                      # NULL perm
+    assert lib.gala_csr_reorder(n, E, _l.ptr(off), _l.ptr(col), None, _l.ptr(perm.contiguous()), _l.ptr(no), _l.ptr(ni),
+                                None, _l.ptr(ws2), 16, _l.stream_ptr()) < 0                 # workspace too small
+    assert lib.gala_permute_rows_f32(_l.ptr(X), _l.ptr(perm.contiguous()), _l.ptr(X), n, 7, 0, _l.stream_ptr()) < 0   # in place
+    assert lib.gala_degree_order(-1, _l.ptr(off), _l.ptr(perm), None, _l.ptr(ws), ws.numel(), _l.stream_ptr()) < 0
+
+
+def test_read_probe_reports_l2_above_hbm():
+    l2 = ops.probe_read_gbs(24 << 20, 100, DEV)
+    hbm = ops.probe_read_gbs(1 << 30, 2, DEV)
+    assert 1000 < hbm < 9000, hbm           # B200 HBM3e: ~6.5 TB/s measured peak
+    assert l2 > hbm, (l2, hbm)
