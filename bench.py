@@ -21,6 +21,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "gala-gnn-acceleration-language_b200"))
 
+# The reference arm is the reference's CPU path "with all the host threads it can use": torchrun exports
+# OMP_NUM_THREADS=1 to its workers, which would silently time that arm on one core.  Only rank 0 runs it
+# (the other ranks exit at once), so give it the machine back -- before any OpenMP runtime is loaded.
+if "--impl" in sys.argv and "reference" in sys.argv and os.environ.get("LOCAL_RANK") is not None:
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
