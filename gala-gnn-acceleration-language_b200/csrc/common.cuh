@@ -29,16 +29,67 @@ __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 
-// Gathered feature rows: GALA_GATHER_CG = 1 reads them with ld.global.cg (L2 only, no L1
-// allocation) instead of ld.global.nc -- see profiles/r01_variants.txt for the measurement.
-#ifndef GALA_GATHER_CG
-#define GALA_GATHER_CG 0
+// Gathered feature rows.  GALA_ROW_POLICY selects the L1 policy of these loads:
+//   0  ld.global.nc (default)          1  ld.global.cg (L2 only)
+//   2  ld.global.nc.L1::evict_first     3  ld.global.nc.L1::no_allocate
+// (measurements: profiles/r01_variants.txt, profiles/r01_l1_policy_variants.txt)
+#ifndef GALA_ROW_POLICY
+#define GALA_ROW_POLICY 0
 #endif
-#if GALA_GATHER_CG
-#define GALA_GATHER_LD(p) __ldcg(p)
+#if GALA_ROW_POLICY == 2
+#define GALA_ROW_QUAL ".L1::evict_first"
+#elif GALA_ROW_POLICY == 3
+#define GALA_ROW_QUAL ".L1::no_allocate"
+#endif
+__device__ __forceinline__ float gather_ld(const float* p) {
+#if GALA_ROW_POLICY == 0
+    return __ldg(p);
+#elif GALA_ROW_POLICY == 1
+    return __ldcg(p);
 #else
-#define GALA_GATHER_LD(p) __ldg(p)
+    float v;
+    asm volatile("ld.global.nc" GALA_ROW_QUAL ".f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
 #endif
+}
+__device__ __forceinline__ float2 gather_ld(const float2* p) {
+#if GALA_ROW_POLICY == 0
+    return __ldg(p);
+#elif GALA_ROW_POLICY == 1
+    return __ldcg(p);
+#else
+    float2 v;
+    asm volatile("ld.global.nc" GALA_ROW_QUAL ".v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+#endif
+}
+__device__ __forceinline__ float4 gather_ld(const float4* p) {
+#if GALA_ROW_POLICY == 0
+    return __ldg(p);
+#elif GALA_ROW_POLICY == 1
+    return __ldcg(p);
+#else
+    float4 v;
+    asm volatile("ld.global.nc" GALA_ROW_QUAL ".v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#endif
+}
+#define GALA_GATHER_LD(p) gather_ld(p)
+
+// Per-column scalars gathered once per edge (aR[col], norm[col]): 4 bytes that cost a whole 32-byte sector
+// when they miss.  GALA_SCALAR_POLICY = 1 asks L1 to keep them (ld.global.nc.L1::evict_last).
+#ifndef GALA_SCALAR_POLICY
+#define GALA_SCALAR_POLICY 0
+#endif
+__device__ __forceinline__ float ld_keep(const float* p) {
+#if GALA_SCALAR_POLICY == 1
+    float v;
+    asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
 
 template <int VEC>
 struct Vec;

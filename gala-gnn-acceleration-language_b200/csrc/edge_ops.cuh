@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(kCtaThreads) sddvv_kernel(const __grid_constan
         return act ? leaky(r, p.slope) : r;
     };
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
-        warp_edges<V4>(e0, e1, lane, [&](int e) { st_stream(p.out + e, f(__ldg(p.b + ld_stream(p.g.cols + e)))); },
+        warp_edges<V4>(e0, e1, lane, [&](int e) { st_stream(p.out + e, f(ld_keep(p.b + ld_stream(p.g.cols + e)))); },
                        [&](int e) {
                            int4 c = ld_stream4(p.g.cols + e);
                            float4 o;
-                           o.x = __ldg(p.b + c.x); o.y = __ldg(p.b + c.y); o.z = __ldg(p.b + c.z); o.w = __ldg(p.b + c.w);
+                           o.x = ld_keep(p.b + c.x); o.y = ld_keep(p.b + c.y); o.z = ld_keep(p.b + c.z); o.w = ld_keep(p.b + c.w);
                            o.x = f(o.x); o.y = f(o.y); o.z = f(o.z); o.w = f(o.w);
                            st_stream4(p.out + e, o);
                        });
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kCtaThreads) gat_bwd_att_kernel(const __grid_c
     float r = 0.0f;
     auto one = [&](float a, float b, int c) {
         const float ds = a * b - a * tot;
-        return (al + __ldg(q.aR + c)) > 0.0f ? ds : ds * slope;
+        return (al + ld_keep(q.aR + c)) > 0.0f ? ds : ds * slope;
     };
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
         warp_edges<V4>(e0, e1, lane, [&](int e) { r += one(p.a[e], p.b[e], ld_stream(p.g.cols + e)); },

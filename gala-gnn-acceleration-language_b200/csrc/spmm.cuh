@@ -261,13 +261,13 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
             if (MODE == MODE_GAT_DOT) {
                 // weight comes from the gathered row (gather_chunk_dot)
             } else if (MODE == MODE_GAT) {
-                float e = softmax_num(leaky(aL_row + __ldg(p.aR + c), p.slope));
+                float e = softmax_num(leaky(aL_row + ld_keep(p.aR + c), p.slope));
                 rs += e;
                 if (write_alpha) p.alpha_out[idx] = e;
                 w = e;
             } else {
                 w = p.vals ? ld_stream(p.vals + idx) : 1.0f;
-                if (p.col_scale) w *= __ldg(p.col_scale + c);
+                if (p.col_scale) w *= ld_keep(p.col_scale + c);
             }
         }
     };

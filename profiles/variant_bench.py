@@ -34,7 +34,9 @@ print(json.dumps({"gat": t(lambda: ops.gat_forward(g, a, a, X, out=Y)),
                   "gat_dot": t(lambda: ops.gat_forward_dot(g, a, X[0].contiguous(), 0.1, X, out=Y)),
                   "spmm": t(lambda: ops.spmm(g, X, out=Y)),
                   "spmm_w": t(lambda: ops.spmm(g, X, vals=w, out=Y)),
-                  "sddmm": t(lambda: ops.sddmm(g, X, X, out=ev))}))
+                  "sddmm": t(lambda: ops.sddmm(g, X, X, out=ev)),
+                  "sddvv": t(lambda: ops.sddvv(g, a, a, "add", out=ev)),
+                  "gcn_scaled": t(lambda: ops.spmm(g, X, out=Y, row_scale=a, col_scale=a))}))
 ''' % PKG
 
 for lib in sorted(glob.glob(os.path.join(PKG, "variants", "*.so"))) + [os.path.join(PKG, "libgala_b200.so")]:
