@@ -36,6 +36,10 @@ print(json.dumps({"gat": t(lambda: ops.gat_forward(g, a, a, X, out=Y)),
                   "spmm_w": t(lambda: ops.spmm(g, X, vals=w, out=Y)),
                   "sddmm": t(lambda: ops.sddmm(g, X, X, out=ev)),
                   "sddvv": t(lambda: ops.sddvv(g, a, a, "add", out=ev)),
+                  "rowsum": t(lambda: ops.edge_rowsum(g, w)),
+                  "softmax_fwd": t(lambda: ops.edge_softmax_fwd(g, w, out=ev)),
+                  "softmax_bwd": t(lambda: ops.edge_softmax_bwd(g, w, w, out=ev)),
+                  "gat_bwd_att": t(lambda: ops.gat_backward_att(g, w, w, a, a)),
                   "gcn_scaled": t(lambda: ops.spmm(g, X, out=Y, row_scale=a, col_scale=a))}))
 ''' % PKG
 
