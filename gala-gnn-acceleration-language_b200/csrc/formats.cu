@@ -240,9 +240,11 @@ void radix_sort_pairs(SortBuffers& b, int64_t n, int bits_lo, int bits_hi, bool 
 __global__ void unpack_sorted_kernel(const uint64_t* __restrict__ keys, int64_t n, int nrows, int* __restrict__ offsets,
                                      int* __restrict__ ids) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        // ids outside [0, nrows) are a caller error (the reference corrupts memory on them, count_atomic
+        // mtx_sort.h:52-64); the clamp keeps the row-pointer writes inside offsets[0..nrows]
         const uint64_t k = keys[e];
-        const int r = (int)(k >> 32);
-        const int p = e > 0 ? (int)(keys[e - 1] >> 32) : -1;
+        const int r = min((int)(uint32_t)(k >> 32), nrows - 1);
+        const int p = e > 0 ? min((int)(uint32_t)(keys[e - 1] >> 32), nrows - 1) : -1;
         ids[e] = (int)(uint32_t)k;
         for (int q = p + 1; q <= r; ++q) offsets[q] = (int)e;
         if (e == n - 1)
@@ -385,8 +387,11 @@ __global__ void pack_permuted_kernel(const int* __restrict__ offsets, const int*
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= nrows) return;
-    const uint64_t hi = (uint64_t)(uint32_t)perm[row] << 32;
-    for (int e = offsets[row] + lane; e < offsets[row + 1]; e += 32) keys[e] = hi | (uint32_t)perm[ids[e]];
+    // perm is required to be a permutation of [0, nrows); stray entries are clamped so that nothing is
+    // written out of bounds (the reference skips such rows and leaves their slots uninitialised)
+    auto at = [&](int i) { return (uint32_t)min(max(perm[min(max(i, 0), nrows - 1)], 0), nrows - 1); };
+    const uint64_t hi = (uint64_t)at(row) << 32;
+    for (int e = offsets[row] + lane; e < offsets[row + 1]; e += 32) keys[e] = hi | at(ids[e]);
 }
 
 // The reference sorts each row's (column, value) PAIRS (reordering.h:1000), so duplicate edges end up ordered by
@@ -417,7 +422,7 @@ __global__ void permute_rows_kernel(const V* __restrict__ X, const int* __restri
     const int64_t total = (int64_t)nrows * kv;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / kv), c = (int)(i - (int64_t)r * kv);
-        const int p = perm[r];
+        const int p = min(max(perm[r], 0), nrows - 1);   // memory-safe for stray entries
         const int64_t src = from ? (int64_t)p * kv + c : i;
         const int64_t dst = from ? i : (int64_t)p * kv + c;
         Y[dst] = X[src];
