@@ -65,3 +65,30 @@ def test_no_cpu_fallback_when_library_missing(monkeypatch):
     monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libgala_b200.so")
     with pytest.raises(ImportError):
         L.load()
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++-isms, no torch types)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "gala_b200.h"\nint main(void) { return gala_b200_abi_version() > 0 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_new_entry_points_validate_arguments():
+    lib = L.load()
+    assert lib.gala_csr_reorder(-1, 0, None, None, None, None, None, None, None, None, 0, None) == -2
+    assert lib.gala_csr_reorder(4, 3, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert lib.gala_permute_rows_f32(None, None, None, 4, 4, 0, None) == -1
+    assert lib.gala_permute_rows_f32(None, None, None, 0, 4, 0, None) == 0          # empty: nothing to do
+    assert lib.gala_degree_order(0, None, None, None, None, 0, None) == 0
+    assert lib.gala_degree_order(5, None, None, None, None, 0, None) == -1
+    assert lib.gala_gat_backward_att_f32(None, None, None, None, None, 0.2, None, None, None) == -1
+    assert lib.gala_b200_probe_read(None, 1024, 1, None, None) == -1
+    assert lib.gala_degree_order_workspace_bytes(1000) > 0
