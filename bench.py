@@ -543,6 +543,12 @@ def kernel_sweep(g, n, nvals, K, peak, dev):
     rec("sddvv_add", time_op(lambda: ops.sddvv(g, a, a, "add", out=ev)), rp + 4 * nvals + 8 * n + 4 * nvals)
     rec("edge_softmax_fwd", time_op(lambda: ops.edge_softmax_fwd(g, w, out=ev)), rp + 8 * nvals)
     rec("edge_rowsum", time_op(lambda: ops.edge_rowsum(g, w)), rp + 4 * nvals + 4 * n)
+    # optional bf16 FEATURE STORAGE (not the headline: fp32 accumulation/outputs, results within 1e-2 of fp32,
+    # BASELINE north_star "bf16 features within 1e-2"): half the gathered bytes on the L2-bound gather
+    Xb = X.to(torch.bfloat16)
+    rec("spmm_k32_bf16_features", time_op(lambda: ops.spmm_bf16(g, Xb, out=Y)), rp + 4 * nvals + 6 * n * K)
+    rec("gat_fused_k32_bf16_features", time_op(lambda: ops.gat_forward_bf16(g, a, a, Xb, out=Y)),
+        rp + 4 * nvals + 8 * n + 6 * n * K)
     return res
 
 

@@ -152,6 +152,26 @@ int launch_spmm(const SpmmParams& p, cudaStream_t st) {
     return last_error();
 }
 
+
+// bf16 feature rows (Vec<8>): K = 8 * LPR with LPR a power of two <= 32, 16-byte aligned rows
+template <int MODE>
+int launch_spmm_bf16(const SpmmParams& p, cudaStream_t st) {
+    if (p.g.nrows == 0) return GALA_OK;
+    if (p.K < 8 || p.K > 256 || (p.K & (p.K - 1)) != 0) return GALA_ERR_UNSUPPORTED;
+    if (!aligned(p.X, 16) || !aligned(p.Y, 16)) return GALA_ERR_MISALIGNED;
+    dim3 grid(p.t.n_hub + (p.t.n_ordered + kWarpsPerCta - 1) / kWarpsPerCta, 1);
+    switch (p.K / 8) {
+        case 1: spmm_kernel<8, 1, 1, MODE, true><<<grid, kCtaThreads, 0, st>>>(p); break;
+        case 2: spmm_kernel<8, 2, 1, MODE, true><<<grid, kCtaThreads, 0, st>>>(p); break;
+        case 4: spmm_kernel<8, 4, 1, MODE, true><<<grid, kCtaThreads, 0, st>>>(p); break;
+        case 8: spmm_kernel<8, 8, 1, MODE, true><<<grid, kCtaThreads, 0, st>>>(p); break;
+        case 16: spmm_kernel<8, 16, 1, MODE, true><<<grid, kCtaThreads, 0, st>>>(p); break;
+        case 32: spmm_kernel<8, 32, 1, MODE, true><<<grid, kCtaThreads, 0, st>>>(p); break;
+        default: return GALA_ERR_UNSUPPORTED;
+    }
+    return last_error();
+}
+
 }  // namespace
 
 namespace gala {
@@ -329,6 +349,52 @@ int gala_gat_forward_f32(const gala_graph_t* g, const float* aL, const float* aR
     HubView h = hub_of(plan, g);
     p.t = task_of(h);
     return launch_spmm<MODE_GAT>(p, S(stream));
+}
+
+int gala_spmm_bf16(const gala_graph_t* g, const float* vals, const uint16_t* X, int32_t K, float* Y,
+                   const gala_epilogue_t* ep, const gala_plan_t* plan, gala_stream_t stream) {
+    if (int rc = check_graph(g)) return rc;
+    if (K < 0) return GALA_ERR_BAD_SHAPE;
+    if ((g->nrows > 0 && K > 0) && (!X || !Y)) return GALA_ERR_NULL_POINTER;
+    SpmmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.g = make_dev(g);
+    p.vals = vals;
+    p.X = reinterpret_cast<const float*>(X);
+    p.Y = Y;
+    p.K = K;
+    if (ep) {
+        p.row_scale = ep->row_scale;
+        p.col_scale = ep->col_scale;
+        p.accumulate = ep->accumulate;
+        p.relu = ep->relu;
+    }
+    HubView h = hub_of(plan, g);
+    p.t = task_of(h);
+    return launch_spmm_bf16<MODE_PLAIN>(p, S(stream));
+}
+
+int gala_gat_forward_bf16(const gala_graph_t* g, const float* aL, const float* aR, const uint16_t* X, int32_t K,
+                          float slope, float* Y, float* alpha_out, int32_t relu, const gala_plan_t* plan,
+                          gala_stream_t stream) {
+    if (int rc = check_graph(g)) return rc;
+    if (K <= 0) return K < 0 ? GALA_ERR_BAD_SHAPE : GALA_ERR_UNSUPPORTED;
+    if (g->nrows > 0 && (!aL || !aR || !X || !Y)) return GALA_ERR_NULL_POINTER;
+    SpmmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.g = make_dev(g);
+    p.X = reinterpret_cast<const float*>(X);
+    p.Y = Y;
+    p.K = K;
+    p.relu = relu;
+    p.aL = aL;
+    p.aR = aR;
+    p.slope = slope;
+    p.alpha_out = alpha_out;
+    p.seed_total = (float)g->segments * 1e-12f;
+    HubView h = hub_of(plan, g);
+    p.t = task_of(h);
+    return launch_spmm_bf16<MODE_GAT>(p, S(stream));
 }
 
 int gala_gat_forward_ex_f32(const gala_graph_t* g, const float* aL, const float* aR, const float* X, int32_t K,

@@ -131,6 +131,30 @@ struct Vec<4> {
     }
 };
 
+// Eight features per lane whose SOURCE rows are stored as bf16 (16 bytes per lane, the optional
+// reduced-precision feature storage: half the gathered bytes).  Accumulators, outputs and read-modify-write
+// stay fp32.  bf16 -> fp32 is exact (a 16-bit shift).
+template <>
+struct Vec<8> {
+    float v[8];
+    __device__ __forceinline__ void load(const float* p) {   // p points at 8 bf16 values
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+        v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xffff0000u);
+        v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __device__ __forceinline__ void load_rw(const float* p) {
+        const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
+
 __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);

@@ -224,10 +224,13 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
     if (!task.valid) return;
     const bool hub_cta = task.hub;
     const int row = task.row, lo = task.lo, hi = task.hi;
-    const uint32_t row_bytes = (uint32_t)p.K * 4u;
+    // VEC == 8 is the bf16-feature flavour: X holds bf16 rows (2 bytes per feature), see Vec<8>
+    constexpr uint32_t XB = VEC == 8 ? 2u : 4u;
+    static_assert(VEC != 8 || (ACC == 1 && EXACT && MODE != MODE_GAT_DOT), "bf16 rows: one exact tile, no dot mode");
+    const uint32_t row_bytes = (uint32_t)p.K * XB;
     // the lane's first feature; lanes past K (non-EXACT shapes) point at the tile start
-    const char* xlane = reinterpret_cast<const char*>(
-        p.X + tile_base + ((EXACT || tile_base + sub * VEC < p.K) ? sub * VEC : 0));
+    const char* xlane = reinterpret_cast<const char*>(p.X) +
+                        (size_t)(tile_base + ((EXACT || tile_base + sub * VEC < p.K) ? sub * VEC : 0)) * XB;
 
     bool fvalid[ACC];
 #pragma unroll
@@ -328,8 +331,12 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
                     o.v[v] = t;
                     if (dense_ep) rowbuf[warp][f0 + v] = t;
                 }
-                if (p.mo.count > 0) multi_store<VEC>(p.mo, (int64_t)row * p.K + f0, o);
-                else if (p.Y) o.store(y);
+                if constexpr (VEC <= 4) {
+                    if (p.mo.count > 0) multi_store<VEC>(p.mo, (int64_t)row * p.K + f0, o);
+                    else if (p.Y) o.store(y);
+                } else {
+                    if (p.Y) o.store(y);
+                }
             }
         }
         if (dense_ep) {

@@ -283,3 +283,35 @@ def probe_read_gbs(nbytes, repeats, device="cuda:0"):
     b.record()
     torch.cuda.synchronize()
     return nbytes * repeats / (a.elapsed_time(b) * 1e-3) / 1e9
+
+
+# ---- optional bf16 feature storage (half the gathered bytes; fp32 accumulation and outputs) --------------
+def _bf16(x):
+    assert x.dtype == torch.bfloat16 and x.is_cuda, "bf16 entry points take torch.bfloat16 CUDA features"
+    return x.contiguous()
+
+
+def spmm_bf16(g, X_bf16, vals=None, out=None, row_scale=None, col_scale=None, accumulate=False, relu=False):
+    """Y(fp32) = A @ X with X stored as bf16 (gala_spmm_bf16).  K in {8,16,32,64,128,256}."""
+    X = _bf16(X_bf16)
+    K = X.shape[1]
+    if out is None:
+        out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
+        assert not accumulate, "accumulate needs a caller-provided output"
+    ep = _l.GalaEpilogue(row_scale=row_scale.data_ptr() if row_scale is not None else None,
+                         col_scale=col_scale.data_ptr() if col_scale is not None else None,
+                         accumulate=int(accumulate), relu=int(relu), schedule=0)
+    _l.check(_l.load().gala_spmm_bf16(C.byref(g.c), _l.ptr(vals), _l.ptr(X), K, _l.ptr(out), C.byref(ep), g._p(),
+                                      _l.stream_ptr()))
+    return out
+
+
+def gat_forward_bf16(g, aL, aR, X_bf16, slope=0.2, relu=False, out=None, alpha_out=None):
+    """Fused GAT layer gathering bf16 feature rows (gala_gat_forward_bf16); logits, softmax, sums in fp32."""
+    X = _bf16(X_bf16)
+    K = X.shape[1]
+    if out is None:
+        out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
+    _l.check(_l.load().gala_gat_forward_bf16(C.byref(g.c), _l.ptr(_f32(aL)), _l.ptr(_f32(aR)), _l.ptr(X), K, slope,
+                                             _l.ptr(out), _l.ptr(alpha_out), int(relu), g._p(), _l.stream_ptr()))
+    return out

@@ -140,6 +140,17 @@ int gala_spmm_sampled_f32(const gala_graph_t *g, const float *vals, const float 
                           float *Y, int32_t nsamples, int32_t ra, int32_t rb, int32_t accumulate,
                           gala_stream_t stream);
 
+/* ---- optional reduced-precision feature storage (not in the reference: its path is fp32 throughout) ---- */
+/* Same kernels with the GATHERED rows stored as bf16 (X: [ncols, K] bf16, row pitch 2K bytes): half the      */
+/* bytes per edge on the L2/HBM-bound gather.  Edge values, attention logits, accumulation and Y stay fp32;   */
+/* the result equals the fp32 entry point run on bf16-rounded X (tests), i.e. within ~4e-3 of the fp32 result */
+/* (north-star bound for bf16 features: 1e-2).  K in {8,16,32,64,128,256}; X and Y 16-byte aligned.           */
+int gala_spmm_bf16(const gala_graph_t *g, const float *vals, const uint16_t *X_bf16, int32_t K, float *Y,
+                   const gala_epilogue_t *epilogue, const gala_plan_t *plan, gala_stream_t stream);
+int gala_gat_forward_bf16(const gala_graph_t *g, const float *aL, const float *aR, const uint16_t *X_bf16,
+                          int32_t K, float slope, float *Y, float *alpha_out, int32_t relu,
+                          const gala_plan_t *plan, gala_stream_t stream);
+
 /* ---- edge kernels ------------------------------------------------------------ */
 /* Replaces node_spmv_backward_of_sddmm_{nln,eaggr} + K3 (cuda.h:505-524,         */
 /* 565-600, 659-678, 737-772): out[i] = sum_s (seed + sum_{e in row i, seg s}     */

@@ -431,3 +431,47 @@ def test_results_are_bit_reproducible(orc):
     a = ops.spmm(g, X, vals=dev(t.vals))
     for _ in range(3):
         assert torch.equal(a, ops.spmm(g, X, vals=dev(t.vals)))
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("K", [8, 32, 64, 256])
+def test_bf16_feature_storage_matches_fp32_path_on_rounded_features(orc, case, K):
+    """Optional bf16 feature rows: the kernels must equal the fp32 oracle evaluated on the bf16-ROUNDED features
+    (1e-5, same bar as the fp32 path) and stay within the north-star bound for bf16 features (1e-2) of the
+    un-rounded fp32 result."""
+    n, e, seed, T, empty, thr = case
+    t = graph_case(orc, n, e, seed, T, empty)
+    g = to_gpu_graph(t, thr)
+    rng = np.random.default_rng(seed + K)
+    X = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    Xb = dev(X).to(torch.bfloat16)
+    Xr = Xb.float().cpu().numpy()
+    for weighted in (False, True):
+        got = ops.spmm_bf16(g, Xb, vals=dev(t.vals) if weighted else None).cpu().numpy()
+        assert rel_err(got, orc.spmm(t, Xr, weighted=weighted)) < FP32_TOL
+        assert rel_err(got, orc.spmm(t, X, weighted=weighted)) < 1e-2
+    aL = rng.normal(size=n).astype(np.float32)
+    aR = rng.normal(size=n).astype(np.float32)
+    alpha = torch.empty(t.nvals, device=DEV)
+    got = ops.gat_forward_bf16(g, dev(aL), dev(aR), Xb, 0.2, relu=True, alpha_out=alpha).cpu().numpy()
+    want, want_alpha = orc.gat_forward(t, aL, aR, Xr, 0.2)
+    assert rel_err(got, np.maximum(want, 0)) < FP32_TOL
+    assert rel_err(alpha.cpu().numpy(), want_alpha) < FP32_TOL
+    assert rel_err(got, np.maximum(orc.gat_forward(t, aL, aR, X, 0.2)[0], 0)) < 1e-2
+    # epilogue options and accumulate on the bf16 path
+    rs = rng.uniform(0.5, 1.5, n).astype(np.float32)
+    Y0 = rng.uniform(-1, 1, (n, K)).astype(np.float32)
+    out = dev(Y0.copy())
+    ops.spmm_bf16(g, Xb, out=out, accumulate=True)
+    assert rel_err(out.cpu().numpy(), Y0 + orc.spmm(t, Xr, weighted=False)) < FP32_TOL
+    got = ops.spmm_bf16(g, Xb, row_scale=dev(rs), relu=True).cpu().numpy()
+    assert rel_err(got, np.maximum(orc.spmm(t, Xr, weighted=False) * rs[:, None], 0)) < FP32_TOL
+
+
+def test_bf16_feature_storage_rejects_unsupported_widths():
+    from gala_b200 import lib as _l
+    offset, ids = make_csr(64, 400, 1)
+    g = ops.TiledGraph(dev(offset), dev(ids), 64)
+    for K in (4, 24, 41, 512):
+        with pytest.raises(_l.GalaError):
+            ops.spmm_bf16(g, torch.zeros(64, K, device=DEV, dtype=torch.bfloat16))
