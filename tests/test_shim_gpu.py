@@ -17,3 +17,14 @@ def test_libtorch_shim_selftest():
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "SHIM SELFTEST OK" in r.stdout
+
+
+def test_plain_c_program_over_the_c_abi():
+    """host/c_abi_example.c: C99, no torch -- COO -> CSR -> column tiling -> plan -> SpMM / fused GAT."""
+    exe = os.path.join(ROOT, "gala-gnn-acceleration-language_b200", "host", "c_abi_example")
+    if not os.path.exists(exe):
+        pytest.skip("host/c_abi_example not built (make -C gala-gnn-acceleration-language_b200/host)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "C ABI EXAMPLE OK" in r.stdout
