@@ -58,8 +58,46 @@ def case(name, n, e, seed, K, T, dup=False):
     print(name, "n", n, "E", ids.shape[0], "segments", tiled.S)
 
 
+def cora_gcn():
+    """BASELINE.json configs[0]: the 2-layer GCN forward of the generated program (codegen/gala.cu:422-459) on a
+    Cora-shape graph through the reference's CPU path -- CSRCMatrix::build, gSpMM<wsumAgg> (oracle/_ref) and
+    torch-CPU Linear (what nn::Linear is).  The features are regenerated from the seed by the tests; graph,
+    weights and logits are stored."""
+    import torch
+    import torch.nn.functional as F
+
+    n, e, feats, hidden, classes = synth.SHAPES["cora"]
+    src, dst = synth.powerlaw_coo_np(n, e, seed=21)
+    offset, ids, ones = orc.ref_csr_build(n, n, src.astype(np.int32), dst.astype(np.int32))
+    rng = np.random.default_rng(22)
+    X = rng.uniform(-0.5, 0.5, (n, feats)).astype(np.float32)
+
+    def lin(o, i):
+        b = 1.0 / np.sqrt(i)
+        return rng.uniform(-b, b, (o, i)).astype(np.float32), rng.uniform(-b, b, o).astype(np.float32)
+    W0, b0 = lin(hidden, feats)
+    W1, b1 = lin(classes, hidden)
+
+    def agg(x):
+        return orc.ref_gspmm_wsum(n, n, offset, ids, ones, np.ascontiguousarray(x, np.float32))
+    deg = agg(np.ones((n, 1), np.float32))                       # degrees via A @ 1 (codegen/gala.cu:437)
+    norm = torch.pow(torch.from_numpy(deg), -0.5).numpy()
+    res = F.linear(torch.from_numpy(X), torch.from_numpy(W0), torch.from_numpy(b0)).numpy()
+    res = norm * res
+    res = agg(res)
+    res = np.maximum(norm * res, 0)
+    res = norm * res
+    res = agg(res)
+    res = norm * res
+    logits = F.linear(torch.from_numpy(res), torch.from_numpy(W1), torch.from_numpy(b1)).numpy()
+    np.savez_compressed(os.path.join(OUT, "cora_gcn.npz"), n=n, feats=feats, x_seed=22, offset=offset, ids=ids,
+                        W0=W0, b0=b0, W1=W1, b1=b1, norm=norm.ravel(), logits=logits)
+    print("cora_gcn n", n, "E", ids.shape[0], "|logits|", float(np.abs(logits).sum()))
+
+
 if __name__ == "__main__":
     assert orc.have_ref(), "build oracle/_ref first: make -C oracle ref"
     case("small_a", 257, 3000, 11, 8, 64)
     case("small_dup", 193, 2200, 12, 5, 50, dup=True)
     case("small_hub", 600, 30000, 13, 32, 100000)
+    cora_gcn()

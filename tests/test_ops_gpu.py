@@ -475,3 +475,24 @@ def test_bf16_feature_storage_rejects_unsupported_widths():
     for K in (4, 24, 41, 512):
         with pytest.raises(_l.GalaError):
             ops.spmm_bf16(g, torch.zeros(64, K, device=DEV, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("dense", ["tcgen05", "torch"])
+def test_cora_gcn_forward_matches_reference_cpu_golden(dense):
+    """BASELINE.json configs[0] on the GPU: the generated 2-layer GCN forward (fused epilogues and op by op)
+    against the logits the reference's CPU path produced for the same graph, features and weights."""
+    from gala_b200 import formats
+    from gala_b200.gcn_model import GCN2
+
+    gd = golden("cora_gcn")
+    n, feats = int(gd["n"]), int(gd["feats"])
+    X = dev(np.random.default_rng(int(gd["x_seed"])).uniform(-0.5, 0.5, (n, feats)).astype(np.float32))
+    ones = torch.ones(gd["ids"].shape[0], device=DEV)
+    g = formats.ord_col_tiling(n, n, dev(gd["offset"]), dev(gd["ids"]), ones, 100000).build_plan(64)   # shipped schedule
+    assert g.segments == 1
+    model = GCN2(feats, 32, 7, DEV)
+    model.fc0, model.fc1 = (dev(gd["W0"]), dev(gd["b0"])), (dev(gd["W1"]), dev(gd["b1"]))
+    model.prepare(g)
+    assert rel_err(model.norm.cpu().numpy(), gd["norm"]) < 1e-6
+    assert rel_err(model.forward(g, X, dense=dense).cpu().numpy(), gd["logits"]) < FP32_TOL
+    assert rel_err(model.forward_literal(g, X).cpu().numpy(), gd["logits"]) < FP32_TOL

@@ -197,3 +197,27 @@ def test_oracle_matches_reference_on_random_inputs(orc):
         tt = orc.ref_csr_transpose(n, n, ro, ri, np.ones_like(w))
         ot2 = orc.csr_transpose(n, n, ro, ri, np.ones_like(w))
         assert all(np.array_equal(a, b) for a, b in zip(tt, ot2))
+
+
+def test_cora_gcn_forward_matches_reference_cpu_path(orc):
+    """BASELINE.json configs[0]: 2-layer GCN on the Cora shape.  The golden logits come from the reference's own
+    CPU path (CSRCMatrix::build + gSpMM<wsumAgg> + torch-CPU Linear, tests/golden/make_golden.py)."""
+    import torch
+    import torch.nn.functional as F
+
+    g = golden("cora_gcn")
+    n, feats = int(g["n"]), int(g["feats"])
+    X = np.random.default_rng(int(g["x_seed"])).uniform(-0.5, 0.5, (n, feats)).astype(np.float32)
+    ones = np.ones(g["ids"].shape[0], np.float32)
+
+    def agg(x):
+        return orc.gspmm_wsum(n, g["offset"], g["ids"], ones, np.ascontiguousarray(x, np.float32))
+    deg = agg(np.ones((n, 1), np.float32))
+    assert np.array_equal(deg.ravel(), np.diff(g["offset"]).astype(np.float32))      # degrees are exact
+    norm = torch.pow(torch.from_numpy(deg), -0.5).numpy()
+    assert np.array_equal(norm.ravel(), g["norm"])
+    res = F.linear(torch.from_numpy(X), torch.from_numpy(g["W0"]), torch.from_numpy(g["b0"])).numpy()
+    res = np.maximum(norm * agg(norm * res), 0)
+    res = norm * agg(norm * res)
+    logits = F.linear(torch.from_numpy(res), torch.from_numpy(g["W1"]), torch.from_numpy(g["b1"])).numpy()
+    assert rel_err(logits, g["logits"]) < 1e-6
