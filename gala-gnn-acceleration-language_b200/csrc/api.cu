@@ -651,6 +651,22 @@ int gala_sddmm_f32(const gala_graph_t* g, const float* A, const float* B, int32_
     Shape sh = pick_shape(K > 0 ? K : 1, a16, a8);
     dim3 grid(h.n + (h.n_ordered + kWarpsPerCta - 1) / kWarpsPerCta);
     cudaStream_t st = S(stream);
+    if (sh.vec == 4 && K == sh.vec * sh.lpr * sh.acc) {   // one exact tile (hidden widths 4..512): predicate-free loop
+#define CALL(V, L, A_) sddmm_kernel<4, L, A_, true><<<grid, kCtaThreads, 0, st>>>(p)
+        switch (sh.lpr * 100 + sh.acc) {
+            case 101: CALL(4, 1, 1); break;
+            case 201: CALL(4, 2, 1); break;
+            case 401: CALL(4, 4, 1); break;
+            case 801: CALL(4, 8, 1); break;
+            case 1601: CALL(4, 16, 1); break;
+            case 3201: CALL(4, 32, 1); break;
+            case 3202: CALL(4, 32, 2); break;
+            case 3204: CALL(4, 32, 4); break;
+            default: return GALA_ERR_UNSUPPORTED;
+        }
+#undef CALL
+        return last_error();
+    }
 #define CALL(V, L, A_) sddmm_kernel<V, L, A_><<<grid, kCtaThreads, 0, st>>>(p)
     GALA_SHAPE_SWITCH(sh, CALL);
 #undef CALL

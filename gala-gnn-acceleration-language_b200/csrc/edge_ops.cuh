@@ -227,7 +227,9 @@ struct SddmmParams {
     int K;
 };
 
-template <int VEC, int LPR, int ACC>
+// EXACT: K == VEC*LPR*ACC (one feature tile, every lane's features valid): no per-lane predicates, no
+// zero-fill of the gathered vectors, no remainder-tile loop.
+template <int VEC, int LPR, int ACC, bool EXACT = false>
 __global__ void __launch_bounds__(kCtaThreads) sddmm_kernel(const __grid_constant__ SddmmParams p) {
     constexpr int EPI = 32 / LPR;
     constexpr int TW = VEC * LPR * ACC;
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(kCtaThreads) sddmm_kernel(const __grid_constan
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR, grp = lane / LPR;
-    const int ntiles = (p.K + TW - 1) / TW;
+    const int ntiles = EXACT ? 1 : (p.K + TW - 1) / TW;
     const uint32_t row_bytes = (uint32_t)p.K * 4u;
 
     float areg[ACC][VEC];
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(kCtaThreads) sddmm_kernel(const __grid_constan
 #pragma unroll
     for (int a = 0; a < ACC; ++a) {
         const int f = (a * LPR + sub) * VEC;
-        fvalid[a] = f < p.K;
+        fvalid[a] = EXACT || f < p.K;
         Vec<VEC> x;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) x.v[v] = 0.0f;
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(kCtaThreads) sddmm_kernel(const __grid_constan
         for (int v = 0; v < VEC; ++v) areg[a][v] = x.v[v];
     }
     // lanes past K read the row start (A is zero there, so the product vanishes)
-    const char* blane = reinterpret_cast<const char*>(p.B + (sub * VEC < p.K ? sub * VEC : 0));
+    const char* blane = reinterpret_cast<const char*>(p.B + ((EXACT || sub * VEC < p.K) ? sub * VEC : 0));
     // after the halving exchange lane `sub` owns edge j = sub of its group, i.e. chunk
     // position sub*EPI + grp
     const int my_pos = sub * EPI + grp;
@@ -274,9 +276,13 @@ __global__ void __launch_bounds__(kCtaThreads) sddmm_kernel(const __grid_constan
                     const char* br = blane + (uint64_t)(uint32_t)max(cj, 0) * row_bytes;
 #pragma unroll
                     for (int a = 0; a < ACC; ++a) {
+                        if (EXACT) {
+                            x[u][a].load(reinterpret_cast<const float*>(br) + a * LPR * VEC);
+                        } else {
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) x[u][a].v[v] = 0.0f;
-                        if (fvalid[a]) x[u][a].load(reinterpret_cast<const float*>(br) + a * LPR * VEC);
+                            for (int v = 0; v < VEC; ++v) x[u][a].v[v] = 0.0f;
+                            if (fvalid[a]) x[u][a].load(reinterpret_cast<const float*>(br) + a * LPR * VEC);
+                        }
                     }
                 }
 #pragma unroll
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(kCtaThreads) sddmm_kernel(const __grid_constan
                     d[j0 + u] = s;
                 }
             }
-            if (ntiles > 1) {  // K > TW: remaining feature tiles (A row from L1)
+            if (!EXACT && ntiles > 1) {  // K > TW: remaining feature tiles (A row from L1)
 #pragma unroll 1
                 for (int j = 0; j < LPR; ++j) {
                     const int cj = __shfl_sync(kFull, c, j * EPI + grp);
