@@ -316,3 +316,68 @@ class PartitionedGATN:
         out = F.linear(agg, *m.fc[-1])
         mark("classifier")
         return out
+
+
+def gcnn_forward_partitioned(model, part, X_local, norm_local, aggregate, hook=None, linear=None):
+    """L-layer GCN (gcn_model.GCNN) on a row partition with all-gather exchanges: hidden layers exchange the
+    transformed, norm-scaled rows; the last hidden output (already pre-scaled) is exchanged once more.
+      aggregate(feats_all, row_scale_local, relu) -> [rows, K];  linear(res_local, i) -> norm * fc_i(res_local)"""
+    run = hook if hook is not None else (lambda name, fn: fn())
+    n2 = norm_local * norm_local
+    if linear is None:
+        def linear(res_loc, i):
+            return norm_local[:, None] * F.linear(res_loc, *model.fc[i])
+    res_loc = X_local
+    for i in range(model.L - 1):
+        t_all = part.all_gather(run(f"linear{i + 1}", lambda: linear(res_loc, i)))
+        res_loc = run(f"gcn_aggregate{i + 1}", lambda: aggregate(t_all, n2 if i == model.L - 2 else norm_local, True))
+    agg = run(f"gcn_aggregate{model.L}", lambda: aggregate(part.all_gather(res_loc), norm_local, False))
+    return F.linear(agg, *model.fc[-1])
+
+
+class PartitionedGCNN:
+    """L-layer GCN runner: the transform of every hidden layer pushes its (norm-scaled) rows to all GPUs from
+    its epilogue (exchange="p2p"); the single exchange of an aggregation OUTPUT (before the last layer) goes
+    through NCCL all-gather.  exchange="nccl": all-gather everywhere."""
+
+    def __init__(self, model, part, device, exchange="p2p"):
+        from . import ops
+
+        self.model, self.ops, self.part = model, ops, part
+        self.graph = ops.TiledGraph(part.offset, part.cols, part.rows, ncols=part.padded_n).build_plan()
+        ones = torch.ones(part.padded_n, 1, device=device)
+        self.norm = torch.pow(ops.spmm(self.graph, ones).reshape(-1), -0.5).contiguous()    # own rows' degrees
+        self.norm2 = (self.norm * self.norm).contiguous()
+        self.px = None
+        self.exchange = "nccl"
+        if exchange == "p2p":
+            self.px = PeerExchange(part, [model.dims[i + 1] for i in range(model.L - 1)], device)
+            self.exchange = "p2p-multicast" if self.px.mos[0].multicast_base else "p2p"
+
+    def _aggregate(self, feats_all, row_scale, relu):
+        return self.ops.spmm(self.graph, feats_all, row_scale=row_scale, relu=relu)
+
+    def forward(self, X_local, hook=None, mark=None):
+        m, px, part, ops = self.model, self.px, self.part, self.ops
+        mark = mark if mark is not None else (lambda name: None)
+        if px is None:
+            def linear(res_loc, i):
+                return ops.linear(res_loc, m.fc[i][0], m.fc[i][1], row_scale=self.norm)
+            return gcnn_forward_partitioned(m, part, X_local, self.norm, self._aggregate, hook, linear)
+        run = hook if hook is not None else (lambda name, fn: fn())
+        res_loc = X_local
+        for i in range(m.L - 1):
+            run(f"linear{i + 1}", lambda: ops.linear(res_loc, m.fc[i][0], m.fc[i][1], row_scale=self.norm, multi_out=px.mos[i]))
+            mark(f"linear{i + 1}+push")
+            px.barrier(i)
+            mark(f"exchange{i + 1}")
+            rs = self.norm2 if i == m.L - 2 else self.norm
+            res_loc = run(f"gcn_aggregate{i + 1}", lambda: ops.spmm(self.graph, px.bufs[i], row_scale=rs, relu=True))
+            mark(f"gcn_aggregate{i + 1}")
+        y_all = part.all_gather(res_loc)
+        mark(f"all_gather{m.L}")
+        agg = run(f"gcn_aggregate{m.L}", lambda: ops.spmm(self.graph, y_all, row_scale=self.norm))
+        mark(f"gcn_aggregate{m.L}")
+        out = F.linear(agg, *m.fc[-1])
+        mark("classifier")
+        return out

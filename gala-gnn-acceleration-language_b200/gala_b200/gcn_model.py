@@ -53,3 +53,46 @@ class GCN2:
         res = run("gcn_aggregate1", lambda: ops.spmm(g, res, row_scale=self.norm2, relu=True))
         res = run("gcn_aggregate2", lambda: ops.spmm(g, res, row_scale=self.norm))
         return F.linear(res, *self.fc1)
+
+
+class GCNN:
+    """L-layer GCN in the shape GALA emits (BASELINE.json configs[4]: 3 layers on the Papers shape).
+    Hidden layers run transform-first (complexityOperatorReordering picks the narrower side):
+        h_i = relu(norm * (A @ (norm * fc_i(h_{i-1}))))
+    the last layer aggregates at the hidden width and applies fc_L afterwards, as GCN2's second layer:
+        out = fc_L(norm * (A @ (norm * h_{L-2})))
+    Every `norm * res` pass lives in an epilogue: the transform scales its rows, the aggregation applies norm
+    (norm^2 before the ReLU on the last hidden layer, which pre-scales the final aggregation's input).
+    dims = [feats, hidden, ..., hidden, classes]."""
+
+    def __init__(self, dims, device, seed=0):
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        self.dims = list(dims)
+        self.L = len(dims) - 1
+        self.fc = [_linear_init(gen, dims[i + 1], dims[i], device) for i in range(self.L)]
+        self.norm = self.norm2 = None
+
+    def prepare(self, g):
+        ones = torch.ones(g.ncols, 1, device=g.device)
+        self.norm = torch.pow(ops.spmm(g, ones).reshape(-1), -0.5).contiguous()
+        self.norm2 = (self.norm * self.norm).contiguous()
+        return self
+
+    def forward_literal(self, g, X):
+        n = self.norm[:, None]
+        res = X
+        for i in range(self.L - 1):
+            res = torch.relu(n * ops.spmm(g, n * F.linear(res, *self.fc[i])))
+        return F.linear(n * ops.spmm(g, n * res), *self.fc[-1])
+
+    def forward(self, g, X, hook=None):
+        run = hook if hook is not None else (lambda name, fn: fn())
+        res = X
+        for i in range(self.L - 1):
+            t = run(f"linear{i + 1}", lambda: ops.linear(res, self.fc[i][0], self.fc[i][1], row_scale=self.norm))
+            last_hidden = i == self.L - 2
+            res = run(f"gcn_aggregate{i + 1}", lambda: ops.spmm(g, t, row_scale=self.norm2 if last_hidden else self.norm,
+                                                                 relu=True))
+        agg = run(f"gcn_aggregate{self.L}", lambda: ops.spmm(g, res, row_scale=self.norm))
+        return F.linear(agg, *self.fc[-1])

@@ -19,6 +19,7 @@ import torch.distributed as dist  # noqa: E402
 
 from gala_b200 import dist_gat, formats, ops, synth  # noqa: E402
 from gala_b200.gat_model import GATN  # noqa: E402
+from gala_b200.gcn_model import GCNN  # noqa: E402
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -84,8 +85,21 @@ for exchange in (("nccl", "p2p") if world > 1 else ("nccl",)):
     worst = max(worst, err)
     say(f"parity [{runner.exchange}] 3-layer GAT on {world} rank(s): rel err {err:.2e}")
     del runner, part
+gfull = ops.TiledGraph(offset, ids, n).build_plan()
+gcn = GCNN(dims, dev, seed=2).prepare(gfull)
+want = gcn.forward_literal(gfull, X)
+for exchange in (("nccl", "p2p") if world > 1 else ("nccl",)):
+    part = dist_gat.RowPartition(offset, ids, n, rank, world)
+    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange)
+    for _ in range(3):
+        out_loc = runner.forward(X[part.row_lo:part.row_hi].contiguous())
+    full = part.unpad(part.all_gather(out_loc))
+    err = float((full - want).double().norm() / want.double().norm())
+    worst = max(worst, err)
+    say(f"parity [{runner.exchange}] 3-layer GCN on {world} rank(s): rel err {err:.2e}")
+    del runner, part
 assert worst < 1e-5
-del offset, ids, X, want, full, out_loc
+del offset, ids, X, want, full, out_loc, gfull, gcn
 torch.cuda.empty_cache()
 
 # ---- phase 2: Papers shape --------------------------------------------------------------------------
@@ -120,6 +134,27 @@ for exchange in (("p2p", "nccl") if world > 1 else ()):
         say("  phases (rank 0):", res["phases_ms_rank0"])
     del runner
     torch.cuda.empty_cache()
+gcn = GCNN(dims, dev, seed=2)
+for exchange in (("p2p", "nccl") if world > 1 else ()):
+    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange)
+    ms = timed(lambda: runner.forward(X_loc))
+    res[f"gcn_ms_{runner.exchange}"] = round(ms, 3)
+    say(f"  GCN [{runner.exchange}] forward {ms:.2f} ms (max over {world} ranks)")
+    if runner.px is not None:
+        marks = []
+
+        def mark(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+        dist.barrier()
+        mark("start")
+        runner.forward(X_loc, mark=mark)
+        torch.cuda.synchronize()
+        res["gcn_phases_ms_rank0"] = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 2) for i in range(1, len(marks))}
+        say("  GCN phases (rank 0):", res["gcn_phases_ms_rank0"])
+    del runner
+    torch.cuda.empty_cache()
 if world == 1:
     g1 = ops.TiledGraph(part.offset, part.cols, part.rows, ncols=part.padded_n).build_plan()
     # [N, 172] logits = 71 GiB do not fit next to the 53 GiB of features on one GPU: the classifier writes
@@ -140,6 +175,20 @@ if world == 1:
     model.forward(g1, X_loc, hook=hook, logits_chunk=sink)
     res["phases_ms"] = phases
     say(f"  single-GPU GATN.forward {ms:.2f} ms; kernels: {phases}")
+    gcn.prepare(g1)
+
+    def gcn_step():
+        r = X_loc
+        for i in range(gcn.L - 1):
+            t = ops.linear(r, gcn.fc[i][0], gcn.fc[i][1], row_scale=gcn.norm)
+            r = ops.spmm(g1, t, row_scale=gcn.norm2 if i == gcn.L - 2 else gcn.norm, relu=True)
+        agg = ops.spmm(g1, r, row_scale=gcn.norm)
+        for lo in range(0, agg.shape[0], sink[0]):       # logits in re-used chunks, as above
+            hi = min(agg.shape[0], lo + sink[0])
+            torch.addmm(gcn.fc[-1][1], agg[lo:hi], gcn.fc[-1][0].t(), out=sink[1][:hi - lo])
+    ms = timed(gcn_step)
+    res["gcn_ms_single_gpu_model"] = round(ms, 3)
+    say(f"  single-GPU 3-layer GCN forward {ms:.2f} ms")
 say(json.dumps(res))
 if rank == 0:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -154,3 +154,51 @@ def test_three_layer_gat_two_ranks_matches_dense_reference(orc, tmp_path):
     t = lin(res, model.fc[-1])
     want = lin(attend(lin(t, model.efcL[-1]).reshape(-1), lin(t, model.efcR[-1]).reshape(-1), res), model.fc[-1])
     assert rel_err(got, want.float().numpy()) < 1e-5
+
+
+def _worker_gcn(rank, world, port, n, e, dims, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import orc
+    from gala_b200.gcn_model import GCNN
+
+    torch.set_num_threads(2)
+    offset, ids = synth.powerlaw_csr_torch(n, e, seed=7, device="cpu")
+    model = GCNN(dims, "cpu", seed=8)
+    X = torch.rand(n, dims[0], generator=torch.Generator().manual_seed(9)) - 0.5
+    part = dist_gat.RowPartition(offset, ids, n, rank, world)
+    t = orc.Tiled.from_csr(part.rows, part.padded_n, part.offset.numpy(), part.cols.numpy())
+
+    def aggregate(feats_all, row_scale, relu):
+        y = torch.from_numpy(orc.spmm(t, feats_all.numpy(), weighted=False)) * row_scale[:, None]
+        return torch.relu(y) if relu else y
+    deg = torch.from_numpy(orc.spmm(t, np.ones((part.padded_n, 1), np.float32), weighted=False)).reshape(-1)
+    out_loc = dist_gat.gcnn_forward_partitioned(model, part, X[part.row_lo:part.row_hi], torch.pow(deg, -0.5), aggregate)
+    gathered = part.unpad(part.all_gather(out_loc))
+    if rank == 0:
+        np.save(out_path, gathered.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_three_layer_gcn_two_ranks_matches_dense_reference(tmp_path):
+    """3-layer GCN, 1-D row partition (BASELINE.json configs[4] in miniature) against dense fp64 math."""
+    import torch.nn.functional as F
+    from gala_b200.gcn_model import GCNN
+
+    n, e, dims = 400, 5000, [10, 8, 8, 6]
+    out_path = str(tmp_path / "gcn_out.npy")
+    mp.spawn(_worker_gcn, args=(2, _free_port(), n, e, dims, out_path), nprocs=2, join=True)
+    got = np.load(out_path)
+    offset, ids = synth.powerlaw_csr_torch(n, e, seed=7, device="cpu")
+    model = GCNN(dims, "cpu", seed=8)
+    X = (torch.rand(n, dims[0], generator=torch.Generator().manual_seed(9)) - 0.5).double()
+    A = torch.zeros(n, n, dtype=torch.float64)
+    rows = torch.repeat_interleave(torch.arange(n), (offset[1:] - offset[:-1]).long())
+    A[rows, ids.long()] = 1.0
+    nrm = A.sum(1).pow(-0.5)[:, None]
+    res = X
+    for i in range(model.L - 1):
+        res = torch.relu(nrm * (A @ (nrm * F.linear(res, model.fc[i][0].double(), model.fc[i][1].double()))))
+    want = F.linear(nrm * (A @ (nrm * res)), model.fc[-1][0].double(), model.fc[-1][1].double())
+    assert rel_err(got, want.float().numpy()) < 1e-5
