@@ -114,7 +114,7 @@ def powerlaw_csr_torch(n, n_edges, seed=0, gamma=0.85, shift=None, device="cuda"
 
 def powerlaw_multigraph_coo_torch(n, n_edges, seed=0, gamma=0.85, device="cuda", chunk=200_000_000):
     """Papers-scale variant: directed power-law multigraph (both endpoints drawn from the same rank
-    distribution as above, node ids permuted; duplicates and self-loops kept, no symmetrisation -- at
+    distribution as above, node ids permuted; duplicates kept, one self loop per node, no symmetrisation -- at
     1.6 G edges torch.unique would need ~3x the memory, and CSRCMatrix::build keeps duplicates anyway).
     Ranks are drawn by inverting the continuous CDF of (i + shift)^-gamma in closed form: element-wise
     fp64 math only, so every GPU of a partitioned run synthesises bit-identical edges (a cumsum-based
@@ -130,11 +130,16 @@ def powerlaw_multigraph_coo_torch(n, n_edges, seed=0, gamma=0.85, device="cuda",
     perm = torch.randperm(n, generator=gen, device=device, dtype=torch.int32)
     rows = torch.empty(n_edges, dtype=torch.int32, device=device)
     cols = torch.empty(n_edges, dtype=torch.int32, device=device)
-    for lo in range(0, n_edges, chunk):
-        m = min(chunk, n_edges - lo)
+    n_rand = max(n_edges - n, 0)          # the last n edges are the self loops the data pipeline adds
+    for lo in range(0, n_rand, chunk):    # (scripts/Data/gala_export_npy.py:73-74): every row has degree >= 1
+        m = min(chunk, n_rand - lo)
         for dst in (rows, cols):
             u = torch.rand(m, generator=gen, device=device, dtype=torch.float64)
             i = ((u * (hi_c - lo_c) + lo_c) ** (1.0 / p) - shift).floor_().clamp_(0, n - 1).long()
             dst[lo:lo + m] = perm[i]
             del u, i
+    k = n_edges - n_rand
+    loops = torch.arange(k, dtype=torch.int32, device=device)
+    rows[n_rand:] = loops
+    cols[n_rand:] = loops
     return rows, cols
