@@ -479,7 +479,8 @@ def main():
                               graph_ms <= eager_ms else "K eager steps") + "; per-kernel events from the eager region"
 
     if not args.no_kernels and world == 1:
-        line["kernels"] = kernel_sweep(g, n, nvals, hidden, peak, dev)
+        line["kernels"] = kernel_sweep(g, n, nvals, hidden, peak, dev,
+                                       (roofline.get("l2") or {}).get("measured_read_gbs"))
 
     if world == 1 and not args.no_cpu_baseline:
         ms, info = cpu_arm(n, e, feats, offset.cpu().numpy(), ids.cpu().numpy(), X.cpu(), model, 1, 0)
@@ -503,7 +504,7 @@ def time_op(fn, reps=10, warm=3):
     return a.elapsed_time(b) / reps
 
 
-def kernel_sweep(g, n, nvals, K, peak, dev):
+def kernel_sweep(g, n, nvals, K, peak, dev, l2_gbs=None):
     """SpMM / SDDMM / edge kernels alone on the same graph: ms, compulsory-byte GB/s, fraction."""
     from gala_b200 import ops
 
@@ -517,14 +518,21 @@ def kernel_sweep(g, n, nvals, K, peak, dev):
     ev = torch.empty(nvals, device=dev)
     res = {}
 
-    def rec(name, ms, nbytes):
+    def rec(name, ms, nbytes, gather_bytes=None):
         gbs = nbytes / (ms * 1e-3) / 1e9
         res[name] = {"ms": round(ms, 4), "alg_GB": round(nbytes / 1e9, 4), "GBps": round(gbs, 1),
                      "frac_of_hbm_peak": round(gbs / peak, 4)}
+        if gather_bytes is not None and l2_gbs:
+            # gather kernels while X is L2-resident: bytes actually requested per launch (every edge gathers its
+            # row) against the L2->SM read bandwidth measured by the probe in this run
+            ggbs = gather_bytes / (ms * 1e-3) / 1e9
+            res[name]["gather_GBps"] = round(ggbs, 1)
+            res[name]["frac_of_l2_read"] = round(ggbs / l2_gbs, 4)
 
     rp = 4 * (n + 1)
-    rec("spmm_k32_unweighted", time_op(lambda: ops.spmm(g, X, out=Y)), rp + 4 * nvals + 8 * n * K)
-    rec("spmm_k32_weighted", time_op(lambda: ops.spmm(g, X, vals=w, out=Y)), rp + 8 * nvals + 8 * n * K)
+    gth = rp + 4 * nvals + 4 * nvals * K + 4 * n * K          # cols + one K-wide row per edge + Y
+    rec("spmm_k32_unweighted", time_op(lambda: ops.spmm(g, X, out=Y)), rp + 4 * nvals + 8 * n * K, gth)
+    rec("spmm_k32_weighted", time_op(lambda: ops.spmm(g, X, vals=w, out=Y)), rp + 8 * nvals + 8 * n * K, gth + 4 * nvals)
     nrm = torch.rand(n, generator=gen, device=dev) + 0.1
     # GCN layer body of the generated model (norm*res -> aggregate -> norm*res -> relu, codegen/gala.cu:441-450)
     # as ONE launch with the fused row/col scale + ReLU epilogue
@@ -539,7 +547,7 @@ def kernel_sweep(g, n, nvals, K, peak, dev):
     res["gcn_2layer_forward"] = {"ms": round(ms, 4), "layer_ms": round(ms / 2, 4),
                                  "launches": "linear(tcgen05)+2 aggregations+cuBLAS classifier"}
     del Xf
-    rec("sddmm_k32", time_op(lambda: ops.sddmm(g, Z, X, out=ev)), rp + 4 * nvals + 8 * n * K + 4 * nvals)
+    rec("sddmm_k32", time_op(lambda: ops.sddmm(g, Z, X, out=ev)), rp + 4 * nvals + 8 * n * K + 4 * nvals, gth + 4 * nvals)
     rec("sddvv_add", time_op(lambda: ops.sddvv(g, a, a, "add", out=ev)), rp + 4 * nvals + 8 * n + 4 * nvals)
     rec("edge_softmax_fwd", time_op(lambda: ops.edge_softmax_fwd(g, w, out=ev)), rp + 8 * nvals)
     rec("edge_rowsum", time_op(lambda: ops.edge_rowsum(g, w)), rp + 4 * nvals + 4 * n)
