@@ -75,6 +75,81 @@ class RowPartition:
         return torch.cat(parts, 0)
 
 
+class NeededRowsPartition:
+    """Same interface as RowPartition, but a rank only ever receives the feature rows its slab references
+    ("all-to-all-v of only the unique remote rows each peer needs, index lists
+    precomputed at partition time").  Local column numbering: [own rows | rows needed from rank 0 | ... |
+    rows needed from rank P-1] (the own block first, the requester's own rank contributes nothing).
+
+    `all_gather(x_local)` keeps its name for the runners above; here it is one all_to_all_single with the
+    precomputed splits and returns [rows + n_remote, K]."""
+
+    def __init__(self, offset, ids, n, rank, world):
+        self.n, self.rank, self.world = n, rank, world
+        self.bounds = partition_rows_by_nnz(offset, world)
+        self.row_lo, self.row_hi = self.bounds[rank], self.bounds[rank + 1]
+        self.rows = self.row_hi - self.row_lo
+        self.max_rows = max(self.bounds[q + 1] - self.bounds[q] for q in range(world))
+        dev = ids.device
+        e_lo, e_hi = int(offset[self.row_lo]), int(offset[self.row_hi])
+        self.local_nvals = e_hi - e_lo
+        self.offset = (offset[self.row_lo:self.row_hi + 1] - e_lo).to(torch.int32).contiguous()
+        bt = torch.tensor(self.bounds, dtype=torch.int64, device=dev)
+        cols = ids[e_lo:e_hi].to(torch.int64)
+        owner = torch.searchsorted(bt, cols, right=True) - 1
+        new_cols = torch.empty_like(cols)
+        mine = owner == rank
+        new_cols[mine] = cols[mine] - self.row_lo
+        base = self.rows
+        want = []                      # per owner: the sorted unique global rows this rank needs from it
+        for q in range(world):
+            if q == rank:
+                want.append(torch.empty(0, dtype=torch.int64, device=dev))
+                continue
+            sel = owner == q
+            uq, inv = torch.unique(cols[sel], return_inverse=True)
+            new_cols[sel] = base + inv
+            base += uq.numel()
+            want.append(uq - self.bounds[q])          # owner-local row indices
+        self.cols = new_cols.to(torch.int32).contiguous()
+        self.padded_n = base                          # columns of the local graph
+        self.recv_splits = [int(w.numel()) for w in want]
+        # tell every owner which of its rows to send here (one exchange of counts, one of indices)
+        counts = torch.tensor(self.recv_splits, dtype=torch.int64, device=dev)
+        send_counts = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(send_counts, counts)
+        self.send_splits = [int(c) for c in send_counts.tolist()]
+        req = torch.cat(want) if base > self.rows else torch.empty(0, dtype=torch.int64, device=dev)
+        self.send_idx = torch.empty(sum(self.send_splits), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(self.send_idx, req, self.send_splits, self.recv_splits)
+        self.n_remote = base - self.rows
+
+    def all_gather(self, x_local):
+        """[rows, K] -> [rows + n_remote, K]: own rows followed by the needed remote rows."""
+        x_local = x_local.contiguous()
+        tail = tuple(x_local.shape[1:])
+        send = x_local[self.send_idx].contiguous()
+        recv = x_local.new_empty((self.n_remote,) + tail)
+        dist.all_to_all_single(recv, send, self.recv_splits, self.send_splits)
+        return torch.cat([x_local, recv], 0)
+
+    def local_slice(self, gathered):
+        return gathered[:self.rows]
+
+    def gather_full(self, x_local):
+        """Every rank's rows in natural node order [n, K] (tests / final gathers only)."""
+        pad = x_local.new_zeros((self.max_rows,) + tuple(x_local.shape[1:]))
+        pad[:self.rows] = x_local
+        out = pad.new_empty((self.world * self.max_rows,) + tuple(x_local.shape[1:]))
+        dist.all_gather_into_tensor(out, pad)
+        return torch.cat([out[q * self.max_rows:q * self.max_rows + self.bounds[q + 1] - self.bounds[q]]
+                          for q in range(self.world)], 0)
+
+    def exchange_fraction(self):
+        """Rows received per exchange relative to the full all-gather (n - rows)."""
+        return self.n_remote / max(self.n - self.rows, 1)
+
+
 def gat2_forward_partitioned(model, part, X_local, aggregate, hook=None):
     """The 2-layer GAT forward of gat_model.GAT2 on a row partition.
     aggregate(aL_local, aR_all, feats_all, relu) -> [rows, K] runs the fused GAT kernel on

@@ -25,7 +25,7 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 dev = f"cuda:{local}"
 dist.init_process_group("nccl", device_id=torch.device(dev))
-scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+scale = float(sys.argv[1]) if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else 1.0
 
 
 def say(*a):
@@ -133,6 +133,19 @@ for exchange in (("p2p", "nccl") if world > 1 else ()):
         res["phases_ms_rank0"] = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 2) for i in range(1, len(marks))}
         say("  phases (rank 0):", res["phases_ms_rank0"])
     del runner
+    torch.cuda.empty_cache()
+if world > 1 and "--needed" in sys.argv:
+    # all-to-all-v of only the rows a slab references (dist_gat.NeededRowsPartition) instead of the full all-gather
+    offset2, ids2 = build(n, e, 0)
+    npart = dist_gat.NeededRowsPartition(offset2, ids2, n, rank, world)
+    del offset2, ids2
+    torch.cuda.empty_cache()
+    runner = dist_gat.PartitionedGATN(model, npart, dev, exchange="nccl")
+    ms = timed(lambda: runner.forward(X_loc))
+    res["ms_needed_rows_a2a"] = round(ms, 3)
+    res["needed_rows_fraction_rank0"] = round(npart.exchange_fraction(), 4)
+    say(f"  [needed-rows all-to-all] forward {ms:.2f} ms; rank 0 receives {npart.exchange_fraction():.1%} of the all-gather rows")
+    del runner, npart
     torch.cuda.empty_cache()
 gcn = GCNN(dims, dev, seed=2)
 for exchange in (("p2p", "nccl") if world > 1 else ()):
