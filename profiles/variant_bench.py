@@ -1,7 +1,6 @@
 """Times the gather kernels for every library build under variants/ (one subprocess per build).
    python profiles/variant_bench.py            -> table on stdout"""
 import glob
-import json
 import os
 import subprocess
 import sys

@@ -91,7 +91,6 @@ def test_format_outputs_are_fully_written_and_bounded(orc):
 
 
 def test_reorder_outputs_stay_in_bounds_and_errors_are_reported():
-    import ctypes as C
     from gala_b200 import lib as _l
 
     n = 777

@@ -1,7 +1,6 @@
 """GPU tests at BASELINE.json's full sizes (Reddit shape: 232,965 nodes, 114.6 M edges).
 The oracle cannot finish these in seconds, so parity is checked through size-independent
 properties plus an independent chunked fp64 torch recomputation of a row sample."""
-import numpy as np
 import pytest
 import torch
 
