@@ -88,7 +88,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // byte offset of element (row r, 4-byte column c) inside a [rows x 32 fp32] K-major SW128 tile
-__device__ __forceinline__ uint32_t sw128(int r, int c) {
+[[maybe_unused]] __device__ __forceinline__ uint32_t sw128(int r, int c) {   // reference form of the swizzle used below
     return (uint32_t)(r * 128 + ((((c >> 2) ^ (r & 7)) << 4) | ((c & 3) << 2)));
 }
 

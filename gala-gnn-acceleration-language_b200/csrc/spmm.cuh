@@ -212,8 +212,7 @@ __device__ __forceinline__ void row_dense_epilogue(const SpmmParams& p, const fl
 template <int VEC, int LPR, int ACC, int MODE, bool EXACT>
 __global__ void GALA_SPMM_BOUNDS
 spmm_kernel(const __grid_constant__ SpmmParams p) {
-    constexpr int TW = VEC * LPR * ACC;  // features covered by one warp pass
-    constexpr int EPI = 32 / LPR;        // edges in flight per load instruction
+    constexpr int TW = VEC * LPR * ACC;  // features covered by one warp pass (32 / LPR edges per load instruction)
     const GraphDev& g = p.g;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
