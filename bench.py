@@ -271,7 +271,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL_DEBUG is left as the caller set it (the driver reads NCCL's INFO log to count ranks); whatever
+        # NCCL prints on fd 1 already goes to stderr (quiet_stdout), so rank 0 still prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from gala_b200 import ops
     from gala_b200.gat_model import GAT2
@@ -417,6 +418,19 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
 
+    # ---- parity of the partitioned forward against the single-GPU forward of the same model on the same
+    # inputs (outside every timed region): every rank computes the whole-graph forward on its own GPU,
+    # compares its slab of rows, and the norms are reduced -> one relative error for the whole output
+    parity = None
+    if world > 1:
+        g_full = ops.TiledGraph(offset, ids, n).build_plan()
+        want = model.forward(g_full, X, mode="literal", dense="torch")[runner.row_lo:runner.row_hi]
+        got = runner.forward(X_in)
+        tt = torch.stack([(got.double() - want.double()).pow(2).sum(), want.double().pow(2).sum()])
+        dist.all_reduce(tt)
+        parity = float((tt[0] / tt[1]).sqrt().item())
+        del g_full, want, got
+
     def finish():
         """Leave without tearing NCCL down: destroy_process_group() after a captured collective can
         wait forever on the watchdog; every rank has passed the final barrier, so just exit."""
@@ -474,6 +488,9 @@ def main():
                     "h2d_bytes_per_step": int(X_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4)},
             "roofline": roofline, "kernel_ms": {k: round(v, 4) for k, v in kern_ms.items()},
             "eager_ms_per_step": round(eager_ms, 4),
+            "parity_rel_err": parity,
+            "parity_against": ("single-GPU op-by-op forward (cuBLAS dense parts) of the same model and inputs, "
+                               "all rows, norm-wise; bound 1e-5") if parity is not None else None,
             "graph_ms_per_step": round(graph_ms, 4) if graph_ms is not None else None}
     config["timed_region"] = ("K replays of the step captured in one CUDA graph" if graph_ms is not None and
                               graph_ms <= eager_ms else "K eager steps") + "; per-kernel events from the eager region"

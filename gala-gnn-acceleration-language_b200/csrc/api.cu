@@ -309,6 +309,9 @@ int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int3
     // (measured, profiles/r01_tiling_*.txt: segment-major only pays when every row still has >= ~100 edges per
     //  segment -- Reddit shape at K = 602: 21.2 -> 19.1 ms; on the Products shape, mean degree 50, it loses)
     if (p.accumulate && p.row_scale) seg_major = false;   // Y_old must not be scaled: keep the single launch
+    // hub rows without a row order: the natural-order fallback decides "hub or not" from the degree it sees, which
+    // is per segment in a segment-major launch -- a row could then be run by its hub CTA AND its warp
+    if (h.n > 0 && !h.order) seg_major = false;
     if (!seg_major) return launch_spmm<MODE_PLAIN>(p, S(stream));
     const float* row_scale = p.row_scale;
     const int relu = p.relu;

@@ -571,19 +571,28 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
     }
 }
 
+// SM count of the CURRENT device (cached per device ordinal; benign if two threads race to fill a slot)
+inline int device_sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cache[dev] = sms;
+    }
+    return cache[dev];
+}
+
 template <int NPAD>
 int launch_linear_v2(const LinearParams& p, cudaStream_t st) {
     constexpr size_t smem = 2 * (size_t)(4 * kBM * 128 + 4 * NPAD * 128) + 1024;
-    static bool configured = false;
-    static int sms = 0;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_v2_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        configured = true;
-    }
+    // the shared-memory opt-in is a per-device function attribute and the grid follows the current device's
+    // SM count: both are set on every launch (host-side, cheap) so that a process driving several GPUs, or
+    // several host threads, needs no shared "configured" state
+    cudaError_t e0 = cudaFuncSetAttribute(linear_tf32x3_v2_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e0 != cudaSuccess) return (int)e0;
+    const int sms = device_sm_count();
     const int64_t ntiles = (p.M + kBM - 1) / kBM;
     const unsigned grid = (unsigned)std::min<int64_t>(ntiles, sms > 0 ? sms : 148);
     linear_tf32x3_v2_kernel<NPAD><<<grid, kV2Threads, smem, st>>>(p);
@@ -594,12 +603,8 @@ int launch_linear_v2(const LinearParams& p, cudaStream_t st) {
 template <int NPAD>
 int launch_linear(const LinearParams& p, cudaStream_t st) {
     constexpr size_t smem = (size_t)kStages * (2 * kBM * 128 + 2 * NPAD * 128) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    cudaError_t e0 = cudaFuncSetAttribute(linear_tf32x3_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e0 != cudaSuccess) return (int)e0;
     const unsigned grid = (unsigned)((p.M + kBM - 1) / kBM);
     linear_tf32x3_kernel<NPAD><<<grid, kThreads, smem, st>>>(p);
     cudaError_t e = cudaGetLastError();

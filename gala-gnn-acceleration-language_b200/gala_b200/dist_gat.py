@@ -82,7 +82,8 @@ class NeededRowsPartition:
     rows needed from rank P-1] (the own block first, the requester's own rank contributes nothing).
 
     `all_gather(x_local)` keeps its name for the runners above; here it is one all_to_all_single with the
-    precomputed splits and returns [rows + n_remote, K]."""
+    precomputed splits and returns [rows + n_remote, K].  Only valid with exchange="nccl": the fused peer
+    exchange (PeerExchange) addresses the padded all-gather layout and rejects this partition."""
 
     def __init__(self, offset, ids, n, rank, world):
         self.n, self.rank, self.world = n, rank, world
@@ -239,6 +240,11 @@ class PeerExchange:
     def __init__(self, part, widths, device):
         import torch.distributed._symmetric_memory as symm
 
+        # every rank's slab sits at rank * max_rows of a [world * max_rows, K] buffer: only the padded
+        # all-gather layout of RowPartition has that shape (NeededRowsPartition numbers its columns per rank)
+        if part.padded_n != part.world * part.max_rows or isinstance(part, NeededRowsPartition):
+            raise ValueError("PeerExchange needs the padded all-gather layout (RowPartition); "
+                             "use exchange=\"nccl\" with NeededRowsPartition")
         self.part = part
         self.bufs, self.hdls, self.mos = [], [], []
         for K in widths:

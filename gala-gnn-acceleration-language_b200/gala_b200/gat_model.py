@@ -78,6 +78,13 @@ class GAT2:
         dense="tcgen05" runs the layer-1 transform (and, in folded mode, its two attention
         projections, fused in the epilogue) on the tensor cores (gala_linear_f32); "torch" = cuBLAS."""
         run = hook if hook is not None else (lambda name, fn: fn())
+        hidden, classes = self.fc0[0].shape[0], self.fc1[0].shape[0]
+        if dense == "tcgen05" and (hidden > ops.LINEAR_MAX_N or hidden > ops.LINEAR_SMALL_MAX or
+                                   classes > ops.LINEAR_SMALL_MAX):
+            # widths outside the hand-written transforms (gala_linear_f32: N <= LINEAR_MAX_N; gala_linear_small_f32:
+            # K, N <= 64): same op sequence with the dense parts on cuBLAS (what the generated program uses)
+            dense = "torch"
+            mode = "folded" if mode == "fused" else mode
         if mode == "fused":
             # three launches, no library kernel: tcgen05 transform (+ layer-1 projections), fused GAT layer
             # (+ layer-2 projections of its own output rows), fused GAT layer (+ classifier on its rows)

@@ -15,6 +15,8 @@ import torch
 from . import lib as _l
 
 DEFAULT_HUB_THRESHOLD = 2048
+LINEAR_MAX_N = 64         # widest output gala_linear_f32 accepts (GALA_ERR_UNSUPPORTED beyond)
+LINEAR_SMALL_MAX = 64     # gala_linear_small_f32: K <= 64 and N <= 64
 
 
 class TiledGraph:
@@ -63,6 +65,9 @@ class TiledGraph:
 
 
 def _f32(t):
+    """Contiguous fp32 CUDA view of `t`.  A non-contiguous argument is copied: the CALLER must bind the
+    result to a local that outlives the launch (never `_l.ptr(_f32(x))` inline -- the copy would be freed
+    when ptr() returns and the caching allocator could hand the same block to the next argument)."""
     assert t.dtype == torch.float32 and t.is_cuda
     return t.contiguous()
 
@@ -97,24 +102,27 @@ def spmm_sampled(g, X, nsamples, ra, rb, vals=None, out=None, accumulate=False):
 
 
 def edge_rowsum(g, vals, seed=1e-12, out=None):
+    vals = _f32(vals)
     if out is None:
         out = torch.empty((g.nrows, 1), dtype=torch.float32, device=vals.device)
-    _l.check(_l.load().gala_edge_rowsum_f32(C.byref(g.c), _l.ptr(_f32(vals)), _l.ptr(out), seed,
+    _l.check(_l.load().gala_edge_rowsum_f32(C.byref(g.c), _l.ptr(vals), _l.ptr(out), seed,
                                             g._p(), _l.stream_ptr()))
     return out
 
 
 def edge_scale_rows_(g, vals, rowval):
     """In place: vals[e] *= rowval[row(e)]."""
-    _l.check(_l.load().gala_edge_scale_rows_f32(C.byref(g.c), _l.ptr(vals), _l.ptr(_f32(rowval)),
+    rowval = _f32(rowval)
+    _l.check(_l.load().gala_edge_scale_rows_f32(C.byref(g.c), _l.ptr(vals), _l.ptr(rowval),
                                                 g._p(), _l.stream_ptr()))
     return vals
 
 
 def sddvv(g, A, B, op="add", leaky_slope=1.0, out=None):
+    A, B = _f32(A), _f32(B)
     if out is None:
         out = torch.empty(g.nvals, dtype=torch.float32, device=A.device)
-    _l.check(_l.load().gala_sddvv_f32(C.byref(g.c), _l.ptr(_f32(A)), _l.ptr(_f32(B)), _l.ptr(out),
+    _l.check(_l.load().gala_sddvv_f32(C.byref(g.c), _l.ptr(A), _l.ptr(B), _l.ptr(out),
                                       0 if op == "add" else 1, leaky_slope, g._p(), _l.stream_ptr()))
     return out
 
@@ -130,18 +138,20 @@ def sddmm(g, A, B, out=None):
 
 
 def edge_softmax_fwd(g, x, out=None, recip=None):
+    x = _f32(x)
     if out is None:
         out = torch.empty_like(x)
-    _l.check(_l.load().gala_edge_softmax_fwd_f32(C.byref(g.c), _l.ptr(_f32(x)), _l.ptr(out),
+    _l.check(_l.load().gala_edge_softmax_fwd_f32(C.byref(g.c), _l.ptr(x), _l.ptr(out),
                                                  _l.ptr(recip), g._p(), _l.stream_ptr()))
     return out
 
 
 def edge_softmax_bwd(g, alpha, dalpha, out=None):
+    alpha, dalpha = _f32(alpha), _f32(dalpha)
     if out is None:
         out = torch.empty_like(alpha)
-    _l.check(_l.load().gala_edge_softmax_bwd_f32(C.byref(g.c), _l.ptr(_f32(alpha)),
-                                                 _l.ptr(_f32(dalpha)), _l.ptr(out), g._p(),
+    _l.check(_l.load().gala_edge_softmax_bwd_f32(C.byref(g.c), _l.ptr(alpha),
+                                                 _l.ptr(dalpha), _l.ptr(out), g._p(),
                                                  _l.stream_ptr()))
     return out
 
@@ -149,21 +159,22 @@ def edge_softmax_bwd(g, alpha, dalpha, out=None):
 def gat_backward_att(g, alpha, dalpha, aL, aR, slope=0.2, out=None):
     """d(attenL) = d(attenR) of one GAT layer from d(alpha): softmax backward + LeakyReLU backward +
     row sum in one kernel (gala_gat_backward_att_f32)."""
+    alpha, dalpha, aL, aR = _f32(alpha), _f32(dalpha), _f32(aL), _f32(aR)
     if out is None:
         out = torch.empty((g.nrows, 1), dtype=torch.float32, device=alpha.device)
-    _l.check(_l.load().gala_gat_backward_att_f32(C.byref(g.c), _l.ptr(_f32(alpha)), _l.ptr(_f32(dalpha)),
-                                                 _l.ptr(_f32(aL)), _l.ptr(_f32(aR)), slope, _l.ptr(out),
+    _l.check(_l.load().gala_gat_backward_att_f32(C.byref(g.c), _l.ptr(alpha), _l.ptr(dalpha),
+                                                 _l.ptr(aL), _l.ptr(aR), slope, _l.ptr(out),
                                                  g._p(), _l.stream_ptr()))
     return out
 
 
 def gat_forward(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None):
     """Fused SDDVV + LeakyReLU + edge-softmax + weighted SpMM (one pass over the edges)."""
-    X = _f32(X)
+    X, aL, aR = _f32(X), _f32(aL), _f32(aR)
     K = X.shape[1]
     if out is None:
         out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
-    _l.check(_l.load().gala_gat_forward_f32(C.byref(g.c), _l.ptr(_f32(aL)), _l.ptr(_f32(aR)),
+    _l.check(_l.load().gala_gat_forward_f32(C.byref(g.c), _l.ptr(aL), _l.ptr(aR),
                                             _l.ptr(X), K, slope, _l.ptr(out), _l.ptr(alpha_out),
                                             int(relu), g._p(), _l.stream_ptr()))
     return out
@@ -173,15 +184,15 @@ def gat_forward_dot(g, aL, wR, bR, X, slope=0.2, relu=False, out=None, alpha_out
     """Fused GAT layer with aR[j] = dot(X[j,:], wR) + bR recomputed inside the kernel from the
     gathered rows (one random gather per edge instead of two).  Falls back to gat_forward with a
     materialised aR when the shape is outside the kernel's range (K % 4 != 0 or K > 32)."""
-    X = _f32(X)
+    X, aL = _f32(X), _f32(aL)
     K = X.shape[1]
-    wR = _f32(wR).reshape(-1)
+    wR = _f32(wR.reshape(-1))
     if K % 4 != 0 or K > 32 or X.data_ptr() % 16 != 0:
         aR = (X @ wR + bR).contiguous()
         return gat_forward(g, aL, aR, X, slope, relu, out, alpha_out)
     if out is None:
         out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
-    _l.check(_l.load().gala_gat_forward_dot_f32(C.byref(g.c), _l.ptr(_f32(aL)), _l.ptr(wR), float(bR),
+    _l.check(_l.load().gala_gat_forward_dot_f32(C.byref(g.c), _l.ptr(aL), _l.ptr(wR), float(bR),
                                                 _l.ptr(X), K, slope, _l.ptr(out), _l.ptr(alpha_out),
                                                 int(relu), g._p(), _l.stream_ptr()))
     return out
@@ -210,12 +221,13 @@ def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None, row_sc
     att = None
     ab = None
     if att_w is not None:
+        att_w = _f32(att_w)
         att = torch.empty((2, M), dtype=torch.float32, device=X.device)
         ab = (C.c_float * 2)(float(att_b[0]), float(att_b[1]))
     _l.check(_l.load().gala_linear_f32(_l.ptr(X), M, K, _l.ptr(W), _l.ptr(bias), N,
                                        _l.ptr(out) if out is not None else None,
                                        _l.ptr(row_scale), int(relu),
-                                       _l.ptr(_f32(att_w)) if att_w is not None else None, ab,
+                                       _l.ptr(att_w), ab,
                                        _l.ptr(att), C.byref(multi_out) if multi_out is not None else None,
                                        _l.stream_ptr()))
     return (out, att) if att_w is not None else out
@@ -226,7 +238,7 @@ def gat_forward_ex(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None
     """Fused GAT layer + dense epilogue on every finished output row: the next layer's two attention
     projections (att_w [2,K], att_b two floats -> att [2, nrows]) and / or the transform that follows
     the aggregation (cls_wT [K,C] = Linear weight transposed -> [nrows, C]).  Returns (Y, att, cls)."""
-    X = _f32(X)
+    X, aL, aR = _f32(X), _f32(aL), _f32(aR)
     K = X.shape[1]
     dev = X.device
     if multi_out is not None:
@@ -239,7 +251,8 @@ def gat_forward_ex(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None
     att = cls = None
     if att_w is not None:
         att = torch.empty((2, g.nrows), dtype=torch.float32, device=dev)
-        ep.att_w = _f32(att_w).data_ptr()
+        att_w = _f32(att_w)
+        ep.att_w = att_w.data_ptr()
         ep.att_b[0], ep.att_b[1] = float(att_b[0]), float(att_b[1])
         ep.att_out = att.data_ptr()
     if cls_wT is not None:
@@ -249,7 +262,7 @@ def gat_forward_ex(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None
         ep.cls_b = cls_b.data_ptr() if cls_b is not None else None
         ep.cls_out = cls.data_ptr()
         ep.cls_n = cls_wT.shape[1]
-    _l.check(_l.load().gala_gat_forward_ex_f32(C.byref(g.c), _l.ptr(_f32(aL)), _l.ptr(_f32(aR)), _l.ptr(X), K,
+    _l.check(_l.load().gala_gat_forward_ex_f32(C.byref(g.c), _l.ptr(aL), _l.ptr(aR), _l.ptr(X), K,
                                                slope, _l.ptr(out) if want_y else None, _l.ptr(alpha_out),
                                                int(relu), C.byref(ep), g._p(), _l.stream_ptr()))
     return out, att, cls
@@ -312,6 +325,7 @@ def gat_forward_bf16(g, aL, aR, X_bf16, slope=0.2, relu=False, out=None, alpha_o
     K = X.shape[1]
     if out is None:
         out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
-    _l.check(_l.load().gala_gat_forward_bf16(C.byref(g.c), _l.ptr(_f32(aL)), _l.ptr(_f32(aR)), _l.ptr(X), K, slope,
+    aL, aR = _f32(aL), _f32(aR)
+    _l.check(_l.load().gala_gat_forward_bf16(C.byref(g.c), _l.ptr(aL), _l.ptr(aR), _l.ptr(X), K, slope,
                                              _l.ptr(out), _l.ptr(alpha_out), int(relu), g._p(), _l.stream_ptr()))
     return out

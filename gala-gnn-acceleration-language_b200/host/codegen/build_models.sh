@@ -28,18 +28,41 @@ build_one() {
   local flag=""; [ "$kind" = "ref" ] && flag="--reference"
   "$HERE/gala_b200_codegen" "$model" "$dataset" "$feats" "$labels" "$tile" "$mode" "$dir/" "$REPO" $flag ${flags//+/ } > "$dir/codegen.log" 2>&1
   # instrumentation of the GENERATED text (identical for both generators)
-  sed -i 's|    if (epoch >= skip_cache_warmup) {|    if (epoch == 1) { std::cout << "CHECK " << std::setprecision(9) << prediction.abs().sum().item<float>() << " " << d_loss.item<float>() << std::endl; }\n    if (epoch >= skip_cache_warmup) {|' "$dir/gala.cu"
+  # (check_epoch.h, injected with -include): CHECK lines at epochs 1, 2 and 5 -- checksum, loss, sum|grad| per parameter
+  sed -i 's|    if (epoch >= skip_cache_warmup) {|    gala_check_epoch(epoch, prediction, d_loss, net);\n    if (epoch >= skip_cache_warmup) {|' "$dir/gala.cu"
   # the generated program never seeds libtorch: weights differ from run to run.  Seed it.
   sed -i 's|auto net = std::make_shared<GALAGNN>|torch::manual_seed(0); auto net = std::make_shared<GALAGNN>|' "$dir/gala.cu"
   local extra="-lcusparse"
   [ "$kind" = "b200" ] && extra="-I$REPO/include -I$REPO/gala-gnn-acceleration-language_b200/host -L$REPO/gala-gnn-acceleration-language_b200 -lgala_b200 -Xlinker -rpath -Xlinker $REPO/gala-gnn-acceleration-language_b200"
   (cd "$dir" && nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -O3 -w -Xcompiler -fopenmp \
-      -DGALA_TORCH -DGN_1 -DPT_0 -DST_0 -DA_ALLOC -I"$REF/codegen" \
+      -DGALA_TORCH -DGN_1 -DPT_0 -DST_0 -DA_ALLOC -I"$REF/codegen" -include "$HERE/check_epoch.h" \
       -I"$TORCH/include" -I"$TORCH/include/torch/csrc/api/include" gala.cu -o gala_model \
       -L"$TORCH/lib" -Xlinker -rpath -Xlinker "$TORCH/lib" -Xlinker --no-as-needed \
       -ltorch -ltorch_cpu -ltorch_cuda -lc10 -lc10_cuda -lgomp $extra > build.log 2>&1 && echo "built $dir") || echo "FAILED $dir (see build.log)"
 }
+# Per-op harness over the STOCK generator's text (ref_ops_harness.cu): the reference's own kernels, wrappers and
+# autograd classes callable one by one.  build_harness <name> <program whose _ref/build/gala.cu is included> <defines>
+build_harness() {
+  local name=$1 prog=$2; shift 2
+  local src="$HERE/_models/${prog}_ref/build/gala.cu" out="$HERE/_models/harness"
+  [ -f "$src" ] || { echo "FAILED harness $name: $src missing (build the $prog program first)"; return; }
+  mkdir -p "$out"
+  (cd "$out" && nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -O3 -w -Xcompiler -fopenmp \
+      -DGALA_TORCH -DGN_1 -DPT_0 -DST_0 -DA_ALLOC -I"$REF/codegen" -include "$HERE/check_epoch.h" \
+      -DGALA_GENERATED="\"$src\"" "$@" \
+      -I"$TORCH/include" -I"$TORCH/include/torch/csrc/api/include" "$HERE/ref_ops_harness.cu" -o "ref_ops_$name" \
+      -L"$TORCH/lib" -Xlinker -rpath -Xlinker "$TORCH/lib" -Xlinker --no-as-needed \
+      -ltorch -ltorch_cpu -ltorch_cuda -lc10 -lc10_cuda -lgomp -lcusparse > "build_$name.log" 2>&1 && echo "built harness $name") || echo "FAILED harness $name (see $out/build_$name.log)"
+}
 JOBS=${JOBS:-4}
+if [ -n "$HARNESS" ]; then   # HARNESS=1 build_models.sh : only the per-op harnesses (their programs must exist)
+  build_harness gat gat_train -DHARNESS_GAT &
+  build_harness agg gcn_inference -DHARNESS_AGG -DHARNESS_DIRECT &
+  build_harness sampled gcn_inference_sample20 -DHARNESS_AGG &
+  build_harness sparser gcn_inference_products_sparser -DHARNESS_AGG -DHARNESS_EDGE_MUL &
+  wait
+  exit 0
+fi
 for spec in $SPECS; do
   IFS=: read -r model mode tile dataset feats labels flags <<< "$spec"
   for kind in ${KINDS:-b200 ref}; do

@@ -11,7 +11,7 @@
 // reference is copied into the repository.
 //
 // usage: gala_b200_codegen <gcn|gat|gin|sage> <dataset> <feat> <labels> <col_tile> <inference|train>
-//                          <outdir> <gala_b200_root> [--reference] [--no-fuse] [--sample S] [--graph-sample S]
+//                          <outdir> <gala_b200_root> [--reference] [--no-fuse] [--sparser] [--sample S] [--graph-sample S]
 #include <cstring>
 #include <iostream>
 #include <map>
@@ -49,17 +49,18 @@ std::string GALAFEContext::opt_input = "";
 int main(int argc, char** argv) {
     if (argc < 9) {
         std::cerr << "usage: gala_b200_codegen <gcn|gat|gin|sage> <dataset> <feat> <labels> <col_tile> "
-                     "<inference|train> <outdir> <gala_b200_root> [--reference] [--no-fuse] [--sample S] [--graph-sample S]\n";
+                     "<inference|train> <outdir> <gala_b200_root> [--reference] [--no-fuse] [--sparser] [--sample S] [--graph-sample S]\n";
         return 2;
     }
     std::string model = argv[1], dataset = argv[2], mode = argv[6], outdir = argv[7], root = argv[8];
     int feat = atoi(argv[3]), labels = atoi(argv[4]), colTile = atoi(argv[5]);
     bool reference = false;
     int sample = 0, graphSample = 0;
-    bool noFuse = false;
+    bool noFuse = false, sparser = false;
     for (int i = 9; i < argc; i++) {
         if (!strcmp(argv[i], "--reference")) reference = true;
         else if (!strcmp(argv[i], "--no-fuse")) noFuse = true;
+        else if (!strcmp(argv[i], "--sparser")) sparser = true;   // G=G.is_sparser(true) (frontend.y:304-305)
         else if (!strcmp(argv[i], "--sample") && i + 1 < argc) sample = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--graph-sample") && i + 1 < argc) graphSample = atoi(argv[++i]);
     }
@@ -95,6 +96,7 @@ int main(int argc, char** argv) {
     m1.addGraphTransformation(FEAT_SIZE, (float)feat);
     m1.addGraphTransformation(LABEL_SIZE, (float)labels);
     if (graphSample) m1.addGraphTransformation(SAMP, (float)graphSample);
+    if (sparser) m1.addGraphTransformation(SPARSE, 1);
     m1.addComputeTransformation(COARSE, 2);
     if (sample) m1.addComputeTransformation(SAMP_CPT, (float)sample);
     m1.addDataTransformation(COL_TILE, (float)colTile);

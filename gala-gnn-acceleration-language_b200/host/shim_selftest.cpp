@@ -29,6 +29,16 @@ static void expect_close(const char* what, const torch::Tensor& got, const torch
     if (!(err < tol)) ++failures;
 }
 
+// for sums that cancel (the attention gradients: every row of softmax-backward sums to ~0): error relative to the
+// magnitude that was summed, the backward-error form of the 1e-5 bound
+static void expect_close_mag(const char* what, const torch::Tensor& got, const torch::Tensor& want, const torch::Tensor& mag,
+                             double tol) {
+    double err = ((got.to(torch::kDouble).flatten() - want.to(torch::kDouble).flatten()).norm() /
+                  mag.to(torch::kDouble).norm().clamp_min(1e-30)).item<double>();
+    std::printf("%-44s err / summed magnitude %.3e %s\n", what, err, err < tol ? "ok" : "FAIL");
+    if (!(err < tol)) ++failures;
+}
+
 int main() {
     if (!torch::cuda::is_available()) {
         std::printf("no CUDA device\n");
@@ -164,6 +174,30 @@ int main() {
         expect_close("gat_layer_AutoGrad d(res)", Xg.grad(), dX_w, 1e-6);
         expect_close("gat_layer_AutoGrad d(attenL)", aLg.grad(), datt_w, 2e-4);   // cancelling row sums
         expect_close("gat_layer_AutoGrad d(attenR)", aRg.grad(), datt_w, 2e-4);
+
+        // ---- the same layer against DENSE libtorch autograd in fp64 (an arbiter that shares no code with the
+        // wrappers above): masked [N,N] attention written with plain ATen ops as the generated program computes
+        // it (common.h:622-675, 1176-1184, 760-773, 835-894), differentiated by torch.
+        auto od = of.device(dev).dtype(torch::kDouble);
+        torch::Tensor mask = (A_w != 0).to(torch::kDouble);
+        torch::Tensor aLd = aL.to(torch::kDouble).detach().requires_grad_(true);
+        torch::Tensor aRd = aR.to(torch::kDouble).detach().requires_grad_(true);
+        torch::Tensor Xdd = Xd.detach().clone().requires_grad_(true);
+        torch::Tensor act = torch::leaky_relu(aLd + aRd.t(), 0.2);
+        act.retain_grad();
+        torch::Tensor num = torch::clamp(torch::exp(act), 0.0, 1e12) * mask;
+        torch::Tensor alpha_d = num / (num.sum(1, true) + S * 1e-12);
+        alpha_d.retain_grad();
+        torch::Tensor Yd = alpha_d.mm(Xdd);
+        Yd.backward(dZ.to(torch::kDouble));
+        expect_close("dense autograd: forward", Yf, Yd, 1e-5);
+        expect_close("dense autograd: d(alpha) = edge_sddmm", da_w, alpha_d.grad().index({r64, c64}), 1e-5);
+        expect_close("dense autograd: softmax backward", sm, act.grad().index({r64, c64}), 1e-5);
+        expect_close_mag("dense autograd: d(attenL)", aLg.grad(), aLd.grad(), (act.grad().abs() * mask).sum(1), 1e-5);
+        // reference semantics of d(res): the forward alpha over slot 2li+1, which is the forward graph itself for
+        // undirected inputs (common.h:876-885) -> alpha @ dZ; the mathematical gradient is alpha^T @ dZ
+        expect_close("reference semantics: d(res) = alpha @ dZ", Xg.grad(), alpha_d.detach().mm(dZ.to(torch::kDouble)), 1e-5);
+        (void)od;
     }
 
     torch::Tensor norm = torch::pow(deg, -0.5);
