@@ -76,17 +76,22 @@ inline int last_error() {
 }
 
 // Pick the vector width / lanes-per-row / accumulators-per-lane for a feature width.
+// The vector width follows the alignment of the GATHERED rows only (base pointer and row pitch `ld`): a row of
+// K = 41 floats stored with pitch 44 is gathered with 128-bit loads (the last one reads 3 floats of padding).
 struct Shape {
     int vec, lpr, acc;
 };
-Shape pick_shape(int K, bool a16, bool a8) {
+Shape shape_for(int K, int vec) {
     Shape s;
-    s.vec = (K % 4 == 0 && a16) ? 4 : (K % 2 == 0 && a8) ? 2 : 1;
-    int units = K / s.vec;
+    s.vec = vec;
+    int units = (K + s.vec - 1) / s.vec;
     s.lpr = 1;
     while (s.lpr < units && s.lpr < 32) s.lpr <<= 1;
     s.acc = units <= 32 ? 1 : units <= 64 ? 2 : 4;
     return s;
+}
+Shape pick_shape(int K, const void* base, int64_t ld) {
+    return shape_for(K, (ld % 4 == 0 && aligned(base, 16)) ? 4 : (ld % 2 == 0 && aligned(base, 8)) ? 2 : 1);
 }
 
 #define GALA_SHAPE_SWITCH(SH, CALL)                                        \
@@ -124,12 +129,12 @@ Shape pick_shape(int K, bool a16, bool a8) {
 template <int MODE>
 int launch_spmm(const SpmmParams& p, cudaStream_t st) {
     if (p.g.nrows == 0 || p.K == 0) return GALA_OK;
-    const bool a16 = aligned(p.X, 16) && (!p.Y || aligned(p.Y, 16));
-    const bool a8 = aligned(p.X, 8) && (!p.Y || aligned(p.Y, 8));
-    Shape sh = pick_shape(p.K, a16, a8);
+    if (p.ldx < p.K || p.ldy < p.K) return GALA_ERR_BAD_SHAPE;
+    Shape sh = pick_shape(p.K, p.X, p.ldx);
     const int tw = sh.vec * sh.lpr * sh.acc;
     dim3 grid(p.t.n_hub + (p.t.n_ordered + kWarpsPerCta - 1) / kWarpsPerCta, (p.K + tw - 1) / tw);
-    if (sh.vec == 4 && p.K % tw == 0) {
+    const bool y16 = !p.Y || (aligned(p.Y, 16) && p.ldy % 4 == 0);
+    if (sh.vec == 4 && p.K % tw == 0 && y16) {
         // K is a whole number of tiles: no per-lane feature predicates in the gather loop
 #define CALL(V, L, A) spmm_kernel<4, L, A, MODE, true><<<grid, kCtaThreads, 0, st>>>(p)
         switch (sh.lpr * 100 + sh.acc) {
@@ -201,6 +206,20 @@ __global__ void __launch_bounds__(256) probe_read_kernel(const uint4* __restrict
         }
     }
     if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) *sink = acc;   // data-dependent, practically never taken
+}
+}  // namespace gala
+
+namespace gala {
+// Xp[r, 0:K] = X[r, 0:K], Xp[r, K:ld_out] = 0: re-pitch packed rows so that every row starts 16-byte aligned
+// (coalesced: consecutive threads write consecutive output elements)
+__global__ void __launch_bounds__(256) pad_rows_kernel(const float* __restrict__ X, int64_t nrows, int K, int64_t ld_in,
+                                                       float* __restrict__ Xp, int64_t ld_out) {
+    const int64_t total = nrows * ld_out;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / ld_out;
+        const int c = (int)(i - r * ld_out);
+        Xp[i] = c < K ? __ldg(X + r * ld_in + c) : 0.0f;
+    }
 }
 }  // namespace gala
 
@@ -276,6 +295,17 @@ int gala_plan_build(const gala_graph_t* g, int32_t hub_threshold, void* workspac
 // column range is gathered from; column-tiled graphs are then executed segment by segment.
 constexpr int64_t kL2ResidentBytes = 96ll << 20;
 
+int gala_pad_rows_f32(const float* X, int64_t nrows, int32_t K, int64_t ld_in, float* Xp, int64_t ld_out,
+                      gala_stream_t stream) {
+    if (nrows < 0 || K < 0 || ld_in < K || ld_out < K) return GALA_ERR_BAD_SHAPE;
+    if (nrows == 0 || ld_out == 0) return GALA_OK;
+    if (!X || !Xp) return GALA_ERR_NULL_POINTER;
+    const int64_t total = nrows * ld_out;
+    const int blocks = (int)std::min<int64_t>((total + 1023) / 1024, 148 * 16);
+    pad_rows_kernel<<<blocks, 256, 0, S(stream)>>>(X, nrows, K, ld_in, Xp, ld_out);
+    return last_error();
+}
+
 int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int32_t K, float* Y,
                   const gala_epilogue_t* ep, const gala_plan_t* plan, gala_stream_t stream) {
     if (int rc = check_graph(g)) return rc;
@@ -289,6 +319,7 @@ int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int3
     p.X = X;
     p.Y = Y;
     p.K = K;
+    p.ldx = p.ldy = K;
     int schedule = 0;
     if (ep) {
         p.row_scale = ep->row_scale;
@@ -296,7 +327,10 @@ int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int3
         p.accumulate = ep->accumulate;
         p.relu = ep->relu;
         schedule = ep->schedule;
+        if (ep->ldx > 0) p.ldx = ep->ldx;
+        if (ep->ldy > 0) p.ldy = ep->ldy;
     }
+    if (p.ldx < K || p.ldy < K) return GALA_ERR_BAD_SHAPE;
     HubView h = hub_of(plan, g);
     p.t = task_of(h);
     // Segment-major schedule: one launch per column segment, accumulating into Y, so that the slice of
@@ -343,6 +377,7 @@ int gala_gat_forward_f32(const gala_graph_t* g, const float* aL, const float* aR
     p.X = X;
     p.Y = Y;
     p.K = K;
+    p.ldx = p.ldy = K;
     p.relu = relu;
     p.aL = aL;
     p.aR = aR;
@@ -366,6 +401,7 @@ int gala_spmm_bf16(const gala_graph_t* g, const float* vals, const uint16_t* X, 
     p.X = reinterpret_cast<const float*>(X);
     p.Y = Y;
     p.K = K;
+    p.ldx = p.ldy = K;
     if (ep) {
         p.row_scale = ep->row_scale;
         p.col_scale = ep->col_scale;
@@ -389,6 +425,7 @@ int gala_gat_forward_bf16(const gala_graph_t* g, const float* aL, const float* a
     p.X = reinterpret_cast<const float*>(X);
     p.Y = Y;
     p.K = K;
+    p.ldx = p.ldy = K;
     p.relu = relu;
     p.aL = aL;
     p.aR = aR;
@@ -422,6 +459,9 @@ int gala_gat_forward_ex_f32(const gala_graph_t* g, const float* aL, const float*
     p.slope = slope;
     p.alpha_out = alpha_out;
     p.seed_total = (float)g->segments * 1e-12f;
+    p.ldx = (ep && ep->ldx > 0) ? ep->ldx : K;
+    p.ldy = (ep && ep->ldy > 0) ? ep->ldy : K;
+    if (p.ldx < K || p.ldy < K) return GALA_ERR_BAD_SHAPE;
     if (has_ep) {
         if (K > kRowBufMax) return GALA_ERR_UNSUPPORTED;
         if (ep->att_w && !ep->att_out) return GALA_ERR_NULL_POINTER;
@@ -443,9 +483,7 @@ int gala_gat_forward_ex_f32(const gala_graph_t* g, const float* aL, const float*
     HubView h = hub_of(plan, g);
     p.t = task_of(h);
     if (has_ep) {   // the dense epilogue needs the whole row in one warp pass: check the tiling the dispatcher picks
-        const bool a16 = aligned(X, 16) && (!Y || aligned(Y, 16));
-        const bool a8 = aligned(X, 8) && (!Y || aligned(Y, 8));
-        Shape sh = pick_shape(K, a16, a8);
+        Shape sh = pick_shape(K, X, p.ldx);
         if (sh.vec * sh.lpr * sh.acc < K) return GALA_ERR_UNSUPPORTED;
     }
     return launch_spmm<MODE_GAT>(p, S(stream));
@@ -465,6 +503,7 @@ int gala_gat_forward_dot_f32(const gala_graph_t* g, const float* aL, const float
     p.X = X;
     p.Y = Y;
     p.K = K;
+    p.ldx = p.ldy = K;
     p.relu = relu;
     p.aL = aL;
     p.wR = wR;
@@ -486,7 +525,8 @@ int gala_gat_forward_dot_f32(const gala_graph_t* g, const float* aL, const float
 }
 
 int gala_spmm_sampled_f32(const gala_graph_t* g, const float* vals, const float* X, int32_t K, float* Y,
-                          int32_t nsamples, int32_t ra, int32_t rb, int32_t accumulate, gala_stream_t stream) {
+                          int32_t nsamples, int32_t ra, int32_t rb, int32_t accumulate, int64_t ldx, int64_t ldy,
+                          gala_stream_t stream) {
     if (int rc = check_graph(g)) return rc;
     if (K < 0 || nsamples < 0) return GALA_ERR_BAD_SHAPE;
     if ((g->nrows > 0 && K > 0) && (!X || !Y)) return GALA_ERR_NULL_POINTER;
@@ -503,9 +543,10 @@ int gala_spmm_sampled_f32(const gala_graph_t* g, const float* vals, const float*
     p.ra = ra;
     p.rb = rb;
     p.accumulate = accumulate;
-    const bool a16 = aligned(X, 16) && aligned(Y, 16);
-    const bool a8 = aligned(X, 8) && aligned(Y, 8);
-    Shape sh = pick_shape(K, a16, a8);
+    p.ldx = ldx > 0 ? ldx : K;
+    p.ldy = ldy > 0 ? ldy : K;
+    if (p.ldx < K || p.ldy < K) return GALA_ERR_BAD_SHAPE;
+    Shape sh = pick_shape(K, X, p.ldx);
     const int tw = sh.vec * sh.lpr * sh.acc;
     dim3 grid((g->nrows + kWarpsPerCta - 1) / kWarpsPerCta, (K + tw - 1) / tw);
     cudaStream_t st = S(stream);
@@ -649,9 +690,9 @@ int gala_sddmm_f32(const gala_graph_t* g, const float* A, const float* B, int32_
     p.B = B;
     p.out = out;
     p.K = K;
-    const bool a16 = aligned(A, 16) && aligned(B, 16);
-    const bool a8 = aligned(A, 8) && aligned(B, 8);
-    Shape sh = pick_shape(K > 0 ? K : 1, a16, a8);
+    const bool a16 = aligned(A, 16) && aligned(B, 16) && K % 4 == 0;
+    const bool a8 = aligned(A, 8) && aligned(B, 8) && K % 2 == 0;
+    Shape sh = shape_for(K > 0 ? K : 1, a16 ? 4 : a8 ? 2 : 1);
     dim3 grid(h.n + (h.n_ordered + kWarpsPerCta - 1) / kWarpsPerCta);
     cudaStream_t st = S(stream);
     if (sh.vec == 4 && K == sh.vec * sh.lpr * sh.acc) {   // one exact tile (hidden widths 4..512): predicate-free loop

@@ -29,6 +29,7 @@ struct SpmmParams {
     const float* __restrict__ X;          // [ncols, K]
     float* __restrict__ Y;                // [nrows, K]
     int K;
+    int64_t ldx, ldy;                     // row pitch of X / Y in elements (>= K; K when the rows are packed)
     const float* __restrict__ row_scale;  // nullable
     const float* __restrict__ col_scale;  // nullable
     int accumulate;
@@ -226,7 +227,10 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
     // VEC == 8 is the bf16-feature flavour: X holds bf16 rows (2 bytes per feature), see Vec<8>
     constexpr uint32_t XB = VEC == 8 ? 2u : 4u;
     static_assert(VEC != 8 || (ACC == 1 && EXACT && MODE != MODE_GAT_DOT), "bf16 rows: one exact tile, no dot mode");
-    const uint32_t row_bytes = (uint32_t)p.K * XB;
+    const uint32_t row_bytes = (uint32_t)p.ldx * XB;
+    // Y rows go out as VEC-wide stores when their pitch and base keep that alignment; otherwise (packed rows of
+    // odd width) element by element -- N*K*4 bytes once per launch, nothing next to the gather
+    const bool yvec = VEC == 1 || VEC == 8 || (p.ldy % VEC == 0 && (reinterpret_cast<uintptr_t>(p.Y) % (VEC * 4)) == 0);
     // the lane's first feature; lanes past K (non-EXACT shapes) point at the tile start
     const char* xlane = reinterpret_cast<const char*>(p.X) +
                         (size_t)(tile_base + ((EXACT || tile_base + sub * VEC < p.K) ? sub * VEC : 0)) * XB;
@@ -318,9 +322,17 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
             for (int a = 0; a < ACC; ++a) {
                 if (!fvalid[a]) continue;
                 const int f0 = tile_base + (a * LPR + sub) * VEC;
-                float* y = p.Y + (int64_t)row * p.K + f0;
+                float* y = p.Y + (int64_t)row * p.ldy + f0;
+                // whole vector inside the row and aligned: one VEC-wide access; else element by element
+                const bool whole = EXACT || (yvec && f0 + VEC <= p.K);
                 Vec<VEC> o;
-                if (p.accumulate) o.load_rw(y);
+                if (p.accumulate) {
+                    if (whole) o.load_rw(y);
+                    else {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) o.v[v] = (f0 + v < p.K) ? y[v] : 0.0f;
+                    }
+                }
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
                     float t = p.scale_after ? acc[a][v] : acc[a][v] * scale;
@@ -328,11 +340,18 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
                     if (p.scale_after) t *= scale;
                     if (p.relu) t = fmaxf(t, 0.0f);
                     o.v[v] = t;
-                    if (dense_ep) rowbuf[warp][f0 + v] = t;
+                    if (dense_ep && (EXACT || f0 + v < p.K)) rowbuf[warp][f0 + v] = t;
                 }
                 if constexpr (VEC <= 4) {
                     if (p.mo.count > 0) multi_store<VEC>(p.mo, (int64_t)row * p.K + f0, o);
-                    else if (p.Y) o.store(y);
+                    else if (p.Y) {
+                        if (whole) o.store(y);
+                        else {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v)
+                                if (f0 + v < p.K) y[v] = o.v[v];
+                        }
+                    }
                 } else {
                     if (p.Y) o.store(y);
                 }
@@ -373,7 +392,7 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
         float t = 0.0f;
 #pragma unroll
         for (int w = 0; w < kWarpsPerCta; ++w) t += part[w * TW + f];
-        float* y = p.Y + (int64_t)row * p.K + tile_base + f;
+        float* y = p.Y + (int64_t)row * p.ldy + tile_base + f;
         if (!p.scale_after) t *= scale;
         if (p.accumulate) t += *y;
         if (p.scale_after) t *= scale;
@@ -405,6 +424,7 @@ struct SampledParams {
     const float* __restrict__ X;
     float* __restrict__ Y;
     int K;
+    int64_t ldx, ldy;
     int nsamples, ra, rb;
     int accumulate;
 };
@@ -422,6 +442,7 @@ spmm_sampled_kernel(const __grid_constant__ SampledParams p) {
     const int tile_base = blockIdx.y * TW;
     const int row = blockIdx.x * kWarpsPerCta + warp;
     if (row >= g.nrows) return;
+    const bool yvec = VEC == 1 || (p.ldy % VEC == 0 && (reinterpret_cast<uintptr_t>(p.Y) % (VEC * 4)) == 0);
 
     bool fvalid[ACC];
 #pragma unroll
@@ -442,7 +463,7 @@ spmm_sampled_kernel(const __grid_constant__ SampledParams p) {
             const int j = (p.ra * ji + p.rb) % jmax;  // cuda.h:320, int arithmetic as emitted
             const int c = __ldg(g.cols + base + j);
             const float w = p.vals ? __ldg(p.vals + base + j) : 1.0f;
-            const float* xr = p.X + (int64_t)c * p.K + tile_base + sub * VEC;
+            const float* xr = p.X + (int64_t)c * p.ldx + tile_base + sub * VEC;
 #pragma unroll
             for (int a = 0; a < ACC; ++a) {
                 if (fvalid[a]) {
@@ -464,12 +485,19 @@ spmm_sampled_kernel(const __grid_constant__ SampledParams p) {
 #pragma unroll
         for (int a = 0; a < ACC; ++a) {
             if (!fvalid[a]) continue;
-            float* y = p.Y + (int64_t)row * p.K + tile_base + (a * LPR + sub) * VEC;
-            Vec<VEC> o;
-            if (p.accumulate) o.load_rw(y);
+            const int f0 = tile_base + (a * LPR + sub) * VEC;
+            float* y = p.Y + (int64_t)row * p.ldy + f0;
+            if (yvec && f0 + VEC <= p.K) {
+                Vec<VEC> o;
+                if (p.accumulate) o.load_rw(y);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) o.v[v] = p.accumulate ? o.v[v] + acc[a][v] : acc[a][v];
-            o.store(y);
+                for (int v = 0; v < VEC; ++v) o.v[v] = p.accumulate ? o.v[v] + acc[a][v] : acc[a][v];
+                o.store(y);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (f0 + v < p.K) y[v] = p.accumulate ? y[v] + acc[a][v] : acc[a][v];
+            }
         }
     }
 }

@@ -19,7 +19,7 @@ EXPORTS = [
     "gala_edge_scale_rows_f32", "gala_sddvv_f32", "gala_sddmm_f32", "gala_edge_softmax_fwd_f32",
     "gala_edge_softmax_bwd_f32", "gala_gat_forward_f32", "gala_gat_forward_dot_f32", "gala_linear_f32",
     "gala_gat_forward_ex_f32", "gala_linear_small_f32", "gala_gat_backward_att_f32",
-    "gala_spmm_bf16", "gala_gat_forward_bf16",
+    "gala_spmm_bf16", "gala_gat_forward_bf16", "gala_pad_rows_f32",
     "gala_csr_from_coo_workspace_bytes", "gala_csr_from_coo", "gala_csr_transpose",
     "gala_col_tile_segments", "gala_col_tile_workspace_bytes", "gala_col_tile", "gala_sample_ab",
     "gala_mask_subgraph_workspace_bytes", "gala_mask_subgraph",
@@ -40,7 +40,7 @@ class GalaPlan(C.Structure):
 
 class GalaEpilogue(C.Structure):
     _fields_ = [("row_scale", C.c_void_p), ("col_scale", C.c_void_p), ("accumulate", C.c_int32),
-                ("relu", C.c_int32), ("schedule", C.c_int32)]
+                ("relu", C.c_int32), ("schedule", C.c_int32), ("ldx", C.c_int64), ("ldy", C.c_int64)]
 
 
 class GalaMultiOut(C.Structure):
@@ -50,7 +50,8 @@ class GalaMultiOut(C.Structure):
 class GalaDenseEpilogue(C.Structure):
     _fields_ = [("att_w", C.c_void_p), ("att_b", C.c_float * 2), ("att_out", C.c_void_p),
                 ("cls_wT", C.c_void_p), ("cls_b", C.c_void_p), ("cls_out", C.c_void_p),
-                ("cls_n", C.c_int32), ("multi_out", C.POINTER(GalaMultiOut))]
+                ("cls_n", C.c_int32), ("multi_out", C.POINTER(GalaMultiOut)), ("ldx", C.c_int64),
+                ("ldy", C.c_int64)]
 
 
 class GalaError(RuntimeError):
@@ -81,7 +82,8 @@ def load():
     sigs = {
         "gala_plan_build": [G, i32, vp, C.c_size_t, P, vp],
         "gala_spmm_f32": [G, vp, vp, i32, vp, E, P, vp],
-        "gala_spmm_sampled_f32": [G, vp, vp, i32, vp, i32, i32, i32, i32, vp],
+        "gala_spmm_sampled_f32": [G, vp, vp, i32, vp, i32, i32, i32, i32, C.c_int64, C.c_int64, vp],
+        "gala_pad_rows_f32": [vp, C.c_int64, i32, C.c_int64, vp, C.c_int64, vp],
         "gala_spmm_bf16": [G, vp, vp, i32, vp, E, P, vp],
         "gala_gat_forward_bf16": [G, vp, vp, vp, i32, f32, vp, vp, i32, P, vp],
         "gala_edge_rowsum_f32": [G, vp, vp, f32, P, vp],

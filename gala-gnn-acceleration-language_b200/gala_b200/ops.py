@@ -75,29 +75,70 @@ def _f32(t):
 SCHEDULES = {"auto": 0, "row_major": 1, "segment_major": 2}
 
 
-def spmm(g, X, vals=None, out=None, row_scale=None, col_scale=None, accumulate=False, relu=False, schedule="auto"):
+def _rows(t):
+    """(tensor, K, row pitch in elements) of a dense fp32 operand: packed [n, K] / [n], or a row-pitched 2-D
+    view (stride(1) == 1, e.g. padded[:, :K]) that is passed to the kernels as it is (ABI v2: ldx / ldy)."""
+    assert t.dtype == torch.float32 and t.is_cuda
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1] and t.shape[0] > 1:
+        return t, t.shape[1], t.stride(0)
+    t = t.contiguous()
+    K = t.shape[1] if t.dim() == 2 else 1
+    return t, K, K
+
+
+def _dptr(t):
+    """Device pointer of a (possibly row-pitched) tensor."""
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def pad_rows(X, multiple=4):
+    """X [n, K] -> a view [n, K] of a fresh [n, ld] buffer with ld = K rounded up to `multiple`, padding zeroed
+    (gala_pad_rows_f32): every row then starts 16-byte aligned and is gathered with 128-bit loads."""
+    X, K, ld_in = _rows(X)
+    n = X.shape[0]
+    ld = (K + multiple - 1) // multiple * multiple
+    buf = torch.empty((n, ld), dtype=torch.float32, device=X.device)
+    _l.check(_l.load().gala_pad_rows_f32(_dptr(X), n, K, ld_in, _l.ptr(buf), ld, _l.stream_ptr()))
+    return buf[:, :K]
+
+
+def _gather_operand(X, pad):
+    """The dense operand whose rows are gathered.  pad="auto": packed rows whose width is not a multiple of 4
+    (41 / 47 classes, 602 features) are re-pitched once -- N*K*8 bytes against E*K*4 gathered."""
+    X, K, ld = _rows(X)
+    if pad == "auto" and K > 4 and (ld % 4 != 0 or X.data_ptr() % 16 != 0):
+        X = pad_rows(X)
+        ld = X.stride(0)
+    return X, K, ld
+
+
+def spmm(g, X, vals=None, out=None, row_scale=None, col_scale=None, accumulate=False, relu=False, schedule="auto",
+         pad="auto"):
     """Y = A @ X (optionally weighted / scaled / accumulated / ReLU'd).  One launch, or -- for
-    column-tiled graphs whose feature matrix exceeds the L2 -- one launch per column segment."""
-    X = _f32(X)
-    K = X.shape[1] if X.dim() == 2 else 1
+    column-tiled graphs whose feature matrix exceeds the L2 -- one launch per column segment.
+    X and out may be row-pitched views; pad=None gathers packed odd-width rows as they are (scalar loads)."""
+    X, K, ldx = _gather_operand(X, pad)
     if out is None:
         out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
         assert not accumulate, "accumulate needs a caller-provided output"
+    assert out.dim() == 1 or out.stride(-1) == 1
+    ldy = out.stride(0) if out.dim() == 2 and out.shape[0] > 1 else K
     ep = _l.GalaEpilogue(row_scale=row_scale.data_ptr() if row_scale is not None else None,
                          col_scale=col_scale.data_ptr() if col_scale is not None else None,
-                         accumulate=int(accumulate), relu=int(relu), schedule=SCHEDULES[schedule])
-    _l.check(_l.load().gala_spmm_f32(C.byref(g.c), _l.ptr(vals), _l.ptr(X), K, _l.ptr(out),
+                         accumulate=int(accumulate), relu=int(relu), schedule=SCHEDULES[schedule],
+                         ldx=ldx, ldy=ldy)
+    _l.check(_l.load().gala_spmm_f32(C.byref(g.c), _l.ptr(vals), _dptr(X), K, _dptr(out),
                                      C.byref(ep), g._p(), _l.stream_ptr()))
     return out
 
 
-def spmm_sampled(g, X, nsamples, ra, rb, vals=None, out=None, accumulate=False):
-    X = _f32(X)
-    K = X.shape[1] if X.dim() == 2 else 1
+def spmm_sampled(g, X, nsamples, ra, rb, vals=None, out=None, accumulate=False, pad="auto"):
+    X, K, ldx = _gather_operand(X, pad)
     if out is None:
         out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
-    _l.check(_l.load().gala_spmm_sampled_f32(C.byref(g.c), _l.ptr(vals), _l.ptr(X), K, _l.ptr(out),
-                                             nsamples, ra, rb, int(accumulate), _l.stream_ptr()))
+    ldy = out.stride(0) if out.dim() == 2 and out.shape[0] > 1 else K
+    _l.check(_l.load().gala_spmm_sampled_f32(C.byref(g.c), _l.ptr(vals), _dptr(X), K, _dptr(out),
+                                             nsamples, ra, rb, int(accumulate), ldx, ldy, _l.stream_ptr()))
     return out
 
 
@@ -170,10 +211,16 @@ def gat_backward_att(g, alpha, dalpha, aL, aR, slope=0.2, out=None):
 
 def gat_forward(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None):
     """Fused SDDVV + LeakyReLU + edge-softmax + weighted SpMM (one pass over the edges)."""
-    X, aL, aR = _f32(X), _f32(aL), _f32(aR)
-    K = X.shape[1]
+    aL, aR = _f32(aL), _f32(aR)
+    X, K, ldx = _gather_operand(X, "auto")
     if out is None:
         out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
+    if ldx != K or not out.is_contiguous():     # row-pitched operands go through the _ex entry point (ldx / ldy)
+        ep = _l.GalaDenseEpilogue(ldx=ldx, ldy=out.stride(0) if out.shape[0] > 1 else K)
+        _l.check(_l.load().gala_gat_forward_ex_f32(C.byref(g.c), _l.ptr(aL), _l.ptr(aR), _dptr(X), K, slope,
+                                                   _dptr(out), _l.ptr(alpha_out), int(relu), C.byref(ep), g._p(),
+                                                   _l.stream_ptr()))
+        return out
     _l.check(_l.load().gala_gat_forward_f32(C.byref(g.c), _l.ptr(aL), _l.ptr(aR),
                                             _l.ptr(X), K, slope, _l.ptr(out), _l.ptr(alpha_out),
                                             int(relu), g._p(), _l.stream_ptr()))

@@ -15,8 +15,11 @@
 
 class B200Generator : public CUDAGenerator {
 public:
-    B200Generator(GALAContext* context, std::string& outputPath, const std::string& galaB200Root)
-        : CUDAGenerator(context, outputPath), root_(galaB200Root) {}
+    // deviceFormats: the generated main prepares its graphs on the GPU (host/gala_b200_host.h re-creates the
+    // reference's host-side classes and functions under their own names on top of the C-ABI) instead of
+    // including the reference's CPU headers.
+    B200Generator(GALAContext* context, std::string& outputPath, const std::string& galaB200Root, bool deviceFormats = true)
+        : CUDAGenerator(context, outputPath), root_(galaB200Root), deviceFormats_(deviceFormats) {}
 
     // replaces CUDAGenerator::initCMake (cuda.h:18-56): no icpx, sm_100a, link libgala_b200
     void initCMake() override {
@@ -43,13 +46,19 @@ public:
             "#include <cuda_runtime_api.h>\n"
             "#include <torch/script.h>\n"
             "#include <cmath>\n#include <iostream>\n#include <parallel/algorithm>\n#include <vector>\n"
-            "#include <bits/stdc++.h>\n#include <omp.h>\n#include <stdlib.h>\n#include <torch/torch.h>\n"
-            "#include \"../src/formats/csrc_matrix.h\"\n"
-            "#include \"../src/formats/dense_matrix.h\"\n"
-            "#include \"../src/ops/aggregators.h\"\n"
-            "#include \"../src/ops/tiling.h\"\n"
-            "#include \"../src/utils/mtx_io.h\"\n"
-            "#include \"../tests/common.h\"\n";
+            "#include <bits/stdc++.h>\n#include <omp.h>\n#include <stdlib.h>\n#include <torch/torch.h>\n";
+        if (deviceFormats_) {
+            // formats, tiling, sampling, sub-graphs and the .npy readers: same names, built on the GPU
+            imports += "#include \"gala_b200_host.h\"\n";
+        } else {
+            imports +=
+                "#include \"../src/formats/csrc_matrix.h\"\n"
+                "#include \"../src/formats/dense_matrix.h\"\n"
+                "#include \"../src/ops/aggregators.h\"\n"
+                "#include \"../src/ops/tiling.h\"\n"
+                "#include \"../src/utils/mtx_io.h\"\n"
+                "#include \"../tests/common.h\"\n";
+        }
         importCode.addCode(imports);
 
         std::string prelude =
@@ -135,6 +144,7 @@ public:
 
 private:
     std::string root_;
+    bool deviceFormats_;
 
     // One line per aggregation flavour instead of kernel text + launch tree; the edge ops
     // (softmax / edge-sum / edge-mul nodes) need nothing: the shim defines their fixed names.

@@ -56,10 +56,11 @@ int main(int argc, char** argv) {
     int feat = atoi(argv[3]), labels = atoi(argv[4]), colTile = atoi(argv[5]);
     bool reference = false;
     int sample = 0, graphSample = 0;
-    bool noFuse = false, sparser = false;
+    bool noFuse = false, sparser = false, hostFormats = false;
     for (int i = 9; i < argc; i++) {
         if (!strcmp(argv[i], "--reference")) reference = true;
         else if (!strcmp(argv[i], "--no-fuse")) noFuse = true;
+        else if (!strcmp(argv[i], "--host-formats")) hostFormats = true;   // keep the reference's CPU data preparation
         else if (!strcmp(argv[i], "--sparser")) sparser = true;   // G=G.is_sparser(true) (frontend.y:304-305)
         else if (!strcmp(argv[i], "--sample") && i + 1 < argc) sample = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--graph-sample") && i + 1 < argc) graphSample = atoi(argv[++i]);
@@ -111,7 +112,7 @@ int main(int argc, char** argv) {
 
     auto ctx = new GALAContext(GPU_DEVICE, SINGLE_NODE_SINGLE);
     std::string outPath = outdir;
-    CUDAGenerator* gen = reference ? new CUDAGenerator(ctx, outPath) : new B200Generator(ctx, outPath, root);
+    CUDAGenerator* gen = reference ? new CUDAGenerator(ctx, outPath) : new B200Generator(ctx, outPath, root, !hostFormats);
     if (GALAFEContext::operator_reordering)
         GALATransformations::complexityOperatorReordering(GALAFEContext::program, GALAFEContext::dependencies,
                                                           GALAFEContext::associations, GALAFEContext::transforms);

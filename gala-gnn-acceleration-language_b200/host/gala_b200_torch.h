@@ -77,6 +77,20 @@ inline torch::TensorOptions out_options(const torch::Tensor& like) {
     return torch::TensorOptions().dtype(torch::kFloat).requires_grad(true).device(like.device());
 }
 
+// The dense operand whose rows are gathered, as (tensor, row pitch).  Packed rows whose width is not a multiple of
+// 4 (the class counts 41 / 47 the shipped schedules aggregate at; the reference handles them with its K % 32
+// remainder kernels, cuda.h:58-168) are re-pitched once with gala_pad_rows_f32 so that every row is gathered with
+// 128-bit loads: N*K*8 bytes against the E*K*4 bytes of the gather.
+inline std::pair<torch::Tensor, int64_t> gather_operand(const torch::Tensor& input_dense, int64_t nrows, int64_t dcols) {
+    auto X = input_dense.contiguous();
+    if (dcols <= 4 || (dcols % 4 == 0 && reinterpret_cast<uintptr_t>(X.data_ptr()) % 16 == 0)) return {X, dcols};
+    const int64_t ld = (dcols + 3) / 4 * 4;
+    auto Xp = torch::empty({nrows, ld}, torch::TensorOptions().dtype(torch::kFloat).device(X.device()));
+    check(gala_pad_rows_f32(X.data_ptr<float>(), nrows, (int)dcols, dcols, Xp.data_ptr<float>(), ld, stream()),
+          "gala_pad_rows_f32");
+    return {Xp, ld};
+}
+
 // aggregate_node_mul_sum*_call: Y = A @ X.  nsamples > 0 selects the sampled flavour
 // (cuda.h:313-320) with global_ra / global_rb.
 inline torch::Tensor aggregate(const torch::Tensor& input_dense, const torch::Tensor& offset_graph,
@@ -85,15 +99,18 @@ inline torch::Tensor aggregate(const torch::Tensor& input_dense, const torch::Te
     // cuda.h:451 uses global_nrows; the cuSPARSE flavour (cuda.h:217) derives it from the row pointers
     const int64_t nrows = global_nrows > 0 ? global_nrows : offset_graph.numel() - 1;
     const int64_t dcols = input_dense.numel() / nrows;
-    auto X = input_dense.contiguous();
+    auto [X, ldx] = gather_operand(input_dense, nrows, dcols);
     auto Y = torch::empty({nrows, dcols}, out_options(input_dense));
     gala_graph_t g = make_graph(offset_graph, columns_graph, bounds, segments > 0 ? segments : 1, nrows);
     const float* vals = weighted ? value_graph.data_ptr<float>() : nullptr;
     if (nsamples > 0) {
         check(gala_spmm_sampled_f32(&g, vals, X.data_ptr<float>(), (int)dcols, Y.data_ptr<float>(), nsamples,
-                                    global_ra, global_rb, 0, stream()), "gala_spmm_sampled_f32");
+                                    global_ra, global_rb, 0, ldx, dcols, stream()), "gala_spmm_sampled_f32");
     } else {
-        check(gala_spmm_f32(&g, vals, X.data_ptr<float>(), (int)dcols, Y.data_ptr<float>(), nullptr,
+        gala_epilogue_t ep = {};
+        ep.ldx = ldx;
+        ep.ldy = dcols;
+        check(gala_spmm_f32(&g, vals, X.data_ptr<float>(), (int)dcols, Y.data_ptr<float>(), &ep,
                             plan_for(g, input_dense), stream()), "gala_spmm_f32");
     }
     return Y;
@@ -107,7 +124,7 @@ inline torch::Tensor gat_forward(const torch::Tensor& res, const torch::Tensor& 
                                  torch::Tensor* alpha_out = nullptr) {
     const int64_t nrows = global_nrows;
     const int64_t dcols = res.numel() / nrows;
-    auto X = res.contiguous();
+    auto [X, ldx] = gather_operand(res, nrows, dcols);
     auto aL = attenL.contiguous();
     auto aR = attenR.contiguous();
     auto Y = torch::empty({nrows, dcols}, out_options(res));
@@ -117,9 +134,12 @@ inline torch::Tensor gat_forward(const torch::Tensor& res, const torch::Tensor& 
         *alpha_out = torch::empty({columns_graph.numel()}, out_options(res));
         alpha = alpha_out->data_ptr<float>();
     }
-    check(gala_gat_forward_f32(&g, aL.data_ptr<float>(), aR.data_ptr<float>(), X.data_ptr<float>(), (int)dcols,
-                               slope, Y.data_ptr<float>(), alpha, relu ? 1 : 0, plan_for(g, res), stream()),
-          "gala_gat_forward_f32");
+    gala_dense_epilogue_t ep = {};
+    ep.ldx = ldx;
+    ep.ldy = dcols;
+    check(gala_gat_forward_ex_f32(&g, aL.data_ptr<float>(), aR.data_ptr<float>(), X.data_ptr<float>(), (int)dcols,
+                                  slope, Y.data_ptr<float>(), alpha, relu ? 1 : 0, &ep, plan_for(g, res), stream()),
+          "gala_gat_forward_ex_f32");
     return Y;
 }
 

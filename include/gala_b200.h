@@ -47,7 +47,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define GALA_B200_ABI_VERSION 1
+#define GALA_B200_ABI_VERSION 2   /* v2: row pitches ldx / ldy, gala_pad_rows_f32 */
 
 #define GALA_OK 0
 #define GALA_ERR_NULL_POINTER (-1)
@@ -100,6 +100,12 @@ typedef struct gala_epilogue {
                                slice of X a segment gathers from stays in L2) when
                                ncols*K*4 exceeds the L2, row-major (one launch)
                                otherwise; or force either                            */
+    int64_t ldx;            /* row pitch of X in elements; 0 = K (packed rows).  A pitch that
+                               is a multiple of 4 on a 16-byte aligned base lets every row be
+                               gathered with 128-bit loads whatever K is (K = 41 stored with
+                               pitch 44: the reference's K % 32 remainder kernels,
+                               cuda.h:58-168, become one pass); gala_pad_rows_f32 re-pitches  */
+    int64_t ldy;            /* row pitch of Y in elements; 0 = K                              */
 } gala_epilogue_t;
 #define GALA_SCHEDULE_AUTO 0
 #define GALA_SCHEDULE_ROW_MAJOR 1
@@ -136,9 +142,17 @@ int gala_spmm_f32(const gala_graph_t *g, const float *vals, const float *X, int3
 /* segment, sum over j = (ra*ji + rb) % deg for ji in [0, nsamples).              */
 /* (ra, rb) = global_ra/global_rb (common.h:817-830).  Y is overwritten unless    */
 /* accumulate != 0.                                                              */
+/* ldx / ldy: row pitches of X / Y in elements, 0 = K.                              */
 int gala_spmm_sampled_f32(const gala_graph_t *g, const float *vals, const float *X, int32_t K,
                           float *Y, int32_t nsamples, int32_t ra, int32_t rb, int32_t accumulate,
-                          gala_stream_t stream);
+                          int64_t ldx, int64_t ldy, gala_stream_t stream);
+
+/* Re-pitch a dense matrix: Xp[r, 0:K] = X[r, 0:K], Xp[r, K:ld_out] = 0 (X with row pitch   */
+/* ld_in >= K, Xp with ld_out >= K).  What a producer that cannot write pitched rows      */
+/* itself runs once (N*K*8 bytes) before aggregating at a width that is not a multiple of */
+/* 4 -- the class counts 41 / 47 of the shipped schedules.                                 */
+int gala_pad_rows_f32(const float *X, int64_t nrows, int32_t K, int64_t ld_in, float *Xp,
+                      int64_t ld_out, gala_stream_t stream);
 
 /* ---- optional reduced-precision feature storage (not in the reference: its path is fp32 throughout) ---- */
 /* Same kernels with the GATHERED rows stored as bf16 (X: [ncols, K] bf16, row pitch 2K bytes): half the      */
@@ -237,6 +251,7 @@ typedef struct gala_dense_epilogue {
     float *cls_out;
     int32_t cls_n;
     const gala_multi_out_t *multi_out; /* nullable: Y rows go to every GPU instead of Y */
+    int64_t ldx, ldy;                  /* row pitches of X / Y in elements, 0 = K       */
 } gala_dense_epilogue_t;
 int gala_gat_forward_ex_f32(const gala_graph_t *g, const float *aL, const float *aR, const float *X,
                             int32_t K, float slope, float *Y, float *alpha_out, int32_t relu,

@@ -37,6 +37,13 @@ for shape, Ks in (("reddit", (1, 32, 41, 64, 128, 602)), ("products", (1, 32, 47
         bmin = 4 * (n + 1) + 4 * g.nvals + 8 * n * K
         bg = 4 * (n + 1) + 4 * g.nvals + 4 * g.nvals * K + 4 * n * K
         line = f"  K={K:4d} spmm {ms:8.4f} ms  B_min {bmin / ms / 1e6:7.0f} GB/s  B_gather {bg / ms / 1e6:7.0f} GB/s"
+        if K % 4 != 0 and K > 4:
+            # the default above re-pitches X once per call (gala_pad_rows_f32, included in its time); next to it:
+            # rows gathered packed with narrow loads (round-1 behaviour) and a producer that wrote pitched rows itself
+            ms_packed = t(lambda: ops.spmm(g, X, out=Y, pad=None), reps=3)
+            Xp = ops.pad_rows(X)
+            ms_pitched = t(lambda: ops.spmm(g, Xp, out=Y))
+            line += f" | packed rows, narrow loads {ms_packed:8.4f} ms | caller-pitched rows {ms_pitched:8.4f} ms"
         if K in (32, 64, 128):
             a = torch.randn(n, device=dev)
             ms2 = t(lambda: ops.gat_forward(g, a, a, X, out=Y))

@@ -420,8 +420,58 @@ def test_misaligned_views_fall_back_to_narrow_loads(orc):
     buf[1:] = dev(X).ravel()
     Xv = buf[1:].view(n, K)                      # 4-byte aligned only
     assert Xv.data_ptr() % 16 != 0
-    got = ops.spmm(g, Xv).cpu().numpy()
+    got = ops.spmm(g, Xv, pad=None).cpu().numpy()           # gathered where it lies: 4-byte loads
     assert rel_err(got, orc.spmm(t, X, weighted=False)) < FP32_TOL
+    got = ops.spmm(g, Xv).cpu().numpy()                     # default: re-pitched once, 128-bit loads
+    assert rel_err(got, orc.spmm(t, X, weighted=False)) < FP32_TOL
+
+
+@pytest.mark.parametrize("case", [CASES[2], CASES[3], CASES[4]])
+@pytest.mark.parametrize("K", [5, 7, 41, 47, 100, 602])
+def test_row_pitched_operands(orc, case, K):
+    """ABI v2 row pitches (ldx / ldy): odd-width rows stored with a 16-byte pitch are gathered with 128-bit loads
+    (the reference runs K % 32 remainder kernels for them, cuda.h:58-168).  Every combination of packed / pitched
+    X and Y gives the same result as the oracle on the packed data; the padding of Y is never written."""
+    n, e, seed, T, empty, thr = case
+    t = graph_case(orc, n, e, seed, T, empty)
+    g = to_gpu_graph(t, thr)
+    rng = np.random.default_rng(seed + K)
+    X = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    want = orc.spmm(t, X, weighted=True)
+    Xd = dev(X)
+    ld = (K + 3) // 4 * 4
+    Xp = ops.pad_rows(Xd)
+    assert Xp.stride(0) == ld and Xp.data_ptr() % 16 == 0 and torch.equal(Xp, Xd)
+    if ld > K:
+        assert float(Xp.as_strided((n, ld - K), (ld, 1), K).abs().max()) == 0.0   # padding zeroed
+    packed_scalar = ops.spmm(g, Xd, vals=dev(t.vals), pad=None)           # packed rows, narrow loads
+    pitched = ops.spmm(g, Xp, vals=dev(t.vals))                            # caller-provided pitched rows
+    auto = ops.spmm(g, Xd, vals=dev(t.vals))                               # default: re-pitched internally
+    for got in (packed_scalar, pitched, auto):
+        assert got.is_contiguous() and rel_err(got.cpu().numpy(), want) < FP32_TOL
+    assert torch.equal(pitched, auto)
+    # pitched OUTPUT: the columns past K keep their sentinel
+    Yp = torch.full((n, ld + 4), 7.0, device=DEV)
+    ops.spmm(g, Xp, vals=dev(t.vals), out=Yp[:, :K])
+    assert torch.equal(Yp[:, :K], pitched) and bool((Yp[:, K:] == 7.0).all())
+    # accumulate + epilogue on pitched rows
+    norm = dev(rng.uniform(0.1, 1.0, n).astype(np.float32))
+    Y0 = dev(rng.uniform(-1, 1, (n, K)).astype(np.float32))
+    Ya = Y0.clone()
+    ops.spmm(g, Xp, vals=dev(t.vals), out=Ya, accumulate=True, relu=True, schedule="row_major")
+    assert rel_err(Ya.cpu().numpy(), np.maximum(want + Y0.cpu().numpy(), 0)) < FP32_TOL
+    y = ops.spmm(g, Xp, vals=dev(t.vals), row_scale=norm, col_scale=norm)
+    ws = orc.Tiled(t.nrows, t.ncols, t.S, t.offsets, t.cols, t.vals * norm.cpu().numpy()[t.cols], t.bounds)
+    assert rel_err(y.cpu().numpy(), norm.cpu().numpy()[:, None] * orc.spmm(ws, X, weighted=True)) < FP32_TOL
+    # sampled flavour and the fused GAT layer take pitched rows too
+    if K in (41, 47):
+        ys = ops.spmm_sampled(g, Xd, 20, 5, 7)
+        assert rel_err(ys.cpu().numpy(), orc.spmm_sampled(t, X, 20, 5, 7)) < FP32_TOL
+        aL, aR = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)
+        yg, _ = orc.gat_forward(t, aL, aR, X)
+        a_out = torch.empty(g.nvals, device=DEV)
+        got = ops.gat_forward(g, dev(aL), dev(aR), Xd, alpha_out=a_out)
+        assert rel_err(got.cpu().numpy(), yg) < FP32_TOL
 
 
 def test_results_are_bit_reproducible(orc):
