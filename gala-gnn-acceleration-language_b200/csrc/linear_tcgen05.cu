@@ -104,6 +104,7 @@ struct LinearParams {
     float* __restrict__ Y;            // [M, N]
     const float* __restrict__ row_scale;  // [M] or nullptr: Y[r,:] *= row_scale[r] (before ReLU)
     const float* __restrict__ att_w;  // [2, N] or nullptr
+    const float* __restrict__ att_b_dev;  // [2] on the device, or nullptr: att_b0 / att_b1 below
     float att_b0, att_b1;
     float* __restrict__ att_out;      // [2, M]
     int64_t M;
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
             for (int j = 0; j < 16; ++j) acc[(c0 + j) % NPAD] += __uint_as_float(u[j]);
         }
         if (r < p.M) {
-            float a0 = p.att_b0, a1 = p.att_b1;
+            float a0 = p.att_b_dev ? __ldg(p.att_b_dev) : p.att_b0, a1 = p.att_b_dev ? __ldg(p.att_b_dev + 1) : p.att_b1;
             const float rscale = p.row_scale ? __ldg(p.row_scale + r) : 1.0f;
 #pragma unroll
             for (int n = 0; n < NPAD; ++n) {
@@ -513,7 +514,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acce_bar[aset]);        // the accumulator set may be overwritten
-            float a0 = p.att_b0, a1 = p.att_b1;
+            float a0 = p.att_b_dev ? __ldg(p.att_b_dev) : p.att_b0, a1 = p.att_b_dev ? __ldg(p.att_b_dev + 1) : p.att_b1;
             if (r < p.M) {
                 const float rscale = p.row_scale ? __ldg(p.row_scale + r) : 1.0f;
 #pragma unroll
@@ -615,7 +616,8 @@ int launch_linear(const LinearParams& p, cudaStream_t st) {
 
 extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float* W, const float* bias, int32_t N, float* Y,
                                const float* row_scale, int32_t relu, const float* att_w, const float* att_b,
-                               float* att_out, const gala_multi_out_t* multi_out, gala_stream_t stream) {
+                               int32_t att_b_on_device, float* att_out, const gala_multi_out_t* multi_out,
+                               gala_stream_t stream) {
     if (M < 0 || K <= 0 || N <= 0) return GALA_ERR_BAD_SHAPE;
     if (N > 64) return GALA_ERR_UNSUPPORTED;   // one CTA holds every output column (GNN hidden / class widths)
     if (M == 0) return GALA_OK;
@@ -640,9 +642,13 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
     p.K = K;
     p.N = N;
     p.relu = relu;
-    if (att_w) {   // att_b is a HOST pointer to two floats
-        p.att_b0 = att_b[0];
-        p.att_b1 = att_b[1];
+    if (att_w) {   // att_b: two floats, on the host (read here) or on the device (read by the kernel)
+        if (att_b_on_device) {
+            p.att_b_dev = att_b;
+        } else {
+            p.att_b0 = att_b[0];
+            p.att_b1 = att_b[1];
+        }
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool v2 = (K % 2 == 0) && (reinterpret_cast<uintptr_t>(X) % 8 == 0) && (reinterpret_cast<uintptr_t>(W) % 8 == 0) &&

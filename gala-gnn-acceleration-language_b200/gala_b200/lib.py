@@ -100,7 +100,7 @@ def load():
     i64, sz = C.c_int64, C.c_size_t
     sigs.update({
         "gala_linear_small_f32": [vp, i64, i32, vp, vp, i32, vp, i32, i32, vp],
-        "gala_linear_f32": [vp, i64, i32, vp, vp, i32, vp, vp, i32, vp, C.POINTER(C.c_float), vp,
+        "gala_linear_f32": [vp, i64, i32, vp, vp, i32, vp, vp, i32, vp, vp, i32, vp,
                             C.POINTER(GalaMultiOut), vp],
         "gala_csr_from_coo": [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp],
         "gala_csr_transpose": [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp],

@@ -91,12 +91,20 @@ def _dptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def pad_rows(X, multiple=4):
-    """X [n, K] -> a view [n, K] of a fresh [n, ld] buffer with ld = K rounded up to `multiple`, padding zeroed
+def pad_pitch(K):
+    """Row pitch (elements) the gather likes for a width that is not a multiple of 4: 16-byte aligned rows, and for
+    rows longer than 64 bytes a multiple of 64 bytes, so that a row never straddles one more 128-byte line than it
+    has to (measured on B200: the gather costs ~1.2 clk per line touched + ~0.25 clk per 32-byte sector per SM;
+    K = 41 at pitch 44 touches 2.25 lines on average, at pitch 48 always 2)."""
+    return (K + 15) // 16 * 16 if K > 16 else (K + 3) // 4 * 4
+
+
+def pad_rows(X, ld=None):
+    """X [n, K] -> a view [n, K] of a fresh [n, ld] buffer (ld = pad_pitch(K) by default), padding zeroed
     (gala_pad_rows_f32): every row then starts 16-byte aligned and is gathered with 128-bit loads."""
     X, K, ld_in = _rows(X)
     n = X.shape[0]
-    ld = (K + multiple - 1) // multiple * multiple
+    ld = pad_pitch(K) if ld is None else ld
     buf = torch.empty((n, ld), dtype=torch.float32, device=X.device)
     _l.check(_l.load().gala_pad_rows_f32(_dptr(X), n, K, ld_in, _l.ptr(buf), ld, _l.stream_ptr()))
     return buf[:, :K]
@@ -106,7 +114,9 @@ def _gather_operand(X, pad):
     """The dense operand whose rows are gathered.  pad="auto": packed rows whose width is not a multiple of 4
     (41 / 47 classes, 602 features) are re-pitched once -- N*K*8 bytes against E*K*4 gathered."""
     X, K, ld = _rows(X)
-    if pad == "auto" and K > 4 and (ld % 4 != 0 or X.data_ptr() % 16 != 0):
+    # (wide rows -- K = 602 -- are left packed: their gather is HBM-bound and the 2 x 32 x 4-accumulator tile of the
+    #  64-bit path covers them with fewer idle lanes than the 128-bit one; measured 24.2 vs 29.9 ms on the Reddit shape)
+    if pad == "auto" and 4 < K <= 256 and (ld % 4 != 0 or X.data_ptr() % 16 != 0):
         X = pad_rows(X)
         ld = X.stride(0)
     return X, K, ld
@@ -266,15 +276,20 @@ def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None, row_sc
     if out is None and multi_out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=X.device)
     att = None
-    ab = None
+    ab, ab_dev = None, 0
     if att_w is not None:
         att_w = _f32(att_w)
         att = torch.empty((2, M), dtype=torch.float32, device=X.device)
-        ab = (C.c_float * 2)(float(att_b[0]), float(att_b[1]))
+        if isinstance(att_b, torch.Tensor) and att_b.is_cuda:      # trained biases stay on the device
+            att_b = _f32(att_b)
+            ab, ab_dev = C.c_void_p(att_b.data_ptr()), 1
+        else:
+            ab_host = (C.c_float * 2)(float(att_b[0]), float(att_b[1]))
+            ab = C.cast(ab_host, C.c_void_p)
     _l.check(_l.load().gala_linear_f32(_l.ptr(X), M, K, _l.ptr(W), _l.ptr(bias), N,
                                        _l.ptr(out) if out is not None else None,
                                        _l.ptr(row_scale), int(relu),
-                                       _l.ptr(att_w), ab,
+                                       _l.ptr(att_w), ab, ab_dev,
                                        _l.ptr(att), C.byref(multi_out) if multi_out is not None else None,
                                        _l.stream_ptr()))
     return (out, att) if att_w is not None else out

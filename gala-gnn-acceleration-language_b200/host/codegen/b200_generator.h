@@ -7,7 +7,7 @@
 // Compiled against the reference tree (-I/root/reference); no reference source is copied.
 #pragma once
 #include <fstream>
-#include <regex>
+#include <iostream>
 #include <sstream>
 #include <unordered_set>
 
@@ -96,53 +96,245 @@ public:
         }
     }
 
-    // Peephole over the emitted forward() text, run after writeCode(): a GAT layer whose four nodes
-    // (aggregate_edge_sum -> LeakyReLU -> non_lnr_op_softmax -> aggregate_node_mul_sum*, emitted by
-    // common.h:622-675, 1176-1184, 735-810, 835-927) all address the same graph slot becomes ONE call of
-    // gala_b200::gat_layer_AutoGrad (gala_b200_torch.h): fused forward kernel, same gradients.  Layers
-    // whose nodes use different slots (training sub-graphs, tests/common.h:20-105) are left as emitted.
-    // Returns the number of layers fused.
-    static int fuseGatLayers(const std::string& path) {
-        std::ifstream in(path);
-        if (!in) return 0;
-        std::stringstream buf;
-        buf << in.rdbuf();
-        std::string text = buf.str();
-        in.close();
-        const std::regex layer(
-            R"(attn = aggregate_edge_sum_AutoGrad::apply\((\w+), (\w+), (\d+)\);\s*)"
-            R"((torch::nn::LeakyReLU leaky_relu\(torch::nn::LeakyReLUOptions\(\)\.negative_slope\(([0-9.]+)\)\);\s*)?)"
-            R"(attn = leaky_relu->forward\(attn\);\s*)"
-            R"(attn = non_lnr_op_softmax_AutoGrad::apply\(attn, (\d+)\);\s*)"
-            R"(if \(ep % mod_v == 0\) \{\s*res = \w+_AutoGrad::apply\(res, attn, (\d+)\);\s*\} else \{\s*)"
-            R"(res = \w+_AutoGrad::apply\(res, attn, (\d+)\);\s*\})");
-        std::string out, slope = "0.2";
-        int fused = 0;
-        auto it = std::sregex_iterator(text.begin(), text.end(), layer);
-        size_t pos = 0;
-        for (; it != std::sregex_iterator(); ++it) {
-            const std::smatch& m = *it;
-            out += text.substr(pos, m.position() - pos);
-            pos = m.position() + m.length();
-            if (m[5].matched) slope = m[5].str();
-            const bool same = m[3] == m[6] && m[3] == m[7] && m[3] == m[8];
-            if (!same) {
-                out += m.str();
-                continue;
-            }
-            out += "res = gala_b200::gat_layer_AutoGrad::apply(res, " + m[1].str() + ", " + m[2].str() + ", " + m[3].str() +
-                   ", " + slope + ");   // fused: edge_sddvv + LeakyReLU + softmax + aggregate";
-            ++fused;
-        }
-        out += text.substr(pos);
-        if (fused) {
-            std::ofstream o(path);
-            o << out;
-        }
-        return fused;
+    // ---- writeCode with a fusion pass between IR lowering and file output -------------------------------
+    // CodeGenerator::writeCode (common.h:1725-1764) is not virtual and writes the file as soon as generateCode()
+    // returns, so the retargeted generator runs the same steps itself (the drivers call writeCodeB200) and, in
+    // between, rewrites the statement list of GALAGNN::forward.  Every compute node of the IR contributes exactly
+    // one entry to model.getForward() (common.h:511-1375: one addCode per node), so the pass works on whole
+    // statements: the DECISION to fuse is taken on the IR (op sequence, graph slots, producers / consumers), the
+    // statements the nodes produced are then parsed (callee + argument list, whitespace-insensitive) and replaced.
+    // If the IR says "fusable" and the statements do not have the expected shape, code generation fails loudly
+    // instead of silently emitting the slow sequence.
+    struct FuseOptions {
+        bool gatLayers = true;   // edge_sddvv + LeakyReLU + softmax + aggregate -> gala_b200::gat_layer_AutoGrad
+        bool linears = true;     // torch::nn::Linear -> gala_b200::Linear (tcgen05 / streaming kernels), projections fused
+    };
+
+    void writeCodeB200(std::vector<CIRNode*>& program, std::vector<RelationEdge*>& dependencies,
+                       std::vector<RelationEdge*>& associations, std::vector<TransformEdge*>& transforms,
+                       const FuseOptions& opt, std::ostream& log) {
+        initCMake();
+        initKernels(program);
+        commonPerCode();
+        generateCode(program, transforms);
+        fuseForward(program, opt, log);
+        // the sections of gala.cu, in the order CodeGenerator::writeCode emits them (common.h:1742-1763)
+        CodeGenerator::writeCode(cmakeCode, outStreamCMake);
+        CodeGenerator::writeCode(importCode, outStreamModel);
+        CodeGenerator::writeCode(kernelCode, outStreamModel);
+        CodeGenerator::writeCode(kernelCallCode, outStreamModel);
+        CodeGenerator::writeCode(*model.getDef(), outStreamModel);
+        CodeGenerator::writeCode(*model.getInitCall(), outStreamModel, ", ", true, true);
+        CodeGenerator::writeCode(*model.getInit(), outStreamModel);
+        CodeGenerator::writeCode(*model.getForwardCallPre(), outStreamModel, "");
+        CodeGenerator::writeCode(*model.getForwardCallInternal(), outStreamModel, "");
+        CodeGenerator::writeCode(*model.getForwardCallPost(), outStreamModel);
+        CodeGenerator::writeCode(*model.getForward(), outStreamModel);
+        CodeGenerator::writeCode(preCode, outStreamModel);
+        CodeGenerator::writeCode(*model.getInv(), outStreamModel);
+        CodeGenerator::writeCode(*model.getPreCall(), outStreamModel, "");
+        CodeGenerator::writeCode(*model.getCall(), outStreamModel, "");
+        CodeGenerator::writeCode(*model.getPostCall(), outStreamModel);
+        CodeGenerator::writeCode(postCode, outStreamModel);
+        closeStream();
     }
 
 private:
+    // ---- statements ------------------------------------------------------------------------------------
+    struct Call {                       // "lhs = callee(arg, ...);"
+        std::string lhs, callee;
+        std::vector<std::string> args;
+    };
+    static std::string squeeze(const std::string& t) {     // drop all whitespace
+        std::string o;
+        for (char c : t)
+            if (!isspace((unsigned char)c)) o.push_back(c);
+        return o;
+    }
+    static bool parseCall(const std::string& text, Call& c) {
+        const std::string t = squeeze(text);
+        if (t.empty() || t.back() != ';') return false;
+        const size_t eq = t.find('='), lp = t.find('('), rp = t.rfind(')');
+        if (eq == std::string::npos || lp == std::string::npos || rp != t.size() - 2 || eq > lp) return false;
+        c.lhs = t.substr(0, eq);
+        c.callee = t.substr(eq + 1, lp - eq - 1);
+        c.args.clear();
+        int depth = 0;
+        std::string cur;
+        for (size_t i = lp + 1; i < rp; ++i) {
+            const char ch = t[i];
+            if (ch == '(' || ch == '{') ++depth;
+            if (ch == ')' || ch == '}') --depth;
+            if (ch == ',' && depth == 0) {
+                c.args.push_back(cur);
+                cur.clear();
+            } else {
+                cur.push_back(ch);
+            }
+        }
+        if (!cur.empty()) c.args.push_back(cur);
+        for (char ch : c.lhs)
+            if (!(isalnum((unsigned char)ch) || ch == '_')) return false;
+        return true;
+    }
+    // "if (ep % mod_v == 0) { A } else { B }" as emitted for every aggregation inside the loop (common.h:1004-1010)
+    static bool parseEpochSwitch(const std::string& text, Call& a, Call& b) {
+        const std::string t = squeeze(text);
+        const std::string head = "if(ep%mod_v==0){", mid = "}else{";
+        if (t.compare(0, head.size(), head) != 0 || t.back() != '}') return false;
+        const size_t m = t.find(mid);
+        if (m == std::string::npos) return false;
+        return parseCall(t.substr(head.size(), m - head.size()), a) &&
+               parseCall(t.substr(m + mid.size(), t.size() - 1 - m - mid.size()), b);
+    }
+    static bool endsWith(const std::string& t, const std::string& suf) {
+        return t.size() >= suf.size() && t.compare(t.size() - suf.size(), suf.size(), suf) == 0;
+    }
+    [[noreturn]] static void fail(const std::string& what, const std::string& stmt) {
+        std::cerr << "B200Generator: the IR describes a fusable pattern but the emitted statement has an unexpected shape ("
+                  << what << "):\n    " << stmt << "\nrefusing to emit the unfused sequence silently; run with --no-fuse "
+                  << "or update host/codegen/b200_generator.h to the reference's new emission\n";
+        std::exit(3);
+    }
+
+    // compute nodes of the forward pass in program order (what generateCode walks, common.h:1378-1470)
+    static std::vector<ComputeNode*> forwardNodes(std::vector<CIRNode*>& program) {
+        std::vector<ComputeNode*> out;
+        for (CIRNode* node : program) {
+            if (auto c = dynamic_cast<ComputeNode*>(node)) {
+                out.push_back(c);
+            } else if (auto loop = dynamic_cast<TrainingLoopNode*>(node)) {
+                for (int ix = 0; ix < loop->getLoopNodeNum(); ix++)
+                    if (auto c2 = dynamic_cast<ComputeNode*>(loop->getNode(ix))) out.push_back(c2);
+            }
+        }
+        return out;
+    }
+
+    void fuseForward(std::vector<CIRNode*>& program, const FuseOptions& opt, std::ostream& log) {
+        Code* fwd = model.getForward();
+        std::vector<ComputeNode*> nodes = forwardNodes(program);
+        auto line = [&](int i) -> std::string& { return *fwd->atLine(i); };
+        auto blank = [&](int i) { line(i) = "        // (fused into the call above)"; };
+        const int n = fwd->getNum();
+
+        // ---- (1) GAT layers: IR says AGGREGATE_EDGE_SUM -> LEAKY_RELU -> SOFTMAX -> AGGREGATE_MUL_SUM over one graph
+        int gatLayersInIR = 0;
+        for (size_t k = 0; k + 3 < nodes.size(); ++k)
+            if (nodes[k]->getOp() == AGGREGATE_EDGE_SUM_OP && nodes[k + 1]->getOp() == NON_LNR_OP_LEAKY_RELU &&
+                nodes[k + 2]->getOp() == NON_LNR_OP_SOFTMAX && nodes[k + 3]->getOp() == AGGREGATE_MUL_SUM_OP)
+                ++gatLayersInIR;
+        int fusedGat = 0, keptGat = 0;
+        if (opt.gatLayers && gatLayersInIR > 0) {
+            std::string slope = "0.2";
+            for (int i = 0; i < n; ++i) {
+                Call a;
+                if (!parseCall(line(i), a) || !endsWith(a.callee, "aggregate_edge_sum_AutoGrad::apply")) continue;
+                if (a.args.size() != 3) fail("edge-sum call: 3 arguments expected", line(i));
+                // following statements: [LeakyReLU declaration] leaky_relu->forward, softmax apply, epoch switch
+                int j = i + 1;
+                if (j < n && squeeze(line(j)).find("torch::nn::LeakyReLUleaky_relu(") == 0) {
+                    const std::string t = squeeze(line(j));
+                    const size_t p = t.find("negative_slope(");
+                    if (p == std::string::npos) fail("LeakyReLU declaration without negative_slope", line(j));
+                    slope = t.substr(p + 15, t.find(')', p) - p - 15);
+                    ++j;
+                }
+                Call l, sm, s0, s1;
+                if (j + 2 >= n + 0 && j + 2 > n - 1 + 0) fail("GAT layer: statements missing after the edge sum", line(i));
+                if (!parseCall(line(j), l) || l.callee != "leaky_relu->forward" || l.args.size() != 1 || l.args[0] != a.lhs)
+                    fail("LeakyReLU call", line(j));
+                if (!parseCall(line(j + 1), sm) || !endsWith(sm.callee, "non_lnr_op_softmax_AutoGrad::apply") ||
+                    sm.args.size() != 2 || sm.args[0] != a.lhs)
+                    fail("edge-softmax call", line(j + 1));
+                if (!parseEpochSwitch(line(j + 2), s0, s1) || s0.args.size() != 3 || s1.args.size() != 3 ||
+                    s0.args[1] != a.lhs || s1.args[1] != a.lhs || s0.lhs != s1.lhs || s0.args[0] != s1.args[0])
+                    fail("weighted aggregation (epoch switch)", line(j + 2));
+                // all four nodes must address the same graph slot (training sub-graphs give the aggregation its own)
+                const bool same = a.args[2] == sm.args[1] && a.args[2] == s0.args[2] && a.args[2] == s1.args[2];
+                if (!same) {
+                    ++keptGat;
+                    continue;
+                }
+                bool relu = false;
+                Call r;
+                if (j + 3 < n && parseCall(line(j + 3), r) && r.callee == "torch::relu" && r.args.size() == 1 &&
+                    r.args[0] == s0.lhs && r.lhs == s0.lhs)
+                    relu = true;
+                line(i) = "        " + s0.lhs + " = gala_b200::gat_layer_AutoGrad::apply(" + s0.args[0] + ", " + a.args[0] + ", " +
+                          a.args[1] + ", " + a.args[2] + ", " + slope + ", " + (relu ? "true" : "false") +
+                          ");   // fused: edge_sddvv + LeakyReLU + edge-softmax + aggregate" + (relu ? " + ReLU" : "");
+                blank(j);
+                blank(j + 1);
+                blank(j + 2);
+                if (relu) blank(j + 3);
+                ++fusedGat;
+            }
+            if (fusedGat + keptGat != gatLayersInIR)
+                fail("the IR holds " + std::to_string(gatLayersInIR) + " GAT layers, the forward text " +
+                     std::to_string(fusedGat + keptGat), "(whole forward)");
+            if (fusedGat) log << "fused " << fusedGat << " GAT layer(s) into gala_b200::gat_layer_AutoGrad\n";
+        }
+
+        // ---- (2) dense transforms: every torch::nn::Linear of the model becomes gala_b200::Linear (same parameters,
+        // same initialisation, forward on this library's kernels); a transform followed by the two attention
+        // projections of its output (FFN_OP, FFN_OP_EDGE, FFN_OP_EDGE in the IR) becomes one call.
+        if (opt.linears) {
+            int nLinear = 0;
+            for (Code* c : {model.getDef(), model.getInit()})
+                for (int i = 0; i < c->getNum(); ++i) {
+                    std::string& t = *c->atLine(i);
+                    for (size_t p = t.find("torch::nn::Linear"); p != std::string::npos; p = t.find("torch::nn::Linear", p + 1)) {
+                        t.replace(p, 17, "gala_b200::Linear");
+                        ++nLinear;
+                    }
+                }
+            int tripletsInIR = 0;
+            for (size_t k = 0; k + 2 < nodes.size(); ++k)
+                if ((nodes[k]->getOp() == FFN_OP || nodes[k]->getOp() == FFN_OP_REPEAT) && nodes[k + 1]->getOp() == FFN_OP_EDGE &&
+                    nodes[k + 2]->getOp() == FFN_OP_EDGE)
+                    ++tripletsInIR;
+            int fusedTriplets = 0;
+            for (int i = 0; i + 2 < n && tripletsInIR > 0; ++i) {
+                Call f, l, r;
+                if (!parseCall(line(i), f) || !endsWith(f.callee, "->forward") || f.callee.compare(0, 2, "fc") != 0) continue;
+                if (!parseCall(line(i + 1), l) || !parseCall(line(i + 2), r)) continue;
+                if (l.callee.compare(0, 3, "efc") != 0 || r.callee.compare(0, 3, "efc") != 0) continue;
+                if (l.args.size() != 1 || r.args.size() != 1 || l.args[0] != f.lhs || r.args[0] != f.lhs || f.args.size() != 1)
+                    fail("transform + attention projections", line(i + 1));
+                const std::string fc = f.callee.substr(0, f.callee.size() - 9), el = l.callee.substr(0, l.callee.size() - 9),
+                                  er = r.callee.substr(0, r.callee.size() - 9);
+                // is the transform's output used by anything but the two projections? (layer 2 of the FFN-recompute
+                // rewrite, middle-end.h:324-375: res_e only feeds the logits -> fold the projections through it)
+                bool usedElsewhere = false;
+                for (int q = i + 3; q < n && !usedElsewhere; ++q) {
+                    const std::string t = squeeze(line(q));
+                    for (size_t p = t.find(f.lhs); p != std::string::npos; p = t.find(f.lhs, p + 1)) {
+                        const bool lb = p == 0 || !(isalnum((unsigned char)t[p - 1]) || t[p - 1] == '_');
+                        const size_t e = p + f.lhs.size();
+                        const bool rb = e >= t.size() || !(isalnum((unsigned char)t[e]) || t[e] == '_');
+                        if (lb && rb) usedElsewhere = true;
+                    }
+                }
+                if (usedElsewhere)
+                    line(i) = "        std::tie(" + f.lhs + ", " + l.lhs + ", " + r.lhs + ") = gala_b200::linear_att(" + fc + ", " + el +
+                              ", " + er + ", " + f.args[0] + ");   // fused: transform + both attention projections";
+                else
+                    line(i) = "        std::tie(" + l.lhs + ", " + r.lhs + ") = gala_b200::folded_att(" + fc + ", " + el + ", " + er +
+                              ", " + f.args[0] + ");   // projections folded through the transform (its output feeds only them)";
+                blank(i + 1);
+                blank(i + 2);
+                ++fusedTriplets;
+            }
+            if (fusedTriplets != tripletsInIR)
+                fail("the IR holds " + std::to_string(tripletsInIR) + " transform+projection groups, the forward text " +
+                     std::to_string(fusedTriplets), "(whole forward)");
+            log << "retargeted " << nLinear << " torch::nn::Linear to gala_b200::Linear";
+            if (fusedTriplets) log << ", fused " << fusedTriplets << " transform + attention-projection group(s)";
+            log << "\n";
+        }
+    }
+
     std::string root_;
     bool deviceFormats_;
 

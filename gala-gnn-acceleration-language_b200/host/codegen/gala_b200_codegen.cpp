@@ -56,11 +56,12 @@ int main(int argc, char** argv) {
     int feat = atoi(argv[3]), labels = atoi(argv[4]), colTile = atoi(argv[5]);
     bool reference = false;
     int sample = 0, graphSample = 0;
-    bool noFuse = false, sparser = false, hostFormats = false;
+    bool noFuse = false, sparser = false, hostFormats = false, torchLinear = false;
     for (int i = 9; i < argc; i++) {
         if (!strcmp(argv[i], "--reference")) reference = true;
         else if (!strcmp(argv[i], "--no-fuse")) noFuse = true;
         else if (!strcmp(argv[i], "--host-formats")) hostFormats = true;   // keep the reference's CPU data preparation
+        else if (!strcmp(argv[i], "--torch-linear")) torchLinear = true;   // keep torch::nn::Linear (cuBLAS)
         else if (!strcmp(argv[i], "--sparser")) sparser = true;   // G=G.is_sparser(true) (frontend.y:304-305)
         else if (!strcmp(argv[i], "--sample") && i + 1 < argc) sample = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--graph-sample") && i + 1 < argc) graphSample = atoi(argv[++i]);
@@ -127,12 +128,16 @@ int main(int argc, char** argv) {
             GALATransformations::trainingSubGraph(GALAFEContext::program, GALAFEContext::dependencies,
                                                   GALAFEContext::associations, GALAFEContext::transforms);
     }
-    gen->writeCode(GALAFEContext::program, GALAFEContext::dependencies, GALAFEContext::associations,
-                   GALAFEContext::transforms);
-    std::cout << "wrote " << outPath << "gala.cu (" << (reference ? "reference kernels" : "gala_b200 bindings") << ")\n";
-    if (!reference && !noFuse) {
-        int fused = B200Generator::fuseGatLayers(outPath + "gala.cu");
-        if (fused) std::cout << "fused " << fused << " GAT layer(s) into gala_b200::gat_layer_AutoGrad\n";
+    if (reference) {
+        gen->writeCode(GALAFEContext::program, GALAFEContext::dependencies, GALAFEContext::associations,
+                       GALAFEContext::transforms);
+    } else {
+        B200Generator::FuseOptions opt;
+        opt.gatLayers = !noFuse;
+        opt.linears = !noFuse && !torchLinear;
+        static_cast<B200Generator*>(gen)->writeCodeB200(GALAFEContext::program, GALAFEContext::dependencies,
+                                                        GALAFEContext::associations, GALAFEContext::transforms, opt, std::cout);
     }
+    std::cout << "wrote " << outPath << "gala.cu (" << (reference ? "reference kernels" : "gala_b200 bindings") << ")\n";
     return 0;
 }

@@ -83,8 +83,9 @@ inline torch::TensorOptions out_options(const torch::Tensor& like) {
 // 128-bit loads: N*K*8 bytes against the E*K*4 bytes of the gather.
 inline std::pair<torch::Tensor, int64_t> gather_operand(const torch::Tensor& input_dense, int64_t nrows, int64_t dcols) {
     auto X = input_dense.contiguous();
-    if (dcols <= 4 || (dcols % 4 == 0 && reinterpret_cast<uintptr_t>(X.data_ptr()) % 16 == 0)) return {X, dcols};
-    const int64_t ld = (dcols + 3) / 4 * 4;
+    if (dcols <= 4 || dcols > 256 || (dcols % 4 == 0 && reinterpret_cast<uintptr_t>(X.data_ptr()) % 16 == 0)) return {X, dcols};
+    // 16-byte aligned rows; rows longer than 64 bytes on a 64-byte pitch so that none straddles an extra 128-byte line
+    const int64_t ld = dcols > 16 ? (dcols + 15) / 16 * 16 : (dcols + 3) / 4 * 4;
     auto Xp = torch::empty({nrows, ld}, torch::TensorOptions().dtype(torch::kFloat).device(X.device()));
     check(gala_pad_rows_f32(X.data_ptr<float>(), nrows, (int)dcols, dcols, Xp.data_ptr<float>(), ld, stream()),
           "gala_pad_rows_f32");
@@ -268,23 +269,27 @@ inline torch::Tensor aggregate_edge_mul_dir(torch::Tensor input_dense1, torch::T
 namespace gala_b200 {
 class gat_layer_AutoGrad : public torch::autograd::Function<gat_layer_AutoGrad> {
 public:
+    // relu: the torch::relu that follows the layer in the emitted forward (common.h:1166) applied inside the kernel
     static torch::Tensor forward(torch::autograd::AutogradContext* ctx, torch::Tensor res, torch::Tensor attenL,
-                                 torch::Tensor attenR, int64_t li, double slope) {
+                                 torch::Tensor attenR, int64_t li, double slope, bool relu = false) {
         ctx->saved_data["li"] = li;
         ctx->saved_data["slope"] = slope;
+        ctx->saved_data["relu"] = relu;
         torch::Tensor alpha;
         torch::Tensor Y = gat_forward(res, attenL, attenR, global_offset_graph[2 * li], global_columns_graph[2 * li],
-                                      global_bounds[2 * li], global_segments[2 * li], (float)slope, false, &alpha);
-        ctx->save_for_backward({alpha, res, attenL, attenR});
+                                      global_bounds[2 * li], global_segments[2 * li], (float)slope, relu, &alpha);
+        ctx->save_for_backward({alpha, res, attenL, attenR, relu ? Y : torch::Tensor()});
         return Y;
     }
 
     static torch::autograd::tensor_list backward(torch::autograd::AutogradContext* ctx,
                                                  torch::autograd::tensor_list grad_outputs) {
-        torch::Tensor dZ = grad_outputs[0].contiguous();
         auto saved = ctx->get_saved_variables();
         torch::Tensor alpha = saved[0], X = saved[1].contiguous();
         torch::Tensor aL = saved[2].contiguous(), aR = saved[3].contiguous();
+        torch::Tensor dZ = grad_outputs[0];
+        if (ctx->saved_data["relu"].toBool()) dZ = dZ * (saved[4] > 0);      // ReLU backward (threshold_backward)
+        dZ = dZ.contiguous();
         const int64_t li = ctx->saved_data["li"].toInt();
         const float slope = (float)ctx->saved_data["slope"].toDouble();
         torch::Tensor off_b = global_offset_graph[2 * li + 1], col_b = global_columns_graph[2 * li + 1];
@@ -296,7 +301,120 @@ public:
         check(gala_gat_backward_att_f32(&g, alpha.data_ptr<float>(), dalpha.data_ptr<float>(), aL.data_ptr<float>(),
                                         aR.data_ptr<float>(), slope, d_att.data_ptr<float>(), plan_for(g, dZ), stream()),
               "gala_gat_backward_att_f32");
-        return {dX, d_att, d_att, torch::Tensor(), torch::Tensor()};
+        return {dX, d_att, d_att, torch::Tensor(), torch::Tensor(), torch::Tensor()};
     }
 };
+
+// ---- dense transforms of the generated model on this library's kernels -------------------------------------------
+// The retargeted generator replaces `torch::nn::Linear` in the emitted GALAGNN (common.h:1185-1281) by
+// gala_b200::Linear: the same module (parameters "weight" / "bias", same initialisation and RNG consumption: it IS a
+// torch::nn::LinearImpl), whose forward runs gala_linear_f32 (tcgen05, 3xTF32) or, for the narrow transforms
+// (K, N <= 64: classifier, Linear(h,1) projections), gala_linear_small_f32.  Backward: dX = dY W, dW = dY^T X,
+// db = sum dY through ATen (cuBLAS), as autograd does for torch::nn::Linear.
+constexpr int64_t kLinearMaxN = 64;
+
+inline torch::Tensor linear_forward(const torch::Tensor& X, const torch::Tensor& W, const torch::Tensor& b) {
+    const int64_t M = X.size(0), K = W.size(1), N = W.size(0);
+    const float* bias = b.defined() ? b.data_ptr<float>() : nullptr;
+    auto Y = torch::empty({M, N}, torch::TensorOptions().dtype(torch::kFloat).device(X.device()));
+    if (K <= 64 && N <= 64) {
+        check(gala_linear_small_f32(X.data_ptr<float>(), M, (int)K, W.data_ptr<float>(), bias, (int)N, Y.data_ptr<float>(), 0, 0,
+                                    stream()), "gala_linear_small_f32");
+    } else if (N <= kLinearMaxN) {
+        check(gala_linear_f32(X.data_ptr<float>(), M, (int)K, W.data_ptr<float>(), bias, (int)N, Y.data_ptr<float>(), nullptr, 0,
+                              nullptr, nullptr, 0, nullptr, nullptr, stream()), "gala_linear_f32");
+    } else {
+        return at::linear(X, W, b);      // wider than the hand-written kernels: cuBLAS
+    }
+    return Y;
+}
+
+class linear_AutoGrad : public torch::autograd::Function<linear_AutoGrad> {
+public:
+    static torch::Tensor forward(torch::autograd::AutogradContext* ctx, torch::Tensor X, torch::Tensor W, torch::Tensor b) {
+        X = X.contiguous();
+        ctx->save_for_backward({X, W});
+        ctx->saved_data["has_bias"] = b.defined();
+        return linear_forward(X, W.contiguous(), b);
+    }
+    static torch::autograd::tensor_list backward(torch::autograd::AutogradContext* ctx, torch::autograd::tensor_list grads) {
+        auto saved = ctx->get_saved_variables();
+        torch::Tensor X = saved[0], W = saved[1], dY = grads[0].contiguous();
+        torch::Tensor dX = ctx->needs_input_grad(0) ? dY.mm(W) : torch::Tensor();
+        torch::Tensor dW = ctx->needs_input_grad(1) ? dY.t().mm(X) : torch::Tensor();
+        torch::Tensor db = (ctx->saved_data["has_bias"].toBool() && ctx->needs_input_grad(2)) ? dY.sum(0) : torch::Tensor();
+        return {dX, dW, db};
+    }
+};
+
+struct LinearImpl : torch::nn::LinearImpl {
+    using torch::nn::LinearImpl::LinearImpl;
+    torch::Tensor forward(const torch::Tensor& input) { return linear_AutoGrad::apply(input, weight, bias); }
+};
+TORCH_MODULE(Linear);
+
+// res = fc(X); attenL = el(res); attenR = er(res) (FFN_OP, FFN_OP_EDGE, FFN_OP_EDGE: frontend.y:987-994) as one
+// node: the tcgen05 transform computes both projections of every output row in its epilogue.
+class linear_att_AutoGrad : public torch::autograd::Function<linear_att_AutoGrad> {
+public:
+    static torch::autograd::tensor_list forward(torch::autograd::AutogradContext* ctx, torch::Tensor X, torch::Tensor W,
+                                                torch::Tensor b, torch::Tensor wl, torch::Tensor bl, torch::Tensor wr,
+                                                torch::Tensor br) {
+        X = X.contiguous();
+        const int64_t M = X.size(0), K = W.size(1), N = W.size(0);
+        auto of = torch::TensorOptions().dtype(torch::kFloat).device(X.device());
+        torch::Tensor att_w = torch::cat({wl.reshape({1, N}), wr.reshape({1, N})}, 0).contiguous();
+        torch::Tensor att_b = torch::cat({bl.reshape({1}), br.reshape({1})}, 0).contiguous();
+        torch::Tensor res, att;
+        if (N <= kLinearMaxN) {
+            res = torch::empty({M, N}, of);
+            att = torch::empty({2, M}, of);
+            check(gala_linear_f32(X.data_ptr<float>(), M, (int)K, W.contiguous().data_ptr<float>(), b.data_ptr<float>(), (int)N,
+                                  res.data_ptr<float>(), nullptr, 0, att_w.data_ptr<float>(), att_b.data_ptr<float>(), 1,
+                                  att.data_ptr<float>(), nullptr, stream()), "gala_linear_f32");
+        } else {
+            res = at::linear(X, W, b);
+            att = at::linear(res, att_w, att_b).t().contiguous();
+        }
+        ctx->save_for_backward({X, W, res, att_w});
+        return {res, att[0].reshape({M, 1}), att[1].reshape({M, 1})};
+    }
+    static torch::autograd::tensor_list backward(torch::autograd::AutogradContext* ctx, torch::autograd::tensor_list grads) {
+        auto saved = ctx->get_saved_variables();
+        torch::Tensor X = saved[0], W = saved[1], res = saved[2], att_w = saved[3];
+        const int64_t M = X.size(0);
+        torch::Tensor g;            // gradient reaching res: its own plus the two projections'
+        torch::Tensor dl = grads[1].defined() ? grads[1].reshape({M, 1}) : torch::Tensor();
+        torch::Tensor dr = grads[2].defined() ? grads[2].reshape({M, 1}) : torch::Tensor();
+        if (grads[0].defined()) g = grads[0];
+        auto add = [&](const torch::Tensor& t) { g = g.defined() ? g + t : t; };
+        if (dl.defined()) add(dl * att_w[0].reshape({1, -1}));
+        if (dr.defined()) add(dr * att_w[1].reshape({1, -1}));
+        g = g.contiguous();
+        torch::Tensor dX = ctx->needs_input_grad(0) ? g.mm(W) : torch::Tensor();
+        torch::Tensor dW = g.t().mm(X), db = g.sum(0);
+        torch::Tensor dwl = dl.defined() ? dl.t().mm(res) : torch::Tensor(), dbl = dl.defined() ? dl.sum(0) : torch::Tensor();
+        torch::Tensor dwr = dr.defined() ? dr.t().mm(res) : torch::Tensor(), dbr = dr.defined() ? dr.sum(0) : torch::Tensor();
+        return {dX, dW, db, dwl, dbl, dwr, dbr};
+    }
+};
+
+template <class L>
+inline std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> linear_att(L& fc, L& el, L& er, const torch::Tensor& X) {
+    auto out = linear_att_AutoGrad::apply(X, fc->weight, fc->bias, el->weight, el->bias, er->weight, er->bias);
+    return {out[0], out[1], out[2]};
+}
+
+// attenL = el(fc(X)), attenR = er(fc(X)) when fc(X) feeds nothing else (layer 2 under the FFN-recompute rewrite,
+// middle-end.h:324-375): the projections are folded through the transform, w = el.w fc.W, b = el.w fc.b + el.b
+// (tiny ATen ops, differentiated by autograd), and one [M,K] x [K,2] streaming pass replaces the [M,K] x [K,N]
+// transform and the two [M,N] x [N,1] projections.
+template <class L>
+inline std::tuple<torch::Tensor, torch::Tensor> folded_att(L& fc, L& el, L& er, const torch::Tensor& X) {
+    torch::Tensor Wf = torch::cat({el->weight.mm(fc->weight), er->weight.mm(fc->weight)}, 0);                    // [2, K]
+    torch::Tensor bf = torch::cat({el->weight.mv(fc->bias) + el->bias, er->weight.mv(fc->bias) + er->bias}, 0);   // [2]
+    torch::Tensor att = linear_AutoGrad::apply(X, Wf, bf).t().contiguous();                                        // [2, M]
+    const int64_t M = X.size(0);
+    return {att[0].reshape({M, 1}), att[1].reshape({M, 1})};
+}
 }  // namespace gala_b200

@@ -200,6 +200,94 @@ int main() {
         (void)od;
     }
 
+    // ---- gat_layer_AutoGrad with the ReLU inside the kernel == layer followed by torch::relu -------------
+    {
+        torch::Tensor X1 = X.clone().requires_grad_(true), l1 = aL.clone().requires_grad_(true), r1 = aR.clone().requires_grad_(true);
+        torch::Tensor X2 = X.clone().requires_grad_(true), l2 = aL.clone().requires_grad_(true), r2 = aR.clone().requires_grad_(true);
+        torch::Tensor y1 = gala_b200::gat_layer_AutoGrad::apply(X1, l1, r1, 0, 0.2, true);
+        torch::Tensor y2 = torch::relu(gala_b200::gat_layer_AutoGrad::apply(X2, l2, r2, 0, 0.2, false));
+        expect_close("gat_layer_AutoGrad fused ReLU: forward", y1, y2, 1e-7);
+        y1.backward(dZ);
+        y2.backward(dZ);
+        expect_close("gat_layer_AutoGrad fused ReLU: d(res)", X1.grad(), X2.grad(), 1e-6);
+        expect_close("gat_layer_AutoGrad fused ReLU: d(attenL)", l1.grad(), l2.grad(), 1e-6);
+    }
+
+    // ---- gala_b200::Linear == torch::nn::Linear (same init under the same seed, same gradients) -----------
+    for (auto shape : std::vector<std::pair<int, int>>{{602, 32}, {32, 41}, {41, 1}, {100, 32}, {32, 47}, {300, 200}}) {
+        const int Fin = shape.first, Fout = shape.second;
+        torch::manual_seed(11);
+        torch::nn::Linear ref(Fin, Fout);
+        torch::manual_seed(11);
+        gala_b200::Linear ours(Fin, Fout);
+        ref->to(dev);
+        ours->to(dev);
+        expect_close("gala_b200::Linear init == torch::nn::Linear", ours->weight, ref->weight, 1e-12);
+        torch::Tensor in1 = (torch::rand({N, Fin}, of.device(dev)) - 0.5).requires_grad_(true);
+        torch::Tensor in2 = in1.detach().clone().requires_grad_(true);
+        torch::Tensor o1 = ours->forward(in1), o2 = ref->forward(in2);
+        char what[96];
+        std::snprintf(what, sizeof(what), "gala_b200::Linear [%d -> %d] forward", Fin, Fout);
+        expect_close(what, o1, at::linear(in2.to(torch::kDouble), ref->weight.to(torch::kDouble), ref->bias.to(torch::kDouble)), 1e-5);
+        torch::Tensor go = torch::rand({N, Fout}, of.device(dev)) - 0.5;
+        o1.backward(go);
+        o2.backward(go);
+        std::snprintf(what, sizeof(what), "gala_b200::Linear [%d -> %d] d(weight)", Fin, Fout);
+        expect_close(what, ours->weight.grad(), ref->weight.grad(), 1e-5);
+        std::snprintf(what, sizeof(what), "gala_b200::Linear [%d -> %d] d(input)", Fin, Fout);
+        expect_close(what, in1.grad(), in2.grad(), 1e-5);
+        expect_close("gala_b200::Linear d(bias)", ours->bias.grad(), ref->bias.grad(), 1e-5);
+    }
+    // ---- linear_att / folded_att == the three Linear calls they replace (values and every gradient) -------
+    {
+        torch::manual_seed(12);
+        gala_b200::Linear fc(64, 32), el(32, 1), er(32, 1);
+        fc->to(dev);
+        el->to(dev);
+        er->to(dev);
+        torch::Tensor in = torch::rand({N, 64}, of.device(dev)) - 0.5;
+        torch::Tensor g0 = torch::rand({N, 32}, of.device(dev)) - 0.5, g1 = torch::rand({N, 1}, of.device(dev)) - 0.5,
+                      g2 = torch::rand({N, 1}, of.device(dev)) - 0.5;
+        auto grads_of = [&]() {
+            std::vector<torch::Tensor> out;
+            for (auto& m : {fc, el, er})
+                for (auto& p : m->parameters()) {
+                    out.push_back(p.grad().clone());
+                    p.mutable_grad() = torch::Tensor();
+                }
+            return out;
+        };
+        torch::Tensor in_a = in.clone().requires_grad_(true);
+        torch::Tensor ra, la, rra;
+        std::tie(ra, la, rra) = gala_b200::linear_att(fc, el, er, in_a);
+        (ra * g0).sum().add((la * g1).sum()).add((rra * g2).sum()).backward();
+        auto ga = grads_of();
+        torch::Tensor in_b = in.clone().requires_grad_(true);
+        torch::Tensor rb = at::linear(in_b, fc->weight, fc->bias);
+        torch::Tensor lb = at::linear(rb, el->weight, el->bias), rrb = at::linear(rb, er->weight, er->bias);
+        (rb * g0).sum().add((lb * g1).sum()).add((rrb * g2).sum()).backward();
+        auto gb = grads_of();
+        expect_close("linear_att: res", ra, rb, 1e-5);
+        expect_close("linear_att: attenL", la, lb, 1e-5);
+        expect_close("linear_att: attenR", rra, rrb, 1e-5);
+        expect_close("linear_att: d(input)", in_a.grad(), in_b.grad(), 1e-5);
+        for (size_t i = 0; i < ga.size(); ++i) expect_close("linear_att: d(parameter)", ga[i], gb[i], 1e-5);
+        // folded projections (layer 2): only the two logits are produced
+        torch::Tensor in_c = in.clone().requires_grad_(true), in_d = in.clone().requires_grad_(true);
+        torch::Tensor lc, rc;
+        std::tie(lc, rc) = gala_b200::folded_att(fc, el, er, in_c);
+        (lc * g1).sum().add((rc * g2).sum()).backward();
+        auto gc = grads_of();
+        torch::Tensor rd = at::linear(in_d, fc->weight, fc->bias);
+        torch::Tensor ld = at::linear(rd, el->weight, el->bias), rrd = at::linear(rd, er->weight, er->bias);
+        (ld * g1).sum().add((rrd * g2).sum()).backward();
+        auto gd = grads_of();
+        expect_close("folded_att: attenL", lc, ld, 1e-5);
+        expect_close("folded_att: attenR", rc, rrd, 1e-5);
+        expect_close("folded_att: d(input)", in_c.grad(), in_d.grad(), 1e-5);
+        for (size_t i = 0; i < gc.size(); ++i) expect_close("folded_att: d(parameter)", gc[i], gd[i], 1e-5);
+    }
+
     torch::Tensor norm = torch::pow(deg, -0.5);
     torch::Tensor ev = aggregate_edge_mul(norm, norm, t_off, t_col, t_val, t_bnd, S);
     expect_close("aggregate_edge_mul", ev, norm.index({r64, 0}) * norm.index({c64, 0}), 1e-6);

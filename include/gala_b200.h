@@ -275,14 +275,15 @@ int gala_gat_forward_dot_f32(const gala_graph_t *g, const float *aL, const float
 /* stays within the fp32 parity bound.  N <= 64 (hidden / class widths of the GNN layers).    */
 /* Optional fused attention projections of a GAT layer (attenL/attenR = Linear(h,1)(res),      */
 /* frontend.y:987-994): att_out[0:M] = Y_pre_relu . att_w[0,:] + att_b[0], att_out[M:2M] the   */
-/* same with row 1.  att_w device [2,N], att_b HOST [2], att_out device [2,M]; all nullable.   */
+/* same with row 1.  att_w device [2,N], att_out device [2,M]; att_b [2] on the HOST, or on the */
+/* device when att_b_on_device != 0 (trained biases: no host read-back per step); all nullable. */
 /* row_scale (device [M], nullable) multiplies output row r before the ReLU: the `norm * res`   */
 /* pass that follows the transform in the generated GCN (codegen/gala.cu:441-443).              */
 /* multi_out (nullable): push the output rows to every GPU instead of Y (N % 4 == 0).          */
 int gala_linear_f32(const float *X, int64_t M, int32_t K, const float *W, const float *bias,
                     int32_t N, float *Y, const float *row_scale, int32_t relu, const float *att_w,
-                    const float *att_b, float *att_out, const struct gala_multi_out *multi_out,
-                    gala_stream_t stream);
+                    const float *att_b, int32_t att_b_on_device, float *att_out,
+                    const struct gala_multi_out *multi_out, gala_stream_t stream);
 
 /* The narrow transforms that follow an aggregation (classifier Linear(h, classes), the two    */
 /* Linear(h,1) attention projections; common.h:1185-1281): K <= 64, N <= 64, exact fp32 FMA,   */

@@ -439,17 +439,20 @@ def test_row_pitched_operands(orc, case, K):
     X = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
     want = orc.spmm(t, X, weighted=True)
     Xd = dev(X)
-    ld = (K + 3) // 4 * 4
+    ld = ops.pad_pitch(K)
     Xp = ops.pad_rows(Xd)
     assert Xp.stride(0) == ld and Xp.data_ptr() % 16 == 0 and torch.equal(Xp, Xd)
     if ld > K:
         assert float(Xp.as_strided((n, ld - K), (ld, 1), K).abs().max()) == 0.0   # padding zeroed
     packed_scalar = ops.spmm(g, Xd, vals=dev(t.vals), pad=None)           # packed rows, narrow loads
     pitched = ops.spmm(g, Xp, vals=dev(t.vals))                            # caller-provided pitched rows
-    auto = ops.spmm(g, Xd, vals=dev(t.vals))                               # default: re-pitched internally
-    for got in (packed_scalar, pitched, auto):
+    auto = ops.spmm(g, Xd, vals=dev(t.vals))                               # default: re-pitched internally (K <= 256)
+    tight = ops.spmm(g, ops.pad_rows(Xd, (K + 3) // 4 * 4), vals=dev(t.vals))   # any 16-byte pitch works
+    for got in (packed_scalar, pitched, auto, tight):
         assert got.is_contiguous() and rel_err(got.cpu().numpy(), want) < FP32_TOL
-    assert torch.equal(pitched, auto)
+    assert torch.equal(pitched, tight)
+    if K <= 256:
+        assert torch.equal(pitched, auto)
     # pitched OUTPUT: the columns past K keep their sentinel
     Yp = torch.full((n, ld + 4), 7.0, device=DEV)
     ops.spmm(g, Xp, vals=dev(t.vals), out=Yp[:, :K])
