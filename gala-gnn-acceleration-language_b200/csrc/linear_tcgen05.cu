@@ -112,8 +112,12 @@ struct LinearParams {
     MultiOut mo;                      // count > 0: output rows pushed to every GPU instead of Y
 };
 
+// NPAD <= 64: the shapes of the GNN layers (hidden / class widths), 2 CTAs per SM, fused row epilogues.
+// NPAD in (64, 256] ("wide": the 172-class classifier of the Papers shape): the same pipeline with one MMA covering all
+// NPAD columns (UMMA_N up to 256), fewer accumulators (TMEM has 512 columns), W loaded in row blocks, and an epilogue
+// that walks the accumulator row 16 columns at a time instead of holding it in registers.
 template <int NPAD>
-__global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid_constant__ LinearParams p) {
+__global__ void __launch_bounds__(kThreads, (NPAD > 64 ? 1 : 2)) linear_tf32x3_kernel(const __grid_constant__ LinearParams p) {
     constexpr uint32_t kABytes = kBM * 128;            // one A tile (hi or lo)
     constexpr uint32_t kBBytes = NPAD * 128;           // one B tile (hi or lo)
     constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
@@ -121,9 +125,11 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
     // accumulation chain drifts (4e-6 relative after 228 MMAs, measured).  The hi*hi products are
     // therefore spread round-robin over kMain accumulators, the small correction terms go to their
     // own accumulator, and the epilogue adds the kMain + 1 partials with IEEE fp32 adds.
-    constexpr int kMain = NPAD == 64 ? 3 : 4;
+    constexpr bool kWide = NPAD > 64;
+    constexpr int kMain = NPAD > 128 ? 1 : NPAD > 64 ? 2 : NPAD == 64 ? 3 : 4;
     constexpr uint32_t kAccCols = (kMain + 1) * NPAD;
-    constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : 256;
+    constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : kAccCols <= 256 ? 256 : 512;
+    static_assert(kAccCols <= 512, "TMEM has 512 columns");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_bar;
@@ -157,7 +163,8 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
         // Software-pipelined: the 32 + NPAD/4 global loads of chunk ch+1 are issued before chunk ch is
         // split and stored, so every producer warp keeps two chunks (8 KB) of HBM requests in flight.
         constexpr int kWRows = NPAD / 4;
-        float va[32], wa[kWRows], vb[32], wb[kWRows];
+        constexpr int kWReg = kWide ? 1 : kWRows;     // wide: W is not staged in registers (row blocks at store time)
+        float va[32], wa[kWReg], vb[32], wb[kWReg];
         // Addressing is hoisted so that the steady state costs one IMAD + LDG per element on the load
         // side and LOP3 + FADD + 2 STS (immediate offsets) on the store side.
         const int64_t wrow0 = row0 + warp * 32;
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
         uint32_t sw[8];   // swizzled 16-byte chunk of this lane's column for row-in-atom j
 #pragma unroll
         for (int j = 0; j < 8; ++j) sw[j] = (uint32_t)((((lane >> 2) ^ j) << 4) | ((lane & 3) << 2));
-        auto load_chunk = [&](int ch, float (&v)[32], float (&w)[kWRows]) {
+        auto load_chunk = [&](int ch, float (&v)[32], float (&w)[kWReg]) {
             const bool kok = ch * kBK + lane < p.K;
             const char* xc = xlane + ch * (kBK * 4);
             const char* wc = wlane + ch * (kBK * 4);
@@ -181,16 +188,18 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
                 for (int i = 0; i < 32; ++i)
                     v[i] = (kok && wrow0 + i < p.M) ? __ldg(reinterpret_cast<const float*>(xc + (uint64_t)i * pitch)) : 0.0f;
             }
-            if (wrows_full && kok) {
+            if constexpr (!kWide) {
+                if (wrows_full && kok) {
 #pragma unroll
-                for (int i = 0; i < kWRows; ++i) w[i] = __ldg(reinterpret_cast<const float*>(wc + (uint64_t)i * pitch));
-            } else {
+                    for (int i = 0; i < kWRows; ++i) w[i] = __ldg(reinterpret_cast<const float*>(wc + (uint64_t)i * pitch));
+                } else {
 #pragma unroll
-                for (int i = 0; i < kWRows; ++i)   // rows >= N are zero
-                    w[i] = (kok && warp * kWRows + i < p.N) ? __ldg(reinterpret_cast<const float*>(wc + (uint64_t)i * pitch)) : 0.0f;
+                    for (int i = 0; i < kWRows; ++i)   // rows >= N are zero
+                        w[i] = (kok && warp * kWRows + i < p.N) ? __ldg(reinterpret_cast<const float*>(wc + (uint64_t)i * pitch)) : 0.0f;
+                }
             }
         };
-        auto store_chunk = [&](int ch, const float (&v)[32], const float (&w)[kWRows]) {
+        auto store_chunk = [&](int ch, const float (&v)[32], const float (&w)[kWReg]) {
             const int s = ch % kStages;
             const uint32_t ph = (uint32_t)((ch / kStages) & 1);
             if (ch >= kStages) mbar_wait(&empty_bar[s], ph ^ 1);
@@ -205,13 +214,37 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
                 *reinterpret_cast<float*>(a_hi + i * 128 + sw[i & 7]) = hi;
                 *reinterpret_cast<float*>(a_lo + i * 128 + sw[i & 7]) = lo;
             }
+            if constexpr (!kWide) {
 #pragma unroll
-            for (int i = 0; i < kWRows; ++i) {   // warp * kWRows is a multiple of 4; row-in-atom = (warp*kWRows + i) & 7
-                float hi, lo;
-                split_tf32(w[i], hi, lo);
-                const uint32_t o = (uint32_t)(i * 128) + sw[(warp * kWRows + i) & 7];
-                *reinterpret_cast<float*>(b_hi + o) = hi;
-                *reinterpret_cast<float*>(b_lo + o) = lo;
+                for (int i = 0; i < kWRows; ++i) {   // warp * kWRows is a multiple of 4; row-in-atom = (warp*kWRows + i) & 7
+                    float hi, lo;
+                    split_tf32(w[i], hi, lo);
+                    const uint32_t o = (uint32_t)(i * 128) + sw[(warp * kWRows + i) & 7];
+                    *reinterpret_cast<float*>(b_hi + o) = hi;
+                    *reinterpret_cast<float*>(b_lo + o) = lo;
+                }
+            } else {
+                // W (L2-resident, N*K*4 bytes) in blocks of 8 rows, loaded right here: kWRows is a multiple of 4
+                const bool kok = ch * kBK + lane < p.K;
+                const char* wc = wlane + ch * (kBK * 4);
+#pragma unroll 1
+                for (int i0 = 0; i0 < kWRows; i0 += 8) {
+                    float w8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        w8[i] = (i0 + i < kWRows && kok && warp * kWRows + i0 + i < p.N)
+                                    ? __ldg(reinterpret_cast<const float*>(wc + (uint64_t)(i0 + i) * pitch)) : 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (i0 + i < kWRows) {
+                            float hi, lo;
+                            split_tf32(w8[i], hi, lo);
+                            const uint32_t o = (uint32_t)((i0 + i) * 128) + sw[(warp * kWRows + i0 + i) & 7];
+                            *reinterpret_cast<float*>(b_hi + o) = hi;
+                            *reinterpret_cast<float*>(b_lo + o) = lo;
+                        }
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
             mbar_arrive(&full_bar[s]);
@@ -229,6 +262,51 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
         mbar_wait(&acc_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int64_t r = row0 + tid;
+      if constexpr (kWide) {
+        // 16 columns at a time: sum the kMain + 1 partial accumulators, bias / row scale / ReLU, 64-byte store
+        const float rscale = (p.row_scale && r < p.M) ? __ldg(p.row_scale + r) : 1.0f;
+        float* yrow = p.Y + r * p.N;
+        const bool y16 = (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.Y) & 15) == 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NPAD; c0 += 16) {
+            if (c0 >= p.N) break;               // warp-uniform: the tcgen05.ld below is warp-collective
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = 0.0f;
+#pragma unroll
+            for (int a = 0; a <= kMain; ++a) {
+                if (a < kMain && a >= nchunks) continue;    // main accumulator a is written only if there are more than a chunks
+                uint32_t u[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * NPAD + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                      "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] += __uint_as_float(u[j]);
+            }
+            if (r < p.M) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float y = o[j] + ((p.bias && c0 + j < p.N) ? __ldg(p.bias + c0 + j) : 0.0f);
+                    y *= rscale;
+                    if (p.relu) y = fmaxf(y, 0.0f);
+                    o[j] = y;
+                }
+                if (y16) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        if (c0 + j < p.N) __stcs(reinterpret_cast<float4*>(yrow + c0 + j), make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < p.N) yrow[c0 + j] = o[j];
+                }
+            }
+        }
+      } else {
         float acc[NPAD];
 #pragma unroll
         for (int n = 0; n < NPAD; ++n) acc[n] = 0.0f;
@@ -286,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const __grid
                 p.att_out[p.M + r] = a1;
             }
         }
+      }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else if (lane == 0) {
         // ---------------- MMA issuer (one thread) ---------------------------------------------------
@@ -619,7 +698,8 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
                                int32_t att_b_on_device, float* att_out, const gala_multi_out_t* multi_out,
                                gala_stream_t stream) {
     if (M < 0 || K <= 0 || N <= 0) return GALA_ERR_BAD_SHAPE;
-    if (N > 64) return GALA_ERR_UNSUPPORTED;   // one CTA holds every output column (GNN hidden / class widths)
+    if (N > 256) return GALA_ERR_UNSUPPORTED;   // one CTA holds every output column (UMMA_N <= 256)
+    if (N > 64 && (att_w || (multi_out && multi_out->count > 0))) return GALA_ERR_UNSUPPORTED;   // row epilogues: N <= 64
     if (M == 0) return GALA_OK;
     const bool multi = multi_out && multi_out->count > 0;
     if (!X || !W || (!Y && !multi) || (att_w && (!att_b || !att_out))) return GALA_ERR_NULL_POINTER;
@@ -662,5 +742,9 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
     if (N <= 16) return launch_linear<16>(p, st);
     if (N <= 32) return launch_linear<32>(p, st);
     if (N <= 48) return launch_linear<48>(p, st);
-    return launch_linear<64>(p, st);
+    if (N <= 64) return launch_linear<64>(p, st);
+    if (N <= 96) return launch_linear<96>(p, st);
+    if (N <= 128) return launch_linear<128>(p, st);
+    if (N <= 176) return launch_linear<176>(p, st);
+    return launch_linear<256>(p, st);
 }

@@ -394,7 +394,7 @@ class PartitionedGATN:
         mark(f"exchange{L}")
         agg = run(f"gat_layer{L}", lambda: ops.gat_forward(self.graph, att[0], aR_all, px.bufs[L - 1], m.slope, relu=False))
         mark(f"gat_layer{L}")
-        out = F.linear(agg, *m.fc[-1])
+        out = run("classifier", lambda: ops.dense(agg, *m.fc[-1]))
         mark("classifier")
         return out
 
@@ -459,6 +459,6 @@ class PartitionedGCNN:
         mark(f"all_gather{m.L}")
         agg = run(f"gcn_aggregate{m.L}", lambda: ops.spmm(self.graph, y_all, row_scale=self.norm))
         mark(f"gcn_aggregate{m.L}")
-        out = F.linear(agg, *m.fc[-1])
+        out = run("classifier", lambda: ops.dense(agg, *m.fc[-1]))
         mark("classifier")
         return out

@@ -79,8 +79,7 @@ class GAT2:
         projections, fused in the epilogue) on the tensor cores (gala_linear_f32); "torch" = cuBLAS."""
         run = hook if hook is not None else (lambda name, fn: fn())
         hidden, classes = self.fc0[0].shape[0], self.fc1[0].shape[0]
-        if dense == "tcgen05" and (hidden > ops.LINEAR_MAX_N or hidden > ops.LINEAR_SMALL_MAX or
-                                   classes > ops.LINEAR_SMALL_MAX):
+        if dense == "tcgen05" and (hidden > ops.LINEAR_SMALL_MAX or classes > ops.LINEAR_SMALL_MAX):
             # widths outside the hand-written transforms (gala_linear_f32: N <= LINEAR_MAX_N; gala_linear_small_f32:
             # K, N <= 64): same op sequence with the dense parts on cuBLAS (what the generated program uses)
             dense = "torch"
@@ -183,9 +182,9 @@ class GATN:
             rows, buf = logits_chunk
             for lo in range(0, agg.shape[0], rows):
                 hi = min(agg.shape[0], lo + rows)
-                torch.addmm(self.fc[-1][1], agg[lo:hi], self.fc[-1][0].t(), out=buf[:hi - lo])
+                run("classifier", lambda: ops.dense(agg[lo:hi], self.fc[-1][0], self.fc[-1][1], out=buf[:hi - lo]))
             return None
-        return F.linear(agg, *self.fc[-1])
+        return run("classifier", lambda: ops.dense(agg, *self.fc[-1]))
 
     def host_biases(self):
         """Reads the folded biases back once (outside any timed step)."""

@@ -95,4 +95,4 @@ class GCNN:
             res = run(f"gcn_aggregate{i + 1}", lambda: ops.spmm(g, t, row_scale=self.norm2 if last_hidden else self.norm,
                                                                  relu=True))
         agg = run(f"gcn_aggregate{self.L}", lambda: ops.spmm(g, res, row_scale=self.norm))
-        return F.linear(agg, *self.fc[-1])
+        return run("classifier", lambda: ops.dense(agg, *self.fc[-1]))

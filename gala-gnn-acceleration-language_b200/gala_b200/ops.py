@@ -15,7 +15,7 @@ import torch
 from . import lib as _l
 
 DEFAULT_HUB_THRESHOLD = 2048
-LINEAR_MAX_N = 64         # widest output gala_linear_f32 accepts (GALA_ERR_UNSUPPORTED beyond)
+LINEAR_MAX_N = 256        # widest output gala_linear_f32 accepts (GALA_ERR_UNSUPPORTED beyond); row epilogues: N <= 64
 LINEAR_SMALL_MAX = 64     # gala_linear_small_f32: K <= 64 and N <= 64
 
 
@@ -272,7 +272,7 @@ def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None, row_sc
     X, W = _f32(X), _f32(W)
     M, K = X.shape
     N = W.shape[0]
-    assert W.shape[1] == K and N <= 64
+    assert W.shape[1] == K
     if out is None and multi_out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=X.device)
     att = None
@@ -341,6 +341,22 @@ def linear_small(X, W, bias=None, relu=False, transpose_out=False, out=None):
     _l.check(_l.load().gala_linear_small_f32(_l.ptr(X), M, K, _l.ptr(W), _l.ptr(bias), N, _l.ptr(out), int(relu),
                                              int(transpose_out), _l.stream_ptr()))
     return out
+
+
+def dense(X, W, bias=None, out=None):
+    """Y = X @ W.T + bias on whichever of this library's transforms covers the shape: the streaming kernel for
+    the narrow ones (K, N <= 64), the tcgen05 kernel up to N = 256, cuBLAS beyond."""
+    K, N = W.shape[1], W.shape[0]
+    if K <= LINEAR_SMALL_MAX and N <= LINEAR_SMALL_MAX:
+        return linear_small(X, W, bias, out=out)
+    if N <= LINEAR_MAX_N:
+        return linear(X, W, bias, out=out)
+    import torch.nn.functional as F
+    y = F.linear(X, W, bias)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
 
 
 def probe_read_gbs(nbytes, repeats, device="cuda:0"):

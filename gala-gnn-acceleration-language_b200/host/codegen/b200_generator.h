@@ -108,6 +108,7 @@ public:
     struct FuseOptions {
         bool gatLayers = true;   // edge_sddvv + LeakyReLU + softmax + aggregate -> gala_b200::gat_layer_AutoGrad
         bool linears = true;     // torch::nn::Linear -> gala_b200::Linear (tcgen05 / streaming kernels), projections fused
+        bool corruptForTest = false;   // test hook: mangle one emitted statement so that the loud-failure path can be exercised
     };
 
     void writeCodeB200(std::vector<CIRNode*>& program, std::vector<RelationEdge*>& dependencies,
@@ -217,6 +218,12 @@ private:
         auto line = [&](int i) -> std::string& { return *fwd->atLine(i); };
         auto blank = [&](int i) { line(i) = "        // (fused into the call above)"; };
         const int n = fwd->getNum();
+        if (opt.corruptForTest)
+            for (int i = 0; i < n; ++i)
+                if (line(i).find("non_lnr_op_softmax_AutoGrad::apply") != std::string::npos) {
+                    line(i) = "attn = some_new_softmax(attn);";
+                    break;
+                }
 
         // ---- (1) GAT layers: IR says AGGREGATE_EDGE_SUM -> LEAKY_RELU -> SOFTMAX -> AGGREGATE_MUL_SUM over one graph
         int gatLayersInIR = 0;

@@ -56,12 +56,13 @@ int main(int argc, char** argv) {
     int feat = atoi(argv[3]), labels = atoi(argv[4]), colTile = atoi(argv[5]);
     bool reference = false;
     int sample = 0, graphSample = 0;
-    bool noFuse = false, sparser = false, hostFormats = false, torchLinear = false;
+    bool noFuse = false, sparser = false, hostFormats = false, torchLinear = false, corruptForTest = false;
     for (int i = 9; i < argc; i++) {
         if (!strcmp(argv[i], "--reference")) reference = true;
         else if (!strcmp(argv[i], "--no-fuse")) noFuse = true;
         else if (!strcmp(argv[i], "--host-formats")) hostFormats = true;   // keep the reference's CPU data preparation
         else if (!strcmp(argv[i], "--torch-linear")) torchLinear = true;   // keep torch::nn::Linear (cuBLAS)
+        else if (!strcmp(argv[i], "--corrupt-forward-for-test")) corruptForTest = true;   // tests/test_codegen_cpu.py
         else if (!strcmp(argv[i], "--sparser")) sparser = true;   // G=G.is_sparser(true) (frontend.y:304-305)
         else if (!strcmp(argv[i], "--sample") && i + 1 < argc) sample = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--graph-sample") && i + 1 < argc) graphSample = atoi(argv[++i]);
@@ -135,6 +136,7 @@ int main(int argc, char** argv) {
         B200Generator::FuseOptions opt;
         opt.gatLayers = !noFuse;
         opt.linears = !noFuse && !torchLinear;
+        opt.corruptForTest = corruptForTest;
         static_cast<B200Generator*>(gen)->writeCodeB200(GALAFEContext::program, GALAFEContext::dependencies,
                                                         GALAFEContext::associations, GALAFEContext::transforms, opt, std::cout);
     }

@@ -311,7 +311,7 @@ public:
 // torch::nn::LinearImpl), whose forward runs gala_linear_f32 (tcgen05, 3xTF32) or, for the narrow transforms
 // (K, N <= 64: classifier, Linear(h,1) projections), gala_linear_small_f32.  Backward: dX = dY W, dW = dY^T X,
 // db = sum dY through ATen (cuBLAS), as autograd does for torch::nn::Linear.
-constexpr int64_t kLinearMaxN = 64;
+constexpr int64_t kLinearMaxN = 256;     // gala_linear_f32; the fused attention projections need N <= 64
 
 inline torch::Tensor linear_forward(const torch::Tensor& X, const torch::Tensor& W, const torch::Tensor& b) {
     const int64_t M = X.size(0), K = W.size(1), N = W.size(0);
@@ -366,7 +366,7 @@ public:
         torch::Tensor att_w = torch::cat({wl.reshape({1, N}), wr.reshape({1, N})}, 0).contiguous();
         torch::Tensor att_b = torch::cat({bl.reshape({1}), br.reshape({1})}, 0).contiguous();
         torch::Tensor res, att;
-        if (N <= kLinearMaxN) {
+        if (N <= 64) {
             res = torch::empty({M, N}, of);
             att = torch::empty({2, M}, of);
             check(gala_linear_f32(X.data_ptr<float>(), M, (int)K, W.contiguous().data_ptr<float>(), b.data_ptr<float>(), (int)N,

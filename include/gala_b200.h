@@ -272,7 +272,8 @@ int gala_gat_forward_dot_f32(const gala_graph_t *g, const float *aL, const float
 /* Replaces torch::nn::Linear of the generated model (common.h:1185-1281; cuBLAS fp32 SIMT   */
 /* through libtorch): Y[M,N] = X[M,K] * W[N,K]^T + bias, optional ReLU.  tcgen05.mma         */
 /* kind::tf32 with the accumulator in TMEM, error-compensated (3xTF32) so that the result     */
-/* stays within the fp32 parity bound.  N <= 64 (hidden / class widths of the GNN layers).    */
+/* stays within the fp32 parity bound.  N <= 256; the fused row epilogues (attention          */
+/* projections, multi_out) need N <= 64 (hidden / class widths of the GNN layers).            */
 /* Optional fused attention projections of a GAT layer (attenL/attenR = Linear(h,1)(res),      */
 /* frontend.y:987-994): att_out[0:M] = Y_pre_relu . att_w[0,:] + att_b[0], att_out[M:2M] the   */
 /* same with row 1.  att_w device [2,N], att_out device [2,M]; att_b [2] on the HOST, or on the */

@@ -11,7 +11,10 @@ DEV = "cuda:0"
 
 
 @pytest.mark.parametrize("M,K,N", [(128, 32, 32), (128, 64, 32), (1000, 602, 32), (5000, 100, 32), (777, 32, 41),
-                                   (300, 1433, 32), (4096, 602, 16), (130, 7, 8), (1, 5, 64), (233000, 602, 32)])
+                                   (300, 1433, 32), (4096, 602, 16), (130, 7, 8), (1, 5, 64), (233000, 602, 32),
+                                   # wide outputs (64 < N <= 256): the 172-class classifier of the Papers shape & co.
+                                   (5000, 32, 172), (1000, 128, 172), (300, 602, 100), (777, 32, 96), (2000, 64, 128),
+                                   (129, 32, 173), (4000, 100, 256), (64, 8, 65)])
 def test_linear_matches_fp64_and_torch_fp32(M, K, N):
     torch.backends.cuda.matmul.allow_tf32 = False
     gen = torch.Generator(device=DEV)
@@ -30,6 +33,16 @@ def test_linear_matches_fp64_and_torch_fp32(M, K, N):
     assert torch.equal(got_relu, torch.relu(got))
     got_nb = ops.linear(X, W)
     assert float((got_nb.double() - (want64 - b.double())).norm() / want64.norm()) < 1e-5
+
+
+def test_linear_width_limits():
+    """N > 256 and row epilogues on wide outputs are refused with GALA_ERR_UNSUPPORTED (no silent fallback)."""
+    from gala_b200 import lib as _l
+    X = torch.rand(256, 32, device=DEV)
+    with pytest.raises(_l.GalaError):
+        ops.linear(X, torch.rand(257, 32, device=DEV))
+    with pytest.raises(_l.GalaError):
+        ops.linear(X, torch.rand(100, 32, device=DEV), att_w=torch.rand(2, 100, device=DEV), att_b=[0.0, 0.0])
 
 
 def test_linear_fused_attention_projections():
