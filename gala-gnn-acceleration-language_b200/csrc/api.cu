@@ -480,6 +480,12 @@ int gala_gat_forward_ex_f32(const gala_graph_t* g, const float* aL, const float*
         p.mo.mc_base = ep->multi_out->multicast_base;
         for (int q = 0; q < p.mo.count; ++q) p.mo.base[q] = ep->multi_out->base[q];
     }
+    if (ep && ep->att_multi_out && ep->att_multi_out->count > 0) {
+        if (!ep->att_w || ep->att_multi_out->count > kMaxPeers) return GALA_ERR_UNSUPPORTED;
+        p.att_mo.count = ep->att_multi_out->count;
+        p.att_mo.mc_base = ep->att_multi_out->multicast_base;
+        for (int q = 0; q < p.att_mo.count; ++q) p.att_mo.base[q] = ep->att_multi_out->base[q];
+    }
     HubView h = hub_of(plan, g);
     p.t = task_of(h);
     if (has_ep) {   // the dense epilogue needs the whole row in one warp pass: check the tiling the dispatcher picks

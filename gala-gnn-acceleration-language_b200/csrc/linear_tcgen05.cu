@@ -110,6 +110,8 @@ struct LinearParams {
     int64_t M;
     int K, N, relu;
     MultiOut mo;                      // count > 0: output rows pushed to every GPU instead of Y
+    MultiOut att_mo;                  // count > 0: the second projection (attenR, one float per row) is ALSO stored
+                                      // at element `row` of every GPU's gathered vector
 };
 
 // NPAD <= 64: the shapes of the GNN layers (hidden / class widths), 2 CTAs per SM, fused row epilogues.
@@ -362,6 +364,11 @@ __global__ void __launch_bounds__(kThreads, (NPAD > 64 ? 1 : 2)) linear_tf32x3_k
             if (p.att_w) {
                 p.att_out[r] = a0;
                 p.att_out[p.M + r] = a1;
+                if (p.att_mo.count > 0) {
+                    Vec<1> o1;
+                    o1.v[0] = a1;
+                    multi_store<1>(p.att_mo, r, o1);
+                }
             }
         }
       }
@@ -612,6 +619,11 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
                 if (p.att_w) {
                     p.att_out[r] = a0;
                     p.att_out[p.M + r] = a1;
+                    if (p.att_mo.count > 0) {
+                        Vec<1> o1;
+                        o1.v[0] = a1;
+                        multi_store<1>(p.att_mo, r, o1);
+                    }
                 }
             }
             if ((p.N & 3) == 0 && (p.mo.count > 0 || (reinterpret_cast<uintptr_t>(p.Y) & 15) == 0)) {
@@ -696,7 +708,7 @@ int launch_linear(const LinearParams& p, cudaStream_t st) {
 extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float* W, const float* bias, int32_t N, float* Y,
                                const float* row_scale, int32_t relu, const float* att_w, const float* att_b,
                                int32_t att_b_on_device, float* att_out, const gala_multi_out_t* multi_out,
-                               gala_stream_t stream) {
+                               const gala_multi_out_t* att_multi_out, gala_stream_t stream) {
     if (M < 0 || K <= 0 || N <= 0) return GALA_ERR_BAD_SHAPE;
     if (N > 256) return GALA_ERR_UNSUPPORTED;   // one CTA holds every output column (UMMA_N <= 256)
     if (N > 64 && (att_w || (multi_out && multi_out->count > 0))) return GALA_ERR_UNSUPPORTED;   // row epilogues: N <= 64
@@ -718,6 +730,12 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
         p.mo.mc_base = multi_out->multicast_base;
         for (int q = 0; q < multi_out->count; ++q) p.mo.base[q] = multi_out->base[q];
     }
+    if (att_multi_out && att_multi_out->count > 0) {
+        if (!att_w || att_multi_out->count > kMaxPeers) return GALA_ERR_UNSUPPORTED;
+        p.att_mo.count = att_multi_out->count;
+        p.att_mo.mc_base = att_multi_out->multicast_base;
+        for (int q = 0; q < att_multi_out->count; ++q) p.att_mo.base[q] = att_multi_out->base[q];
+    }
     p.M = M;
     p.K = K;
     p.N = N;
@@ -731,8 +749,11 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
         }
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // the persistent variant runs one CTA per SM: with fewer than ~3 tiles per CTA its last wave is mostly empty
+    // (a rank's 228 tiles on 148 CTAs at 8 GPUs: 65 % efficiency); the 2-CTA/SM kernel covers those in one wave
+    const int64_t ntiles = (M + kBM - 1) / kBM;
     const bool v2 = (K % 2 == 0) && (reinterpret_cast<uintptr_t>(X) % 8 == 0) && (reinterpret_cast<uintptr_t>(W) % 8 == 0) &&
-                    M >= 4 * kBM;
+                    ntiles >= 3 * (int64_t)device_sm_count();
     if (v2) {
         if (N <= 16) return launch_linear_v2<16>(p, st);
         if (N <= 32) return launch_linear_v2<32>(p, st);

@@ -53,6 +53,8 @@ struct SpmmParams {
     float* __restrict__ cls_out;          // [nrows, cls_n]
     int cls_n;
     MultiOut mo;                          // count > 0: Y rows go to every GPU (Y itself unused)
+    MultiOut att_mo;                      // count > 0: the second projection of the epilogue (next layer's attenR) is also
+                                          // stored at element `row` of every GPU's gathered vector
 };
 
 
@@ -184,6 +186,11 @@ __device__ __forceinline__ void row_dense_epilogue(const SpmmParams& p, const fl
         if (lane == 0) {
             p.att_out[row] = a0 + p.att_b0;
             p.att_out[p.g.nrows + row] = a1 + p.att_b1;
+            if (p.att_mo.count > 0) {
+                Vec<1> o1;
+                o1.v[0] = a1 + p.att_b1;
+                multi_store<1>(p.att_mo, row, o1);
+            }
         }
     }
     if (p.cls_wT) {

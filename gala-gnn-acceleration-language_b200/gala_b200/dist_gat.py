@@ -247,21 +247,27 @@ class PeerExchange:
                              "use exchange=\"nccl\" with NeededRowsPartition")
         self.part = part
         self.bufs, self.hdls, self.mos = [], [], []
+        self.att_bufs, self.att_mos = [], []
+        from . import ops
         for K in widths:
-            buf = symm.empty((part.padded_n, K), dtype=torch.float32, device=device)
-            buf.zero_()   # padding rows are never written
-            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            # one symmetric allocation per exchange: [padded_n, K] feature rows followed by [padded_n] floats, the
+            # right-hand attention scalar of every row (the only other quantity a GAT layer gathers by column)
+            flat = symm.empty((part.padded_n * (K + 1),), dtype=torch.float32, device=device)
+            flat.zero_()   # padding rows are never written
+            hdl = symm.rendezvous(flat, dist.group.WORLD)
             off = part.rank * part.max_rows * K * 4
-            mc = None
+            att_off = part.padded_n * K * 4 + part.rank * part.max_rows * 4
+            mc = mc_att = None
             try:
                 if hdl.has_multicast_support and hdl.multicast_ptr:
-                    mc = hdl.multicast_ptr + off
+                    mc, mc_att = hdl.multicast_ptr + off, hdl.multicast_ptr + att_off
             except Exception:
-                mc = None
-            from . import ops
-            self.bufs.append(buf)
+                mc = mc_att = None
+            self.bufs.append(flat[:part.padded_n * K].view(part.padded_n, K))
+            self.att_bufs.append(flat[part.padded_n * K:])
             self.hdls.append(hdl)
             self.mos.append(ops.make_multi_out([p + off for p in hdl.buffer_ptrs], mc))
+            self.att_mos.append(ops.make_multi_out([p + att_off for p in hdl.buffer_ptrs], mc_att))
         torch.cuda.synchronize()
         dist.barrier()
 
@@ -297,21 +303,22 @@ class PartitionedGAT:
                 self.px = None
 
     def forward_p2p(self, X_local, hook=None):
-        """Folded-projection forward with the two exchanges fused into the producing kernels."""
+        """Folded-projection forward with both exchanges fused into the producing kernels: every kernel pushes its
+        output rows AND the right-hand attention scalar of those rows (computed in its epilogue) into all GPUs'
+        gathered buffers, the left-hand scalar stays local.  Three launches and two device barriers per step; nothing
+        is recomputed on gathered rows."""
         run = hook if hook is not None else (lambda name, fn: fn())
-        m, px, part, ops = self.model, self.px, self.part, self.ops
-        run("linear1", lambda: ops.linear(X_local, m.fc0[0], m.fc0[1], multi_out=px.mos[0]))
+        m, px, ops = self.model, self.px, self.ops
+        _, a = run("linear1", lambda: ops.linear(X_local, m.fc0[0], m.fc0[1], att_w=m.W_att1, att_b=m.b_att1_host,
+                                                 multi_out=px.mos[0], att_multi_out=px.att_mos[0]))
         px.barrier(0)
-        res_all = px.bufs[0]
-        a = F.linear(res_all, m.W_att1, m.b_att1).t().contiguous()
-        run("gat_layer1", lambda: ops.gat_forward_ex(self.graph, part.local_slice(a[0]).contiguous(), a[1], res_all,
-                                                     m.slope, relu=True, multi_out=px.mos[1]))
+        _, a2, _ = run("gat_layer1", lambda: ops.gat_forward_ex(self.graph, a[0], px.att_bufs[0], px.bufs[0], m.slope,
+                                                                relu=True, att_w=m.W_att2, att_b=m.b_att2_host,
+                                                                multi_out=px.mos[1], att_multi_out=px.att_mos[1]))
         px.barrier(1)
-        y_all = px.bufs[1]
-        a = F.linear(y_all, m.W_att2, m.b_att2).t().contiguous()
-        _, _, out = run("gat_layer2", lambda: ops.gat_forward_ex(self.graph, part.local_slice(a[0]).contiguous(), a[1],
-                                                                 y_all, m.slope, relu=False, cls_wT=m.fc1_wT,
-                                                                 cls_b=m.fc1[1], want_y=False))
+        _, _, out = run("gat_layer2", lambda: ops.gat_forward_ex(self.graph, a2[0], px.att_bufs[1], px.bufs[1], m.slope,
+                                                                 relu=False, cls_wT=m.fc1_wT, cls_b=m.fc1[1],
+                                                                 want_y=False))
         return out
 
     def _aggregate(self, aL, aR, feats, relu):
@@ -366,31 +373,27 @@ class PartitionedGATN:
                 return y, att
             return gatn_forward_partitioned(m, part, X_local, self._aggregate, hook, linear_att, aggregate_att)
         run = hook if hook is not None else (lambda name, fn: fn())
-
-        def gather_vec(v):
-            return part.all_gather(v.reshape(-1, 1)).reshape(-1)
-
         res_loc, att = X_local, None
         for i in range(L - 1):
-            # the transform pushes its rows to every GPU while it computes and projects them onto the
-            # attention vectors; only the right-hand scalar per row goes through a (small) all-gather
+            # the transform pushes its rows to every GPU while it computes, projects them onto the attention
+            # vectors in its epilogue and pushes the right-hand scalar of every row the same way
             _, a = run(f"linear{i + 1}", lambda: ops.linear(res_loc, m.fc[i][0], m.fc[i][1], att_w=m.W_att[i],
-                                                            att_b=bh[i], multi_out=px.mos[i]))
+                                                            att_b=bh[i], multi_out=px.mos[i], att_multi_out=px.att_mos[i]))
             mark(f"linear{i + 1}+push")
-            aR_all = gather_vec(a[1])
             px.barrier(i)
+            aR_all = px.att_bufs[i]
             mark(f"exchange{i + 1}")
             if i == L - 2:
                 _, att, _ = run(f"gat_layer{i + 1}", lambda: ops.gat_forward_ex(
                     self.graph, a[0], aR_all, px.bufs[i], m.slope, relu=True, att_w=m.W_att[-1], att_b=bh[-1],
-                    multi_out=px.mos[L - 1]))
+                    multi_out=px.mos[L - 1], att_multi_out=px.att_mos[L - 1]))
                 mark(f"gat_layer{i + 1}+push")
             else:
                 res_loc = run(f"gat_layer{i + 1}", lambda: ops.gat_forward(self.graph, a[0], aR_all, px.bufs[i],
                                                                            m.slope, relu=True))
                 mark(f"gat_layer{i + 1}")
-        aR_all = gather_vec(att[1])
         px.barrier(L - 1)
+        aR_all = px.att_bufs[L - 1]
         mark(f"exchange{L}")
         agg = run(f"gat_layer{L}", lambda: ops.gat_forward(self.graph, att[0], aR_all, px.bufs[L - 1], m.slope, relu=False))
         mark(f"gat_layer{L}")

@@ -51,7 +51,7 @@ class GalaDenseEpilogue(C.Structure):
     _fields_ = [("att_w", C.c_void_p), ("att_b", C.c_float * 2), ("att_out", C.c_void_p),
                 ("cls_wT", C.c_void_p), ("cls_b", C.c_void_p), ("cls_out", C.c_void_p),
                 ("cls_n", C.c_int32), ("multi_out", C.POINTER(GalaMultiOut)), ("ldx", C.c_int64),
-                ("ldy", C.c_int64)]
+                ("ldy", C.c_int64), ("att_multi_out", C.POINTER(GalaMultiOut))]
 
 
 class GalaError(RuntimeError):
@@ -101,7 +101,7 @@ def load():
     sigs.update({
         "gala_linear_small_f32": [vp, i64, i32, vp, vp, i32, vp, i32, i32, vp],
         "gala_linear_f32": [vp, i64, i32, vp, vp, i32, vp, vp, i32, vp, vp, i32, vp,
-                            C.POINTER(GalaMultiOut), vp],
+                            C.POINTER(GalaMultiOut), C.POINTER(GalaMultiOut), vp],
         "gala_csr_from_coo": [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp],
         "gala_csr_transpose": [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp],
         "gala_col_tile": [i32, i32, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp],

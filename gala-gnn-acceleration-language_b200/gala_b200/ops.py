@@ -265,7 +265,8 @@ def make_multi_out(bases, multicast_base=None):
     return mo
 
 
-def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None, row_scale=None, multi_out=None):
+def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None, row_scale=None, multi_out=None,
+           att_multi_out=None):
     """Y = X @ W.T + bias on the tensor cores (tcgen05 kind::tf32, 3xTF32 error compensation).
     With att_w [2,N] / att_b (two floats) also returns att [2,M] = the two attention
     projections of the pre-activation output rows (fused epilogue)."""
@@ -291,12 +292,13 @@ def linear(X, W, bias=None, relu=False, att_w=None, att_b=None, out=None, row_sc
                                        _l.ptr(row_scale), int(relu),
                                        _l.ptr(att_w), ab, ab_dev,
                                        _l.ptr(att), C.byref(multi_out) if multi_out is not None else None,
+                                       C.byref(att_multi_out) if att_multi_out is not None else None,
                                        _l.stream_ptr()))
     return (out, att) if att_w is not None else out
 
 
 def gat_forward_ex(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None, att_w=None, att_b=None,
-                   cls_wT=None, cls_b=None, want_y=True, multi_out=None):
+                   cls_wT=None, cls_b=None, want_y=True, multi_out=None, att_multi_out=None):
     """Fused GAT layer + dense epilogue on every finished output row: the next layer's two attention
     projections (att_w [2,K], att_b two floats -> att [2, nrows]) and / or the transform that follows
     the aggregation (cls_wT [K,C] = Linear weight transposed -> [nrows, C]).  Returns (Y, att, cls)."""
@@ -310,6 +312,8 @@ def gat_forward_ex(g, aL, aR, X, slope=0.2, relu=False, out=None, alpha_out=None
     ep = _l.GalaDenseEpilogue()
     if multi_out is not None:
         ep.multi_out = C.pointer(multi_out)
+    if att_multi_out is not None:
+        ep.att_multi_out = C.pointer(att_multi_out)
     att = cls = None
     if att_w is not None:
         att = torch.empty((2, g.nrows), dtype=torch.float32, device=dev)

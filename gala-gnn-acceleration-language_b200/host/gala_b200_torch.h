@@ -322,7 +322,7 @@ inline torch::Tensor linear_forward(const torch::Tensor& X, const torch::Tensor&
                                     stream()), "gala_linear_small_f32");
     } else if (N <= kLinearMaxN) {
         check(gala_linear_f32(X.data_ptr<float>(), M, (int)K, W.data_ptr<float>(), bias, (int)N, Y.data_ptr<float>(), nullptr, 0,
-                              nullptr, nullptr, 0, nullptr, nullptr, stream()), "gala_linear_f32");
+                              nullptr, nullptr, 0, nullptr, nullptr, nullptr, stream()), "gala_linear_f32");
     } else {
         return at::linear(X, W, b);      // wider than the hand-written kernels: cuBLAS
     }
@@ -371,7 +371,7 @@ public:
             att = torch::empty({2, M}, of);
             check(gala_linear_f32(X.data_ptr<float>(), M, (int)K, W.contiguous().data_ptr<float>(), b.data_ptr<float>(), (int)N,
                                   res.data_ptr<float>(), nullptr, 0, att_w.data_ptr<float>(), att_b.data_ptr<float>(), 1,
-                                  att.data_ptr<float>(), nullptr, stream()), "gala_linear_f32");
+                                  att.data_ptr<float>(), nullptr, nullptr, stream()), "gala_linear_f32");
         } else {
             res = at::linear(X, W, b);
             att = at::linear(res, att_w, att_b).t().contiguous();

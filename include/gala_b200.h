@@ -252,6 +252,8 @@ typedef struct gala_dense_epilogue {
     int32_t cls_n;
     const gala_multi_out_t *multi_out; /* nullable: Y rows go to every GPU instead of Y */
     int64_t ldx, ldy;                  /* row pitches of X / Y in elements, 0 = K       */
+    const gala_multi_out_t *att_multi_out; /* nullable: att_out[nrows+row] (the next layer's attenR, the scalar every
+                                          GPU gathers by column) is also stored at element `row` of the given bases */
 } gala_dense_epilogue_t;
 int gala_gat_forward_ex_f32(const gala_graph_t *g, const float *aL, const float *aR, const float *X,
                             int32_t K, float slope, float *Y, float *alpha_out, int32_t relu,
@@ -281,10 +283,13 @@ int gala_gat_forward_dot_f32(const gala_graph_t *g, const float *aL, const float
 /* row_scale (device [M], nullable) multiplies output row r before the ReLU: the `norm * res`   */
 /* pass that follows the transform in the generated GCN (codegen/gala.cu:441-443).              */
 /* multi_out (nullable): push the output rows to every GPU instead of Y (N % 4 == 0).          */
+/* att_multi_out (nullable): att_out[M + r] (attenR of row r) is also stored at element r of     */
+/* every GPU's gathered vector -- the one scalar per node a partitioned GAT layer exchanges.     */
 int gala_linear_f32(const float *X, int64_t M, int32_t K, const float *W, const float *bias,
                     int32_t N, float *Y, const float *row_scale, int32_t relu, const float *att_w,
                     const float *att_b, int32_t att_b_on_device, float *att_out,
-                    const struct gala_multi_out *multi_out, gala_stream_t stream);
+                    const struct gala_multi_out *multi_out, const struct gala_multi_out *att_multi_out,
+                    gala_stream_t stream);
 
 /* The narrow transforms that follow an aggregation (classifier Linear(h, classes), the two    */
 /* Linear(h,1) attention projections; common.h:1185-1281): K <= 64, N <= 64, exact fp32 FMA,   */
