@@ -220,7 +220,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU feature exchange: fused into the kernels over peer memory, or NCCL all-gather")
-    ap.add_argument("--mode", default="folded", choices=["folded", "fused", "literal", "dot"],
+    ap.add_argument("--mode", default="folded", choices=["folded", "folded_dot", "fused", "literal", "dot"],
                     help="how the dense ops around the fused GAT kernel run (gala_b200/gat_model.py)")
     ap.add_argument("--dense", default="tcgen05", choices=["tcgen05", "torch"],
                     help="layer-1 feature transform: hand-written tcgen05 3xTF32 kernel or cuBLAS fp32 via torch")
@@ -302,7 +302,7 @@ def main():
         X_in = X
         mode = args.mode
         step_fn = lambda hook=None: model.forward(g, X_in, hook, mode=mode, dense=args.dense)   # noqa: E731
-        launches_per_step = {"folded": 5, "fused": 3}.get(mode, 2) if args.dense == "tcgen05" else 2
+        launches_per_step = {"folded": 5, "folded_dot": 5, "fused": 3}.get(mode, 2) if args.dense == "tcgen05" else 2
         config["parallelism"] = "single GPU"
         config["dense"] = ("layer-1 X*W + attention projections: gala_linear_f32 (tcgen05 kind::tf32, 3xTF32)"
                            if args.dense == "tcgen05" else "cuBLAS fp32 through torch")
@@ -395,7 +395,13 @@ def main():
     out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
     X_stage = torch.empty_like(X_in)
 
+    e2e_chunks = 8 if (world == 1 and args.dense == "tcgen05" and mode in ("folded", "folded_dot")) else 1
+
     def e2e_step():
+        if e2e_chunks > 1:
+            # the public host-buffer call: chunked upload on a copy stream overlapped with the row-tiled transform
+            model.forward_host(g, X_host, out_host, chunks=e2e_chunks, mode=mode, stage=X_stage)
+            return
         X_stage.copy_(X_host, non_blocking=True)
         o = (runner.forward(X_stage) if world > 1 else model.forward(g, X_stage, mode=mode, dense=args.dense))
         out_host.copy_(o, non_blocking=True)
@@ -485,7 +491,11 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
             "e2e": {"value": round(e2e_ms, 4), "unit": "ms",
-                    "h2d_bytes_per_step": int(X_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4)},
+                    "h2d_bytes_per_step": int(X_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
+                    "h2d_chunks": e2e_chunks,
+                    "call": ("GAT2.forward_host: pinned host features uploaded in row blocks on a copy stream, each block "
+                             "consumed by the row-tiled transform as it lands; logits copied back to pinned host memory")
+                            if e2e_chunks > 1 else "H2D copy, forward, D2H copy on one stream"},
             "roofline": roofline, "kernel_ms": {k: round(v, 4) for k, v in kern_ms.items()},
             "eager_ms_per_step": round(eager_ms, 4),
             "parity_rel_err": parity,
@@ -566,6 +576,18 @@ def kernel_sweep(g, n, nvals, K, peak, dev, l2_gbs=None):
     del Xf
     rec("sddmm_k32", time_op(lambda: ops.sddmm(g, Z, X, out=ev)), rp + 4 * nvals + 8 * n * K + 4 * nvals, gth + 4 * nvals)
     rec("sddvv_add", time_op(lambda: ops.sddvv(g, a, a, "add", out=ev)), rp + 4 * nvals + 8 * n + 4 * nvals)
+    # the 4-byte gather B[col] touches one 128-byte line per edge: the SM's L1 serves ~1 line-wavefront per clock
+    # (B300_MICROARCH.md "L1tex wavefront queue": rt_L1tex_wf ~ 1.0 cyc/wf), which bounds this kernel before HBM does
+    props = torch.cuda.get_device_properties(dev)
+    clk_hz = 1.965e9
+    wf_ms = nvals / (props.multi_processor_count * clk_hz) * 1e3
+    res["sddvv_add"]["l1_wavefront_bound_ms"] = round(wf_ms, 4)
+    res["sddvv_add"]["frac_of_l1_wavefront_bound"] = round(wf_ms / res["sddvv_add"]["ms"], 4)
+    rec("gat_fused_k32", time_op(lambda: ops.gat_forward(g, a, a, X, out=Y)), rp + 4 * nvals + 8 * n + 8 * n * K,
+        gth + 4 * nvals)
+    wR = (torch.rand(K, generator=gen, device=dev) - 0.5).contiguous()
+    rec("gat_fused_dot_k32", time_op(lambda: ops.gat_forward_dot(g, a, wR, 0.1, X, out=Y)), rp + 4 * nvals + 4 * n + 8 * n * K,
+        gth)
     rec("edge_softmax_fwd", time_op(lambda: ops.edge_softmax_fwd(g, w, out=ev)), rp + 8 * nvals)
     rec("edge_rowsum", time_op(lambda: ops.edge_rowsum(g, w)), rp + 4 * nvals + 4 * n)
     # optional bf16 FEATURE STORAGE (not the headline: fp32 accumulation/outputs, results within 1e-2 of fp32,

@@ -20,10 +20,15 @@ int check_graph(const gala_graph_t* g) {
     if (!g) return GALA_ERR_NULL_POINTER;
     if (g->nrows < 0 || g->ncols < 0 || g->nvals < 0 || g->segments < 1) return GALA_ERR_BAD_SHAPE;
     if (g->nvals > 0x7fffffffLL) return GALA_ERR_UNSUPPORTED;  // int32 edge ids (common.h:1682)
-    if (g->segments > kMaxSeg) return GALA_ERR_UNSUPPORTED;
     if (g->nrows > 0 && !g->offsets) return GALA_ERR_NULL_POINTER;
     if (g->nvals > 0 && !g->cols) return GALA_ERR_NULL_POINTER;
     if (g->segments > 1 && !g->bounds) return GALA_ERR_NULL_POINTER;
+    if (g->segments > kMaxSeg) {
+        // beyond the parameter array the kernels derive the segment starts themselves, which needs the layout
+        // ord_col_tiling_torch produces: segments stored back to back (host check of the host array)
+        for (int s = 1; s < g->segments; ++s)
+            if (g->bounds[2 * s] != g->bounds[2 * s - 1]) return GALA_ERR_UNSUPPORTED;
+    }
     return GALA_OK;
 }
 
@@ -35,7 +40,7 @@ GraphDev make_dev(const gala_graph_t* g) {
     d.S = g->segments;
     for (int s = 0; s < kMaxSeg; ++s) d.seg_base[s] = 0;
     if (g->bounds)
-        for (int s = 0; s < g->segments; ++s) d.seg_base[s] = g->bounds[2 * s];
+        for (int s = 0; s < std::min<int>(g->segments, kMaxSeg); ++s) d.seg_base[s] = g->bounds[2 * s];
     return d;
 }
 
@@ -241,7 +246,7 @@ const char* gala_b200_error_string(int code) {
         case GALA_OK: return "success";
         case GALA_ERR_NULL_POINTER: return "gala_b200: required pointer is NULL";
         case GALA_ERR_BAD_SHAPE: return "gala_b200: negative or inconsistent size";
-        case GALA_ERR_UNSUPPORTED: return "gala_b200: unsupported configuration (segments > 64, nvals >= 2^31, ...)";
+        case GALA_ERR_UNSUPPORTED: return "gala_b200: unsupported configuration (nvals >= 2^31, width outside the kernel's range, ...)";
         case GALA_ERR_WORKSPACE: return "gala_b200: workspace too small";
         case GALA_ERR_MISALIGNED: return "gala_b200: pointer is not 4-byte aligned";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "gala_b200: unknown error";

@@ -7,7 +7,8 @@
 
 namespace gala {
 
-constexpr int kMaxSeg = 64;       // column segments handled by one launch
+constexpr int kMaxSeg = 64;       // column segments whose start offsets travel in the kernel parameters; graphs with
+                                  // more segments derive them on the fly (see seg_start)
 constexpr int kWarpsPerCta = 8;   // 256-thread CTAs everywhere
 constexpr int kCtaThreads = kWarpsPerCta * 32;
 constexpr unsigned kFull = 0xffffffffu;
@@ -18,8 +19,19 @@ struct GraphDev {
     const int* __restrict__ cols;     // [E]
     int nrows;
     int S;
-    int seg_base[kMaxSeg];            // bounds[2s] of the segments in this launch
+    int seg_base[kMaxSeg];            // bounds[2s] of the segments in this launch (S <= kMaxSeg)
 };
+
+// Start offset of segment s in cols / vals.  Up to kMaxSeg segments it comes from the kernel parameters; beyond
+// (the reference accepts any number of column segments, tiling.h:222-283) the segments are stored back to back, so
+// bounds[2s] is the running sum of the segments' edge counts, offsets[s'*(N+1) + N]: `run` carries it while a row
+// walks its segments in order (one extra cached load per segment, the same address for every row).
+__device__ __forceinline__ int seg_start(const GraphDev& g, int s, int& run) {
+    if (g.S <= kMaxSeg) return g.seg_base[s];
+    const int here = run;
+    run += __ldg(g.offsets + (int64_t)s * (g.nrows + 1) + g.nrows);
+    return here;
+}
 
 // ---- cache-hinted loads / stores -------------------------------------------
 // Streams that are read exactly once (column indices, edge values) go through
@@ -176,14 +188,15 @@ __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.0f ?
 // ranges into cols / vals.
 template <class F>
 __device__ __forceinline__ void for_each_chunk(const GraphDev& g, int row, int lo, int hi, F&& f) {
-    int pos = 0;
+    int pos = 0, run = g.seg_base[0];
 #pragma unroll 1
     for (int s = 0; s < g.S; ++s) {
         const int* off = g.offsets + (int64_t)s * (g.nrows + 1) + row;
         int b = __ldg(off), e = __ldg(off + 1);
         int len = e - b;
+        const int sb = seg_start(g, s, run);
         int a0 = max(lo - pos, 0), a1 = min(hi - pos, len);
-        if (a0 < a1) f(g.seg_base[s] + b + a0, g.seg_base[s] + b + a1);
+        if (a0 < a1) f(sb + b + a0, sb + b + a1);
         pos += len;
     }
 }
@@ -192,7 +205,7 @@ __device__ __forceinline__ void for_each_chunk(const GraphDev& g, int row, int l
 // aligned body (4 edges per lane per step, 4 steps unrolled = 2 KB in flight per warp),
 // scalar accesses on the ragged head and tail.  VEC4 = false keeps everything scalar
 // (edge arrays that are not 16-byte aligned).
-template <bool VEC4, class FS, class FV>
+template <bool VEC4, int UNR = 4, class FS, class FV>
 __device__ __forceinline__ void warp_edges(int e0, int e1, int lane, FS&& scalar, FV&& vec4) {
     if (!VEC4) {
 #pragma unroll 4
@@ -202,7 +215,7 @@ __device__ __forceinline__ void warp_edges(int e0, int e1, int lane, FS&& scalar
     const int a0 = min((e0 + 3) & ~3, e1);
     const int a1 = max(a0, e1 & ~3);
     if (e0 + lane < a0) scalar(e0 + lane);
-#pragma unroll 4
+#pragma unroll UNR
     for (int e = a0 + lane * 4; e < a1; e += 128) vec4(e);
     if (a1 + lane < e1) scalar(a1 + lane);
 }

@@ -75,6 +75,7 @@ class GAT2:
           mode="fused"  : folded projections AND the dense ops that follow each aggregation computed in
                           the kernels' epilogues (gala_linear_f32 + 2 x gala_gat_forward_ex_f32)
           mode="dot"    : aR recomputed inside the kernel (gala_gat_forward_dot_f32)
+          mode="folded_dot": "folded" (own kernels for every dense op) + aR recomputed inside the kernel
         dense="tcgen05" runs the layer-1 transform (and, in folded mode, its two attention
         projections, fused in the epilogue) on the tensor cores (gala_linear_f32); "torch" = cuBLAS."""
         run = hook if hook is not None else (lambda name, fn: fn())
@@ -93,6 +94,14 @@ class GAT2:
             _, _, out = run("gat_layer2", lambda: ops.gat_forward_ex(g, a2[0], a2[1], res, self.slope, relu=False,
                                                                      cls_wT=self.fc1_wT, cls_b=self.fc1[1], want_y=False))
             return out
+        if dense == "tcgen05" and mode == "folded_dot":
+            # as "folded", with the right-hand attention term recomputed inside the aggregation kernel from the row
+            # it gathers (gala_gat_forward_dot_f32: one gather per edge instead of two); aR is never read
+            res, a = run("linear1", lambda: ops.linear(X, self.fc0[0], self.fc0[1], att_w=self.W_att1, att_b=self.b_att1_host))
+            res = run("gat_layer1", lambda: ops.gat_forward_dot(g, a[0], self.wR1, self.bR1, res, self.slope, relu=True))
+            a = run("att2", lambda: ops.linear_small(res, self.W_att2, self.b_att2, transpose_out=True))
+            agg = run("gat_layer2", lambda: ops.gat_forward_dot(g, a[0], self.wR2, self.bR2, res, self.slope, relu=False))
+            return run("classifier", lambda: ops.linear_small(agg, self.fc1[0], self.fc1[1]))
         if dense == "tcgen05" and mode == "folded":
             # five launches, all this repository's kernels (no library call in the step)
             res, a = run("linear1", lambda: ops.linear(X, self.fc0[0], self.fc0[1], att_w=self.W_att1, att_b=self.b_att1_host))
@@ -119,6 +128,45 @@ class GAT2:
         aL, aR = self.attention_inputs(t, self.efc2, self.efc3)
         agg = run("gat_layer2", lambda: ops.gat_forward(g, aL, aR, res, self.slope, relu=False))
         return F.linear(agg, *self.fc1)
+
+
+    def forward_host(self, g, X_host, out_host=None, chunks=8, mode="folded", stage=None):
+        """The same forward for features that live in (pinned) HOST memory: the [N, F] matrix is uploaded in `chunks`
+        row blocks on a copy stream while the row-tiled layer-1 transform already consumes the blocks that have
+        landed (it reads X front to back exactly once), so the PCIe transfer and the transform overlap; the logits
+        are copied back into out_host (pinned) if given.  Returns the device logits."""
+        n, dev = X_host.shape[0], g.device
+        if stage is None:
+            stage = torch.empty(X_host.shape, dtype=torch.float32, device=dev)
+        hidden = self.fc0[0].shape[0]
+        res = torch.empty((n, hidden), dtype=torch.float32, device=dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs, main = self._copy_stream, torch.cuda.current_stream()
+        cs.wait_stream(main)                      # the staging buffer may still be read by the previous step
+        step = (n + chunks - 1) // chunks
+        step = (step + 127) // 128 * 128          # whole 128-row tiles per block
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            with torch.cuda.stream(cs):
+                stage[lo:hi].copy_(X_host[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            main.wait_event(ev)
+            ops.linear(stage[lo:hi], self.fc0[0], self.fc0[1], out=res[lo:hi])
+        a = ops.linear_small(res, self.W_att1, self.b_att1, transpose_out=True)
+        if mode == "folded_dot":
+            res = ops.gat_forward_dot(g, a[0], self.wR1, self.bR1, res, self.slope, relu=True)
+            a = ops.linear_small(res, self.W_att2, self.b_att2, transpose_out=True)
+            agg = ops.gat_forward_dot(g, a[0], self.wR2, self.bR2, res, self.slope, relu=False)
+        else:
+            res = ops.gat_forward(g, a[0], a[1], res, self.slope, relu=True)
+            a = ops.linear_small(res, self.W_att2, self.b_att2, transpose_out=True)
+            agg = ops.gat_forward(g, a[0], a[1], res, self.slope, relu=False)
+        out = ops.linear_small(agg, self.fc1[0], self.fc1[1])
+        if out_host is not None:
+            out_host.copy_(out, non_blocking=True)
+        return out
 
 
 class GATN:

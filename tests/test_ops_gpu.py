@@ -477,6 +477,29 @@ def test_row_pitched_operands(orc, case, K):
         assert rel_err(got.cpu().numpy(), yg) < FP32_TOL
 
 
+@pytest.mark.parametrize("n,e,T,thr", [(2000, 40000, 20, 64), (1500, 30000, 7, None)])
+def test_more_than_64_column_segments(orc, n, e, T, thr):
+    """The reference accepts any number of column segments (tiling.h:222-283); beyond 64 the kernels derive the
+    segment starts from the per-segment row pointers instead of taking them as parameters."""
+    t = graph_case(orc, n, e, 77, T)
+    assert t.S > 64
+    g = to_gpu_graph(t, thr)
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-0.5, 0.5, (n, 32)).astype(np.float32)
+    aL, aR = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)
+    assert rel_err(ops.spmm(g, dev(X), vals=dev(t.vals)).cpu().numpy(), orc.spmm(t, X, weighted=True)) < FP32_TOL
+    assert rel_err(ops.spmm(g, dev(X), vals=dev(t.vals), schedule="segment_major").cpu().numpy(),
+                   orc.spmm(t, X, weighted=True)) < FP32_TOL
+    assert np.array_equal(ops.sddvv(g, dev(aL), dev(aR), "add").cpu().numpy(), orc.sddvv(t, aL, aR, "add"))
+    assert rel_err(ops.edge_rowsum(g, dev(t.vals)).cpu().numpy().ravel(), orc.edge_rowsum(t, t.vals)) < FP32_TOL
+    a_want, _ = orc.edge_softmax_fwd(t, t.vals)
+    assert rel_err(ops.edge_softmax_fwd(g, dev(t.vals)).cpu().numpy(), a_want) < FP32_TOL
+    y_want, _ = orc.gat_forward(t, aL, aR, X)
+    assert rel_err(ops.gat_forward(g, dev(aL), dev(aR), dev(X)).cpu().numpy(), y_want) < FP32_TOL
+    assert rel_err(ops.spmm_sampled(g, dev(X), 20, 5, 7).cpu().numpy(), orc.spmm_sampled(t, X, 20, 5, 7)) < FP32_TOL
+    assert rel_err(ops.sddmm(g, dev(X), dev(X)).cpu().numpy(), orc.sddmm(t, X, X)) < FP32_TOL
+
+
 def test_results_are_bit_reproducible(orc):
     t = graph_case(orc, 3000, 400000, 2, 700)
     g = to_gpu_graph(t, 256)
