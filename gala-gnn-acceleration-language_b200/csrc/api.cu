@@ -23,12 +23,8 @@ int check_graph(const gala_graph_t* g) {
     if (g->nrows > 0 && !g->offsets) return GALA_ERR_NULL_POINTER;
     if (g->nvals > 0 && !g->cols) return GALA_ERR_NULL_POINTER;
     if (g->segments > 1 && !g->bounds) return GALA_ERR_NULL_POINTER;
-    if (g->segments > kMaxSeg) {
-        // beyond the parameter array the kernels derive the segment starts themselves, which needs the layout
-        // ord_col_tiling_torch produces: segments stored back to back (host check of the host array)
-        for (int s = 1; s < g->segments; ++s)
-            if (g->bounds[2 * s] != g->bounds[2 * s - 1]) return GALA_ERR_UNSUPPORTED;
-    }
+    // more segments than the kernel parameters hold: the kernels read the segment starts from a device copy of bounds
+    if (g->segments > kMaxSeg && !g->bounds_dev) return GALA_ERR_NULL_POINTER;
     return GALA_OK;
 }
 
@@ -38,6 +34,7 @@ GraphDev make_dev(const gala_graph_t* g) {
     d.cols = g->cols;
     d.nrows = g->nrows;
     d.S = g->segments;
+    d.bounds_dev = g->bounds_dev;
     for (int s = 0; s < kMaxSeg; ++s) d.seg_base[s] = 0;
     if (g->bounds)
         for (int s = 0; s < std::min<int>(g->segments, kMaxSeg); ++s) d.seg_base[s] = g->bounds[2 * s];
@@ -483,12 +480,14 @@ int gala_gat_forward_ex_f32(const gala_graph_t* g, const float* aL, const float*
     if (multi) {
         p.mo.count = ep->multi_out->count;
         p.mo.mc_base = ep->multi_out->multicast_base;
+        p.mo.need = ep->multi_out->need_mask;
         for (int q = 0; q < p.mo.count; ++q) p.mo.base[q] = ep->multi_out->base[q];
     }
     if (ep && ep->att_multi_out && ep->att_multi_out->count > 0) {
         if (!ep->att_w || ep->att_multi_out->count > kMaxPeers) return GALA_ERR_UNSUPPORTED;
         p.att_mo.count = ep->att_multi_out->count;
         p.att_mo.mc_base = ep->att_multi_out->multicast_base;
+        p.att_mo.need = ep->att_multi_out->need_mask;
         for (int q = 0; q < p.att_mo.count; ++q) p.att_mo.base[q] = ep->att_multi_out->base[q];
     }
     HubView h = hub_of(plan, g);

@@ -8,7 +8,7 @@
 namespace gala {
 
 constexpr int kMaxSeg = 64;       // column segments whose start offsets travel in the kernel parameters; graphs with
-                                  // more segments derive them on the fly (see seg_start)
+                                  // more segments read them from gala_graph_t.bounds_dev (see seg_start)
 constexpr int kWarpsPerCta = 8;   // 256-thread CTAs everywhere
 constexpr int kCtaThreads = kWarpsPerCta * 32;
 constexpr unsigned kFull = 0xffffffffu;
@@ -20,17 +20,14 @@ struct GraphDev {
     int nrows;
     int S;
     int seg_base[kMaxSeg];            // bounds[2s] of the segments in this launch (S <= kMaxSeg)
+    const int* __restrict__ bounds_dev;   // device copy of bounds[2S], read instead when S > kMaxSeg
 };
 
-// Start offset of segment s in cols / vals.  Up to kMaxSeg segments it comes from the kernel parameters; beyond
-// (the reference accepts any number of column segments, tiling.h:222-283) the segments are stored back to back, so
-// bounds[2s] is the running sum of the segments' edge counts, offsets[s'*(N+1) + N]: `run` carries it while a row
-// walks its segments in order (one extra cached load per segment, the same address for every row).
-__device__ __forceinline__ int seg_start(const GraphDev& g, int s, int& run) {
-    if (g.S <= kMaxSeg) return g.seg_base[s];
-    const int here = run;
-    run += __ldg(g.offsets + (int64_t)s * (g.nrows + 1) + g.nrows);
-    return here;
+// Start offset of segment s in cols / vals: from the kernel parameters up to kMaxSeg segments, from the caller's
+// device copy of `bounds` beyond (gala_graph_t.bounds_dev; the reference accepts any number of column segments,
+// tiling.h:222-283).  No state is carried between segments: the gather kernels sit at their register limit.
+__device__ __forceinline__ int seg_start(const GraphDev& g, int s) {
+    return g.S <= kMaxSeg ? g.seg_base[s] : __ldg(g.bounds_dev + 2 * s);
 }
 
 // ---- cache-hinted loads / stores -------------------------------------------
@@ -174,9 +171,26 @@ __device__ __forceinline__ float warp_sum(float x) {
 }
 
 // exp -> clamp(0, 1e12) of the reference's edge-softmax (common.h:760-761).
-// expf (not __expf): the 1e-5 parity bound leaves no room for ex2.approx at large |x|.
+// GALA_FAST_EXP = 0: expf.  1: 2^(x*log2e) on the SFU (ex2.approx, max relative error 2^-22) with the rounding error of
+// the product x*log2e carried as a first-order correction, ~3e-7 relative over the whole range that survives the clamp
+// (x <= 27.7) -- inside the 1e-5 parity bound, which plain __expf (error growing with |x|) is not guaranteed to be.
+#ifndef GALA_FAST_EXP
+#define GALA_FAST_EXP 0
+#endif
+__device__ __forceinline__ float softmax_exp(float x) {
+#if GALA_FAST_EXP
+    const float t = x * 1.4426950216293335f;                         // hi part of log2(e)
+    float r = fmaf(x, 1.4426950216293335f, -t);                      // exact rounding error of the product
+    r = fmaf(x, 1.9259629911266175e-8f, r);                          // + x * lo part of log2(e)
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return fmaf(e, r * 0.6931471805599453f, e);                      // 2^(t+r) = 2^t * (1 + r ln2 + ...)
+#else
+    return expf(x);
+#endif
+}
 __device__ __forceinline__ float softmax_num(float x) {
-    float e = expf(x);
+    float e = softmax_exp(x);
     return e > 1e12f ? 1e12f : e;
 }
 
@@ -188,15 +202,17 @@ __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.0f ?
 // ranges into cols / vals.
 template <class F>
 __device__ __forceinline__ void for_each_chunk(const GraphDev& g, int row, int lo, int hi, F&& f) {
-    int pos = 0, run = g.seg_base[0];
+    int pos = 0;
 #pragma unroll 1
     for (int s = 0; s < g.S; ++s) {
         const int* off = g.offsets + (int64_t)s * (g.nrows + 1) + row;
         int b = __ldg(off), e = __ldg(off + 1);
         int len = e - b;
-        const int sb = seg_start(g, s, run);
         int a0 = max(lo - pos, 0), a1 = min(hi - pos, len);
-        if (a0 < a1) f(sb + b + a0, sb + b + a1);
+        if (a0 < a1) {
+            const int sb = seg_start(g, s);
+            f(sb + b + a0, sb + b + a1);
+        }
         pos += len;
     }
 }
@@ -242,6 +258,7 @@ constexpr int kMaxPeers = 8;
 struct MultiOut {
     float* base[kMaxPeers];
     float* mc_base;
+    const unsigned char* need;   // per-row bit mask (bit q: GPU q gathers this row) or nullptr = every GPU; peer stores only
     int count;
 };
 
@@ -257,14 +274,16 @@ __device__ __forceinline__ void multimem_store(float* p, const float (&v)[VEC]) 
         asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory");
 }
 
-// store VEC consecutive floats of an output row at element offset `off` of every destination
+// store VEC consecutive floats of output row `row` at element offset `off` of every destination that gathers the row
 template <int VEC>
-__device__ __forceinline__ void multi_store(const MultiOut& mo, int64_t off, const Vec<VEC>& o) {
+__device__ __forceinline__ void multi_store(const MultiOut& mo, int64_t off, const Vec<VEC>& o, int64_t row) {
     if (mo.mc_base) {
         multimem_store<VEC>(mo.mc_base + off, o.v);
     } else {
+        const unsigned need = mo.need ? (unsigned)__ldg(mo.need + row) : 0xffu;
 #pragma unroll 1
-        for (int q = 0; q < mo.count; ++q) o.store(mo.base[q] + off);
+        for (int q = 0; q < mo.count; ++q)
+            if ((need >> q) & 1u) o.store(mo.base[q] + off);
     }
 }
 

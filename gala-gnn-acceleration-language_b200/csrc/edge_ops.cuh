@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kCtaThreads) edge_rowsum_kernel(const __grid_c
     const int lane = threadIdx.x & 31;
     float s = 0.0f;
 #ifndef GALA_ROWSUM_UNROLL
-#define GALA_ROWSUM_UNROLL 8     // 128-bit loads in flight per lane (x 512 bytes per warp)
+#define GALA_ROWSUM_UNROLL 4     // 128-bit loads in flight per lane; measured on B200: 4 -> 0.111 ms, 8 -> 0.117, 16 -> 0.122
 #endif
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
         warp_edges<V4, GALA_ROWSUM_UNROLL>(e0, e1, lane, [&](int e) { s += ld_stream(p.a + e); },
@@ -99,91 +99,33 @@ __global__ void __launch_bounds__(kCtaThreads) sddvv_kernel(const __grid_constan
 }
 
 // ---- edge-softmax forward: alpha = clamp(exp(x)) / (seed + sum_row clamp(exp(x))) --------
-// One read and one write per edge, exp evaluated once: a warp's share of a row (up to kSmCache x 128 edges) stays in
-// registers between the row sum and the scaling.  Longer shares stash the numerators in the output array and rescale
-// them in a second pass (served by L2: the row was written microseconds earlier).
-#ifndef GALA_SOFTMAX_CACHE
-#define GALA_SOFTMAX_CACHE 8     // float4 per lane held in registers (x 128 edges per warp); 0 = always two passes
-#endif
+// (Measured alternatives, profiles/r02_variants_dot_pipeline_softmax_cache.txt, Reddit shape: keeping a warp's share of
+//  the row in registers between the two passes -- one read, one exp per edge -- 0.29 ms; stashing the numerators in the
+//  output and rescaling -- 0.26 ms; this two-pass form, second read from L2, exp evaluated twice -- 0.25 ms.)
 template <bool V4>
 __global__ void __launch_bounds__(kCtaThreads) edge_softmax_fwd_kernel(const __grid_constant__ EdgeParams p) {
     RowTask t = row_task(p.g, p.t);
     if (!t.valid) return;
     const int lane = threadIdx.x & 31;
-    constexpr int kCache = GALA_SOFTMAX_CACHE;
-    if (V4 && kCache > 0 && p.g.S == 1) {
-        // the warp's edge range [e0, e1) of this row (one segment: a single contiguous range)
-        const int b = __ldg(p.g.offsets + t.row), len = __ldg(p.g.offsets + t.row + 1) - b;
-        const int e0 = p.g.seg_base[0] + b + min(t.lo, len), e1 = p.g.seg_base[0] + b + min(t.hi, len);
-        const int a0 = min((e0 + 3) & ~3, e1), a1 = max(a0, e1 & ~3);
-        const bool fits = a1 - a0 <= kCache * 128;
-        const bool all_fit = t.hub ? __syncthreads_and(fits) : fits;     // hub rows: every warp of the CTA takes the same path
-        if (all_fit) {
-            float hv = 0.0f, tv = 0.0f, s = 0.0f;
-            float4 v[kCache > 0 ? kCache : 1];
-            if (e0 + lane < a0) {
-                hv = softmax_num(ld_stream(p.a + e0 + lane));
-                s += hv;
-            }
-#pragma unroll
-            for (int i = 0; i < kCache; ++i) {
-                const int e = a0 + (i * 32 + lane) * 4;
-                v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (e < a1) v[i] = ld_stream4(p.a + e);
-            }
-#pragma unroll
-            for (int i = 0; i < kCache; ++i) {
-                const int e = a0 + (i * 32 + lane) * 4;
-                if (e < a1) {
-                    v[i].x = softmax_num(v[i].x); v[i].y = softmax_num(v[i].y);
-                    v[i].z = softmax_num(v[i].z); v[i].w = softmax_num(v[i].w);
-                    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-                }
-            }
-            if (a1 + lane < e1) {
-                tv = softmax_num(ld_stream(p.a + a1 + lane));
-                s += tv;
-            }
-            s = warp_sum(s);
-            if (t.hub) s = cta_sum_ordered(s);
-            const float r = 1.0f / (s + p.seed);
-            if (p.out2 && threadIdx.x == (t.hub ? 0 : (threadIdx.x & ~31))) p.out2[t.row] = r;
-            if (e0 + lane < a0) st_stream(p.out + e0 + lane, hv * r);
-#pragma unroll
-            for (int i = 0; i < kCache; ++i) {
-                const int e = a0 + (i * 32 + lane) * 4;
-                if (e < a1) st_stream4(p.out + e, make_float4(v[i].x * r, v[i].y * r, v[i].z * r, v[i].w * r));
-            }
-            if (a1 + lane < e1) st_stream(p.out + a1 + lane, tv * r);
-            return;
-        }
-    }
-    // general path (several column segments, long shares, unaligned arrays): numerators stashed in the output
     float s = 0.0f;
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
-        warp_edges<V4>(e0, e1, lane,
-                       [&](int e) {
-                           const float x = softmax_num(p.a[e]);
-                           s += x;
-                           p.out[e] = x;
-                       },
+        warp_edges<V4>(e0, e1, lane, [&](int e) { s += softmax_num(p.a[e]); },
                        [&](int e) {
                            float4 v = *reinterpret_cast<const float4*>(p.a + e);
-                           v.x = softmax_num(v.x); v.y = softmax_num(v.y); v.z = softmax_num(v.z); v.w = softmax_num(v.w);
-                           s += (v.x + v.y) + (v.z + v.w);
-                           *reinterpret_cast<float4*>(p.out + e) = v;
+                           s += (softmax_num(v.x) + softmax_num(v.y)) + (softmax_num(v.z) + softmax_num(v.w));
                        });
     });
     s = warp_sum(s);
     if (t.hub) s = cta_sum_ordered(s);
     const float r = 1.0f / (s + p.seed);
     if (p.out2 && threadIdx.x == (t.hub ? 0 : (threadIdx.x & ~31))) p.out2[t.row] = r;
-    // second pass over what this warp wrote itself (same lanes, same addresses: no cross-thread ordering needed)
+    // second pass: the row was just read, so it is served from L1/L2
     for_each_chunk(p.g, t.row, t.lo, t.hi, [&](int e0, int e1) {
-        warp_edges<V4>(e0, e1, lane, [&](int e) { p.out[e] = p.out[e] * r; },
+        warp_edges<V4>(e0, e1, lane, [&](int e) { p.out[e] = softmax_num(p.a[e]) * r; },
                        [&](int e) {
-                           float4 v = *reinterpret_cast<const float4*>(p.out + e);
-                           v.x *= r; v.y *= r; v.z *= r; v.w *= r;
+                           float4 v = *reinterpret_cast<const float4*>(p.a + e);
+                           v.x = softmax_num(v.x) * r; v.y = softmax_num(v.y) * r;
+                           v.z = softmax_num(v.z) * r; v.w = softmax_num(v.w) * r;
                            *reinterpret_cast<float4*>(p.out + e) = v;
                        });
     });

@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, (NPAD > 64 ? 1 : 2)) linear_tf32x3_k
                     if (n < p.N) {
                         Vec<4> o;
                         o.v[0] = acc[n]; o.v[1] = acc[n + 1]; o.v[2] = acc[n + 2]; o.v[3] = acc[n + 3];
-                        multi_store<4>(p.mo, r * p.N + n, o);
+                        multi_store<4>(p.mo, r * p.N + n, o, r);
                     }
             } else if ((p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(yrow) & 15) == 0) {
 #pragma unroll
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, (NPAD > 64 ? 1 : 2)) linear_tf32x3_k
                 if (p.att_mo.count > 0) {
                     Vec<1> o1;
                     o1.v[0] = a1;
-                    multi_store<1>(p.att_mo, r, o1);
+                    multi_store<1>(p.att_mo, r, o1, r);
                 }
             }
         }
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
                     if (p.att_mo.count > 0) {
                         Vec<1> o1;
                         o1.v[0] = a1;
-                        multi_store<1>(p.att_mo, r, o1);
+                        multi_store<1>(p.att_mo, r, o1, r);
                     }
                 }
             }
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
                         const float4 v = *reinterpret_cast<const float4*>(&st[rr][cv * 4]);
                         Vec<4> o;
                         o.v[0] = v.x; o.v[1] = v.y; o.v[2] = v.z; o.v[3] = v.w;
-                        if (p.mo.count > 0) multi_store<4>(p.mo, row * p.N + cv * 4, o);
+                        if (p.mo.count > 0) multi_store<4>(p.mo, row * p.N + cv * 4, o, row);
                         else o.store(p.Y + row * p.N + cv * 4);
                     }
                 }
@@ -728,12 +728,14 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
     if (multi) {
         p.mo.count = multi_out->count;
         p.mo.mc_base = multi_out->multicast_base;
+        p.mo.need = multi_out->need_mask;
         for (int q = 0; q < multi_out->count; ++q) p.mo.base[q] = multi_out->base[q];
     }
     if (att_multi_out && att_multi_out->count > 0) {
         if (!att_w || att_multi_out->count > kMaxPeers) return GALA_ERR_UNSUPPORTED;
         p.att_mo.count = att_multi_out->count;
         p.att_mo.mc_base = att_multi_out->multicast_base;
+        p.att_mo.need = att_multi_out->need_mask;
         for (int q = 0; q < att_multi_out->count; ++q) p.att_mo.base[q] = att_multi_out->base[q];
     }
     p.M = M;

@@ -168,61 +168,6 @@ __device__ __forceinline__ void gather_chunk_dot(const char* __restrict__ xlane,
 }
 
 
-// The same chunk in two halves, for the software-pipelined loop of MODE_GAT_DOT: dot_load issues the LPR row gathers
-// of a chunk, dot_consume turns the rows (in registers by then) into logits, softmax numerators and the weighted sum.
-// The kernel keeps two chunks in registers: the gathers of chunk i+1 are in flight while chunk i is reduced, so the
-// dependent chain gather -> dot -> exchange -> exp -> broadcast -> FMA no longer serialises with the L2 latency.
-template <int VEC, int LPR>
-__device__ __forceinline__ void dot_load(const char* __restrict__ xlane, uint32_t row_bytes, int grp, int c,
-                                         int (&cj)[LPR], Vec<VEC> (&x)[LPR]) {
-    constexpr int EPI = 32 / LPR;
-#pragma unroll
-    for (int u = 0; u < LPR; ++u) cj[u] = __shfl_sync(kFull, c, u * EPI + grp);
-#pragma unroll
-    for (int u = 0; u < LPR; ++u)
-        x[u].load(reinterpret_cast<const float*>(xlane + (uint64_t)(uint32_t)max(cj[u], 0) * row_bytes));
-}
-
-template <int VEC, int LPR>
-__device__ __forceinline__ void dot_consume(const int (&cj)[LPR], const Vec<VEC> (&x)[LPR], int sub, int grp, int base, int e1,
-                                            const float (&wreg)[VEC], float aL_row, float bR, float slope,
-                                            float* __restrict__ alpha_out, float& rs, float (&acc)[1][VEC]) {
-    constexpr int EPI = 32 / LPR;
-    float d[LPR];
-#pragma unroll
-    for (int u = 0; u < LPR; ++u) {
-        float t = 0.0f;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) t = fmaf(x[u].v[v], wreg[v], t);
-        d[u] = t;
-    }
-#pragma unroll
-    for (int o = LPR >> 1, n = LPR; o > 0; o >>= 1, n >>= 1) {
-        const bool upper = (sub & o) != 0;
-#pragma unroll
-        for (int i = 0; i < (n >> 1); ++i) {
-            const float send = upper ? d[i] : d[i + (n >> 1)];
-            const float keep = upper ? d[i + (n >> 1)] : d[i];
-            d[i] = keep + __shfl_xor_sync(kFull, send, o);
-        }
-    }
-    const int pos = base + sub * EPI + grp;      // the chunk position this lane owns after the exchange
-    float e = 0.0f;
-    if (pos < e1) {
-        e = softmax_num(leaky(aL_row + (d[0] + bR), slope));
-        rs += e;
-        if (alpha_out) alpha_out[pos] = e;
-    }
-#pragma unroll
-    for (int u = 0; u < LPR; ++u) {
-        const float wj = __shfl_sync(kFull, e, grp * LPR + u);   // 0 for invalid edges
-        const bool ok = cj[u] >= 0;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[0][v] = fmaf(wj, ok ? x[u].v[v] : 0.0f, acc[0][v]);
-    }
-}
-
-
 constexpr int kRowBufMax = 128;   // widest output row the fused dense epilogue handles
 
 // Dense epilogue of one finished output row held in shared memory (K floats): the next layer's two
@@ -244,7 +189,7 @@ __device__ __forceinline__ void row_dense_epilogue(const SpmmParams& p, const fl
             if (p.att_mo.count > 0) {
                 Vec<1> o1;
                 o1.v[0] = a1 + p.att_b1;
-                multi_store<1>(p.att_mo, row, o1);
+                multi_store<1>(p.att_mo, row, o1, row);
             }
         }
     }
@@ -264,11 +209,12 @@ __device__ __forceinline__ void row_dense_epilogue(const SpmmParams& p, const fl
 #ifndef GALA_SPMM_MINB
 #define GALA_SPMM_MINB 5
 #endif
-#ifndef GALA_GATDOT_PIPELINE
-#define GALA_GATDOT_PIPELINE 1   // MODE_GAT_DOT: two chunks in registers, gathers of chunk i+1 in flight while chunk i is reduced
-#endif
 #ifndef GALA_GATDOT_MINB
-#define GALA_GATDOT_MINB (GALA_GATDOT_PIPELINE ? 2 : 3)   // the dot mode keeps 8 (16 when pipelined) rows + 8 partial dots live
+#define GALA_GATDOT_MINB 3   // the dot mode keeps 8 rows + 8 partial dots live
+// (a software-pipelined form -- two chunks in registers, the gathers of chunk i+1 in flight while chunk i is reduced --
+//  was measured in round 2: 1.53 ms at 128 registers / 2 CTAs per SM against 1.16 ms for this one and 1.07 ms for the
+//  two-gather MODE_GAT; profiles/r02_variants_dot_pipeline_softmax_cache.txt.  Occupancy, not the dependent chain, is
+//  what the gather lives on.)
 #endif
 #if GALA_SPMM_MINB > 0
 #define GALA_SPMM_BOUNDS __launch_bounds__(kCtaThreads, (MODE == MODE_GAT_DOT ? GALA_GATDOT_MINB : GALA_SPMM_MINB))
@@ -343,14 +289,15 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
         }
     };
 
-    if constexpr (MODE == MODE_GAT_DOT && !GALA_GATDOT_PIPELINE) {
-        for_each_chunk(g, row, lo, hi, [&](int e0, int e1) {
-            int c_nxt;
-            float w_nxt;
-            fetch(e0 + lane, e1, c_nxt, w_nxt);
-            for (int base = e0; base < e1; base += 32) {
-                const int c = c_nxt;
-                if (base + 32 < e1) fetch(base + 32 + lane, e1, c_nxt, w_nxt);
+    for_each_chunk(g, row, lo, hi, [&](int e0, int e1) {
+        int c_nxt;
+        float w_nxt;
+        fetch(e0 + lane, e1, c_nxt, w_nxt);
+        for (int base = e0; base < e1; base += 32) {
+            const int c = c_nxt;
+            const float w = w_nxt;
+            if (base + 32 < e1) fetch(base + 32 + lane, e1, c_nxt, w_nxt);
+            if constexpr (MODE == MODE_GAT_DOT) {
                 float* ao = write_alpha ? p.alpha_out : nullptr;
                 if (base + 32 <= e1)
                     gather_chunk_dot<VEC, LPR, true>(xlane, row_bytes, sub, grp, c, base, e1, wreg, aL_row, p.bR,
@@ -358,54 +305,12 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
                 else
                     gather_chunk_dot<VEC, LPR, false>(xlane, row_bytes, sub, grp, c, base, e1, wreg, aL_row, p.bR,
                                                       p.slope, ao, rs, acc);
-            }
-        });
-    } else if constexpr (MODE == MODE_GAT_DOT) {
-        // two chunks in registers (A, B): while one is reduced, the gathers of the other are in flight
-        float* ao = write_alpha ? p.alpha_out : nullptr;
-        for_each_chunk(g, row, lo, hi, [&](int e0, int e1) {
-            int cA[LPR], cB[LPR];
-            Vec<VEC> xA[LPR], xB[LPR];
-            int c0, c1 = -1;
-            float wdummy;
-            fetch(e0 + lane, e1, c0, wdummy);
-            if (e0 + 32 < e1) fetch(e0 + 32 + lane, e1, c1, wdummy);
-            dot_load<VEC, LPR>(xlane, row_bytes, grp, c0, cA, xA);
-            for (int base = e0; base < e1; base += 64) {
-                const bool hasB = base + 32 < e1;
-                int c2 = -1, c3 = -1;
-                if (hasB) {
-                    dot_load<VEC, LPR>(xlane, row_bytes, grp, c1, cB, xB);
-                    if (base + 64 < e1) fetch(base + 64 + lane, e1, c2, wdummy);
-                }
-                dot_consume<VEC, LPR>(cA, xA, sub, grp, base, e1, wreg, aL_row, p.bR, p.slope, ao, rs, acc);
-                if (!hasB) break;
-                const bool hasA = base + 64 < e1;
-                if (hasA) {
-                    dot_load<VEC, LPR>(xlane, row_bytes, grp, c2, cA, xA);
-                    if (base + 96 < e1) fetch(base + 96 + lane, e1, c3, wdummy);
-                }
-                dot_consume<VEC, LPR>(cB, xB, sub, grp, base + 32, e1, wreg, aL_row, p.bR, p.slope, ao, rs, acc);
-                c1 = c3;
-                if (!hasA) break;
-            }
-        });
-    } else {
-        for_each_chunk(g, row, lo, hi, [&](int e0, int e1) {
-            int c_nxt;
-            float w_nxt;
-            fetch(e0 + lane, e1, c_nxt, w_nxt);
-            for (int base = e0; base < e1; base += 32) {
-                const int c = c_nxt;
-                const float w = w_nxt;
-                if (base + 32 < e1) fetch(base + 32 + lane, e1, c_nxt, w_nxt);
-                if (base + 32 <= e1)
-                    gather_chunk<VEC, LPR, ACC, true, EXACT>(xlane, row_bytes, grp, c, w, weighted, fvalid, acc);
-                else
-                    gather_chunk<VEC, LPR, ACC, false, EXACT>(xlane, row_bytes, grp, c, w, weighted, fvalid, acc);
-            }
-        });
-    }
+            } else if (base + 32 <= e1)
+                gather_chunk<VEC, LPR, ACC, true, EXACT>(xlane, row_bytes, grp, c, w, weighted, fvalid, acc);
+            else
+                gather_chunk<VEC, LPR, ACC, false, EXACT>(xlane, row_bytes, grp, c, w, weighted, fvalid, acc);
+        }
+    });
 
     // combine the EPI edge groups of the warp (fixed tree -> deterministic)
 #pragma unroll
@@ -449,7 +354,7 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
                     if (dense_ep && (EXACT || f0 + v < p.K)) rowbuf[warp][f0 + v] = t;
                 }
                 if constexpr (VEC <= 4) {
-                    if (p.mo.count > 0) multi_store<VEC>(p.mo, (int64_t)row * p.K + f0, o);
+                    if (p.mo.count > 0) multi_store<VEC>(p.mo, (int64_t)row * p.K + f0, o, row);
                     else if (p.Y) {
                         if (whole) o.store(y);
                         else {
@@ -506,7 +411,7 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
         if (p.mo.count > 0) {
             Vec<1> o1;
             o1.v[0] = t;
-            multi_store<1>(p.mo, (int64_t)row * p.K + tile_base + f, o1);
+            multi_store<1>(p.mo, (int64_t)row * p.K + tile_base + f, o1, row);
         } else if (p.Y) {
             *y = t;
         }
@@ -559,14 +464,12 @@ spmm_sampled_kernel(const __grid_constant__ SampledParams p) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[a][v] = 0.0f;
 
-    int run = g.seg_base[0];
     for (int s = 0; s < g.S; ++s) {
         const int* off = g.offsets + (int64_t)s * (g.nrows + 1) + row;
         const int b = __ldg(off);
         const int jmax = __ldg(off + 1) - b;
-        const int sb = seg_start(g, s, run);
         if (jmax <= 0) continue;
-        const int base = sb + b;
+        const int base = seg_start(g, s) + b;
         for (int ji = grp; ji < p.nsamples; ji += EPI) {
             const int j = (p.ra * ji + p.rb) % jmax;  // cuda.h:320, int arithmetic as emitted
             const int c = __ldg(g.cols + base + j);

@@ -30,7 +30,7 @@ EXPORTS = [
 class GalaGraph(C.Structure):
     _fields_ = [("offsets", C.c_void_p), ("cols", C.c_void_p), ("bounds", C.c_void_p),
                 ("nrows", C.c_int32), ("ncols", C.c_int32), ("segments", C.c_int32),
-                ("nvals", C.c_int64)]
+                ("nvals", C.c_int64), ("bounds_dev", C.c_void_p)]
 
 
 class GalaPlan(C.Structure):
@@ -44,7 +44,8 @@ class GalaEpilogue(C.Structure):
 
 
 class GalaMultiOut(C.Structure):
-    _fields_ = [("base", C.c_void_p * 8), ("multicast_base", C.c_void_p), ("count", C.c_int32)]
+    _fields_ = [("base", C.c_void_p * 8), ("multicast_base", C.c_void_p), ("count", C.c_int32),
+                ("need_mask", C.c_void_p)]
 
 
 class GalaDenseEpilogue(C.Structure):

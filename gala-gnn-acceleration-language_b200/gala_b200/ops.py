@@ -39,9 +39,12 @@ class TiledGraph:
         self.bounds = np.ascontiguousarray(bounds, dtype=np.int32)  # host, as in the reference
         assert self.bounds.shape[0] == 2 * self.segments
         assert offsets.numel() == self.segments * (self.nrows + 1)
+        # more than 64 segments: the kernels read the segment starts from a device copy of bounds
+        self.bounds_dev = torch.from_numpy(self.bounds).to(cols.device) if self.segments > 64 else None
         self.c = _l.GalaGraph(offsets=self.offsets.data_ptr(), cols=self.cols.data_ptr(),
                               bounds=self.bounds.ctypes.data, nrows=self.nrows, ncols=self.ncols,
-                              segments=self.segments, nvals=self.nvals)
+                              segments=self.segments, nvals=self.nvals,
+                              bounds_dev=self.bounds_dev.data_ptr() if self.bounds_dev is not None else None)
         self.plan = None
         self._plan_ws = None
 
@@ -255,13 +258,15 @@ def gat_forward_dot(g, aL, wR, bR, X, slope=0.2, relu=False, out=None, alpha_out
     return out
 
 
-def make_multi_out(bases, multicast_base=None):
-    """bases: per-GPU addresses (ints) of this rank's slab inside every peer-mapped gathered buffer."""
+def make_multi_out(bases, multicast_base=None, need_mask=None):
+    """bases: per-GPU addresses (ints) of this rank's slab inside every peer-mapped gathered buffer.
+    need_mask: uint8 device tensor [rows of this rank], bit q = GPU q references the row (peer stores only)."""
     mo = _l.GalaMultiOut()
     for q, b in enumerate(bases):
         mo.base[q] = int(b)
     mo.multicast_base = int(multicast_base) if multicast_base else None
     mo.count = len(bases)
+    mo.need_mask = int(need_mask.data_ptr()) if need_mask is not None else None
     return mo
 
 

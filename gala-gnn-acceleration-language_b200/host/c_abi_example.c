@@ -79,6 +79,7 @@ int main(void) {
     g.ncols = N;
     g.segments = S;
     g.nvals = E;
+    g.bounds_dev = NULL;   /* only needed beyond 64 column segments */
     gala_plan_t plan;
     size_t pw_b = gala_plan_workspace_bytes(&g);
     void *pws = dmalloc(pw_b);

@@ -57,6 +57,14 @@ inline gala_graph_t make_graph(const torch::Tensor& offset_graph, const torch::T
     g.ncols = (int32_t)nrows;
     g.segments = segments;
     g.nvals = columns_graph.numel();
+    g.bounds_dev = nullptr;
+    if (segments > 64) {      // beyond 64 segments the kernels read the segment starts from a device copy of bounds
+        static std::unordered_map<const void*, torch::Tensor> dev_bounds;     // one per graph, keyed by the host array
+        auto it = dev_bounds.find(g.bounds);
+        if (it == dev_bounds.end() || it->second.numel() != bounds.numel())
+            it = dev_bounds.insert_or_assign(g.bounds, bounds.to(columns_graph.device())).first;
+        g.bounds_dev = it->second.data_ptr<int>();
+    }
     return g;
 }
 

@@ -32,7 +32,8 @@
  * [bounds[2s], bounds[2s+1]) and row i of segment s owns
  * bounds[2s] + offsets[s*(nrows+1)+i .. i+1).  A plain CSR is segments = 1.
  * `bounds` is a HOST array exactly as in the generated code (cuda.h:472-475 reads
- * it on the host); it may be NULL when segments == 1.
+ * it on the host); it may be NULL when segments == 1.  Graphs with more than 64 segments
+ * also pass a device copy of it (bounds_dev).
  */
 #ifndef GALA_B200_H
 #define GALA_B200_H
@@ -66,6 +67,8 @@ typedef struct gala_graph {
     int32_t ncols;          /* columns == rows of the gathered dense operand         */
     int32_t segments;       /* S >= 1                                                */
     int64_t nvals;          /* E                                                     */
+    const int32_t *bounds_dev; /* device copy of bounds [2 * segments]; required iff segments > 64
+                                  (up to 64 segment starts travel in the kernel parameters), else may be NULL */
 } gala_graph_t;
 
 /*
@@ -240,6 +243,9 @@ typedef struct gala_multi_out {
     float *base[8];
     float *multicast_base;
     int32_t count;
+    const uint8_t *need_mask; /* device [rows of this rank] or NULL: bit q set = GPU q references the row and gets it.
+                                 The "exchange only the rows a peer needs" of a 1-D partition as
+                                 predicated peer stores; ignored on the multicast path (the switch replicates to all). */
 } gala_multi_out_t;
 
 typedef struct gala_dense_epilogue {

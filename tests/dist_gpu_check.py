@@ -23,7 +23,7 @@ X = torch.rand(n, feats, generator=torch.Generator(device=dev).manual_seed(1), d
 g = ops.TiledGraph(offset, ids, n).build_plan()
 want = model.forward(g, X, mode="literal", dense="torch")
 err = 0.0
-for exchange in ("nccl", "p2p"):
+for exchange in ("nccl", "p2p", "p2p-needed"):
     runner = dist_gat.PartitionedGAT(model, offset, ids, n, rank, world, dev, exchange=exchange)
     for rep in range(3):    # repeated steps exercise the buffer re-use ordering of the peer exchange
         out_loc = runner.forward(X[runner.row_lo:runner.row_hi].contiguous())

@@ -43,14 +43,14 @@ def test_argument_errors_return_codes_not_exits():
     assert lib.gala_spmm_f32(None, None, None, 4, None, None, None, None) == -1
     g = L.GalaGraph(offsets=None, cols=None, bounds=None, nrows=-3, ncols=0, segments=1, nvals=0)
     assert lib.gala_spmm_f32(C.byref(g), None, None, 4, None, None, None, None) == -2
-    # any number of column segments is accepted (the reference has no limit); what is required is the host `bounds`
+    # any number of column segments is accepted (the reference has no limit); beyond 64 the device copy of `bounds`
+    # is required as well
+    import numpy as np
+    b = np.zeros(2000, np.int32)
     g = L.GalaGraph(offsets=None, cols=None, bounds=None, nrows=0, ncols=0, segments=1000, nvals=0)
     assert lib.gala_spmm_f32(C.byref(g), None, None, 4, None, None, None, None) == -1
-    import numpy as np
-    gaps = np.zeros(2000, np.int32)
-    gaps[2] = 5                       # segment 1 does not start where segment 0 ends: not the tiled layout
-    g = L.GalaGraph(offsets=None, cols=None, bounds=gaps.ctypes.data, nrows=0, ncols=0, segments=1000, nvals=0)
-    assert lib.gala_spmm_f32(C.byref(g), None, None, 4, None, None, None, None) == -3
+    g = L.GalaGraph(offsets=None, cols=None, bounds=b.ctypes.data, nrows=0, ncols=0, segments=1000, nvals=0)
+    assert lib.gala_spmm_f32(C.byref(g), None, None, 4, None, None, None, None) == -1
     g = L.GalaGraph(offsets=None, cols=None, bounds=None, nrows=8, ncols=8, segments=1, nvals=0)
     assert lib.gala_spmm_f32(C.byref(g), None, None, 4, None, None, None, None) == -1
     with pytest.raises(L.GalaError):

@@ -283,3 +283,40 @@ def test_needed_rows_exchange_matches_all_gather_results(orc, tmp_path):
         res = torch.relu(nrm * (A @ (nrm * lin(res, c.fc[i]))))
     want_gcn = lin(nrm * (A @ (nrm * res)), c.fc[-1])
     assert rel_err(got[1], want_gcn.float().numpy()) < 1e-5
+
+
+def _worker_masks(rank, world, port, n, e, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    offset, ids = synth.powerlaw_csr_torch(n, e, seed=9, device="cpu")
+    part = dist_gat.RowPartition(offset, ids, n, rank, world)
+    mask = part.need_masks(ids, offset)
+    np.save(f"{out_path}.{rank}.npy", mask.numpy())
+    np.save(f"{out_path}.{rank}.bounds.npy", np.array(part.bounds))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_need_masks_mark_exactly_the_rows_each_peer_references(tmp_path):
+    """RowPartition.need_masks (the predicate of the fused needed-rows exchange): bit q of row r's mask is set iff
+    rank q's slab has an edge whose column is r, and every row carries its owner's bit."""
+    n, e, world = 500, 3000, 3
+    out_path = str(tmp_path / "mask")
+    mp.spawn(_worker_masks, args=(world, _free_port(), n, e, out_path), nprocs=world, join=True)
+    offset, ids = synth.powerlaw_csr_torch(n, e, seed=9, device="cpu")
+    offset, ids = offset.numpy(), ids.numpy()
+    bounds = np.load(f"{out_path}.0.bounds.npy")
+    some_unneeded = False
+    for owner in range(world):
+        mask = np.load(f"{out_path}.{owner}.npy")
+        lo, hi = bounds[owner], bounds[owner + 1]
+        assert mask.shape[0] == max(hi - lo, 1)
+        for q in range(world):
+            cols_q = ids[offset[bounds[q]]:offset[bounds[q + 1]]]            # columns referenced by rank q's slab
+            ref = np.zeros(n, bool)
+            ref[cols_q] = True
+            want = ref[lo:hi] if q != owner else np.ones(hi - lo, bool)
+            got = ((mask[:hi - lo] >> q) & 1).astype(bool)
+            assert np.array_equal(got, want), (owner, q)
+            some_unneeded |= not want.all()
+    assert some_unneeded          # the graph is sparse enough for the masks to matter
