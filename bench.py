@@ -225,6 +225,8 @@ def main():
     ap.add_argument("--dense", default="tcgen05", choices=["tcgen05", "torch"],
                     help="layer-1 feature transform: hand-written tcgen05 3xTF32 kernel or cuBLAS fp32 via torch")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel sweep (SpMM/SDDMM GB/s)")
+    ap.add_argument("--no-generated", action="store_true",
+                    help="skip the generated-program lines (GAT training epoch of the GALA-generated gala.cu, both generators)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -508,6 +510,26 @@ def main():
     if not args.no_kernels and world == 1:
         line["kernels"] = kernel_sweep(g, n, nvals, hidden, peak, dev,
                                        (roofline.get("l2") or {}).get("measured_read_gbs"))
+
+    # ---- BASELINE configs[1] is "GAT inference + training": the training epoch is measured on what GALA generates --
+    # the gala.cu emitted for tests/GALA-DSL/gat/Reddit (train driver and inference driver), compiled once with the
+    # reference's stock CUDAGenerator (its own kernels, sm_100a) and once with the retargeted generator (this library),
+    # run here on the full-size synthetic Reddit-shape dataset in the on-disk .npy format.  Secondary keys; they need
+    # the binaries host/codegen/build_models.sh builds in the authoring container (shipped with the tree).
+    if world == 1 and not args.no_generated and not (args.nodes or args.edges):
+        try:
+            torch.cuda.synchronize()
+            sys.path.insert(0, os.path.join(ROOT, "profiles"))
+            import run_generated_full
+            recs = run_generated_full.run("Reddit", ["gat_inference", "gat_train"])
+            line["generated_programs"] = {
+                "what": ("GALA-generated 2-layer GAT programs (100 epochs, Adam) on the Reddit-shape dataset: mean forward "
+                         "ms and forward+backward+Adam ms as the program prints them, start-up seconds (data load + format "
+                         "construction + H2D); generator ref = the reference's own CUDA kernels compiled for sm_100a, "
+                         "b200 = this library through the retargeted generator"),
+                "runs": recs}
+        except Exception as ex:   # secondary measurement: never fails the bench line
+            line["generated_programs"] = {"error": f"{type(ex).__name__}: {ex}"}
 
     if world == 1 and not args.no_cpu_baseline:
         ms, info = cpu_arm(n, e, feats, offset.cpu().numpy(), ids.cpu().numpy(), X.cpu(), model, 1, 0)

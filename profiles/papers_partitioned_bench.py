@@ -26,6 +26,12 @@ torch.cuda.set_device(local)
 dev = f"cuda:{local}"
 dist.init_process_group("nccl", device_id=torch.device(dev))
 scale = float(sys.argv[1]) if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else 1.0
+# --exchanges p2p,p2p-needed,nccl : which exchanges to time (default all three);  p2p-needed = rows stored only into the
+# GPUs whose slabs reference them (predicated peer stores from the producing kernels' epilogues)
+EXCHANGES = ("p2p", "p2p-needed", "nccl")
+for i, a in enumerate(sys.argv):
+    if a == "--exchanges":
+        EXCHANGES = tuple(sys.argv[i + 1].split(","))
 
 
 def say(*a):
@@ -75,9 +81,10 @@ model = GATN(dims, dev, seed=0).host_biases()
 X = torch.rand(n, dims[0], generator=torch.Generator(device=dev).manual_seed(1), device=dev) - 0.5
 want = model.forward_literal(ops.TiledGraph(offset, ids, n).build_plan(), X)
 worst = 0.0
-for exchange in (("nccl", "p2p") if world > 1 else ("nccl",)):
+for exchange in (("nccl", "p2p", "p2p-needed") if world > 1 else ("nccl",)):
     part = dist_gat.RowPartition(offset, ids, n, rank, world)
-    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange)
+    need = part.need_masks(ids, offset) if exchange == "p2p-needed" else None
+    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange, need_mask=need)
     for _ in range(3):
         out_loc = runner.forward(X[part.row_lo:part.row_hi].contiguous())
     full = part.unpad(part.all_gather(out_loc))
@@ -88,9 +95,10 @@ for exchange in (("nccl", "p2p") if world > 1 else ("nccl",)):
 gfull = ops.TiledGraph(offset, ids, n).build_plan()
 gcn = GCNN(dims, dev, seed=2).prepare(gfull)
 want = gcn.forward_literal(gfull, X)
-for exchange in (("nccl", "p2p") if world > 1 else ("nccl",)):
+for exchange in (("nccl", "p2p", "p2p-needed") if world > 1 else ("nccl",)):
     part = dist_gat.RowPartition(offset, ids, n, rank, world)
-    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange)
+    need = part.need_masks(ids, offset) if exchange == "p2p-needed" else None
+    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange, need_mask=need)
     for _ in range(3):
         out_loc = runner.forward(X[part.row_lo:part.row_hi].contiguous())
     full = part.unpad(part.all_gather(out_loc))
@@ -108,14 +116,19 @@ n, e = int(n * scale), int(e * scale)
 dims = [feats, hidden, hidden, classes]
 offset, ids = build(n, e, 0)
 part = dist_gat.RowPartition(offset, ids, n, rank, world)
+need_mask = None
+if world > 1 and "p2p-needed" in EXCHANGES:
+    need_mask = part.need_masks(ids, offset)
+    say(f"needed-rows masks: rank 0's rows are referenced by {part.need_fraction:.1%} of the (row, peer) pairs")
 del ids
 torch.cuda.empty_cache()
 model = GATN(dims, dev, seed=0).host_biases()
 X_loc = torch.rand(part.rows, feats, device=dev) - 0.5
 say(f"papers shape x{scale}: n={n} E={e}; rank 0 holds rows [{part.row_lo},{part.row_hi}) nnz {part.local_nvals}")
 res = {"workload": f"3-layer GAT forward, papers100M shape x{scale}", "n_gpus": world, "nodes": n, "edges": e}
-for exchange in (("p2p", "nccl") if world > 1 else ()):
-    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange)
+for exchange in (EXCHANGES if world > 1 else ()):
+    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange,
+                                      need_mask=need_mask if exchange == "p2p-needed" else None)
     ms = timed(lambda: runner.forward(X_loc))
     res[f"ms_{runner.exchange}"] = round(ms, 3)
     say(f"  [{runner.exchange}] forward {ms:.2f} ms (max over {world} ranks)")
@@ -130,8 +143,8 @@ for exchange in (("p2p", "nccl") if world > 1 else ()):
         mark("start")
         runner.forward(X_loc, mark=mark)
         torch.cuda.synchronize()
-        res["phases_ms_rank0"] = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 2) for i in range(1, len(marks))}
-        say("  phases (rank 0):", res["phases_ms_rank0"])
+        res[f"phases_ms_rank0_{runner.exchange}"] = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 2) for i in range(1, len(marks))}
+        say("  phases (rank 0):", res[f"phases_ms_rank0_{runner.exchange}"])
     del runner
     torch.cuda.empty_cache()
 if world > 1 and "--needed" in sys.argv:
@@ -148,8 +161,9 @@ if world > 1 and "--needed" in sys.argv:
     del runner, npart
     torch.cuda.empty_cache()
 gcn = GCNN(dims, dev, seed=2)
-for exchange in (("p2p", "nccl") if world > 1 else ()):
-    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange)
+for exchange in (EXCHANGES if world > 1 else ()):
+    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange,
+                                      need_mask=need_mask if exchange == "p2p-needed" else None)
     ms = timed(lambda: runner.forward(X_loc))
     res[f"gcn_ms_{runner.exchange}"] = round(ms, 3)
     say(f"  GCN [{runner.exchange}] forward {ms:.2f} ms (max over {world} ranks)")
@@ -164,8 +178,8 @@ for exchange in (("p2p", "nccl") if world > 1 else ()):
         mark("start")
         runner.forward(X_loc, mark=mark)
         torch.cuda.synchronize()
-        res["gcn_phases_ms_rank0"] = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 2) for i in range(1, len(marks))}
-        say("  GCN phases (rank 0):", res["gcn_phases_ms_rank0"])
+        res[f"gcn_phases_ms_rank0_{runner.exchange}"] = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 2) for i in range(1, len(marks))}
+        say("  GCN phases (rank 0):", res[f"gcn_phases_ms_rank0_{runner.exchange}"])
     del runner
     torch.cuda.empty_cache()
 if world == 1:
