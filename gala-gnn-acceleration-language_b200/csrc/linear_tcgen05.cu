@@ -417,7 +417,7 @@ constexpr int kV2Producers = 8;
 constexpr int kV2Threads = (kV2Producers + 1 + 4) * 32;   // 416
 
 template <int NPAD>
-__global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const __grid_constant__ LinearParams p) {
+__global__ void __maxnreg__(152) linear_tf32x3_v2_kernel(const __grid_constant__ LinearParams p) {
     constexpr int kSK = 64;                                  // floats of K per super-stage (2 atoms)
     constexpr uint32_t kAtomA = kBM * 128;                   // 16 KB: [128 rows x 32 fp32]
     constexpr uint32_t kAtomB = NPAD * 128;
@@ -473,13 +473,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
         }
         const char* wlane = reinterpret_cast<const char*>(p.W + (int64_t)(warp * kWRows) * p.K + 2 * lane);
         const bool wrows_full = warp * kWRows + kWRows <= p.N;
-        float2 va[16], vb[16], wa[kWRows], wb[kWRows];
+        float2 va[16], vb[16];
         const float2 zero2 = make_float2(0.0f, 0.0f);
 
-        auto load_ss = [&](const char* xlane, bool rows_full, int64_t wrow0, int ss, float2 (&v)[16], float2 (&w)[kWRows]) {
+        auto load_ss = [&](const char* xlane, bool rows_full, int64_t wrow0, int ss, float2 (&v)[16]) {
             const bool kok = ss * kSK + 2 * lane < p.K;   // K even: the pair is in or out together
             const char* xc = xlane + ss * (kSK * 4);
-            const char* wc = wlane + ss * (kSK * 4);
             if (rows_full && kok) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = __ldg(reinterpret_cast<const float2*>(xc + (uint64_t)i * pitch));
@@ -488,13 +487,19 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
                 for (int i = 0; i < 16; ++i)
                     v[i] = (kok && wrow0 + i < p.M) ? __ldg(reinterpret_cast<const float2*>(xc + (uint64_t)i * pitch)) : zero2;
             }
+        };
+        auto store_ss = [&](uint32_t g, const float2 (&v)[16]) {
+            const uint32_t s = g & 1;
+            // this warp's rows of W for the stage (L2-resident, a few hundred bytes): requested here, consumed after the
+            // A rows have been split, so their latency hides behind the wait for the stage and the A stores
+            const int ss = (int)(g % (uint32_t)nss);
+            const bool kok = ss * kSK + 2 * lane < p.K;
+            const char* wc = wlane + ss * (kSK * 4);
+            float2 w[kWRows];
 #pragma unroll
             for (int i = 0; i < kWRows; ++i)
                 w[i] = (kok && (wrows_full || warp * kWRows + i < p.N))
                            ? __ldg(reinterpret_cast<const float2*>(wc + (uint64_t)i * pitch)) : zero2;
-        };
-        auto store_ss = [&](uint32_t g, const float2 (&v)[16], const float2 (&w)[kWRows]) {
-            const uint32_t s = g & 1;
             if (g >= 2) mbar_wait(&empty_bar[s], ((g >> 1) & 1) ^ 1);
             uint8_t* a_hi = smem + (size_t)s * kStageBytes + warp * (16 * 128);
             uint8_t* a_lo = a_hi + 2 * kAtomA;
@@ -520,21 +525,47 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
             mbar_arrive(&full_bar[s]);
         };
 
-        uint32_t g = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t wrow0 = tile * kBM + warp * 16;
+        // The (tile, super-stage) pairs this CTA processes form one flat sequence g = 0, 1, ...: the register pipeline
+        // below never drains at a tile boundary.  GALA_LINEAR_REGBUF super-stages are in flight per lane (x 16 rows x
+        // 8 bytes): 2 = the round-1 form (64 KB per SM), 3 = 96 KB, above the ~75 KB the HBM latency-bandwidth
+        // product asks of one SM.
+#ifndef GALA_LINEAR_REGBUF
+#define GALA_LINEAR_REGBUF 3
+#endif
+        const uint32_t my_tiles = blockIdx.x < ntiles ? (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+        const uint32_t total = my_tiles * (uint32_t)nss;
+        auto load_g = [&](uint32_t g, float2 (&v)[16]) {
+            if (g >= total) return;
+            const uint32_t it = g / (uint32_t)nss;
+            const int ss = (int)(g - it * (uint32_t)nss);
+            const int64_t wrow0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + warp * 16;
             const char* xlane = reinterpret_cast<const char*>(p.X + wrow0 * p.K + 2 * lane);
-            const bool rows_full = wrow0 + 16 <= p.M;
-            load_ss(xlane, rows_full, wrow0, 0, va, wa);
-            for (int ss = 0; ss < nss; ss += 2) {
-                if (ss + 1 < nss) load_ss(xlane, rows_full, wrow0, ss + 1, vb, wb);
-                store_ss(g++, va, wa);
-                if (ss + 1 < nss) {
-                    if (ss + 2 < nss) load_ss(xlane, rows_full, wrow0, ss + 2, va, wa);
-                    store_ss(g++, vb, wb);
-                }
-            }
+            load_ss(xlane, wrow0 + 16 <= p.M, wrow0, ss, v);
+        };
+#if GALA_LINEAR_REGBUF == 3
+        float2 vc[16];
+        load_g(0, va);
+        load_g(1, vb);
+        for (uint32_t g = 0; g < total; g += 3) {
+            load_g(g + 2, vc);
+            store_ss(g, va);
+            if (g + 1 >= total) break;
+            load_g(g + 3, va);
+            store_ss(g + 1, vb);
+            if (g + 2 >= total) break;
+            load_g(g + 4, vb);
+            store_ss(g + 2, vc);
         }
+#else
+        load_g(0, va);
+        for (uint32_t g = 0; g < total; g += 2) {
+            load_g(g + 1, vb);
+            store_ss(g, va);
+            if (g + 1 >= total) break;
+            load_g(g + 2, va);
+            store_ss(g + 1, vb);
+        }
+#endif
     } else if (warp == kV2Producers) {
         // ------------------------------- MMA issuer -----------------------------------------------
         if (lane == 0) {

@@ -29,7 +29,11 @@ def t(fn, reps=20):
     for _ in range(reps): fn()
     e_.record(); torch.cuda.synchronize()
     return s.elapsed_time(e_) / reps
-print(json.dumps({"gat": t(lambda: ops.gat_forward(g, a, a, X, out=Y)),
+Xf = torch.rand(n, f, generator=gen, device=dev) - 0.5
+Wf = (torch.rand(K, f, generator=gen, device=dev) - 0.5) * 0.1
+Yf = torch.empty(n, K, device=dev)
+print(json.dumps({"linear_602_32": t(lambda: ops.linear(Xf, Wf, out=Yf)),
+                  "gat": t(lambda: ops.gat_forward(g, a, a, X, out=Y)),
                   "gat_dot": t(lambda: ops.gat_forward_dot(g, a, X[0].contiguous(), 0.1, X, out=Y)),
                   "spmm": t(lambda: ops.spmm(g, X, out=Y)),
                   "spmm_w": t(lambda: ops.spmm(g, X, vals=w, out=Y)),
