@@ -417,7 +417,7 @@ constexpr int kV2Producers = 8;
 constexpr int kV2Threads = (kV2Producers + 1 + 4) * 32;   // 416
 
 template <int NPAD>
-__global__ void __maxnreg__(152) linear_tf32x3_v2_kernel(const __grid_constant__ LinearParams p) {
+__global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const __grid_constant__ LinearParams p) {
     constexpr int kSK = 64;                                  // floats of K per super-stage (2 atoms)
     constexpr uint32_t kAtomA = kBM * 128;                   // 16 KB: [128 rows x 32 fp32]
     constexpr uint32_t kAtomB = NPAD * 128;
@@ -527,10 +527,11 @@ __global__ void __maxnreg__(152) linear_tf32x3_v2_kernel(const __grid_constant__
 
         // The (tile, super-stage) pairs this CTA processes form one flat sequence g = 0, 1, ...: the register pipeline
         // below never drains at a tile boundary.  GALA_LINEAR_REGBUF super-stages are in flight per lane (x 16 rows x
-        // 8 bytes): 2 = the round-1 form (64 KB per SM), 3 = 96 KB, above the ~75 KB the HBM latency-bandwidth
-        // product asks of one SM.
+        // 8 bytes = 64 KB per SM at 2).  A third buffer (96 KB, above the ~75 KB the HBM latency-bandwidth product
+        // asks of one SM) does not fit: 13 warps put 4 on one SM sub-partition, whose 16 K registers cap a thread at
+        // 128, and the third buffer spills (156 bytes at N = 32).
 #ifndef GALA_LINEAR_REGBUF
-#define GALA_LINEAR_REGBUF 3
+#define GALA_LINEAR_REGBUF 2
 #endif
         const uint32_t my_tiles = blockIdx.x < ntiles ? (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
         const uint32_t total = my_tiles * (uint32_t)nss;
