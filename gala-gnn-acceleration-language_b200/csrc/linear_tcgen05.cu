@@ -708,6 +708,221 @@ inline int device_sm_count() {
     return cache[dev];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Wide output, small K (the classifier Linear(hidden, classes) with 64 < classes <= 256 and hidden <= 64: 172 classes
+// on the Papers shape).  The output is 5x the input here, so the kernel is a store stream: persistent, one CTA per SM,
+//   * W (N x K) is split into hi / lo ONCE per CTA and stays in shared memory in UMMA's swizzled layout;
+//   * warps 0-3 load / split the 128 x K tile of X (two register buffers over the flat (tile, atom) sequence);
+//   * warp 4 issues the MMAs into ONE accumulator of NPAD columns (at most 24 accumulations: no drift to spread),
+//     two accumulator sets in TMEM (2 x NPAD <= 512 columns);
+//   * warps 5-8 drain set i (16 columns at a time: bias / row scale / ReLU, 64-byte streaming stores) while the tensor
+//     core fills set i+1.
+constexpr int kWsThreads = 9 * 32;
+
+template <int NPAD, int NATOM>
+__global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kernel(const __grid_constant__ LinearParams p) {
+    constexpr uint32_t kAtomA = kBM * 128;                 // [128 rows x 32 fp32]
+    constexpr uint32_t kAtomB = NPAD * 128;
+    constexpr uint32_t kWBytes = 2 * NATOM * kAtomB;       // hi atoms, then lo atoms
+    constexpr uint32_t kStageBytes = 2 * kAtomA;           // one atom of A: hi, lo
+    constexpr uint32_t kTmemCols = 2 * NPAD <= 256 ? 256 : 512;
+    static_assert(2 * NPAD <= 512 && NPAD % 16 == 0, "two accumulator sets in TMEM");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w_hi = smem;
+    uint8_t* w_lo = smem + NATOM * kAtomB;
+    uint8_t* a_stage = smem + kWBytes;
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], accf_bar[2], acce_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles = (p.M + kBM - 1) / kBM;
+    const uint32_t my_tiles = blockIdx.x < ntiles ? (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full_bar[s], 128);
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&accf_bar[s], 1);
+            mbar_init(&acce_bar[s], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // W -> hi / lo, swizzled K-major, resident for the whole kernel (rows >= N and columns >= K are zero)
+    for (int idx = tid; idx < NPAD * NATOM * 32; idx += kWsThreads) {
+        const int n = idx / (NATOM * 32), k = idx - n * (NATOM * 32);
+        const float w = (n < p.N && k < p.K) ? __ldg(p.W + (int64_t)n * p.K + k) : 0.0f;
+        float hi, lo;
+        split_tf32(w, hi, lo);
+        const int atom = k >> 5, kk = k & 31;
+        const uint32_t o = (uint32_t)atom * kAtomB + (uint32_t)(n * 128) + (uint32_t)((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2));
+        *reinterpret_cast<float*>(w_hi + o) = hi;
+        *reinterpret_cast<float*>(w_lo + o) = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp < 4) {
+        // ------------------------------- producers: 32 rows each, one float per lane per row and atom ------------
+        const uint32_t pitch = (uint32_t)p.K * 4u;
+        const uint32_t total = my_tiles * NATOM;
+        uint32_t sw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sw[j] = (uint32_t)((((lane >> 2) ^ j) << 4) | ((lane & 3) << 2));
+        float va[32], vb[32];
+        auto load_g = [&](uint32_t g, float (&v)[32]) {
+            if (g >= total) return;
+            const uint32_t it = g / NATOM;
+            const int atom = (int)(g - it * NATOM);
+            const int64_t wrow0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + warp * 32;
+            const bool kok = atom * 32 + lane < p.K;
+            const char* xc = reinterpret_cast<const char*>(p.X + wrow0 * p.K + atom * 32 + lane);
+            if (kok && wrow0 + 32 <= p.M) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __ldcs(reinterpret_cast<const float*>(xc + (uint64_t)i * pitch));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    v[i] = (kok && wrow0 + i < p.M) ? __ldcs(reinterpret_cast<const float*>(xc + (uint64_t)i * pitch)) : 0.0f;
+            }
+        };
+        auto store_g = [&](uint32_t g, const float (&v)[32]) {
+            const uint32_t s = g & 1;
+            if (g >= 2) mbar_wait(&empty_bar[s], ((g >> 1) & 1) ^ 1);
+            uint8_t* a_hi = a_stage + (size_t)s * kStageBytes + warp * 4096;
+            uint8_t* a_lo = a_hi + kAtomA;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float hi, lo;
+                split_tf32(v[i], hi, lo);
+                *reinterpret_cast<float*>(a_hi + i * 128 + sw[i & 7]) = hi;
+                *reinterpret_cast<float*>(a_lo + i * 128 + sw[i & 7]) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full_bar[s]);
+        };
+        load_g(0, va);
+        for (uint32_t g = 0; g < total; g += 2) {
+            load_g(g + 1, vb);
+            store_g(g, va);
+            if (g + 1 >= total) break;
+            load_g(g + 2, va);
+            store_g(g + 1, vb);
+        }
+    } else if (warp == 4) {
+        // ------------------------------- MMA issuer ---------------------------------------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(NPAD);
+            uint32_t g = 0;
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const uint32_t aset = it & 1;
+                if (it >= 2) mbar_wait(&acce_bar[aset], ((it >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + aset * NPAD;
+                for (int atom = 0; atom < NATOM; ++atom, ++g) {
+                    const uint32_t s = g & 1;
+                    mbar_wait(&full_bar[s], (g >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(a_stage + (size_t)s * kStageBytes), a_lo = a_hi + kAtomA;
+                    const uint32_t b_hi = smem_u32(w_hi) + (uint32_t)atom * kAtomB, b_lo = smem_u32(w_lo) + (uint32_t)atom * kAtomB;
+                    if (atom * 32 < p.K) {
+#pragma unroll
+                        for (int k8 = 0; k8 < 4; ++k8) {
+                            const uint32_t ko = (uint32_t)k8 * 32;
+                            umma_tf32(acc, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, (atom | k8) != 0);
+                            umma_tf32(acc, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                            umma_tf32(acc, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&accf_bar[aset]);
+            }
+        }
+    } else {
+        // ------------------------------- epilogue warps ------------------------------------------------------------
+        const int q = warp & 3;                  // TMEM lane quarter this warp may read
+        const bool y16 = (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.Y) & 15) == 0;
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t aset = it & 1;
+            mbar_wait(&accf_bar[aset], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t r = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + q * 32 + lane;
+            const float rscale = (p.row_scale && r < p.M) ? __ldg(p.row_scale + r) : 1.0f;
+            float* yrow = p.Y + r * p.N;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NPAD; c0 += 32) {
+                if (c0 >= p.N) break;            // warp-uniform
+                uint32_t u[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + aset * NPAD + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                      "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                    : "r"(taddr));
+                if (c0 + 16 < NPAD)
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+                          "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+                        : "r"(taddr + 16));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (r < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (c0 + j < p.N) {
+                            float o[4];
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) {
+                                float y = __uint_as_float(u[j + v]) + ((p.bias && c0 + j + v < p.N) ? __ldg(p.bias + c0 + j + v) : 0.0f);
+                                y *= rscale;
+                                o[v] = p.relu ? fmaxf(y, 0.0f) : y;
+                            }
+                            if (y16) {
+                                __stcs(reinterpret_cast<float4*>(yrow + c0 + j), make_float4(o[0], o[1], o[2], o[3]));
+                            } else {
+#pragma unroll
+                                for (int v = 0; v < 4; ++v)
+                                    if (c0 + j + v < p.N) yrow[c0 + j + v] = o[v];
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acce_bar[aset]);        // the accumulator set may be overwritten
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+template <int NPAD, int NATOM>
+int launch_linear_wide_smallk(const LinearParams& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)2 * NATOM * NPAD * 128 + (size_t)2 * 2 * kBM * 128 + 1024;
+    cudaError_t e0 = cudaFuncSetAttribute(linear_tf32x3_wide_smallk_kernel<NPAD, NATOM>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e0 != cudaSuccess) return (int)e0;
+    const int64_t ntiles = (p.M + kBM - 1) / kBM;
+    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, device_sm_count());
+    linear_tf32x3_wide_smallk_kernel<NPAD, NATOM><<<grid, kWsThreads, smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GALA_OK : (int)e;
+}
+
 template <int NPAD>
 int launch_linear_v2(const LinearParams& p, cudaStream_t st) {
     constexpr size_t smem = 2 * (size_t)(4 * kBM * 128 + 4 * NPAD * 128) + 1024;
@@ -798,6 +1013,17 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
     if (N <= 32) return launch_linear<32>(p, st);
     if (N <= 48) return launch_linear<48>(p, st);
     if (N <= 64) return launch_linear<64>(p, st);
+    if (K <= 64 && ntiles >= 2 * (int64_t)device_sm_count()) {
+        // wide output, small K (classifier): W resident, persistent, accumulators double-buffered
+        if (K <= 32) {
+            if (N <= 128) return launch_linear_wide_smallk<128, 1>(p, st);
+            if (N <= 176) return launch_linear_wide_smallk<176, 1>(p, st);
+            return launch_linear_wide_smallk<256, 1>(p, st);
+        }
+        if (N <= 128) return launch_linear_wide_smallk<128, 2>(p, st);
+        if (N <= 176) return launch_linear_wide_smallk<176, 2>(p, st);
+        // N > 176 with K > 32: W alone would take 128 KB next to the A stages -- the general wide kernel below
+    }
     if (N <= 96) return launch_linear<96>(p, st);
     if (N <= 128) return launch_linear<128>(p, st);
     if (N <= 176) return launch_linear<176>(p, st);

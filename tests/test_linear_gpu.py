@@ -14,7 +14,10 @@ DEV = "cuda:0"
                                    (300, 1433, 32), (4096, 602, 16), (130, 7, 8), (1, 5, 64), (233000, 602, 32),
                                    # wide outputs (64 < N <= 256): the 172-class classifier of the Papers shape & co.
                                    (5000, 32, 172), (1000, 128, 172), (300, 602, 100), (777, 32, 96), (2000, 64, 128),
-                                   (129, 32, 173), (4000, 100, 256), (64, 8, 65)])
+                                   (129, 32, 173), (4000, 100, 256), (64, 8, 65),
+                                   # wide output + small K + enough tiles for the persistent classifier kernel
+                                   (40000, 32, 172), (50000, 64, 128), (38000, 20, 200), (40001, 48, 173),
+                                   (300000, 32, 172), (45000, 64, 256)])
 def test_linear_matches_fp64_and_torch_fp32(M, K, N):
     torch.backends.cuda.matmul.allow_tf32 = False
     gen = torch.Generator(device=DEV)
