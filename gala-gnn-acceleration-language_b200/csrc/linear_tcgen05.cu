@@ -719,7 +719,10 @@ inline int device_sm_count() {
 //     core fills set i+1.
 constexpr int kWsThreads = 9 * 32;
 
-template <int NPAD, int NATOM>
+//   * STAGED (whenever the shared memory is there: K <= 32): an epilogue warp transposes its 32 x N block through shared
+//     memory and writes it as ONE contiguous run (32 rows of a packed [M, N] matrix are 32*N*4 consecutive bytes):
+//     full 128-byte lines per store instruction instead of 32 scattered 16-byte pieces (688 vs 5504 L2 requests per tile).
+template <int NPAD, int NATOM, bool STAGED>
 __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kernel(const __grid_constant__ LinearParams p) {
     constexpr uint32_t kAtomA = kBM * 128;                 // [128 rows x 32 fp32]
     constexpr uint32_t kAtomB = NPAD * 128;
@@ -732,12 +735,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
     uint8_t* w_hi = smem;
     uint8_t* w_lo = smem + NATOM * kAtomB;
     uint8_t* a_stage = smem + kWBytes;
+    constexpr int kOutPitch = NPAD + 4;                    // floats; 16-byte aligned rows, conflict-free 128-bit row writes
+    float* out_stage = reinterpret_cast<float*>(a_stage + 2 * kStageBytes);   // STAGED: [4 warps][32 rows][kOutPitch]
     __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], accf_bar[2], acce_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float bias_s[NPAD];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (p.M + kBM - 1) / kBM;
     const uint32_t my_tiles = blockIdx.x < ntiles ? (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    for (int n = tid; n < NPAD; n += kWsThreads) bias_s[n] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -876,29 +883,69 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
                           "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
                         : "r"(taddr + 16));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (r < p.M) {
+                float* srow = out_stage + ((size_t)q * 32 + lane) * kOutPitch + c0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (c0 + j < p.N) {
-                            float o[4];
-#pragma unroll
-                            for (int v = 0; v < 4; ++v) {
-                                float y = __uint_as_float(u[j + v]) + ((p.bias && c0 + j + v < p.N) ? __ldg(p.bias + c0 + j + v) : 0.0f);
-                                y *= rscale;
-                                o[v] = p.relu ? fmaxf(y, 0.0f) : y;
-                            }
+                for (int j = 0; j < 32; j += 4) {
+                    if (c0 + j < NPAD && c0 + j < p.N) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[c0 + j]);     // broadcast read
+                        float4 o;
+                        o.x = (__uint_as_float(u[j]) + b4.x) * rscale;
+                        o.y = (__uint_as_float(u[j + 1]) + b4.y) * rscale;
+                        o.z = (__uint_as_float(u[j + 2]) + b4.z) * rscale;
+                        o.w = (__uint_as_float(u[j + 3]) + b4.w) * rscale;
+                        if (p.relu) {
+                            o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);
+                        }
+                        if constexpr (STAGED) {
+                            *reinterpret_cast<float4*>(srow + j) = o;
+                        } else if (r < p.M) {
                             if (y16) {
-                                __stcs(reinterpret_cast<float4*>(yrow + c0 + j), make_float4(o[0], o[1], o[2], o[3]));
+                                __stcs(reinterpret_cast<float4*>(yrow + c0 + j), o);
                             } else {
+                                const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                                 for (int v = 0; v < 4; ++v)
-                                    if (c0 + j + v < p.N) yrow[c0 + j + v] = o[v];
+                                    if (c0 + j + v < p.N) yrow[c0 + j + v] = ov[v];
                             }
                         }
                     }
                 }
             }
+            // the accumulator set is in registers / shared memory now: hand it back before the stores go out
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acce_bar[aset]);
+            if constexpr (STAGED) {
+                __syncwarp();
+                const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + q * 32;
+                const int rows_here = (int)max((int64_t)0, min((int64_t)32, p.M - row0));
+                const float* sbase = out_stage + (size_t)q * 32 * kOutPitch;
+                if (y16) {
+                    const int vpr = p.N >> 2;                                 // float4 per row
+                    float4* ybase = reinterpret_cast<float4*>(p.Y + row0 * p.N);   // 32 packed rows = one contiguous run
+                    for (int idx = lane; idx < rows_here * vpr; idx += 32) {
+                        const int rr = idx / vpr, cv = idx - rr * vpr;
+                        __stcs(ybase + idx, *reinterpret_cast<const float4*>(sbase + rr * kOutPitch + cv * 4));
+                    }
+                } else {
+                    float* ybase = p.Y + row0 * p.N;
+                    for (int idx = lane; idx < rows_here * p.N; idx += 32) {
+                        const int rr = idx / p.N, c = idx - rr * p.N;
+                        ybase[idx] = sbase[rr * kOutPitch + c];
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+template <int NPAD, int NATOM>            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acce_bar[aset]);        // the accumulator set may be overwritten
         }
     }
@@ -912,13 +959,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
 
 template <int NPAD, int NATOM>
 int launch_linear_wide_smallk(const LinearParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)2 * NATOM * NPAD * 128 + (size_t)2 * 2 * kBM * 128 + 1024;
-    cudaError_t e0 = cudaFuncSetAttribute(linear_tf32x3_wide_smallk_kernel<NPAD, NATOM>,
+    constexpr size_t base = (size_t)2 * NATOM * NPAD * 128 + (size_t)2 * 2 * kBM * 128 + 1024;
+    constexpr size_t stage = (size_t)4 * 32 * (NPAD + 4) * 4;
+    constexpr bool STAGED = base + stage <= 225 * 1024;
+    constexpr size_t smem = base + (STAGED ? stage : 0);
+    cudaError_t e0 = cudaFuncSetAttribute(linear_tf32x3_wide_smallk_kernel<NPAD, NATOM, STAGED>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e0 != cudaSuccess) return (int)e0;
     const int64_t ntiles = (p.M + kBM - 1) / kBM;
     const unsigned grid = (unsigned)std::min<int64_t>(ntiles, device_sm_count());
-    linear_tf32x3_wide_smallk_kernel<NPAD, NATOM><<<grid, kWsThreads, smem, st>>>(p);
+    linear_tf32x3_wide_smallk_kernel<NPAD, NATOM, STAGED><<<grid, kWsThreads, smem, st>>>(p);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GALA_OK : (int)e;
 }

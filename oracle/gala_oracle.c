@@ -14,8 +14,11 @@
  * and the committed fixtures under tests/golden/ were produced by that
  * library.  The edge kernels (K3..K7, edge-softmax) exist in the reference only
  * as CUDA text inside src/codegen/cuda.h; they are restated here line by line
- * and are "parity unpinned" beyond hand-checked small cases (no GPU in the
- * authoring container to execute the reference strings).
+ * and pinned ON THE B200 against the reference's own emitted kernels, wrappers
+ * and autograd classes: host/codegen/ref_ops_harness.cu wraps the text the stock
+ * CUDAGenerator emits at build time and tests/test_ref_kernels_gpu.py compares
+ * every restated op with it element by element (K4/K5/K7 bit-exact, sums within
+ * 1e-5; the authoring container has no GPU, so that check runs with -m gpu).
  *
  * All citations are file:line relative to /root/reference.
  * Index type int32, value type float32 everywhere (src/codegen/common.h:1682-1693).
