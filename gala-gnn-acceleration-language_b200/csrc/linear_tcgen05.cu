@@ -945,18 +945,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
     }
 }
 
-template <int NPAD, int NATOM>            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&acce_bar[aset]);        // the accumulator set may be overwritten
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 4) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-    }
-}
-
 template <int NPAD, int NATOM>
 int launch_linear_wide_smallk(const LinearParams& p, cudaStream_t st) {
     constexpr size_t base = (size_t)2 * NATOM * NPAD * 128 + (size_t)2 * 2 * kBM * 128 + 1024;
