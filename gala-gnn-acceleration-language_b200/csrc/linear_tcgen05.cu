@@ -785,8 +785,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
         uint32_t sw[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) sw[j] = (uint32_t)((((lane >> 2) ^ j) << 4) | ((lane & 3) << 2));
-        float va[32], vb[32];
-        auto load_g = [&](uint32_t g, float (&v)[32]) {
+        // kBuf tile-atoms are in flight per lane (kBuf x 16 KB per SM): a tile is only 128 x K x 4 bytes here, so the
+        // register pipeline has to be deep for the loads to cover the HBM latency
+        constexpr int kBuf = 4;
+        float v[kBuf][32];
+        auto load_g = [&](uint32_t g, float (&vv)[32]) {
             if (g >= total) return;
             const uint32_t it = g / NATOM;
             const int atom = (int)(g - it * NATOM);
@@ -795,14 +798,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
             const char* xc = reinterpret_cast<const char*>(p.X + wrow0 * p.K + atom * 32 + lane);
             if (kok && wrow0 + 32 <= p.M) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __ldcs(reinterpret_cast<const float*>(xc + (uint64_t)i * pitch));
+                for (int i = 0; i < 32; ++i) vv[i] = __ldcs(reinterpret_cast<const float*>(xc + (uint64_t)i * pitch));
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    v[i] = (kok && wrow0 + i < p.M) ? __ldcs(reinterpret_cast<const float*>(xc + (uint64_t)i * pitch)) : 0.0f;
+                    vv[i] = (kok && wrow0 + i < p.M) ? __ldcs(reinterpret_cast<const float*>(xc + (uint64_t)i * pitch)) : 0.0f;
             }
         };
-        auto store_g = [&](uint32_t g, const float (&v)[32]) {
+        auto store_g = [&](uint32_t g, const float (&vv)[32]) {
             const uint32_t s = g & 1;
             if (g >= 2) mbar_wait(&empty_bar[s], ((g >> 1) & 1) ^ 1);
             uint8_t* a_hi = a_stage + (size_t)s * kStageBytes + warp * 4096;
@@ -810,20 +813,24 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 float hi, lo;
-                split_tf32(v[i], hi, lo);
+                split_tf32(vv[i], hi, lo);
                 *reinterpret_cast<float*>(a_hi + i * 128 + sw[i & 7]) = hi;
                 *reinterpret_cast<float*>(a_lo + i * 128 + sw[i & 7]) = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&full_bar[s]);
         };
-        load_g(0, va);
-        for (uint32_t g = 0; g < total; g += 2) {
-            load_g(g + 1, vb);
-            store_g(g, va);
-            if (g + 1 >= total) break;
-            load_g(g + 2, va);
-            store_g(g + 1, vb);
+#pragma unroll
+        for (int b = 0; b < kBuf - 1; ++b) load_g((uint32_t)b, v[b]);
+        for (uint32_t g0 = 0; g0 < total; g0 += kBuf) {
+#pragma unroll
+            for (int b = 0; b < kBuf; ++b) {
+                const uint32_t g = g0 + b;
+                if (g < total) {
+                    load_g(g + kBuf - 1, v[(b + kBuf - 1) % kBuf]);
+                    store_g(g, v[b]);
+                }
+            }
         }
     } else if (warp == 4) {
         // ------------------------------- MMA issuer ---------------------------------------------------------------
