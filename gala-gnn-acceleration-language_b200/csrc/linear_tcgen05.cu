@@ -715,9 +715,10 @@ inline int device_sm_count() {
 //   * warps 0-3 load / split the 128 x K tile of X (two register buffers over the flat (tile, atom) sequence);
 //   * warp 4 issues the MMAs into ONE accumulator of NPAD columns (at most 24 accumulations: no drift to spread),
 //     two accumulator sets in TMEM (2 x NPAD <= 512 columns);
-//   * warps 5-8 drain set i (16 columns at a time: bias / row scale / ReLU, 64-byte streaming stores) while the tensor
-//     core fills set i+1.
-constexpr int kWsThreads = 9 * 32;
+//   * warps 5-12 drain set i while the tensor core fills set i+1: two warps per TMEM lane quarter, each taking every
+//     other 32-column group (bias / row scale / ReLU) -- the epilogue is the long stage of this kernel (5x more bytes
+//     leave than enter), so it gets the warps.
+constexpr int kWsThreads = 13 * 32;
 
 //   * STAGED (whenever the shared memory is there: K <= 32): an epilogue warp transposes its 32 x N block through shared
 //     memory and writes it as ONE contiguous run (32 rows of a packed [M, N] matrix are 32*N*4 consecutive bytes):
@@ -751,7 +752,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
             mbar_init(&full_bar[s], 128);
             mbar_init(&empty_bar[s], 1);
             mbar_init(&accf_bar[s], 1);
-            mbar_init(&acce_bar[s], 128);
+            mbar_init(&acce_bar[s], 256);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -787,7 +788,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
         for (int j = 0; j < 8; ++j) sw[j] = (uint32_t)((((lane >> 2) ^ j) << 4) | ((lane & 3) << 2));
         // kBuf tile-atoms are in flight per lane (kBuf x 16 KB per SM): a tile is only 128 x K x 4 bytes here, so the
         // register pipeline has to be deep for the loads to cover the HBM latency
-        constexpr int kBuf = 4;
+        constexpr int kBuf = 2;     // (4 measured no faster: the epilogue, not the loads, is the long stage)
         float v[kBuf][32];
         auto load_g = [&](uint32_t g, float (&vv)[32]) {
             if (g >= total) return;
@@ -864,8 +865,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
         }
     } else {
         // ------------------------------- epilogue warps ------------------------------------------------------------
-        const int q = warp & 3;                  // TMEM lane quarter this warp may read
+        const int q = warp & 3;                  // TMEM lane quarter this warp may read (warp id mod 4)
+        const int half = (warp - 5) >> 2;        // the two warps of a quarter take alternate 32-column groups
         const bool y16 = (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.Y) & 15) == 0;
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };   // the 2 warps of this quarter
         for (uint32_t it = 0; it < my_tiles; ++it) {
             const uint32_t aset = it & 1;
             mbar_wait(&accf_bar[aset], (it >> 1) & 1);
@@ -874,7 +877,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
             const float rscale = (p.row_scale && r < p.M) ? __ldg(p.row_scale + r) : 1.0f;
             float* yrow = p.Y + r * p.N;
 #pragma unroll 1
-            for (int c0 = 0; c0 < NPAD; c0 += 32) {
+            for (int c0 = half * 32; c0 < NPAD; c0 += 64) {
                 if (c0 >= p.N) break;            // warp-uniform
                 uint32_t u[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + aset * NPAD + (uint32_t)c0;
@@ -922,25 +925,32 @@ __global__ void __launch_bounds__(kWsThreads, 1) linear_tf32x3_wide_smallk_kerne
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acce_bar[aset]);
             if constexpr (STAGED) {
-                __syncwarp();
-                const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + q * 32;
-                const int rows_here = (int)max((int64_t)0, min((int64_t)32, p.M - row0));
-                const float* sbase = out_stage + (size_t)q * 32 * kOutPitch;
+                pair_sync();                     // both column halves of the quarter's 32 rows are staged
+                // 32 packed rows of Y are one contiguous run; each of the two warps writes 16 of them
+                const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + q * 32 + half * 16;
+                const int rows_here = (int)max((int64_t)0, min((int64_t)16, p.M - row0));
+                const float* sbase = out_stage + ((size_t)q * 32 + half * 16) * kOutPitch;
                 if (y16) {
                     const int vpr = p.N >> 2;                                 // float4 per row
-                    float4* ybase = reinterpret_cast<float4*>(p.Y + row0 * p.N);   // 32 packed rows = one contiguous run
+                    float4* ybase = reinterpret_cast<float4*>(p.Y + row0 * p.N);
+                    int rr = 0, cv = lane;
+                    while (cv >= vpr) { cv -= vpr; ++rr; }
                     for (int idx = lane; idx < rows_here * vpr; idx += 32) {
-                        const int rr = idx / vpr, cv = idx - rr * vpr;
                         __stcs(ybase + idx, *reinterpret_cast<const float4*>(sbase + rr * kOutPitch + cv * 4));
+                        cv += 32;
+                        while (cv >= vpr) { cv -= vpr; ++rr; }
                     }
                 } else {
                     float* ybase = p.Y + row0 * p.N;
+                    int rr = 0, c = lane;
+                    while (c >= p.N) { c -= p.N; ++rr; }
                     for (int idx = lane; idx < rows_here * p.N; idx += 32) {
-                        const int rr = idx / p.N, c = idx - rr * p.N;
                         ybase[idx] = sbase[rr * kOutPitch + c];
+                        c += 32;
+                        while (c >= p.N) { c -= p.N; ++rr; }
                     }
                 }
-                __syncwarp();
+                pair_sync();                     // the staging rows may be overwritten by the next tile
             }
         }
     }
