@@ -312,7 +312,8 @@ int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int3
                   const gala_epilogue_t* ep, const gala_plan_t* plan, gala_stream_t stream) {
     if (int rc = check_graph(g)) return rc;
     if (K < 0) return GALA_ERR_BAD_SHAPE;
-    if ((g->nrows > 0 && K > 0) && (!X || !Y)) return GALA_ERR_NULL_POINTER;
+    const bool pushes = ep && ep->multi_out && ep->multi_out->count > 0;
+    if ((g->nrows > 0 && K > 0) && (!X || (!Y && !pushes))) return GALA_ERR_NULL_POINTER;
     if (!aligned(X, 4) || !aligned(Y, 4)) return GALA_ERR_MISALIGNED;
     SpmmParams p;
     std::memset(&p, 0, sizeof(p));
@@ -331,6 +332,13 @@ int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int3
         schedule = ep->schedule;
         if (ep->ldx > 0) p.ldx = ep->ldx;
         if (ep->ldy > 0) p.ldy = ep->ldy;
+        if (ep->multi_out && ep->multi_out->count > 0) {
+            if (ep->multi_out->count > kMaxPeers) return GALA_ERR_UNSUPPORTED;
+            p.mo.count = ep->multi_out->count;
+            p.mo.mc_base = ep->multi_out->multicast_base;
+            p.mo.need = ep->multi_out->need_mask;
+            for (int q = 0; q < p.mo.count; ++q) p.mo.base[q] = ep->multi_out->base[q];
+        }
     }
     if (p.ldx < K || p.ldy < K) return GALA_ERR_BAD_SHAPE;
     HubView h = hub_of(plan, g);
@@ -345,6 +353,7 @@ int gala_spmm_f32(const gala_graph_t* g, const float* vals, const float* X, int3
     // (measured, profiles/r01_tiling_*.txt: segment-major only pays when every row still has >= ~100 edges per
     //  segment -- Reddit shape at K = 602: 21.2 -> 19.1 ms; on the Products shape, mean degree 50, it loses)
     if (p.accumulate && p.row_scale) seg_major = false;   // Y_old must not be scaled: keep the single launch
+    if (p.mo.count > 0) seg_major = false;                // rows are pushed once, when they are complete
     // hub rows without a row order: the natural-order fallback decides "hub or not" from the degree it sees, which
     // is per segment in a segment-major launch -- a row could then be run by its hub CTA AND its warp
     if (h.n > 0 && !h.order) seg_major = false;

@@ -436,7 +436,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nss = (p.K + kSK - 1) / kSK;
-    const int64_t ntiles = (p.M + kBM - 1) / kBM;
+    // Every CTA owns one contiguous, equally long range of rows and walks it in 128-row tiles (the last one partial):
+    // the bytes per CTA are equal whatever M is.  (Round-robin over fixed 128-row tiles left the last wave mostly empty
+    // when a rank holds only ~1.5 tiles per SM: 228 tiles on 148 CTAs at 8 GPUs.)
+    const int64_t rows_per_cta = ((p.M + gridDim.x - 1) / gridDim.x + 7) & ~int64_t(7);
+    const int64_t row_lo = min(p.M, (int64_t)blockIdx.x * rows_per_cta), row_hi = min(p.M, row_lo + rows_per_cta);
+    const uint32_t my_tiles = (uint32_t)((row_hi - row_lo + kBM - 1) / kBM);
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -485,7 +490,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    v[i] = (kok && wrow0 + i < p.M) ? __ldg(reinterpret_cast<const float2*>(xc + (uint64_t)i * pitch)) : zero2;
+                    v[i] = (kok && wrow0 + i < row_hi) ? __ldg(reinterpret_cast<const float2*>(xc + (uint64_t)i * pitch)) : zero2;
             }
         };
         auto store_ss = [&](uint32_t g, const float2 (&v)[16]) {
@@ -533,15 +538,14 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
 #ifndef GALA_LINEAR_REGBUF
 #define GALA_LINEAR_REGBUF 2
 #endif
-        const uint32_t my_tiles = blockIdx.x < ntiles ? (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
         const uint32_t total = my_tiles * (uint32_t)nss;
         auto load_g = [&](uint32_t g, float2 (&v)[16]) {
             if (g >= total) return;
             const uint32_t it = g / (uint32_t)nss;
             const int ss = (int)(g - it * (uint32_t)nss);
-            const int64_t wrow0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + warp * 16;
+            const int64_t wrow0 = row_lo + (int64_t)it * kBM + warp * 16;
             const char* xlane = reinterpret_cast<const char*>(p.X + wrow0 * p.K + 2 * lane);
-            load_ss(xlane, wrow0 + 16 <= p.M, wrow0, ss, v);
+            load_ss(xlane, wrow0 + 16 <= row_hi, wrow0, ss, v);
         };
 #if GALA_LINEAR_REGBUF == 3
         float2 vc[16];
@@ -572,7 +576,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(NPAD);
             uint32_t g = 0, it = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            for (; it < my_tiles; ++it) {
                 const uint32_t aset = it & 1;
                 if (it >= 2) mbar_wait(&acce_bar[aset], ((it >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -608,11 +612,11 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
         // ------------------------------- epilogue warps -------------------------------------------
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
         uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        for (; it < my_tiles; ++it) {
             const uint32_t aset = it & 1;
             mbar_wait(&accf_bar[aset], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int64_t r = tile * kBM + q * 32 + lane;
+            const int64_t r = row_lo + (int64_t)it * kBM + q * 32 + lane;
             float acc[NPAD];
 #pragma unroll
             for (int n = 0; n < NPAD; ++n) acc[n] = 0.0f;
@@ -633,7 +637,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acce_bar[aset]);        // the accumulator set may be overwritten
             float a0 = p.att_b_dev ? __ldg(p.att_b_dev) : p.att_b0, a1 = p.att_b_dev ? __ldg(p.att_b_dev + 1) : p.att_b1;
-            if (r < p.M) {
+            if (r < row_hi) {
                 const float rscale = p.row_scale ? __ldg(p.row_scale + r) : 1.0f;
 #pragma unroll
                 for (int n = 0; n < NPAD; ++n) {
@@ -666,11 +670,11 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
                     if (n < p.N) *reinterpret_cast<float4*>(&st[lane][n]) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
                 __syncwarp();
                 const int vec_per_row = p.N >> 2;
-                const int64_t tile_row0 = tile * kBM + q * 32;
+                const int64_t tile_row0 = row_lo + (int64_t)it * kBM + q * 32;
                 for (int idx = lane; idx < 32 * vec_per_row; idx += 32) {
                     const int rr = idx / vec_per_row, cv = idx - rr * vec_per_row;
                     const int64_t row = tile_row0 + rr;
-                    if (row < p.M) {
+                    if (row < row_hi) {
                         const float4 v = *reinterpret_cast<const float4*>(&st[rr][cv * 4]);
                         Vec<4> o;
                         o.v[0] = v.x; o.v[1] = v.y; o.v[2] = v.z; o.v[3] = v.w;
@@ -679,7 +683,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
                     }
                 }
                 __syncwarp();
-            } else if (r < p.M) {
+            } else if (r < row_hi) {
                 float* yrow = p.Y + r * p.N;
 #pragma unroll
                 for (int n = 0; n < NPAD; ++n)
@@ -1053,11 +1057,9 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
         }
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // the persistent variant runs one CTA per SM: with fewer than ~3 tiles per CTA its last wave is mostly empty
-    // (a rank's 228 tiles on 148 CTAs at 8 GPUs: 65 % efficiency); the 2-CTA/SM kernel covers those in one wave
     const int64_t ntiles = (M + kBM - 1) / kBM;
     const bool v2 = (K % 2 == 0) && (reinterpret_cast<uintptr_t>(X) % 8 == 0) && (reinterpret_cast<uintptr_t>(W) % 8 == 0) &&
-                    ntiles >= 3 * (int64_t)device_sm_count();
+                    M >= 4 * kBM;
     if (v2) {
         if (N <= 16) return launch_linear_v2<16>(p, st);
         if (N <= 32) return launch_linear_v2<32>(p, st);

@@ -474,7 +474,9 @@ class PartitionedGCNN:
         self.px = None
         self.exchange = "nccl"
         if exchange in ("p2p", "p2p-needed"):
-            self.px = PeerExchange(part, [model.dims[i + 1] for i in range(model.L - 1)], device, need_mask=need_mask)
+            # one buffer per hidden transform, plus one for the aggregated rows the last layer gathers
+            self.px = PeerExchange(part, [model.dims[i + 1] for i in range(model.L - 1)] + [model.dims[-2]], device,
+                                   need_mask=need_mask)
             self.exchange = ("p2p-needed" if need_mask is not None else
                              "p2p-multicast" if self.px.mos[0].multicast_base else "p2p")
 
@@ -496,10 +498,18 @@ class PartitionedGCNN:
             px.barrier(i)
             mark(f"exchange{i + 1}")
             rs = self.norm2 if i == m.L - 2 else self.norm
-            res_loc = run(f"gcn_aggregate{i + 1}", lambda: ops.spmm(self.graph, px.bufs[i], row_scale=rs, relu=True))
-            mark(f"gcn_aggregate{i + 1}")
-        y_all = part.all_gather(res_loc)
-        mark(f"all_gather{m.L}")
+            if i == m.L - 2:
+                # the last hidden aggregation pushes its finished rows to the GPUs that gather them (same fused
+                # exchange as the transforms) instead of an NCCL all-gather of its output
+                run(f"gcn_aggregate{i + 1}", lambda: ops.spmm(self.graph, px.bufs[i], row_scale=rs, relu=True,
+                                                             multi_out=px.mos[m.L - 1]))
+                mark(f"gcn_aggregate{i + 1}+push")
+            else:
+                res_loc = run(f"gcn_aggregate{i + 1}", lambda: ops.spmm(self.graph, px.bufs[i], row_scale=rs, relu=True))
+                mark(f"gcn_aggregate{i + 1}")
+        px.barrier(m.L - 1)
+        y_all = px.bufs[m.L - 1]
+        mark(f"exchange{m.L}")
         agg = run(f"gcn_aggregate{m.L}", lambda: ops.spmm(self.graph, y_all, row_scale=self.norm))
         mark(f"gcn_aggregate{m.L}")
         out = run("classifier", lambda: ops.dense(agg, *m.fc[-1]))

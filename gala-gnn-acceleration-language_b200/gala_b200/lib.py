@@ -40,7 +40,8 @@ class GalaPlan(C.Structure):
 
 class GalaEpilogue(C.Structure):
     _fields_ = [("row_scale", C.c_void_p), ("col_scale", C.c_void_p), ("accumulate", C.c_int32),
-                ("relu", C.c_int32), ("schedule", C.c_int32), ("ldx", C.c_int64), ("ldy", C.c_int64)]
+                ("relu", C.c_int32), ("schedule", C.c_int32), ("ldx", C.c_int64), ("ldy", C.c_int64),
+                ("multi_out", C.c_void_p)]
 
 
 class GalaMultiOut(C.Structure):

@@ -126,11 +126,19 @@ def _gather_operand(X, pad):
 
 
 def spmm(g, X, vals=None, out=None, row_scale=None, col_scale=None, accumulate=False, relu=False, schedule="auto",
-         pad="auto"):
+         pad="auto", multi_out=None):
     """Y = A @ X (optionally weighted / scaled / accumulated / ReLU'd).  One launch, or -- for
     column-tiled graphs whose feature matrix exceeds the L2 -- one launch per column segment.
     X and out may be row-pitched views; pad=None gathers packed odd-width rows as they are (scalar loads)."""
     X, K, ldx = _gather_operand(X, pad)
+    if multi_out is not None:      # the finished rows are pushed into every GPU's gathered buffer instead of `out`
+        ep = _l.GalaEpilogue(row_scale=row_scale.data_ptr() if row_scale is not None else None,
+                             col_scale=col_scale.data_ptr() if col_scale is not None else None,
+                             accumulate=0, relu=int(relu), schedule=SCHEDULES["row_major"], ldx=ldx, ldy=K,
+                             multi_out=C.addressof(multi_out))
+        _l.check(_l.load().gala_spmm_f32(C.byref(g.c), _l.ptr(vals), _dptr(X), K, None, C.byref(ep), g._p(),
+                                         _l.stream_ptr()))
+        return None
     if out is None:
         out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
         assert not accumulate, "accumulate needs a caller-provided output"

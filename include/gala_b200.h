@@ -109,6 +109,8 @@ typedef struct gala_epilogue {
                                pitch 44: the reference's K % 32 remainder kernels,
                                cuda.h:58-168, become one pass); gala_pad_rows_f32 re-pitches  */
     int64_t ldy;            /* row pitch of Y in elements; 0 = K                              */
+    const struct gala_multi_out *multi_out; /* nullable: the finished rows go to every GPU (packed, pitch K)
+                               instead of Y -- see gala_multi_out_t below                     */
 } gala_epilogue_t;
 #define GALA_SCHEDULE_AUTO 0
 #define GALA_SCHEDULE_ROW_MAJOR 1
