@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "edge_ops.cuh"
+#include "edge_tiles.cuh"
 #include "plan.cuh"
 #include "spmm.cuh"
 
@@ -250,9 +251,13 @@ const char* gala_b200_error_string(int code) {
     }
 }
 
+static size_t plan_tiles(const gala_graph_t* g) {   // edge tiles of a single-segment graph (0: no table)
+    return (g->segments == 1 && g->nvals > 0 && g->nvals <= 0x7fffffffLL) ? (size_t)((g->nvals + kTileEdges - 1) / kTileEdges) : 0;
+}
+
 size_t gala_plan_workspace_bytes(const gala_graph_t* g) {
     if (!g || g->nrows < 0) return 0;
-    return (2 * (size_t)g->nrows + 4 + 2 * kPlanBins) * sizeof(int32_t);
+    return (2 * (size_t)g->nrows + 4 + 2 * kPlanBins + 2 * (plan_tiles(g) + 1) + 4) * sizeof(int32_t);
 }
 
 int gala_plan_build(const gala_graph_t* g, int32_t hub_threshold, void* workspace, size_t workspace_bytes,
@@ -271,8 +276,19 @@ int gala_plan_build(const gala_graph_t* g, int32_t hub_threshold, void* workspac
     plan->n_hub = 0;
     plan->n_ordered = g->nrows;
     plan->hub_threshold = hub_threshold;
+    plan->tile_rows = nullptr;
+    plan->n_tiles = 0;
+    plan->tile_edges = kTileEdges;
     if (g->nrows == 0) return GALA_OK;
     cudaStream_t st = S(stream);
+    if (const size_t nt = plan_tiles(g)) {   // (first row, first edge) of every edge tile: one binary search per tile
+        int* tile_rows = cursor + kPlanBins;
+        tile_rows += (4 - ((reinterpret_cast<uintptr_t>(tile_rows) / 4) & 3)) & 3;   // 16-byte aligned pairs
+        plan_tiles_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, st>>>(g->offsets, g->nrows, (int)nt,
+                                                                            reinterpret_cast<int2*>(tile_rows));
+        plan->tile_rows = tile_rows;
+        plan->n_tiles = (int)nt;
+    }
     cudaError_t e = cudaMemsetAsync(ws, 0, 4 * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(hist, 0, 2 * kPlanBins * sizeof(int), st);
@@ -575,6 +591,45 @@ int gala_spmm_sampled_f32(const gala_graph_t* g, const float* vals, const float*
     return last_error();
 }
 
+// Edge-parallel form (edge_tiles.cuh) of a streaming edge kernel: single-segment graph, a plan that carries the tile
+// table, 16-byte aligned edge arrays (bulk copies).  Returns false when the row-structured kernel must run instead.
+extern "C++" {
+template <int OP>
+static bool launch_tiles(const gala_graph_t* g, const gala_plan_t* plan, TileParams& tp, cudaStream_t st, int* rc) {
+#ifdef GALA_NO_EDGE_TILES
+    return false;
+#endif
+    if (!plan || !plan->tile_rows || plan->tile_edges != kTileEdges || g->segments != 1 || g->nvals <= 0) return false;
+    if (plan->n_tiles != (int)((g->nvals + kTileEdges - 1) / kTileEdges)) return false;
+    if (!aligned(tp.a, 16) || (tp.b && !aligned(tp.b, 16)) || (tp.out && !aligned(tp.out, 16))) return false;
+    if (!aligned(g->offsets, 16) || !aligned(plan->tile_rows, 8)) return false;
+    tp.offsets = g->offsets;
+    tp.tiles = reinterpret_cast<const int2*>(plan->tile_rows);
+    tp.nrows = g->nrows;
+    tp.n_tiles = plan->n_tiles;
+    tp.nvals = (int)g->nvals;
+    const size_t smem = kTileStages * tile_stage_bytes(OP);
+    const int per_sm = tile_narr(OP) == 1 ? 2 : 1;           // persistent CTAs: what the shared-memory ring allows
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)std::min<int64_t>(plan->n_tiles, (int64_t)sms * per_sm);
+    const int64_t deg = g->nvals / std::max(g->nrows, 1);    // lanes per row follow the mean degree
+    auto go = [&](auto kern) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            kern<<<grid, kTileThreads, smem, st>>>(tp);
+            e = cudaGetLastError();
+        }
+        *rc = e == cudaSuccess ? GALA_OK : (int)e;
+    };
+    if (deg >= 96) go(edge_tile_kernel<OP, 32>);
+    else if (deg >= 32) go(edge_tile_kernel<OP, 16>);
+    else if (deg >= 12) go(edge_tile_kernel<OP, 8>);
+    else go(edge_tile_kernel<OP, 4>);
+    return true;
+}
+}  // extern "C++"
+
 static int edge_common(const gala_graph_t* g, const gala_plan_t* plan, EdgeParams& p, dim3& grid) {
     if (int rc = check_graph(g)) return rc;
     std::memset(&p, 0, sizeof(p));
@@ -598,6 +653,14 @@ int gala_edge_rowsum_f32(const gala_graph_t* g, const float* vals, float* out, f
     const bool v4 = aligned(vals, 16);
     // reference: `local_C = 1e-12` once per segment, then C += local_C (cuda.h:512-522)
     p.seed = (float)g->segments * seed;
+    {
+        TileParams tp = {};
+        tp.a = vals;
+        tp.row_out = out;
+        tp.seed = p.seed;
+        int rc = GALA_OK;
+        if (launch_tiles<TILE_ROWSUM>(g, plan, tp, S(stream), &rc)) return rc;
+    }
     if (v4) edge_rowsum_kernel<true><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     else edge_rowsum_kernel<false><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     return last_error();
@@ -613,6 +676,14 @@ int gala_edge_scale_rows_f32(const gala_graph_t* g, float* vals, const float* ro
     p.a = rowval;
     p.out = vals;
     const bool v4 = aligned(vals, 16);
+    {
+        TileParams tp = {};
+        tp.a = vals;
+        tp.out = vals;
+        tp.row_in = rowval;
+        int rc = GALA_OK;
+        if (launch_tiles<TILE_SCALE>(g, plan, tp, S(stream), &rc)) return rc;
+    }
     if (v4) edge_scale_kernel<true><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     else edge_scale_kernel<false><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     return last_error();
@@ -649,6 +720,15 @@ int gala_edge_softmax_fwd_f32(const gala_graph_t* g, const float* x, float* alph
     p.out2 = recip;
     const bool v4 = aligned(x, 16) && aligned(alpha, 16);
     p.seed = (float)g->segments * 1e-12f;
+    {
+        TileParams tp = {};
+        tp.a = x;
+        tp.out = alpha;
+        tp.row_out = recip;
+        tp.seed = p.seed;
+        int rc = GALA_OK;
+        if (launch_tiles<TILE_SOFTMAX_FWD>(g, plan, tp, S(stream), &rc)) return rc;
+    }
     if (v4) edge_softmax_fwd_kernel<true><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     else edge_softmax_fwd_kernel<false><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     return last_error();
@@ -666,6 +746,15 @@ int gala_edge_softmax_bwd_f32(const gala_graph_t* g, const float* alpha, const f
     p.out = out;
     p.seed = (float)g->segments * 1e-12f;
     const bool v4 = aligned(alpha, 16) && aligned(dalpha, 16) && aligned(out, 16);
+    {
+        TileParams tp = {};
+        tp.a = alpha;
+        tp.b = dalpha;
+        tp.out = out;
+        tp.seed = p.seed;
+        int rc = GALA_OK;
+        if (launch_tiles<TILE_SOFTMAX_BWD>(g, plan, tp, S(stream), &rc)) return rc;
+    }
     if (v4) edge_softmax_bwd_kernel<true><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     else edge_softmax_bwd_kernel<false><<<grid, kCtaThreads, 0, S(stream)>>>(p);
     return last_error();

@@ -48,7 +48,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define GALA_B200_ABI_VERSION 2   /* v2: row pitches ldx / ldy, gala_pad_rows_f32 */
+#define GALA_B200_ABI_VERSION 3   /* v2: row pitches ldx / ldy, gala_pad_rows_f32; v3: edge tiles in gala_plan_t */
 
 #define GALA_OK 0
 #define GALA_ERR_NULL_POINTER (-1)
@@ -78,6 +78,14 @@ typedef struct gala_graph {
  * a block carry rows of equal length and long rows are scheduled first).  Built
  * once per graph on the device, reused by every call.  All kernels accept
  * plan == NULL (pure warp-per-row in natural row order).
+ *
+ * Edge tiles (single-segment graphs): the edge arrays cut into spans of `tile_edges`
+ * consecutive edges, tile t owning the rows that start inside it (an nnz split of the
+ * rows, cf. nnz_ord_row_tile_info, src/ops/tiling.h:1656-1708).  With them the streaming
+ * edge kernels (row sum, row scaling, edge-softmax forward / backward) run
+ * edge-parallel: persistent thread blocks stage tile after tile in shared memory with
+ * bulk copies, whatever the degree distribution.  tile_rows == NULL: row-structured
+ * kernels.
  */
 typedef struct gala_plan {
     const int32_t *hub_rows;  /* device, [n_hub]: rows run by a whole CTA              */
@@ -85,6 +93,10 @@ typedef struct gala_plan {
     int32_t n_hub;
     int32_t n_ordered;        /* == nrows - n_hub                                      */
     int32_t hub_threshold;
+    const int32_t *tile_rows; /* device, [2 * (n_tiles + 1)]: (first row, first edge) of every edge
+                                 tile, closed by (nrows, nvals); 8-byte aligned; or NULL        */
+    int32_t n_tiles;          /* ceil(nvals / tile_edges)                              */
+    int32_t tile_edges;       /* edges per tile the table was built for                */
 } gala_plan_t;
 
 /* Fused epilogue / prologue of the SpMM (all fields optional):                   */
