@@ -279,6 +279,7 @@ int gala_plan_build(const gala_graph_t* g, int32_t hub_threshold, void* workspac
     plan->tile_rows = nullptr;
     plan->n_tiles = 0;
     plan->tile_edges = kTileEdges;
+    plan->tile_policy = GALA_TILES_AUTO;
     if (g->nrows == 0) return GALA_OK;
     cudaStream_t st = S(stream);
     if (const size_t nt = plan_tiles(g)) {   // (first row, first edge) of every edge tile: one binary search per tile
@@ -609,11 +610,16 @@ static bool launch_tiles(const gala_graph_t* g, const gala_plan_t* plan, TilePar
     tp.n_tiles = plan->n_tiles;
     tp.nvals = (int)g->nvals;
     const size_t smem = kTileStages * tile_stage_bytes(OP);
-    const int per_sm = tile_narr(OP) == 1 ? 2 : 1;           // persistent CTAs: what the shared-memory ring allows
+    const int per_sm = tile_ctas_per_sm(OP);                 // persistent CTAs: what the shared-memory ring allows
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)std::min<int64_t>(plan->n_tiles, (int64_t)sms * per_sm);
     const int64_t deg = g->nvals / std::max(g->nrows, 1);    // lanes per row follow the mean degree
+    // Measured on B200 (profiles/r02_edge_tiles.txt): the tile pipeline wins 2-3x on short-row graphs (Products shape,
+    // mean degree 50: softmax 1.04 -> 0.44 ms) and for the reduction-free row scaling on every shape (Reddit 0.22 ->
+    // 0.17 ms, 81 % of the HBM peak); with rows of hundreds of edges the one-warp-per-row loops inside a tile are the
+    // long pole and the row-structured kernels (LPT row order, 64 warps per SM) are as fast or faster.
+    if (plan->tile_policy != GALA_TILES_ALWAYS && OP != TILE_SCALE && deg >= 96) return false;
     auto go = [&](auto kern) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) {

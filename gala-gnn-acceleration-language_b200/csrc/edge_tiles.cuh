@@ -6,18 +6,19 @@
 // tiles of kTileEdges consecutive edges; tile t owns the rows that START inside [t*kTileEdges, (t+1)*kTileEdges)
 // (plan->tile_rows, a binary search per tile on the row pointers at plan time -- cf. the nnz split of
 // nnz_ord_row_tile_info, reference src/ops/tiling.h:1656-1708), so a tile's edges are one contiguous, disjoint span
-// of the edge arrays whatever the degree distribution.  Persistent CTAs walk the tiles round-robin through a
-// two-stage shared-memory ring:
-//   1. one elected thread moves the next tile's span AND its row pointers global -> shared memory with 1-D bulk
-//      copies (cp.async.bulk, the TMA engine: no registers, completion on the stage's mbarrier) while the CTA works on
-//      the current tile;
-//   2. the rows of the tile are reduced and rescaled IN shared memory by groups of G lanes (G follows the mean
-//      degree, so short-row graphs keep their lanes busy);
-//   3. the finished span goes back with one bulk store (16-byte aligned interior) plus <= 6 scalar stores.
-// Every edge array is read once and written once from / to HBM with full-line accesses, independent of row length, and
-// no global-memory latency sits between the phases of a tile.
+// of the edge arrays whatever the degree distribution.  Persistent, warp-specialised CTAs walk the tiles round-robin
+// through a three-stage shared-memory ring:
+//   producer warp   moves each tile's span AND its row pointers global -> shared memory with 1-D bulk copies
+//                   (cp.async.bulk, the TMA engine: no registers, completion on the stage's "full" mbarrier), two tiles
+//                   ahead of the consumers, and writes every finished span back with one bulk store (16-byte aligned
+//                   interior) plus <= 6 scalar stores once the consumers have arrived on the stage's "done" mbarrier;
+//   16 consumer warps  a flat, row-agnostic pass for the per-edge arithmetic (exp / products), then the rows of the
+//                   tile reduced and rescaled IN shared memory by groups of G lanes (G follows the mean degree).
+// Every edge array is read once and written once from / to HBM with full-line accesses, independent of row length,
+// and no global-memory latency sits between the phases of a tile.
 // Rows that do not fit the staged window (longer than the window, or behind such a row in the same tile) are
-// processed by the whole CTA straight from global memory, two passes, like a hub row of the row-structured kernels.
+// processed by the consumer warps together, straight from global memory, two passes, like a hub row of the
+// row-structured kernels.
 // Single-segment graphs only (the GAT schedules: col_tile >= ncols); column-tiled graphs keep the row-structured form.
 #pragma once
 #include "edge_ops.cuh"
@@ -25,17 +26,28 @@
 namespace gala {
 
 constexpr int kTileEdges = 4096;   // edges per tile == gala_plan_t.tile_edges
-constexpr int kTileCap = 12288;    // staged window, floats per edge array: a row of <= 8192 edges always fits
+constexpr int kTileCap = 8192;     // staged window, floats per edge array: a row of <= 4096 edges always fits
 constexpr int kTileRowCap = 1024;  // row pointers staged per tile; rows beyond read theirs from global memory
-constexpr int kTileStages = 2;
-constexpr int kTileThreads = 512;
+#ifndef GALA_TILE_STAGES
+#define GALA_TILE_STAGES 3
+#endif
+constexpr int kTileStages = GALA_TILE_STAGES;
+constexpr int kTileConsumers = 512;                  // 16 consumer warps
+constexpr int kTileThreads = kTileConsumers + 32;    // + the producer warp
 constexpr int kBatch = 8;          // shared-memory loads in flight per thread in the tile loops
 
 enum : int { TILE_ROWSUM = 0, TILE_SCALE = 1, TILE_SOFTMAX_FWD = 2, TILE_SOFTMAX_BWD = 3 };
 
 __host__ __device__ constexpr int tile_narr(int op) { return op == TILE_SOFTMAX_BWD ? 2 : 1; }   // staged edge arrays
+__host__ __device__ constexpr size_t tile_stage_bytes(int op);
+__host__ __device__ constexpr int tile_ctas_per_sm(int op);
 __host__ __device__ constexpr size_t tile_stage_bytes(int op) {
     return (size_t)tile_narr(op) * kTileCap * 4 + (size_t)(kTileRowCap + 8) * 4;
+}
+
+// persistent CTAs per SM: what the shared-memory ring leaves room for (227 KB per SM, 1 KB reserved per CTA)
+__host__ __device__ constexpr int tile_ctas_per_sm(int op) {
+    return 2 * (kTileStages * tile_stage_bytes(op) + 2048) <= 227 * 1024 ? 2 : 1;
 }
 
 struct TileParams {
@@ -83,20 +95,20 @@ __device__ __forceinline__ float group_sum(float x, unsigned mask) {
     return x;
 }
 
-// Sum over the CTA's warps in warp order -- all threads get the total.
-__device__ __forceinline__ float tile_cta_sum(float warp_total) {
-    __shared__ float s_part[kTileThreads / 32];
+// Sum over the consumer warps in warp order -- all of their threads get the total.
+__device__ __forceinline__ float tile_cta_sum(float warp_total) {   // consumer warps only (named barrier 1)
+    __shared__ float s_part[kTileConsumers / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) s_part[warp] = warp_total;
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory");
     float t = 0.0f;
 #pragma unroll
-    for (int w = 0; w < kTileThreads / 32; ++w) t += s_part[w];
-    __syncthreads();
+    for (int w = 0; w < kTileConsumers / 32; ++w) t += s_part[w];
+    asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory");
     return t;
 }
 
-// Visit the edges [e0, e1) with the whole CTA: 128-bit accesses over the 16-byte aligned body, scalar head and tail.
+// Visit the edges [e0, e1) with all consumer warps: 128-bit accesses over the 16-byte aligned body, scalar head and tail.
 template <class FS, class FV>
 __device__ __forceinline__ void cta_edges(int e0, int e1, FS&& scalar, FV&& vec4) {
     const int tid = threadIdx.x;
@@ -104,7 +116,7 @@ __device__ __forceinline__ void cta_edges(int e0, int e1, FS&& scalar, FV&& vec4
     const int a1 = max(a0, e1 & ~3);
     if (e0 + tid < a0) scalar(e0 + tid);
 #pragma unroll 2
-    for (int e = a0 + tid * 4; e < a1; e += kTileThreads * 4) vec4(e);
+    for (int e = a0 + tid * 4; e < a1; e += kTileConsumers * 4) vec4(e);
     if (a1 + tid < e1) scalar(a1 + tid);
 }
 
@@ -150,73 +162,109 @@ __device__ __forceinline__ TileGeom tile_geom(const TileParams& p, int2 m0, int2
     return g;
 }
 
+// First row of the tile whose edges reach past the staged window (offsets[r + 1] > w_end); exists when ee > w_end.
+__device__ __forceinline__ int tile_split_row(const int* __restrict__ offsets, const TileGeom& g, int w_end) {
+    int lo = g.r_begin, hi = g.r_end - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid + 1) > w_end) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
 template <int OP, int G>
-__global__ void __launch_bounds__(kTileThreads) edge_tile_kernel(const __grid_constant__ TileParams p) {
+__global__ void __launch_bounds__(kTileThreads, tile_ctas_per_sm(OP))
+edge_tile_kernel(const __grid_constant__ TileParams p) {
     constexpr int NARR = tile_narr(OP);
     constexpr bool kSum = OP != TILE_SCALE;                            // a row reduction precedes the output
     constexpr bool kEdgeOut = OP != TILE_ROWSUM;
-    constexpr int SLOTS = kTileThreads / G;
+    constexpr bool kFlat = OP == TILE_SOFTMAX_FWD || OP == TILE_SOFTMAX_BWD;
+    constexpr int SLOTS = kTileConsumers / G;
+    constexpr int RB = G >= 32 ? kBatch : 4;                           // loads in flight per lane in the row loops
     extern __shared__ __align__(128) unsigned char s_raw[];            // kTileStages x [NARR windows | row pointers]
-    __shared__ __align__(8) uint64_t s_bar[kTileStages];
-    __shared__ int s_split[kTileStages];
+    __shared__ __align__(8) uint64_t s_full[kTileStages], s_done[kTileStages];
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int sub = lane % G;
-    const unsigned gmask = G == 32 ? kFull : (((1u << G) - 1u) << (lane - sub));
     auto win = [&](int s) { return reinterpret_cast<float*>(s_raw + (size_t)s * tile_stage_bytes(OP)); };
     auto offs = [&](int s) { return reinterpret_cast<int*>(s_raw + (size_t)s * tile_stage_bytes(OP) + (size_t)NARR * kTileCap * 4); };
-    // tile descriptors are read one iteration before they are needed: no global-memory latency between tiles
-    auto meta = [&](int t) { return t <= p.n_tiles ? __ldg(p.tiles + t) : make_int2(0, 0); };
-
-    // one thread: arm the stage's barrier and start the bulk copies of a tile (an empty tile just completes the phase)
-    auto issue = [&](const TileGeom& g, int s) {
-        const uint32_t bar = tile_smem_u32(&s_bar[s]);
-        if (g.r_begin >= g.r_end || (g.n_bulk == 0 && g.n_off_bulk == 0)) {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-            return;
-        }
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                     "r"((uint32_t)((NARR * g.n_bulk + g.n_off_bulk) * 4))
-                     : "memory");
-        if (g.n_bulk > 0) {
-            tile_bulk_load(win(s), p.a + g.a0, g.n_bulk * 4, &s_bar[s]);
-            if (NARR > 1) tile_bulk_load(win(s) + kTileCap, p.b + g.a0, g.n_bulk * 4, &s_bar[s]);
-        }
-        if (g.n_off_bulk > 0) tile_bulk_load(offs(s), p.offsets + g.ra0, g.n_off_bulk * 4, &s_bar[s]);
-    };
-
+    auto meta = [&](int t) { return __ldg(p.tiles + min(t, p.n_tiles)); };
     const int stride = gridDim.x;
-    int t = blockIdx.x;
-    if (t >= p.n_tiles) return;
-    int2 m_cur0 = meta(t), m_cur1 = meta(t + 1);
-    int2 m_nxt0 = meta(t + stride), m_nxt1 = meta(t + stride + 1);
+    const int first = blockIdx.x;
+    if (first >= p.n_tiles) return;
+    const int n_my = (p.n_tiles - first + stride - 1) / stride;        // tiles of this CTA: first + k * stride
+
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kTileStages; ++s)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tile_smem_u32(&s_bar[s])));
+        for (int s = 0; s < kTileStages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tile_smem_u32(&s_full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tile_smem_u32(&s_done[s])), "r"(kTileConsumers / 32));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        issue(tile_geom(p, m_cur0, m_cur1), 0);
     }
     __syncthreads();
 
-    TileOp<OP> op{0.0f};
-    for (int k = 0; t < p.n_tiles; ++k, t += stride) {
-        const int s = k & 1;
-        const bool more = t + stride < p.n_tiles;
-        const int2 m_far0 = meta(t + 2 * stride), m_far1 = meta(t + 2 * stride + 1);   // consumed next iteration
-        const TileGeom g = tile_geom(p, m_cur0, m_cur1);
-        // the next tile streams in while this one is worked on; its stage was last read by warp 0 (stores of tile k-1)
-        if (tid == 0) {
-            s_split[s] = g.r_end;
-            if (more) {
-                if (kEdgeOut) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                issue(tile_geom(p, m_nxt0, m_nxt1), s ^ 1);
+    if (tid >= kTileConsumers) {
+        // ================= producer warp: bulk loads two tiles ahead, bulk stores of the finished tiles =================
+        auto issue = [&](int k) {   // lane 0: arm the stage's barrier, start the copies (an empty tile completes the phase)
+            const int s = k % kTileStages, t = first + k * stride;
+            const TileGeom g = tile_geom(p, meta(t), meta(t + 1));
+            const uint32_t bar = tile_smem_u32(&s_full[s]);
+            if (g.r_begin >= g.r_end || (g.n_bulk == 0 && g.n_off_bulk == 0)) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+                return;
             }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                         "r"((uint32_t)((NARR * g.n_bulk + g.n_off_bulk) * 4))
+                         : "memory");
+            if (g.n_bulk > 0) {
+                tile_bulk_load(win(s), p.a + g.a0, g.n_bulk * 4, &s_full[s]);
+                if (NARR > 1) tile_bulk_load(win(s) + kTileCap, p.b + g.a0, g.n_bulk * 4, &s_full[s]);
+            }
+            if (g.n_off_bulk > 0) tile_bulk_load(offs(s), p.offsets + g.ra0, g.n_off_bulk * 4, &s_full[s]);
+        };
+        if (lane == 0)
+            for (int k = 0; k < min(kTileStages, n_my); ++k) issue(k);
+        for (int k = 0; k < n_my; ++k) {
+            const int s = k % kTileStages, t = first + k * stride;
+            const TileGeom g = tile_geom(p, meta(t), meta(t + 1));     // (issued before the wait: off its critical path)
+            tile_wait(&s_done[s], (k / kTileStages) & 1);
+            if (kEdgeOut && g.r_begin < g.r_end) {
+                const int w_end = g.a0 + g.n_win;
+                int e_split = g.ee;                                    // edges [eb, e_split) were finished in the window
+                if (g.ee > w_end) e_split = __ldg(p.offsets + tile_split_row(p.offsets, g, w_end));
+                const float* s_a = win(s);
+                const int b0 = min((g.eb + 3) & ~3, e_split), b1 = max(b0, e_split & ~3);
+                if (lane == 0 && b1 > b0) {
+                    tile_bulk_store(p.out + b0, s_a + (b0 - g.a0), (uint32_t)(b1 - b0) * 4u);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (lane < b0 - g.eb) p.out[g.eb + lane] = s_a[g.eb + lane - g.a0];
+                if (lane >= 8 && lane - 8 < e_split - b1) p.out[b1 + lane - 8] = s_a[b1 + lane - 8 - g.a0];
+                __syncwarp();
+                // the store reads the window asynchronously: it must have done so before the stage is refilled / released
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            if (lane == 0 && k + kTileStages < n_my) issue(k + kTileStages);
+            __syncwarp();
         }
-        m_cur0 = m_nxt0; m_cur1 = m_nxt1; m_nxt0 = m_far0; m_nxt1 = m_far1;
-        tile_wait(&s_bar[s], (k >> 1) & 1);
+        return;
+    }
+
+    // ================= consumer warps =================
+    const int sub = lane % G;
+    const unsigned gmask = G == 32 ? kFull : (((1u << G) - 1u) << (lane - sub));
+    auto consumer_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory"); };
+    TileOp<OP> op{0.0f};
+    int2 m0 = meta(first), m1 = meta(first + 1);
+    for (int k = 0; k < n_my; ++k) {
+        const int s = k % kTileStages, t = first + k * stride;
+        const TileGeom g = tile_geom(p, m0, m1);
+        m0 = meta(t + stride); m1 = meta(t + stride + 1);              // next tile's descriptor: consumed one iteration on
+        tile_wait(&s_full[s], (k / kTileStages) & 1);
         if (g.r_begin >= g.r_end) {                                    // tile inside one long row: no row starts here
-            __syncthreads();   // nobody may still be waiting on this stage's barrier when thread 0 re-arms it (tile k+2)
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tile_smem_u32(&s_done[s])) : "memory");
             continue;
         }
         float* s_a = win(s);
@@ -229,66 +277,64 @@ __global__ void __launch_bounds__(kTileThreads) edge_tile_kernel(const __grid_co
             }
             if (tid >= 32 && tid - 32 < g.n_off - g.n_off_bulk)
                 s_off[g.n_off_bulk + tid - 32] = p.offsets[g.ra0 + g.n_off_bulk + tid - 32];
-            __syncthreads();                                           // (CTA-uniform branch) before the flat pass reads them
+            consumer_sync();                                           // (CTA-uniform branch)
         }
         // ---- flat pass, balanced whatever the rows look like: the per-edge arithmetic that needs no row total ----
         // (loads batched ahead of the arithmetic and the stores: eight shared-memory reads in flight per thread)
-        if (OP == TILE_SOFTMAX_FWD || OP == TILE_SOFTMAX_BWD) {
-            for (int i = tid; i < g.n_win; i += kBatch * kTileThreads) {
+        if (kFlat) {
+            for (int i = tid; i < g.n_win; i += kBatch * kTileConsumers) {
                 float va[kBatch], vb[kBatch];
 #pragma unroll
                 for (int u = 0; u < kBatch; ++u) {
-                    const int j = min(i + u * kTileThreads, kTileCap - 1);
+                    const int j = min(i + u * kTileConsumers, kTileCap - 1);
                     va[u] = s_a[j];
                     if (OP == TILE_SOFTMAX_BWD) vb[u] = s_b[j];
                 }
 #pragma unroll
                 for (int u = 0; u < kBatch; ++u)
-                    if (i + u * kTileThreads < g.n_win) {
-                        if (OP == TILE_SOFTMAX_FWD) s_a[i + u * kTileThreads] = softmax_num(va[u]);
-                        else s_b[i + u * kTileThreads] = va[u] * vb[u];
+                    if (i + u * kTileConsumers < g.n_win) {
+                        if (OP == TILE_SOFTMAX_FWD) s_a[i + u * kTileConsumers] = softmax_num(va[u]);
+                        else s_b[i + u * kTileConsumers] = va[u] * vb[u];
                     }
             }
+            consumer_sync();
         }
-        __syncthreads();                                               // flat pass, s_split, tail elements
         const int a0 = g.a0, w_end = g.a0 + g.n_win;
         auto row_ptr = [&](int r) { return r - g.ra0 < g.n_off ? s_off[r - g.ra0] : __ldg(p.offsets + r); };
+        // rows [split, r_end) reach past the window (CTA-uniform; only tiles holding a row longer than the window)
+        const int split = g.ee > w_end ? tile_split_row(p.offsets, g, w_end) : g.r_end;
 
         // ---- rows whose edges lie inside the window: G lanes per row, sums and rescaling in shared memory ----
-        for (int r = g.r_begin + tid / G; r < g.r_end; r += SLOTS) {
+        for (int r = g.r_begin + tid / G; r < split; r += SLOTS) {
             const int lo = row_ptr(r), hi = row_ptr(r + 1);
-            if (hi > w_end) {                                          // this row and all behind it: streamed below
-                if (sub == 0) atomicMin(&s_split[s], r);
-                break;
-            }
             if (OP == TILE_SCALE) op.row_scalar = __ldg(p.row_in + r);
             float tot = 0.0f;
             const int end = hi - a0;
             if (kSum) {
                 const float* src = OP == TILE_SOFTMAX_BWD ? s_b : s_a;
                 float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                for (int i = lo - a0 + sub; i < end; i += kBatch * G) {
-                    float v[kBatch];
+                for (int i = lo - a0 + sub; i < end; i += RB * G) {
+                    float v[RB];
 #pragma unroll
-                    for (int u = 0; u < kBatch; ++u) v[u] = i + u * G < end ? src[i + u * G] : 0.0f;
+                    for (int u = 0; u < RB; ++u) v[u] = i + u * G < end ? src[i + u * G] : 0.0f;
 #pragma unroll
-                    for (int u = 0; u < kBatch; ++u) acc[u & 3] += v[u];
+                    for (int u = 0; u < RB; ++u) acc[u & 3] += v[u];
                 }
                 tot = group_sum<G>((acc[0] + acc[1]) + (acc[2] + acc[3]), gmask) + p.seed;
                 if (OP == TILE_SOFTMAX_FWD) tot = 1.0f / tot;
                 if ((OP == TILE_ROWSUM || OP == TILE_SOFTMAX_FWD) && sub == 0 && p.row_out) p.row_out[r] = tot;
             }
             if (kEdgeOut) {
-                for (int i = lo - a0 + sub; i < end; i += kBatch * G) {
-                    float va[kBatch], vb[kBatch];
+                for (int i = lo - a0 + sub; i < end; i += RB * G) {
+                    float va[RB], vb[RB];
 #pragma unroll
-                    for (int u = 0; u < kBatch; ++u) {
+                    for (int u = 0; u < RB; ++u) {
                         const int j = min(i + u * G, kTileCap - 1);
                         va[u] = s_a[j];
                         if (OP == TILE_SOFTMAX_BWD) vb[u] = s_b[j];
                     }
 #pragma unroll
-                    for (int u = 0; u < kBatch; ++u)
+                    for (int u = 0; u < RB; ++u)
                         if (i + u * G < end) {
                             if (OP == TILE_SOFTMAX_BWD) s_a[i + u * G] = vb[u] - va[u] * tot;   // alpha*dalpha - alpha*tot
                             else s_a[i + u * G] = op.post(va[u], 0.0f, tot);
@@ -296,22 +342,12 @@ __global__ void __launch_bounds__(kTileThreads) edge_tile_kernel(const __grid_co
                 }
             }
         }
+        // hand the stage to the producer warp (bulk store, then the next bulk loads)
         if (kEdgeOut) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> bulk store
-        __syncthreads();
-        const int split = s_split[s];
-        if (kEdgeOut && tid < 32) {   // warp 0 alone touches the stage from here on (it also issues the next copies into it)
-            const int e_split = split < g.r_end ? row_ptr(split) : g.ee;   // edges [eb, e_split) are finished in the window
-            const int b0 = min((g.eb + 3) & ~3, e_split), b1 = max(b0, e_split & ~3);
-            if (tid == 0 && b1 > b0) {
-                tile_bulk_store(p.out + b0, s_a + (b0 - a0), (uint32_t)(b1 - b0) * 4u);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            if (tid < b0 - g.eb) p.out[g.eb + tid] = s_a[g.eb + tid - a0];
-            if (tid >= 8 && tid - 8 < e_split - b1) p.out[b1 + tid - 8] = s_a[b1 + tid - 8 - a0];
-            __syncwarp();
-        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tile_smem_u32(&s_done[s])) : "memory");
 
-        // ---- rows past the window: the whole CTA per row, two passes over global memory ----
+        // ---- rows past the window: all consumer warps per row, two passes over global memory ----
         for (int r = split; r < g.r_end; ++r) {
             const int lo = __ldg(p.offsets + r), hi = __ldg(p.offsets + r + 1);
             if (OP == TILE_SCALE) op.row_scalar = __ldg(p.row_in + r);
@@ -347,8 +383,6 @@ __global__ void __launch_bounds__(kTileThreads) edge_tile_kernel(const __grid_co
             }
         }
     }
-    // the last bulk store reads its window asynchronously: it must have done so before the shared memory goes away
-    if (kEdgeOut && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // tiles[t] = (first row r with offsets[r] >= t * kTileEdges, offsets[r]) for t < n_tiles;  tiles[n_tiles] = (nrows, E).

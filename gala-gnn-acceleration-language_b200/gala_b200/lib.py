@@ -36,7 +36,7 @@ class GalaGraph(C.Structure):
 class GalaPlan(C.Structure):
     _fields_ = [("hub_rows", C.c_void_p), ("row_order", C.c_void_p), ("n_hub", C.c_int32),
                 ("n_ordered", C.c_int32), ("hub_threshold", C.c_int32), ("tile_rows", C.c_void_p),
-                ("n_tiles", C.c_int32), ("tile_edges", C.c_int32)]
+                ("n_tiles", C.c_int32), ("tile_edges", C.c_int32), ("tile_policy", C.c_int32)]
 
 
 class GalaEpilogue(C.Structure):

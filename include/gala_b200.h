@@ -97,7 +97,12 @@ typedef struct gala_plan {
                                  tile, closed by (nrows, nvals); 8-byte aligned; or NULL        */
     int32_t n_tiles;          /* ceil(nvals / tile_edges)                              */
     int32_t tile_edges;       /* edges per tile the table was built for                */
+    int32_t tile_policy;      /* GALA_TILES_AUTO: edge-parallel kernels where they measured
+                                 faster (row scaling; every op when the mean degree is below
+                                 96); GALA_TILES_ALWAYS: whenever the table is usable      */
 } gala_plan_t;
+#define GALA_TILES_AUTO 0
+#define GALA_TILES_ALWAYS 1
 
 /* Fused epilogue / prologue of the SpMM (all fields optional):                   */
 /*   Y[i,:] = act( row_scale[i] * sum_e w_e * col_scale[col_e] * X[col_e,:]       */

@@ -35,6 +35,7 @@ for shape in shapes:
     n, e, *_ = synth.SHAPES[shape]
     offset, ids = synth.powerlaw_csr_torch(n, e, seed=0, device=dev)
     g = ops.TiledGraph(offset, ids, n).build_plan()
+    g.plan.tile_policy = 1      # GALA_TILES_ALWAYS
     gr = ops.TiledGraph(offset, ids, n).build_plan()
     gr.plan.tile_rows = None
     E = g.nvals
@@ -51,6 +52,8 @@ for shape in shapes:
         ("edge_softmax_fwd", 4 * (n + 1) + 8 * E, lambda G: ops.edge_softmax_fwd(G, x, out=out)),
         ("edge_softmax_bwd", 4 * (n + 1) + 12 * E, lambda G: ops.edge_softmax_bwd(G, alpha, da, out=out)),
     ]
+    if os.environ.get("GALA_TILE_SKIP_BWD"):
+        table = table[:3]
     for name, nbytes, fn in table:
         ms_t = t(lambda: fn(g))
         ms_r = t(lambda: fn(gr))

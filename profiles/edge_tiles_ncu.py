@@ -12,6 +12,7 @@ dev = "cuda:0"
 n, e, *_ = synth.SHAPES[sys.argv[1] if len(sys.argv) > 1 else "reddit"]
 offset, ids = synth.powerlaw_csr_torch(n, e, seed=0, device=dev)
 g = ops.TiledGraph(offset, ids, n).build_plan()
+g.plan.tile_policy = 1      # GALA_TILES_ALWAYS
 x = torch.randn(g.nvals, device=dev)
 out = torch.empty_like(x)
 rs = torch.empty(n, 1, device=dev)

@@ -16,7 +16,7 @@ from util import FP32_TOL, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-TILE = 4096     # csrc/edge_tiles.cuh: kTileEdges (window: 12288 edges, 1024 staged row pointers)
+TILE = 4096     # csrc/edge_tiles.cuh: kTileEdges (window: 8192 edges, 1024 staged row pointers)
 
 
 def dev(a):
@@ -74,6 +74,7 @@ def graphs(orc, name):
     tiled = ops.TiledGraph(dev(t.offsets), dev(t.cols), n, n, t.bounds, 1).build_plan(2048)
     rowwise = ops.TiledGraph(dev(t.offsets), dev(t.cols), n, n, t.bounds, 1).build_plan(2048)
     assert tiled.plan.tile_rows and tiled.plan.n_tiles == (t.nvals + TILE - 1) // TILE
+    tiled.plan.tile_policy = 1           # GALA_TILES_ALWAYS: also where the default policy prefers the row-structured kernels
     rowwise.plan.tile_rows = None        # same plan without the tile table: the row-structured kernels run
     return t, tiled, rowwise
 
