@@ -125,6 +125,106 @@ __global__ void __launch_bounds__(256) linear_tiny_kernel(const __grid_constant_
     }
 }
 
+// The same warp-per-row transform with the row epilogues of gala_linear_f32 (row scale, the two attention
+// projections, rows and right-hand attention scalars pushed to every GPU that gathers them).  A LIGHT kernel on
+// purpose -- 256-thread CTAs, < 64 registers, a capped grid: the row-block pipeline of the partitioned runners
+// (dist_gat) runs it on a side stream NEXT TO the gather kernel, and while its peer stores wait on NVLink it must
+// not hold the registers and shared memory the gather needs (the persistent tcgen05 kernel takes 53 K of an SM's
+// 64 K registers).
+struct SmallExParams {
+    SmallParams s;
+    const float* __restrict__ row_scale;
+    const float* __restrict__ att_w;   // [2, N] or nullptr
+    float att_b0, att_b1;
+    float* __restrict__ att_out;       // [2, M]
+    MultiOut mo, att_mo;
+};
+
+template <int KP, bool TWO>   // TWO: N > 32 (a second output column per lane)
+__global__ void __launch_bounds__(256) linear_small_ex_kernel(const __grid_constant__ SmallExParams q) {
+    const SmallParams& p = q.s;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    __shared__ float sW[64 * 65];
+    for (int i = threadIdx.x; i < p.N * p.K; i += blockDim.x) sW[(i / p.K) * (p.K + 1) + (i % p.K)] = __ldg(p.W + i);
+    __syncthreads();
+    float w0[KP], w1[TWO ? KP : 1];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        w0[k] = (lane < p.N && k < p.K) ? sW[lane * (p.K + 1) + k] : 0.0f;
+        if (TWO) w1[k] = (lane + 32 < p.N && k < p.K) ? sW[(lane + 32) * (p.K + 1) + k] : 0.0f;
+    }
+    const float b0 = (p.bias && lane < p.N) ? __ldg(p.bias + lane) : 0.0f;
+    const float b1 = (p.bias && lane + 32 < p.N) ? __ldg(p.bias + lane + 32) : 0.0f;
+    float al0 = 0.0f, al1 = 0.0f, ar0 = 0.0f, ar1 = 0.0f;      // this lane's columns of the two attention vectors
+    if (q.att_w) {
+        if (lane < p.N) { al0 = __ldg(q.att_w + lane); ar0 = __ldg(q.att_w + p.N + lane); }
+        if (lane + 32 < p.N) { al1 = __ldg(q.att_w + lane + 32); ar1 = __ldg(q.att_w + p.N + lane + 32); }
+    }
+    constexpr int R = 4;
+    for (int64_t row0 = warp_global * R; row0 < p.M; row0 += nwarps * R) {
+        float x0[R], x1[R], o0[R], o1[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r;
+            const float* xr = p.X + row * p.K;
+            x0[r] = (row < p.M && lane < p.K) ? ld_stream(xr + lane) : 0.0f;
+            x1[r] = 0.0f;
+            if (KP > 32) x1[r] = (row < p.M && lane + 32 < p.K) ? ld_stream(xr + lane + 32) : 0.0f;
+            o0[r] = b0;
+            o1[r] = b1;
+        }
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float xk = __shfl_sync(kFull, k < 32 ? x0[r] : x1[r], k & 31);
+                o0[r] = fmaf(xk, w0[k], o0[r]);
+                if (TWO) o1[r] = fmaf(xk, w1[k], o1[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r;
+            if (row >= p.M) break;                                   // (warp-uniform)
+            float a = o0[r], c = o1[r];
+            if (q.att_w) {   // projections of the pre-activation, unscaled row, as in gala_linear_f32
+                const float aL = warp_sum(fmaf(a, al0, c * al1)) + q.att_b0;
+                const float aR = warp_sum(fmaf(a, ar0, c * ar1)) + q.att_b1;
+                if (lane == 0) {
+                    q.att_out[row] = aL;
+                    q.att_out[p.M + row] = aR;
+                    if (q.att_mo.count > 0) {
+                        Vec<1> o;
+                        o.v[0] = aR;
+                        multi_store<1>(q.att_mo, row, o, row);
+                    }
+                }
+            }
+            if (q.row_scale) {
+                const float rs = __ldg(q.row_scale + row);
+                a *= rs;
+                c *= rs;
+            }
+            if (p.relu) {
+                a = fmaxf(a, 0.0f);
+                c = fmaxf(c, 0.0f);
+            }
+            Vec<1> va, vc;
+            va.v[0] = a;
+            vc.v[0] = c;
+            if (q.mo.count > 0) {                                    // 32 lanes x 4 bytes: one 128-byte line per peer
+                if (lane < p.N) multi_store<1>(q.mo, row * p.N + lane, va, row);
+                if (lane + 32 < p.N) multi_store<1>(q.mo, row * p.N + lane + 32, vc, row);
+            } else {
+                if (lane < p.N) st_stream(p.Y + row * p.N + lane, a);
+                if (lane + 32 < p.N) st_stream(p.Y + row * p.N + lane + 32, c);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int gala_linear_small_f32(const float* X, int64_t M, int32_t K, const float* W, const float* bias, int32_t N,
@@ -151,6 +251,59 @@ extern "C" int gala_linear_small_f32(const float* X, int64_t M, int32_t K, const
     else if (N <= 4) linear_tiny_kernel<4><<<(unsigned)std::min<int64_t>((M + 63) / 64, 148 * 8), 256, 0, st>>>(p);
     else if (K <= 32) linear_small_kernel<32><<<grid, 256, 0, st>>>(p);
     else linear_small_kernel<64><<<grid, 256, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GALA_OK : (int)e;
+}
+
+
+extern "C" int gala_linear_small_ex_f32(const float* X, int64_t M, int32_t K, const float* W, const float* bias, int32_t N,
+                                        float* Y, const float* row_scale, int32_t relu, const float* att_w,
+                                        const float* att_b, float* att_out, const gala_multi_out_t* multi_out,
+                                        const gala_multi_out_t* att_multi_out, int32_t max_ctas, gala_stream_t stream) {
+    if (M < 0 || K <= 0 || N <= 0) return GALA_ERR_BAD_SHAPE;
+    if (K > 64 || N > 64) return GALA_ERR_UNSUPPORTED;
+    if (M == 0) return GALA_OK;
+    const bool multi = multi_out && multi_out->count > 0;
+    if (!X || !W || (!Y && !multi) || (att_w && (!att_b || !att_out))) return GALA_ERR_NULL_POINTER;
+    if (multi && multi_out->count > kMaxPeers) return GALA_ERR_UNSUPPORTED;
+    SmallExParams q;
+    std::memset(&q, 0, sizeof(q));
+    q.s.X = X;
+    q.s.W = W;
+    q.s.bias = bias;
+    q.s.Y = Y;
+    q.s.M = M;
+    q.s.K = K;
+    q.s.N = N;
+    q.s.relu = relu;
+    q.row_scale = row_scale;
+    q.att_w = att_w;
+    q.att_out = att_out;
+    if (att_w) {
+        q.att_b0 = att_b[0];
+        q.att_b1 = att_b[1];
+    }
+    if (multi) {
+        q.mo.count = multi_out->count;
+        q.mo.mc_base = multi_out->multicast_base;
+        q.mo.need = multi_out->need_mask;
+        for (int i = 0; i < multi_out->count; ++i) q.mo.base[i] = multi_out->base[i];
+    }
+    if (att_multi_out && att_multi_out->count > 0) {
+        if (!att_w || att_multi_out->count > kMaxPeers) return GALA_ERR_UNSUPPORTED;
+        q.att_mo.count = att_multi_out->count;
+        q.att_mo.mc_base = att_multi_out->multicast_base;
+        q.att_mo.need = att_multi_out->need_mask;
+        for (int i = 0; i < att_multi_out->count; ++i) q.att_mo.base[i] = att_multi_out->base[i];
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t warps_needed = (M + 3) / 4;
+    int64_t cap = max_ctas > 0 ? max_ctas : 148 * 2;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, cap));
+    if (K <= 32 && N <= 32) linear_small_ex_kernel<32, false><<<grid, 256, 0, st>>>(q);
+    else if (K <= 32) linear_small_ex_kernel<32, true><<<grid, 256, 0, st>>>(q);
+    else if (N <= 32) linear_small_ex_kernel<64, false><<<grid, 256, 0, st>>>(q);
+    else linear_small_ex_kernel<64, true><<<grid, 256, 0, st>>>(q);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GALA_OK : (int)e;
 }

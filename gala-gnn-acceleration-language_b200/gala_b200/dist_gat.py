@@ -281,6 +281,7 @@ class PeerExchange:
         self.part = part
         self.bufs, self.hdls, self.mos = [], [], []
         self.att_bufs, self.att_mos = [], []
+        self._addr = []      # per exchange: (peer bases of the rows, multicast base, peer bases of the scalars, multicast, K)
         from . import ops
         for K in widths:
             # one symmetric allocation per exchange: [padded_n, K] feature rows followed by [padded_n] floats, the
@@ -301,12 +302,45 @@ class PeerExchange:
             self.hdls.append(hdl)
             self.mos.append(ops.make_multi_out([p + off for p in hdl.buffer_ptrs], mc, need_mask))
             self.att_mos.append(ops.make_multi_out([p + att_off for p in hdl.buffer_ptrs], mc_att, need_mask))
+            self._addr.append(([p + off for p in hdl.buffer_ptrs], mc, [p + att_off for p in hdl.buffer_ptrs], mc_att, K))
         self.need_mask = need_mask
         torch.cuda.synchronize()
         dist.barrier()
 
     def barrier(self, i):
         self.hdls[i].barrier(channel=i)
+
+    def block_out(self, i, row0):
+        """(rows, scalars) multi-outs of exchange i for a producer that starts at local row `row0` of this rank's slab
+        (the row-block pipeline launches one transform per block)."""
+        from . import ops
+        bases, mc, att_bases, mc_att, K = self._addr[i]
+        need = self.need_mask[row0:] if self.need_mask is not None else None
+        mo = ops.make_multi_out([b + row0 * K * 4 for b in bases], mc + row0 * K * 4 if mc else None, need)
+        att_mo = ops.make_multi_out([b + row0 * 4 for b in att_bases], mc_att + row0 * 4 if mc_att else None, need)
+        return mo, att_mo
+
+
+class RowBlocks:
+    """A rank's slab cut into `nblocks` row blocks of equal nnz, each with its own graph view and plan: the unit of
+    the row-block pipeline -- while block j of layer l is aggregated, the transformed rows of block j-1 for layer
+    l+1 are already on their way to the other GPUs (side stream), so that exchange hides behind this aggregation
+    instead of following it (SURVEY.md section 8e "the local part computes while remote rows arrive")."""
+
+    def __init__(self, part, nblocks, device):
+        from . import ops
+        self.cuts = partition_rows_by_nnz(part.offset.to(torch.int64), nblocks)
+        self.graphs = []
+        for j in range(nblocks):
+            lo, hi = self.cuts[j], self.cuts[j + 1]
+            g = ops.TiledGraph(part.offset[lo:hi + 1], part.cols, hi - lo, ncols=part.padded_n).build_plan()
+            g.plan.tile_rows = None      # (the edge-tile table assumes row pointers that start at 0; not used here)
+            self.graphs.append(g)
+        self.side = torch.cuda.Stream(device=device, priority=-1)
+        self.n = nblocks
+
+    def span(self, j):
+        return self.cuts[j], self.cuts[j + 1]
 
 
 class PartitionedGAT:
@@ -377,19 +411,33 @@ class PartitionedGATN:
     """L-layer runner (gat_model.GATN).  `part` is any object with RowPartition's interface, so that a
     rank can build its slab without ever holding the whole graph."""
 
-    def __init__(self, model, part, device, exchange="p2p", need_mask=None):
+    def __init__(self, model, part, device, exchange="p2p", need_mask=None, pipeline=0, push_ctas=0):
+        """pipeline = B > 1 (fused exchanges only): hidden aggregations run in B row blocks and the next layer's
+        transform + push of a finished block runs on a side stream under the aggregation of the following blocks."""
         from . import ops
 
         self.model, self.ops, self.part = model, ops, part
         self.graph = ops.TiledGraph(part.offset, part.cols, part.rows, ncols=part.padded_n).build_plan()
         self.px = None
         self.exchange = "nccl"
+        self.blocks = None
+        self.push_ctas = push_ctas
         if exchange in ("p2p", "p2p-needed"):
             assert (exchange == "p2p-needed") == (need_mask is not None), "p2p-needed takes RowPartition.need_masks()"
             self.px = PeerExchange(part, [model.dims[i + 1] for i in range(model.L - 1)] + [model.dims[-2]], device,
                                    need_mask=need_mask)
             self.exchange = ("p2p-needed" if need_mask is not None else
                              "p2p-multicast" if self.px.mos[0].multicast_base else "p2p")
+            if pipeline > 1 and model.L > 2 and max(model.dims[1:-1]) <= 64:
+                self.blocks = RowBlocks(part, pipeline, device)
+                self.exchange += f"+pipeline{pipeline}"
+                # per-forward buffers are allocated once: they are written on one stream and read on the other
+                self._res = [torch.empty(part.rows, model.dims[i + 1], device=device) for i in range(model.L - 2)]
+                self._att = [[torch.empty(2, hi - lo, device=device) for lo, hi in map(self.blocks.span, range(pipeline))]
+                             for _ in range(model.L - 2)]
+                self._aL = [torch.empty(part.rows, device=device) for _ in range(model.L - 2)]
+                self._outs = [[self.px.block_out(i + 1, self.blocks.cuts[j]) for j in range(pipeline)]
+                              for i in range(model.L - 2)]
 
     def _aggregate(self, aL, aR, feats, relu):
         return self.ops.gat_forward(self.graph, aL.contiguous(), aR.contiguous(), feats, self.model.slope, relu=relu)
@@ -413,6 +461,8 @@ class PartitionedGATN:
             return gatn_forward_partitioned(m, part, X_local, self._aggregate, hook, linear_att, aggregate_att)
         run = hook if hook is not None else (lambda name, fn: fn())
         res_loc, att = X_local, None
+        if self.blocks is not None:
+            return self._forward_pipelined(X_local, mark)
         for i in range(L - 1):
             # the transform pushes its rows to every GPU while it computes, projects them onto the attention
             # vectors in its epilogue and pushes the right-hand scalar of every row the same way
@@ -440,6 +490,53 @@ class PartitionedGATN:
         mark("classifier")
         return out
 
+    def _forward_pipelined(self, X_local, mark):
+        """Row-block pipeline: layer i's aggregation runs block by block on the main stream; as soon as a block is
+        done, the side stream transforms it for layer i+1 and pushes rows + attention scalars to the GPUs that
+        gather them (the light linear_small_ex kernel, so the aggregation keeps its registers).  The exchange of
+        layer i+1 is then over when the aggregation of layer i ends, instead of starting there."""
+        m, px, ops, bl = self.model, self.px, self.ops, self.blocks
+        bh, L = m._bh, m.L
+        main = torch.cuda.current_stream()
+        _, a = ops.linear(X_local, m.fc[0][0], m.fc[0][1], att_w=m.W_att[0], att_b=bh[0],
+                          multi_out=px.mos[0], att_multi_out=px.att_mos[0])
+        aL = a[0]
+        mark("linear1+push")
+        px.barrier(0)
+        mark("exchange1")
+        for i in range(L - 2):
+            res, aL_next = self._res[i], self._aL[i]
+            for j in range(bl.n):
+                lo, hi = bl.span(j)
+                ops.gat_forward(bl.graphs[j], aL[lo:hi], px.att_bufs[i], px.bufs[i], m.slope, relu=True, out=res[lo:hi])
+                ev = torch.cuda.Event()
+                ev.record(main)
+                bl.side.wait_event(ev)
+                with torch.cuda.stream(bl.side):
+                    mo, att_mo = self._outs[i][j]
+                    ops.linear_small_ex(res[lo:hi], m.fc[i + 1][0], m.fc[i + 1][1], att_w=m.W_att[i + 1], att_b=bh[i + 1],
+                                        att_out=self._att[i][j], multi_out=mo, att_multi_out=att_mo,
+                                        max_ctas=self.push_ctas)
+                    aL_next[lo:hi].copy_(self._att[i][j][0])
+            done = torch.cuda.Event()
+            done.record(bl.side)
+            main.wait_event(done)
+            mark(f"gat_layer{i + 1} || linear{i + 2}+push")
+            px.barrier(i + 1)
+            mark(f"exchange{i + 2}")
+            aL = aL_next
+        _, att, _ = ops.gat_forward_ex(self.graph, aL, px.att_bufs[L - 2], px.bufs[L - 2], m.slope, relu=True,
+                                       att_w=m.W_att[-1], att_b=bh[-1], multi_out=px.mos[L - 1],
+                                       att_multi_out=px.att_mos[L - 1])
+        mark(f"gat_layer{L - 1}+push")
+        px.barrier(L - 1)
+        mark(f"exchange{L}")
+        agg = ops.gat_forward(self.graph, att[0], px.att_bufs[L - 1], px.bufs[L - 1], m.slope, relu=False)
+        mark(f"gat_layer{L}")
+        out = ops.dense(agg, *m.fc[-1])
+        mark("classifier")
+        return out
+
 
 def gcnn_forward_partitioned(model, part, X_local, norm_local, aggregate, hook=None, linear=None):
     """L-layer GCN (gcn_model.GCNN) on a row partition with all-gather exchanges: hidden layers exchange the
@@ -463,10 +560,12 @@ class PartitionedGCNN:
     its epilogue (exchange="p2p"); the single exchange of an aggregation OUTPUT (before the last layer) goes
     through NCCL all-gather.  exchange="nccl": all-gather everywhere."""
 
-    def __init__(self, model, part, device, exchange="p2p", need_mask=None):
+    def __init__(self, model, part, device, exchange="p2p", need_mask=None, pipeline=0, push_ctas=0):
         from . import ops
 
         self.model, self.ops, self.part = model, ops, part
+        self.blocks = None
+        self.push_ctas = push_ctas
         self.graph = ops.TiledGraph(part.offset, part.cols, part.rows, ncols=part.padded_n).build_plan()
         ones = torch.ones(part.padded_n, 1, device=device)
         self.norm = torch.pow(ops.spmm(self.graph, ones).reshape(-1), -0.5).contiguous()    # own rows' degrees
@@ -479,6 +578,12 @@ class PartitionedGCNN:
                                    need_mask=need_mask)
             self.exchange = ("p2p-needed" if need_mask is not None else
                              "p2p-multicast" if self.px.mos[0].multicast_base else "p2p")
+            if pipeline > 1 and model.L > 2 and max(model.dims[1:-1]) <= 64:
+                self.blocks = RowBlocks(part, pipeline, device)
+                self.exchange += f"+pipeline{pipeline}"
+                self._res = [torch.empty(part.rows, model.dims[i + 1], device=device) for i in range(model.L - 2)]
+                self._outs = [[self.px.block_out(i + 1, self.blocks.cuts[j]) for j in range(pipeline)]
+                              for i in range(model.L - 2)]
 
     def _aggregate(self, feats_all, row_scale, relu):
         return self.ops.spmm(self.graph, feats_all, row_scale=row_scale, relu=relu)
@@ -492,6 +597,8 @@ class PartitionedGCNN:
             return gcnn_forward_partitioned(m, part, X_local, self.norm, self._aggregate, hook, linear)
         run = hook if hook is not None else (lambda name, fn: fn())
         res_loc = X_local
+        if self.blocks is not None:
+            return self._forward_pipelined(X_local, mark)
         for i in range(m.L - 1):
             run(f"linear{i + 1}", lambda: ops.linear(res_loc, m.fc[i][0], m.fc[i][1], row_scale=self.norm, multi_out=px.mos[i]))
             mark(f"linear{i + 1}+push")
@@ -513,5 +620,42 @@ class PartitionedGCNN:
         agg = run(f"gcn_aggregate{m.L}", lambda: ops.spmm(self.graph, y_all, row_scale=self.norm))
         mark(f"gcn_aggregate{m.L}")
         out = run("classifier", lambda: ops.dense(agg, *m.fc[-1]))
+        mark("classifier")
+        return out
+
+    def _forward_pipelined(self, X_local, mark):
+        """Row-block pipeline (see PartitionedGATN._forward_pipelined): the norm-scaled transform of a finished block
+        for the next layer is pushed from the side stream while the following blocks are aggregated."""
+        m, px, ops, bl = self.model, self.px, self.ops, self.blocks
+        L = m.L
+        main = torch.cuda.current_stream()
+        ops.linear(X_local, m.fc[0][0], m.fc[0][1], row_scale=self.norm, multi_out=px.mos[0])
+        mark("linear1+push")
+        px.barrier(0)
+        mark("exchange1")
+        for i in range(L - 2):
+            res = self._res[i]
+            for j in range(bl.n):
+                lo, hi = bl.span(j)
+                ops.spmm(bl.graphs[j], px.bufs[i], row_scale=self.norm[lo:hi], relu=True, out=res[lo:hi])
+                ev = torch.cuda.Event()
+                ev.record(main)
+                bl.side.wait_event(ev)
+                with torch.cuda.stream(bl.side):
+                    ops.linear_small_ex(res[lo:hi], m.fc[i + 1][0], m.fc[i + 1][1], row_scale=self.norm[lo:hi],
+                                        multi_out=self._outs[i][j][0], max_ctas=self.push_ctas)
+            done = torch.cuda.Event()
+            done.record(bl.side)
+            main.wait_event(done)
+            mark(f"gcn_aggregate{i + 1} || linear{i + 2}+push")
+            px.barrier(i + 1)
+            mark(f"exchange{i + 2}")
+        ops.spmm(self.graph, px.bufs[L - 2], row_scale=self.norm2, relu=True, multi_out=px.mos[L - 1])
+        mark(f"gcn_aggregate{L - 1}+push")
+        px.barrier(L - 1)
+        mark(f"exchange{L}")
+        agg = ops.spmm(self.graph, px.bufs[L - 1], row_scale=self.norm)
+        mark(f"gcn_aggregate{L}")
+        out = ops.dense(agg, *m.fc[-1])
         mark("classifier")
         return out

@@ -360,6 +360,32 @@ def linear_small(X, W, bias=None, relu=False, transpose_out=False, out=None):
     return out
 
 
+def linear_small_ex(X, W, bias=None, relu=False, row_scale=None, att_w=None, att_b=None, out=None, att_out=None,
+                    multi_out=None, att_multi_out=None, max_ctas=0):
+    """The narrow transform (K, N <= 64, exact fp32) with the row epilogues of `linear`: row scale, the two attention
+    projections (att_b: two host floats) into att_out [2, M], rows / right-hand scalars pushed to every GPU.  A light
+    kernel (at most max_ctas 256-thread blocks) meant to run on a side stream next to an aggregation kernel."""
+    X, W = _f32(X), _f32(W)
+    M, K = X.shape
+    N = W.shape[0]
+    if out is None and multi_out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=X.device)
+    ab = None
+    if att_w is not None:
+        att_w = _f32(att_w)
+        if att_out is None:
+            att_out = torch.empty((2, M), dtype=torch.float32, device=X.device)
+        ab_host = (C.c_float * 2)(float(att_b[0]), float(att_b[1]))
+        ab = C.cast(ab_host, C.c_void_p)
+    _l.check(_l.load().gala_linear_small_ex_f32(_l.ptr(X), M, K, _l.ptr(W), _l.ptr(bias), N,
+                                                _l.ptr(out) if out is not None else None, _l.ptr(row_scale),
+                                                int(relu), _l.ptr(att_w), ab, _l.ptr(att_out),
+                                                C.byref(multi_out) if multi_out is not None else None,
+                                                C.byref(att_multi_out) if att_multi_out is not None else None,
+                                                int(max_ctas), _l.stream_ptr()))
+    return (out, att_out) if att_w is not None else out
+
+
 def dense(X, W, bias=None, out=None):
     """Y = X @ W.T + bias on whichever of this library's transforms covers the shape: the streaming kernel for
     the narrow ones (K, N <= 64), the tcgen05 kernel up to N = 256, cuBLAS beyond."""

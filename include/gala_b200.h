@@ -324,6 +324,19 @@ int gala_linear_small_f32(const float *X, int64_t M, int32_t K, const float *W, 
                           int32_t N, float *Y, int32_t relu, int32_t transpose_out,
                           gala_stream_t stream);
 
+/* The same narrow transform with the row epilogues of gala_linear_f32 (row_scale before the ReLU, the  */
+/* two attention projections of the pre-activation row into att_out [2, M] with att_b[2] on the HOST,    */
+/* output rows / right-hand attention scalars pushed to every GPU through multi_out / att_multi_out).    */
+/* A deliberately light kernel (256-thread blocks, at most max_ctas of them; 0 = default) that can run   */
+/* on a side stream next to an aggregation kernel: the row-block pipeline of the partitioned layers      */
+/* hides the push of layer l+1's transformed rows behind layer l's aggregation.   */
+int gala_linear_small_ex_f32(const float *X, int64_t M, int32_t K, const float *W, const float *bias,
+                             int32_t N, float *Y, const float *row_scale, int32_t relu,
+                             const float *att_w, const float *att_b, float *att_out,
+                             const struct gala_multi_out *multi_out,
+                             const struct gala_multi_out *att_multi_out, int32_t max_ctas,
+                             gala_stream_t stream);
+
 /* ---- format construction on the device ---------- */
 /* All integer outputs are bit-exact against the reference functions named below.       */
 

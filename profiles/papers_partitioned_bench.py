@@ -28,10 +28,19 @@ dist.init_process_group("nccl", device_id=torch.device(dev))
 scale = float(sys.argv[1]) if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else 1.0
 # --exchanges p2p,p2p-needed,nccl : which exchanges to time (default all three);  p2p-needed = rows stored only into the
 # GPUs whose slabs reference them (predicated peer stores from the producing kernels' epilogues)
+# a mode may carry "+pipeB": the row-block pipeline with B blocks (dist_gat.RowBlocks), e.g. p2p-needed+pipe4
 EXCHANGES = ("p2p", "p2p-needed", "nccl")
+PUSH_CTAS = 0
 for i, a in enumerate(sys.argv):
     if a == "--exchanges":
         EXCHANGES = tuple(sys.argv[i + 1].split(","))
+    if a == "--push-ctas":
+        PUSH_CTAS = int(sys.argv[i + 1])
+
+
+def split_mode(mode):
+    base, _, pipe = mode.partition("+pipe")
+    return base, int(pipe) if pipe else 0
 
 
 def say(*a):
@@ -81,10 +90,11 @@ model = GATN(dims, dev, seed=0).host_biases()
 X = torch.rand(n, dims[0], generator=torch.Generator(device=dev).manual_seed(1), device=dev) - 0.5
 want = model.forward_literal(ops.TiledGraph(offset, ids, n).build_plan(), X)
 worst = 0.0
-for exchange in (("nccl", "p2p", "p2p-needed") if world > 1 else ("nccl",)):
+for mode in (("nccl", "p2p", "p2p-needed", "p2p+pipe3", "p2p-needed+pipe4") if world > 1 else ("nccl",)):
+    exchange, pipe = split_mode(mode)
     part = dist_gat.RowPartition(offset, ids, n, rank, world)
     need = part.need_masks(ids, offset) if exchange == "p2p-needed" else None
-    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange, need_mask=need)
+    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange, need_mask=need, pipeline=pipe)
     for _ in range(3):
         out_loc = runner.forward(X[part.row_lo:part.row_hi].contiguous())
     full = part.unpad(part.all_gather(out_loc))
@@ -95,10 +105,11 @@ for exchange in (("nccl", "p2p", "p2p-needed") if world > 1 else ("nccl",)):
 gfull = ops.TiledGraph(offset, ids, n).build_plan()
 gcn = GCNN(dims, dev, seed=2).prepare(gfull)
 want = gcn.forward_literal(gfull, X)
-for exchange in (("nccl", "p2p", "p2p-needed") if world > 1 else ("nccl",)):
+for mode in (("nccl", "p2p", "p2p-needed", "p2p+pipe3", "p2p-needed+pipe4") if world > 1 else ("nccl",)):
+    exchange, pipe = split_mode(mode)
     part = dist_gat.RowPartition(offset, ids, n, rank, world)
     need = part.need_masks(ids, offset) if exchange == "p2p-needed" else None
-    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange, need_mask=need)
+    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange, need_mask=need, pipeline=pipe)
     for _ in range(3):
         out_loc = runner.forward(X[part.row_lo:part.row_hi].contiguous())
     full = part.unpad(part.all_gather(out_loc))
@@ -117,7 +128,7 @@ dims = [feats, hidden, hidden, classes]
 offset, ids = build(n, e, 0)
 part = dist_gat.RowPartition(offset, ids, n, rank, world)
 need_mask = None
-if world > 1 and "p2p-needed" in EXCHANGES:
+if world > 1 and any(split_mode(m)[0] == "p2p-needed" for m in EXCHANGES):
     need_mask = part.need_masks(ids, offset)
     say(f"needed-rows masks: rank 0's rows are referenced by {part.need_fraction:.1%} of the (row, peer) pairs")
 del ids
@@ -126,8 +137,9 @@ model = GATN(dims, dev, seed=0).host_biases()
 X_loc = torch.rand(part.rows, feats, device=dev) - 0.5
 say(f"papers shape x{scale}: n={n} E={e}; rank 0 holds rows [{part.row_lo},{part.row_hi}) nnz {part.local_nvals}")
 res = {"workload": f"3-layer GAT forward, papers100M shape x{scale}", "n_gpus": world, "nodes": n, "edges": e}
-for exchange in (EXCHANGES if world > 1 else ()):
-    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange,
+for mode in (EXCHANGES if world > 1 else ()):
+    exchange, pipe = split_mode(mode)
+    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange, pipeline=pipe, push_ctas=PUSH_CTAS,
                                       need_mask=need_mask if exchange == "p2p-needed" else None)
     ms = timed(lambda: runner.forward(X_loc))
     res[f"ms_{runner.exchange}"] = round(ms, 3)
@@ -161,8 +173,9 @@ if world > 1 and "--needed" in sys.argv:
     del runner, npart
     torch.cuda.empty_cache()
 gcn = GCNN(dims, dev, seed=2)
-for exchange in (EXCHANGES if world > 1 else ()):
-    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange,
+for mode in (EXCHANGES if world > 1 else ()):
+    exchange, pipe = split_mode(mode)
+    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange, pipeline=pipe, push_ctas=PUSH_CTAS,
                                       need_mask=need_mask if exchange == "p2p-needed" else None)
     ms = timed(lambda: runner.forward(X_loc))
     res[f"gcn_ms_{runner.exchange}"] = round(ms, 3)
@@ -212,7 +225,7 @@ if world == 1:
         agg = ops.spmm(g1, r, row_scale=gcn.norm)
         for lo in range(0, agg.shape[0], sink[0]):       # logits in re-used chunks, as above
             hi = min(agg.shape[0], lo + sink[0])
-            torch.addmm(gcn.fc[-1][1], agg[lo:hi], gcn.fc[-1][0].t(), out=sink[1][:hi - lo])
+            ops.dense(agg[lo:hi], gcn.fc[-1][0], gcn.fc[-1][1], out=sink[1][:hi - lo])
     ms = timed(gcn_step)
     res["gcn_ms_single_gpu_model"] = round(ms, 3)
     say(f"  single-GPU 3-layer GCN forward {ms:.2f} ms")

@@ -86,3 +86,24 @@ def test_linear_small_matches_fp64(M, K, N):
     got_t = ops.linear_small(X, W, b, transpose_out=True)
     assert torch.equal(got_t.t().contiguous(), got)
     assert torch.equal(ops.linear_small(X, W, b, relu=True), torch.relu(got))
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 32, 32), (4099, 32, 8), (777, 64, 64), (513, 20, 41)])
+def test_linear_small_ex_row_epilogues(M, K, N):
+    """gala_linear_small_ex_f32 (the light transform of the row-block pipeline): bias, row scale before the ReLU, the
+    two attention projections of the pre-activation row -- against fp64 torch, <= 1e-6 like the tcgen05 kernel."""
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    X = torch.rand(M, K, device="cuda", generator=g) - 0.5
+    W = torch.rand(N, K, device="cuda", generator=g) - 0.5
+    b = torch.rand(N, device="cuda", generator=g) - 0.5
+    rs = torch.rand(M, device="cuda", generator=g) + 0.5
+    aw = torch.rand(2, N, device="cuda", generator=g) - 0.5
+    ab = [0.25, -0.5]
+    y, att = ops.linear_small_ex(X, W, b, relu=True, row_scale=rs, att_w=aw, att_b=ab, max_ctas=7)
+    pre = X.double() @ W.double().t() + b.double()
+    want = torch.relu(pre * rs.double()[:, None])
+    want_att = (pre @ aw.double().t() + torch.tensor(ab, device="cuda", dtype=torch.float64)).t()
+    assert float((y.double() - want).norm() / want.norm()) < 1e-6
+    assert float((att.double() - want_att).norm() / want_att.norm()) < 1e-6
+    y2 = ops.linear_small_ex(X, W, b)
+    assert float((y2.double() - pre).norm() / pre.norm()) < 1e-6
