@@ -226,6 +226,47 @@ __global__ void __launch_bounds__(256) pad_rows_kernel(const float* __restrict__
 }
 }  // namespace gala
 
+// Rows (and one optional scalar per row) copied from a local matrix into every GPU that gathers them: the exchange
+// step of a partitioned layer as its own light kernel, for producers whose epilogue cannot write full lines (the
+// tcgen05 transform holds one output row per thread: 16-byte pieces of 32 different rows per store instruction) or
+// whose rows should travel while the NEXT row block is still being computed.  Every store instruction of a warp
+// writes whole 128-byte lines of the destination (K % 4 == 0: K/4 lanes per row, float4 each).
+struct PushParams {
+    const float* __restrict__ X;
+    const float* __restrict__ scalars;
+    int64_t M, ldx;
+    int K;
+    MultiOut mo, smo;
+};
+__global__ void __launch_bounds__(256) push_rows_kernel(const __grid_constant__ PushParams p) {
+    const int vpr = p.K >> 2;                                         // float4 per row
+    const int64_t total = p.M * vpr;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int U = 4;                                              // independent loads in flight per thread
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+        Vec<4> v[U];
+        int64_t row[U];
+        int c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            row[u] = i / vpr;
+            c[u] = (int)(i - row[u] * vpr);
+            if (i < total) v[u].load_rw(p.X + row[u] * p.ldx + c[u] * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i0 + u * stride < total) {
+                multi_store<4>(p.mo, row[u] * p.K + c[u] * 4, v[u], row[u]);
+                if (p.scalars && c[u] == 0 && p.smo.count > 0) {
+                    Vec<1> s;
+                    s.v[0] = __ldg(p.scalars + row[u]);
+                    multi_store<1>(p.smo, row[u], s, row[u]);
+                }
+            }
+    }
+}
+
 extern "C" {
 
 int gala_b200_abi_version(void) { return GALA_B200_ABI_VERSION; }
@@ -828,6 +869,39 @@ int gala_sddmm_f32(const gala_graph_t* g, const float* A, const float* B, int32_
 #define CALL(V, L, A_) sddmm_kernel<V, L, A_><<<grid, kCtaThreads, 0, st>>>(p)
     GALA_SHAPE_SWITCH(sh, CALL);
 #undef CALL
+    return last_error();
+}
+
+int gala_push_rows_f32(const float* X, int64_t M, int32_t K, int64_t ldx, const float* scalars,
+                       const gala_multi_out_t* multi_out, const gala_multi_out_t* scalar_multi_out, int32_t max_ctas,
+                       gala_stream_t stream) {
+    if (M < 0 || K <= 0) return GALA_ERR_BAD_SHAPE;
+    if (M == 0) return GALA_OK;
+    if (!X || !multi_out || multi_out->count <= 0) return GALA_ERR_NULL_POINTER;
+    if (multi_out->count > kMaxPeers || (K & 3) != 0) return GALA_ERR_UNSUPPORTED;
+    PushParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.X = X;
+    p.scalars = scalars;
+    p.M = M;
+    p.ldx = ldx > 0 ? ldx : K;
+    p.K = K;
+    if (p.ldx < K || p.ldx % 4 != 0 || !aligned(X, 16)) return GALA_ERR_MISALIGNED;
+    p.mo.count = multi_out->count;
+    p.mo.mc_base = multi_out->multicast_base;
+    p.mo.need = multi_out->need_mask;
+    for (int q = 0; q < multi_out->count; ++q) p.mo.base[q] = multi_out->base[q];
+    if (scalars && scalar_multi_out && scalar_multi_out->count > 0) {
+        if (scalar_multi_out->count > kMaxPeers) return GALA_ERR_UNSUPPORTED;
+        p.smo.count = scalar_multi_out->count;
+        p.smo.mc_base = scalar_multi_out->multicast_base;
+        p.smo.need = scalar_multi_out->need_mask;
+        for (int q = 0; q < scalar_multi_out->count; ++q) p.smo.base[q] = scalar_multi_out->base[q];
+    }
+    const int64_t units = M * (K / 4);
+    const int64_t cap = max_ctas > 0 ? max_ctas : 148;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((units + 1023) / 1024, cap));
+    push_rows_kernel<<<grid, 256, 0, S(stream)>>>(p);
     return last_error();
 }
 

@@ -281,6 +281,8 @@ class PeerExchange:
         self.part = part
         self.bufs, self.hdls, self.mos = [], [], []
         self.att_bufs, self.att_mos = [], []
+        self._peer = []
+        self.copy_streams = None
         self._addr = []      # per exchange: (peer bases of the rows, multicast base, peer bases of the scalars, multicast, K)
         from . import ops
         for K in widths:
@@ -303,12 +305,42 @@ class PeerExchange:
             self.mos.append(ops.make_multi_out([p + off for p in hdl.buffer_ptrs], mc, need_mask))
             self.att_mos.append(ops.make_multi_out([p + att_off for p in hdl.buffer_ptrs], mc_att, need_mask))
             self._addr.append(([p + off for p in hdl.buffer_ptrs], mc, [p + att_off for p in hdl.buffer_ptrs], mc_att, K))
+            # every GPU's copy of the buffer as a local tensor (peer-mapped): destinations of copy-engine transfers
+            self._peer.append([hdl.get_buffer(q, (part.padded_n * (K + 1),), torch.float32) for q in range(part.world)])
         self.need_mask = need_mask
         torch.cuda.synchronize()
         dist.barrier()
 
     def barrier(self, i):
         self.hdls[i].barrier(channel=i)
+
+    def dma_push(self, i, lo, hi, rows, scalars, after):
+        """Rows [lo, hi) of this rank's slab (and their right-hand attention scalars) into every GPU's gathered buffer
+        of exchange i with device-to-device copies -- the copy engines move them, no SM is involved, so an aggregation
+        kernel running at the same time keeps the whole GPU.  One stream per destination; every copy waits for the
+        event `after` (the producer of the block).  Sends every row to every GPU (a copy engine cannot skip the rows a
+        destination does not reference)."""
+        part = self.part
+        if self.copy_streams is None:
+            self.copy_streams = [torch.cuda.Stream(device=rows.device) for _ in range(part.world)]
+        K = rows.shape[1]
+        r0 = part.rank * part.max_rows
+        for d in range(part.world):
+            q = (part.rank + d) % part.world          # staggered: the ranks do not all start on the same destination
+            st = self.copy_streams[q]
+            st.wait_event(after)
+            with torch.cuda.stream(st):
+                flat = self._peer[i][q]
+                flat[(r0 + lo) * K:(r0 + hi) * K].view(hi - lo, K).copy_(rows, non_blocking=True)
+                if scalars is not None:
+                    a0 = part.padded_n * K + r0
+                    flat[a0 + lo:a0 + hi].copy_(scalars, non_blocking=True)
+
+    def dma_join(self, main):
+        for st in self.copy_streams or ():
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
 
     def block_out(self, i, row0):
         """(rows, scalars) multi-outs of exchange i for a producer that starts at local row `row0` of this rank's slab
@@ -411,9 +443,13 @@ class PartitionedGATN:
     """L-layer runner (gat_model.GATN).  `part` is any object with RowPartition's interface, so that a
     rank can build its slab without ever holding the whole graph."""
 
-    def __init__(self, model, part, device, exchange="p2p", need_mask=None, pipeline=0, push_ctas=0):
-        """pipeline = B > 1 (fused exchanges only): hidden aggregations run in B row blocks and the next layer's
-        transform + push of a finished block runs on a side stream under the aggregation of the following blocks."""
+    def __init__(self, model, part, device, exchange="p2p", need_mask=None, pipeline=0, push_ctas=0, phases="m"):
+        """pipeline = B > 1 (fused exchanges only): producers of exchanged rows run in B row blocks and a finished block
+        is sent from a side stream under the computation of the following blocks.  phases: which exchanges do so --
+        f(irst transform), m(iddle: aggregation || next transform + push), l(ast hidden aggregation); the others keep
+        the push in the producing kernel's epilogue.  Upper case (F, M, L): the finished block travels by copy engine
+        (PeerExchange.dma_push: device-to-device copies on per-destination streams, no SM involved) instead of by a
+        kernel on the side stream."""
         from . import ops
 
         self.model, self.ops, self.part = model, ops, part
@@ -421,23 +457,25 @@ class PartitionedGATN:
         self.px = None
         self.exchange = "nccl"
         self.blocks = None
-        self.push_ctas = push_ctas
+        self.push_ctas, self.phases = push_ctas, phases
         if exchange in ("p2p", "p2p-needed"):
             assert (exchange == "p2p-needed") == (need_mask is not None), "p2p-needed takes RowPartition.need_masks()"
             self.px = PeerExchange(part, [model.dims[i + 1] for i in range(model.L - 1)] + [model.dims[-2]], device,
                                    need_mask=need_mask)
             self.exchange = ("p2p-needed" if need_mask is not None else
                              "p2p-multicast" if self.px.mos[0].multicast_base else "p2p")
-            if pipeline > 1 and model.L > 2 and max(model.dims[1:-1]) <= 64:
+            if pipeline > 1 and max(model.dims[1:-1]) <= 64:
                 self.blocks = RowBlocks(part, pipeline, device)
-                self.exchange += f"+pipeline{pipeline}"
+                self.exchange += f"+pipeline{pipeline}" + ("" if phases == "m" else ":" + phases)
                 # per-forward buffers are allocated once: they are written on one stream and read on the other
-                self._res = [torch.empty(part.rows, model.dims[i + 1], device=device) for i in range(model.L - 2)]
+                L = model.L
+                self._t0 = torch.empty(part.rows, model.dims[1], device=device)
+                self._t = [torch.empty(part.rows, model.dims[i + 2], device=device) for i in range(max(L - 2, 0))]
+                self._res = [torch.empty(part.rows, model.dims[i + 1], device=device) for i in range(L - 1)]
                 self._att = [[torch.empty(2, hi - lo, device=device) for lo, hi in map(self.blocks.span, range(pipeline))]
-                             for _ in range(model.L - 2)]
-                self._aL = [torch.empty(part.rows, device=device) for _ in range(model.L - 2)]
-                self._outs = [[self.px.block_out(i + 1, self.blocks.cuts[j]) for j in range(pipeline)]
-                              for i in range(model.L - 2)]
+                             for _ in range(max(L - 2, 0))]
+                self._aL = [torch.empty(part.rows, device=device) for _ in range(L)]
+                self._outs = [[self.px.block_out(i, self.blocks.cuts[j]) for j in range(pipeline)] for i in range(L)]
 
     def _aggregate(self, aL, aR, feats, relu):
         return self.ops.gat_forward(self.graph, aL.contiguous(), aR.contiguous(), feats, self.model.slope, relu=relu)
@@ -491,50 +529,145 @@ class PartitionedGATN:
         return out
 
     def _forward_pipelined(self, X_local, mark):
-        """Row-block pipeline: layer i's aggregation runs block by block on the main stream; as soon as a block is
-        done, the side stream transforms it for layer i+1 and pushes rows + attention scalars to the GPUs that
-        gather them (the light linear_small_ex kernel, so the aggregation keeps its registers).  The exchange of
-        layer i+1 is then over when the aggregation of layer i ends, instead of starting there."""
+        """Row-block pipeline: every producer of exchanged rows runs block by block on the main stream, and as soon as
+        a block is done the side stream sends it to the GPUs that gather it -- the first transform and the last hidden
+        aggregation through the copy kernel (gala_push_rows_f32: whole lines per store), the transforms in between
+        fused with their push in the light linear_small_ex kernel (so the aggregation that runs next to it keeps its
+        registers).  Each exchange is then (nearly) over when its producer ends, instead of starting there."""
         m, px, ops, bl = self.model, self.px, self.ops, self.blocks
         bh, L = m._bh, m.L
         main = torch.cuda.current_stream()
-        _, a = ops.linear(X_local, m.fc[0][0], m.fc[0][1], att_w=m.W_att[0], att_b=bh[0],
-                          multi_out=px.mos[0], att_multi_out=px.att_mos[0])
-        aL = a[0]
-        mark("linear1+push")
+        keep = []        # tensors handed from the main to the side stream stay referenced until the streams have joined
+
+        def after_block(fn):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            bl.side.wait_event(ev)
+            with torch.cuda.stream(bl.side):
+                fn()
+
+        def join():
+            done = torch.cuda.Event()
+            done.record(bl.side)
+            main.wait_event(done)
+
+        # first transform (tensor cores, local rows) || push
+        t0, aL = self._t0, self._aL[0]
+        if "F" in self.phases:
+            for j in range(bl.n):
+                lo, hi = bl.span(j)
+                _, a = ops.linear(X_local[lo:hi], m.fc[0][0], m.fc[0][1], att_w=m.W_att[0], att_b=bh[0], out=t0[lo:hi])
+                aL[lo:hi].copy_(a[0])
+                keep.append(a)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                px.dma_push(0, lo, hi, t0[lo:hi], a[1], ev)
+            px.dma_join(main)
+            mark("linear1 || copy")
+        elif "f" in self.phases:
+            for j in range(bl.n):
+                lo, hi = bl.span(j)
+                _, a = ops.linear(X_local[lo:hi], m.fc[0][0], m.fc[0][1], att_w=m.W_att[0], att_b=bh[0], out=t0[lo:hi])
+                aL[lo:hi].copy_(a[0])
+                keep.append(a)
+                mo, att_mo = self._outs[0][j]
+                after_block(lambda: ops.push_rows(t0[lo:hi], mo, scalars=a[1], scalar_multi_out=att_mo,
+                                                  max_ctas=self.push_ctas))
+            join()
+            mark("linear1 || push")
+        else:
+            _, a = ops.linear(X_local, m.fc[0][0], m.fc[0][1], att_w=m.W_att[0], att_b=bh[0],
+                              multi_out=px.mos[0], att_multi_out=px.att_mos[0])
+            aL = a[0]
+            mark("linear1+push")
         px.barrier(0)
         mark("exchange1")
+        # hidden aggregations || the next layer's transform + push
         for i in range(L - 2):
-            res, aL_next = self._res[i], self._aL[i]
+            res, aL_next = self._res[i], self._aL[i + 1]
+            if "M" in self.phases:
+                tn = self._t[i]
+                for j in range(bl.n):
+                    lo, hi = bl.span(j)
+                    ops.gat_forward(bl.graphs[j], aL[lo:hi], px.att_bufs[i], px.bufs[i], m.slope, relu=True, out=res[lo:hi])
+                    _, a = ops.linear(res[lo:hi], m.fc[i + 1][0], m.fc[i + 1][1], att_w=m.W_att[i + 1], att_b=bh[i + 1],
+                                      out=tn[lo:hi])
+                    aL_next[lo:hi].copy_(a[0])
+                    keep.append(a)
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    px.dma_push(i + 1, lo, hi, tn[lo:hi], a[1], ev)
+                px.dma_join(main)
+                mark(f"gat_layer{i + 1}, linear{i + 2} || copy")
+                px.barrier(i + 1)
+                mark(f"exchange{i + 2}")
+                aL = aL_next
+                continue
+            if "m" not in self.phases:
+                ops.gat_forward(self.graph, aL, px.att_bufs[i], px.bufs[i], m.slope, relu=True, out=res)
+                mark(f"gat_layer{i + 1}")
+                _, a = ops.linear(res, m.fc[i + 1][0], m.fc[i + 1][1], att_w=m.W_att[i + 1], att_b=bh[i + 1],
+                                  multi_out=px.mos[i + 1], att_multi_out=px.att_mos[i + 1])
+                mark(f"linear{i + 2}+push")
+                px.barrier(i + 1)
+                mark(f"exchange{i + 2}")
+                aL = a[0]
+                continue
             for j in range(bl.n):
                 lo, hi = bl.span(j)
                 ops.gat_forward(bl.graphs[j], aL[lo:hi], px.att_bufs[i], px.bufs[i], m.slope, relu=True, out=res[lo:hi])
-                ev = torch.cuda.Event()
-                ev.record(main)
-                bl.side.wait_event(ev)
-                with torch.cuda.stream(bl.side):
-                    mo, att_mo = self._outs[i][j]
+                mo, att_mo = self._outs[i + 1][j]
+
+                def transform_push(lo=lo, hi=hi, j=j, mo=mo, att_mo=att_mo):
                     ops.linear_small_ex(res[lo:hi], m.fc[i + 1][0], m.fc[i + 1][1], att_w=m.W_att[i + 1], att_b=bh[i + 1],
                                         att_out=self._att[i][j], multi_out=mo, att_multi_out=att_mo,
                                         max_ctas=self.push_ctas)
                     aL_next[lo:hi].copy_(self._att[i][j][0])
-            done = torch.cuda.Event()
-            done.record(bl.side)
-            main.wait_event(done)
+                after_block(transform_push)
+            join()
             mark(f"gat_layer{i + 1} || linear{i + 2}+push")
             px.barrier(i + 1)
             mark(f"exchange{i + 2}")
             aL = aL_next
-        _, att, _ = ops.gat_forward_ex(self.graph, aL, px.att_bufs[L - 2], px.bufs[L - 2], m.slope, relu=True,
-                                       att_w=m.W_att[-1], att_b=bh[-1], multi_out=px.mos[L - 1],
-                                       att_multi_out=px.att_mos[L - 1])
-        mark(f"gat_layer{L - 1}+push")
+        # last hidden aggregation (next layer's attention projections in its epilogue) || push
+        res, aL_last = self._res[L - 2], self._aL[L - 1]
+        if "L" in self.phases:
+            for j in range(bl.n):
+                lo, hi = bl.span(j)
+                _, att, _ = ops.gat_forward_ex(bl.graphs[j], aL[lo:hi], px.att_bufs[L - 2], px.bufs[L - 2], m.slope,
+                                               relu=True, att_w=m.W_att[-1], att_b=bh[-1], out=res[lo:hi])
+                aL_last[lo:hi].copy_(att[0])
+                keep.append(att)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                px.dma_push(L - 1, lo, hi, res[lo:hi], att[1], ev)
+            px.dma_join(main)
+            mark(f"gat_layer{L - 1} || copy")
+        elif "l" in self.phases:
+            for j in range(bl.n):
+                lo, hi = bl.span(j)
+                _, att, _ = ops.gat_forward_ex(bl.graphs[j], aL[lo:hi], px.att_bufs[L - 2], px.bufs[L - 2], m.slope,
+                                               relu=True, att_w=m.W_att[-1], att_b=bh[-1], out=res[lo:hi])
+                aL_last[lo:hi].copy_(att[0])
+                keep.append(att)
+                mo, att_mo = self._outs[L - 1][j]
+                after_block(lambda: ops.push_rows(res[lo:hi], mo, scalars=att[1], scalar_multi_out=att_mo,
+                                                  max_ctas=self.push_ctas))
+            join()
+            mark(f"gat_layer{L - 1} || push")
+        else:
+            _, att, _ = ops.gat_forward_ex(self.graph, aL, px.att_bufs[L - 2], px.bufs[L - 2], m.slope, relu=True,
+                                           att_w=m.W_att[-1], att_b=bh[-1], multi_out=px.mos[L - 1],
+                                           att_multi_out=px.att_mos[L - 1])
+            aL_last = att[0]
+            mark(f"gat_layer{L - 1}+push")
         px.barrier(L - 1)
         mark(f"exchange{L}")
-        agg = ops.gat_forward(self.graph, att[0], px.att_bufs[L - 1], px.bufs[L - 1], m.slope, relu=False)
+        agg = ops.gat_forward(self.graph, aL_last, px.att_bufs[L - 1], px.bufs[L - 1], m.slope, relu=False)
         mark(f"gat_layer{L}")
         out = ops.dense(agg, *m.fc[-1])
         mark("classifier")
+        keep.clear()
         return out
 
 
@@ -560,12 +693,12 @@ class PartitionedGCNN:
     its epilogue (exchange="p2p"); the single exchange of an aggregation OUTPUT (before the last layer) goes
     through NCCL all-gather.  exchange="nccl": all-gather everywhere."""
 
-    def __init__(self, model, part, device, exchange="p2p", need_mask=None, pipeline=0, push_ctas=0):
+    def __init__(self, model, part, device, exchange="p2p", need_mask=None, pipeline=0, push_ctas=0, phases="m"):
         from . import ops
 
         self.model, self.ops, self.part = model, ops, part
         self.blocks = None
-        self.push_ctas = push_ctas
+        self.push_ctas, self.phases = push_ctas, phases
         self.graph = ops.TiledGraph(part.offset, part.cols, part.rows, ncols=part.padded_n).build_plan()
         ones = torch.ones(part.padded_n, 1, device=device)
         self.norm = torch.pow(ops.spmm(self.graph, ones).reshape(-1), -0.5).contiguous()    # own rows' degrees
@@ -578,12 +711,13 @@ class PartitionedGCNN:
                                    need_mask=need_mask)
             self.exchange = ("p2p-needed" if need_mask is not None else
                              "p2p-multicast" if self.px.mos[0].multicast_base else "p2p")
-            if pipeline > 1 and model.L > 2 and max(model.dims[1:-1]) <= 64:
+            if pipeline > 1 and max(model.dims[1:-1]) <= 64:
                 self.blocks = RowBlocks(part, pipeline, device)
-                self.exchange += f"+pipeline{pipeline}"
-                self._res = [torch.empty(part.rows, model.dims[i + 1], device=device) for i in range(model.L - 2)]
-                self._outs = [[self.px.block_out(i + 1, self.blocks.cuts[j]) for j in range(pipeline)]
-                              for i in range(model.L - 2)]
+                self.exchange += f"+pipeline{pipeline}" + ("" if phases == "m" else ":" + phases)
+                self._t0 = torch.empty(part.rows, model.dims[1], device=device)
+                self._t = [torch.empty(part.rows, model.dims[i + 2], device=device) for i in range(max(model.L - 2, 0))]
+                self._res = [torch.empty(part.rows, model.dims[i + 1], device=device) for i in range(model.L - 1)]
+                self._outs = [[self.px.block_out(i, self.blocks.cuts[j]) for j in range(pipeline)] for i in range(model.L)]
 
     def _aggregate(self, feats_all, row_scale, relu):
         return self.ops.spmm(self.graph, feats_all, row_scale=row_scale, relu=relu)
@@ -624,34 +758,102 @@ class PartitionedGCNN:
         return out
 
     def _forward_pipelined(self, X_local, mark):
-        """Row-block pipeline (see PartitionedGATN._forward_pipelined): the norm-scaled transform of a finished block
-        for the next layer is pushed from the side stream while the following blocks are aggregated."""
+        """Row-block pipeline (see PartitionedGATN._forward_pipelined): every producer of exchanged rows runs block by
+        block, the side stream sends a finished block while the following blocks are computed."""
         m, px, ops, bl = self.model, self.px, self.ops, self.blocks
         L = m.L
         main = torch.cuda.current_stream()
-        ops.linear(X_local, m.fc[0][0], m.fc[0][1], row_scale=self.norm, multi_out=px.mos[0])
-        mark("linear1+push")
+
+        def after_block(fn):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            bl.side.wait_event(ev)
+            with torch.cuda.stream(bl.side):
+                fn()
+
+        def join():
+            done = torch.cuda.Event()
+            done.record(bl.side)
+            main.wait_event(done)
+
+        t0 = self._t0
+        if "F" in self.phases:
+            for j in range(bl.n):
+                lo, hi = bl.span(j)
+                ops.linear(X_local[lo:hi], m.fc[0][0], m.fc[0][1], row_scale=self.norm[lo:hi], out=t0[lo:hi])
+                ev = torch.cuda.Event()
+                ev.record(main)
+                px.dma_push(0, lo, hi, t0[lo:hi], None, ev)
+            px.dma_join(main)
+            mark("linear1 || copy")
+        elif "f" in self.phases:
+            for j in range(bl.n):
+                lo, hi = bl.span(j)
+                ops.linear(X_local[lo:hi], m.fc[0][0], m.fc[0][1], row_scale=self.norm[lo:hi], out=t0[lo:hi])
+                mo = self._outs[0][j][0]
+                after_block(lambda: ops.push_rows(t0[lo:hi], mo, max_ctas=self.push_ctas))
+            join()
+            mark("linear1 || push")
+        else:
+            ops.linear(X_local, m.fc[0][0], m.fc[0][1], row_scale=self.norm, multi_out=px.mos[0])
+            mark("linear1+push")
         px.barrier(0)
         mark("exchange1")
         for i in range(L - 2):
             res = self._res[i]
+            if "M" in self.phases:
+                tn = self._t[i]
+                for j in range(bl.n):
+                    lo, hi = bl.span(j)
+                    ops.spmm(bl.graphs[j], px.bufs[i], row_scale=self.norm[lo:hi], relu=True, out=res[lo:hi])
+                    ops.linear(res[lo:hi], m.fc[i + 1][0], m.fc[i + 1][1], row_scale=self.norm[lo:hi], out=tn[lo:hi])
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    px.dma_push(i + 1, lo, hi, tn[lo:hi], None, ev)
+                px.dma_join(main)
+                mark(f"gcn_aggregate{i + 1}, linear{i + 2} || copy")
+                px.barrier(i + 1)
+                mark(f"exchange{i + 2}")
+                continue
+            if "m" not in self.phases:
+                ops.spmm(self.graph, px.bufs[i], row_scale=self.norm, relu=True, out=res)
+                mark(f"gcn_aggregate{i + 1}")
+                ops.linear(res, m.fc[i + 1][0], m.fc[i + 1][1], row_scale=self.norm, multi_out=px.mos[i + 1])
+                mark(f"linear{i + 2}+push")
+                px.barrier(i + 1)
+                mark(f"exchange{i + 2}")
+                continue
             for j in range(bl.n):
                 lo, hi = bl.span(j)
                 ops.spmm(bl.graphs[j], px.bufs[i], row_scale=self.norm[lo:hi], relu=True, out=res[lo:hi])
-                ev = torch.cuda.Event()
-                ev.record(main)
-                bl.side.wait_event(ev)
-                with torch.cuda.stream(bl.side):
-                    ops.linear_small_ex(res[lo:hi], m.fc[i + 1][0], m.fc[i + 1][1], row_scale=self.norm[lo:hi],
-                                        multi_out=self._outs[i][j][0], max_ctas=self.push_ctas)
-            done = torch.cuda.Event()
-            done.record(bl.side)
-            main.wait_event(done)
+                mo = self._outs[i + 1][j][0]
+                after_block(lambda: ops.linear_small_ex(res[lo:hi], m.fc[i + 1][0], m.fc[i + 1][1],
+                                                        row_scale=self.norm[lo:hi], multi_out=mo, max_ctas=self.push_ctas))
+            join()
             mark(f"gcn_aggregate{i + 1} || linear{i + 2}+push")
             px.barrier(i + 1)
             mark(f"exchange{i + 2}")
-        ops.spmm(self.graph, px.bufs[L - 2], row_scale=self.norm2, relu=True, multi_out=px.mos[L - 1])
-        mark(f"gcn_aggregate{L - 1}+push")
+        res = self._res[L - 2]
+        if "L" in self.phases:
+            for j in range(bl.n):
+                lo, hi = bl.span(j)
+                ops.spmm(bl.graphs[j], px.bufs[L - 2], row_scale=self.norm2[lo:hi], relu=True, out=res[lo:hi])
+                ev = torch.cuda.Event()
+                ev.record(main)
+                px.dma_push(L - 1, lo, hi, res[lo:hi], None, ev)
+            px.dma_join(main)
+            mark(f"gcn_aggregate{L - 1} || copy")
+        elif "l" in self.phases:
+            for j in range(bl.n):
+                lo, hi = bl.span(j)
+                ops.spmm(bl.graphs[j], px.bufs[L - 2], row_scale=self.norm2[lo:hi], relu=True, out=res[lo:hi])
+                mo = self._outs[L - 1][j][0]
+                after_block(lambda: ops.push_rows(res[lo:hi], mo, max_ctas=self.push_ctas))
+            join()
+            mark(f"gcn_aggregate{L - 1} || push")
+        else:
+            ops.spmm(self.graph, px.bufs[L - 2], row_scale=self.norm2, relu=True, multi_out=px.mos[L - 1])
+            mark(f"gcn_aggregate{L - 1}+push")
         px.barrier(L - 1)
         mark(f"exchange{L}")
         agg = ops.spmm(self.graph, px.bufs[L - 1], row_scale=self.norm)

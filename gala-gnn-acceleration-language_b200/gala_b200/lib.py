@@ -18,7 +18,7 @@ EXPORTS = [
     "gala_plan_build", "gala_spmm_f32", "gala_spmm_sampled_f32", "gala_edge_rowsum_f32",
     "gala_edge_scale_rows_f32", "gala_sddvv_f32", "gala_sddmm_f32", "gala_edge_softmax_fwd_f32",
     "gala_edge_softmax_bwd_f32", "gala_gat_forward_f32", "gala_gat_forward_dot_f32", "gala_linear_f32",
-    "gala_gat_forward_ex_f32", "gala_linear_small_f32", "gala_linear_small_ex_f32", "gala_gat_backward_att_f32",
+    "gala_gat_forward_ex_f32", "gala_linear_small_f32", "gala_linear_small_ex_f32", "gala_push_rows_f32", "gala_gat_backward_att_f32",
     "gala_spmm_bf16", "gala_gat_forward_bf16", "gala_pad_rows_f32",
     "gala_csr_from_coo_workspace_bytes", "gala_csr_from_coo", "gala_csr_transpose",
     "gala_col_tile_segments", "gala_col_tile_workspace_bytes", "gala_col_tile", "gala_sample_ab",
@@ -105,6 +105,7 @@ def load():
         "gala_linear_small_f32": [vp, i64, i32, vp, vp, i32, vp, i32, i32, vp],
         "gala_linear_small_ex_f32": [vp, i64, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp,
                                      C.POINTER(GalaMultiOut), C.POINTER(GalaMultiOut), i32, vp],
+        "gala_push_rows_f32": [vp, i64, i32, i64, vp, C.POINTER(GalaMultiOut), C.POINTER(GalaMultiOut), i32, vp],
         "gala_linear_f32": [vp, i64, i32, vp, vp, i32, vp, vp, i32, vp, vp, i32, vp,
                             C.POINTER(GalaMultiOut), C.POINTER(GalaMultiOut), vp],
         "gala_csr_from_coo": [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp],

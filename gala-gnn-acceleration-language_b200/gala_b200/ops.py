@@ -386,6 +386,17 @@ def linear_small_ex(X, W, bias=None, relu=False, row_scale=None, att_w=None, att
     return (out, att_out) if att_w is not None else out
 
 
+def push_rows(X, multi_out, scalars=None, scalar_multi_out=None, max_ctas=0):
+    """Store the rows of X [M, K] (and one scalar per row) into every GPU that gathers them (gala_push_rows_f32)."""
+    X = _f32(X)
+    M, K = X.shape
+    if scalars is not None:
+        scalars = _f32(scalars)
+    _l.check(_l.load().gala_push_rows_f32(_l.ptr(X), M, K, K, _l.ptr(scalars), C.byref(multi_out),
+                                          C.byref(scalar_multi_out) if scalar_multi_out is not None else None,
+                                          int(max_ctas), _l.stream_ptr()))
+
+
 def dense(X, W, bias=None, out=None):
     """Y = X @ W.T + bias on whichever of this library's transforms covers the shape: the streaming kernel for
     the narrow ones (K, N <= 64), the tcgen05 kernel up to N = 256, cuBLAS beyond."""

@@ -337,6 +337,16 @@ int gala_linear_small_ex_f32(const float *X, int64_t M, int32_t K, const float *
                              const struct gala_multi_out *att_multi_out, int32_t max_ctas,
                              gala_stream_t stream);
 
+/* The exchange step of a partitioned layer as its own light kernel: rows of the local matrix X [M, K]   */
+/* (row pitch ldx, 0 = K; K % 4 == 0) and, optionally, one scalar per row are stored into every GPU that */
+/* gathers them (multi_out / scalar_multi_out as above), whole 128-byte lines per store instruction.      */
+/* For producers that finish row block b while block b+1 is still being computed (the copy runs on a      */
+/* side stream), with at most max_ctas 256-thread blocks (0 = 148).                                        */
+int gala_push_rows_f32(const float *X, int64_t M, int32_t K, int64_t ldx, const float *scalars,
+                       const struct gala_multi_out *multi_out,
+                       const struct gala_multi_out *scalar_multi_out, int32_t max_ctas,
+                       gala_stream_t stream);
+
 /* ---- format construction on the device ---------- */
 /* All integer outputs are bit-exact against the reference functions named below.       */
 

@@ -39,8 +39,12 @@ for i, a in enumerate(sys.argv):
 
 
 def split_mode(mode):
+    """"p2p-needed+pipe4:fm@74" -> ("p2p-needed", 4 row blocks, at most 74 CTAs for the side-stream push kernels,
+    phases f(irst) and m(iddle) pipelined -- default m; upper case = by copy engine)"""
+    mode, _, ctas = mode.partition("@")
+    mode, _, phases = mode.partition(":")
     base, _, pipe = mode.partition("+pipe")
-    return base, int(pipe) if pipe else 0
+    return base, int(pipe) if pipe else 0, int(ctas) if ctas else PUSH_CTAS, phases or "m"
 
 
 def say(*a):
@@ -90,11 +94,11 @@ model = GATN(dims, dev, seed=0).host_biases()
 X = torch.rand(n, dims[0], generator=torch.Generator(device=dev).manual_seed(1), device=dev) - 0.5
 want = model.forward_literal(ops.TiledGraph(offset, ids, n).build_plan(), X)
 worst = 0.0
-for mode in (("nccl", "p2p", "p2p-needed", "p2p+pipe3", "p2p-needed+pipe4") if world > 1 else ("nccl",)):
-    exchange, pipe = split_mode(mode)
+for mode in (("nccl", "p2p", "p2p-needed", "p2p+pipe3:fml", "p2p-needed+pipe4", "p2p-needed+pipe3:FML") if world > 1 else ("nccl",)):
+    exchange, pipe, _, phases = split_mode(mode)
     part = dist_gat.RowPartition(offset, ids, n, rank, world)
     need = part.need_masks(ids, offset) if exchange == "p2p-needed" else None
-    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange, need_mask=need, pipeline=pipe)
+    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange, need_mask=need, pipeline=pipe, phases=phases)
     for _ in range(3):
         out_loc = runner.forward(X[part.row_lo:part.row_hi].contiguous())
     full = part.unpad(part.all_gather(out_loc))
@@ -105,11 +109,11 @@ for mode in (("nccl", "p2p", "p2p-needed", "p2p+pipe3", "p2p-needed+pipe4") if w
 gfull = ops.TiledGraph(offset, ids, n).build_plan()
 gcn = GCNN(dims, dev, seed=2).prepare(gfull)
 want = gcn.forward_literal(gfull, X)
-for mode in (("nccl", "p2p", "p2p-needed", "p2p+pipe3", "p2p-needed+pipe4") if world > 1 else ("nccl",)):
-    exchange, pipe = split_mode(mode)
+for mode in (("nccl", "p2p", "p2p-needed", "p2p+pipe3:fml", "p2p-needed+pipe4", "p2p-needed+pipe3:FML") if world > 1 else ("nccl",)):
+    exchange, pipe, _, phases = split_mode(mode)
     part = dist_gat.RowPartition(offset, ids, n, rank, world)
     need = part.need_masks(ids, offset) if exchange == "p2p-needed" else None
-    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange, need_mask=need, pipeline=pipe)
+    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange, need_mask=need, pipeline=pipe, phases=phases)
     for _ in range(3):
         out_loc = runner.forward(X[part.row_lo:part.row_hi].contiguous())
     full = part.unpad(part.all_gather(out_loc))
@@ -138,9 +142,11 @@ X_loc = torch.rand(part.rows, feats, device=dev) - 0.5
 say(f"papers shape x{scale}: n={n} E={e}; rank 0 holds rows [{part.row_lo},{part.row_hi}) nnz {part.local_nvals}")
 res = {"workload": f"3-layer GAT forward, papers100M shape x{scale}", "n_gpus": world, "nodes": n, "edges": e}
 for mode in (EXCHANGES if world > 1 else ()):
-    exchange, pipe = split_mode(mode)
-    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange, pipeline=pipe, push_ctas=PUSH_CTAS,
+    exchange, pipe, ctas, phases = split_mode(mode)
+    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange, pipeline=pipe, push_ctas=ctas, phases=phases,
                                       need_mask=need_mask if exchange == "p2p-needed" else None)
+    if ctas:
+        runner.exchange += f"@{ctas}"
     ms = timed(lambda: runner.forward(X_loc))
     res[f"ms_{runner.exchange}"] = round(ms, 3)
     say(f"  [{runner.exchange}] forward {ms:.2f} ms (max over {world} ranks)")
@@ -174,9 +180,11 @@ if world > 1 and "--needed" in sys.argv:
     torch.cuda.empty_cache()
 gcn = GCNN(dims, dev, seed=2)
 for mode in (EXCHANGES if world > 1 else ()):
-    exchange, pipe = split_mode(mode)
-    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange, pipeline=pipe, push_ctas=PUSH_CTAS,
+    exchange, pipe, ctas, phases = split_mode(mode)
+    runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange, pipeline=pipe, push_ctas=ctas, phases=phases,
                                       need_mask=need_mask if exchange == "p2p-needed" else None)
+    if ctas:
+        runner.exchange += f"@{ctas}"
     ms = timed(lambda: runner.forward(X_loc))
     res[f"gcn_ms_{runner.exchange}"] = round(ms, 3)
     say(f"  GCN [{runner.exchange}] forward {ms:.2f} ms (max over {world} ranks)")
