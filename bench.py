@@ -522,11 +522,16 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "profiles"))
             import run_generated_full
             recs = run_generated_full.run("Reddit", ["gat_inference", "gat_train"])
+            # BASELINE configs[2] (GIN / GraphSAGE training, Products shape) and configs[3] (GCN with neighbour sampling,
+            # Products shape, gala_inference_sample path): the generated programs of those schedules, same two generators
+            recs += run_generated_full.run("Products", ["gin_train_products", "sage_train_products",
+                                                        "gcn_inference_products_sample20"])
             line["generated_programs"] = {
-                "what": ("GALA-generated 2-layer GAT programs (100 epochs, Adam) on the Reddit-shape dataset: mean forward "
-                         "ms and forward+backward+Adam ms as the program prints them, start-up seconds (data load + format "
-                         "construction + H2D); generator ref = the reference's own CUDA kernels compiled for sm_100a, "
-                         "b200 = this library through the retargeted generator"),
+                "what": ("GALA-generated programs (100 epochs, Adam) on full-size synthetic datasets: 2-layer GAT on the Reddit "
+                         "shape (BASELINE configs[1]), GIN / GraphSAGE training and GCN + aggrFn.sample(20) on the Products "
+                         "shape (configs[2], configs[3]); mean forward ms and forward+backward+Adam ms as the program prints "
+                         "them, start-up seconds (data load + format construction + H2D); generator ref = the reference's "
+                         "own CUDA kernels compiled for sm_100a, b200 = this library through the retargeted generator"),
                 "runs": recs}
         except Exception as ex:   # secondary measurement: never fails the bench line
             line["generated_programs"] = {"error": f"{type(ex).__name__}: {ex}"}
@@ -612,12 +617,45 @@ def kernel_sweep(g, n, nvals, K, peak, dev, l2_gbs=None):
         gth)
     rec("edge_softmax_fwd", time_op(lambda: ops.edge_softmax_fwd(g, w, out=ev)), rp + 8 * nvals)
     rec("edge_rowsum", time_op(lambda: ops.edge_rowsum(g, w)), rp + 4 * nvals + 4 * n)
+    # K4 row scaling runs edge-parallel (csrc/edge_tiles.cuh: nnz-split tiles staged by bulk copies) on every shape
+    rec("edge_scale_rows", time_op(lambda: ops.edge_scale_rows_(g, ev, a)), rp + 8 * nvals + 4 * n)
+    ev2 = torch.rand(nvals, generator=gen, device=dev)
+    rec("edge_softmax_bwd", time_op(lambda: ops.edge_softmax_bwd(g, w, ev2, out=ev)), rp + 12 * nvals)
+    del ev2
+    res["edge_kernels_products_shape"] = edge_tiles_products(peak, dev)
     # optional bf16 FEATURE STORAGE (not the headline: fp32 accumulation/outputs, results within 1e-2 of fp32,
     # BASELINE north_star "bf16 features within 1e-2"): half the gathered bytes on the L2-bound gather
     Xb = X.to(torch.bfloat16)
     rec("spmm_k32_bf16_features", time_op(lambda: ops.spmm_bf16(g, Xb, out=Y)), rp + 4 * nvals + 6 * n * K)
     rec("gat_fused_k32_bf16_features", time_op(lambda: ops.gat_forward_bf16(g, a, a, Xb, out=Y)),
         rp + 4 * nvals + 8 * n + 6 * n * K)
+    return res
+
+
+def edge_tiles_products(peak, dev):
+    """The streaming edge kernels on the Products shape (mean degree 50: BASELINE configs[2]/[3]), where the default
+    dispatch takes the edge-parallel tile kernels; the row-structured kernels (a plan without the tile table) beside."""
+    from gala_b200 import ops, synth
+
+    n, e, *_ = synth.SHAPES["products"]
+    offset, ids = synth.powerlaw_csr_torch(n, e, seed=0, device=dev)
+    g = ops.TiledGraph(offset, ids, n).build_plan()
+    gr = ops.TiledGraph(offset, ids, n).build_plan()
+    gr.plan.tile_rows = None
+    E = g.nvals
+    x, da, out = torch.randn(E, device=dev), torch.randn(E, device=dev), torch.empty(E, device=dev)
+    rs, a = torch.empty(n, 1, device=dev), torch.randn(n, device=dev)
+    res = {"nodes": n, "edges": E, "tiles": int(g.plan.n_tiles)}
+    for name, nbytes, fn in (
+            ("edge_rowsum", 4 * (n + 1) + 4 * E + 4 * n, lambda G: ops.edge_rowsum(G, x, out=rs)),
+            ("edge_scale_rows", 4 * (n + 1) + 8 * E + 4 * n, lambda G: ops.edge_scale_rows_(G, out, a)),
+            ("edge_softmax_fwd", 4 * (n + 1) + 8 * E, lambda G: ops.edge_softmax_fwd(G, x, out=out)),
+            ("edge_softmax_bwd", 4 * (n + 1) + 12 * E, lambda G: ops.edge_softmax_bwd(G, x, da, out=out))):
+        ms_t, ms_r = time_op(lambda: fn(g)), time_op(lambda: fn(gr))
+        res[name] = {"ms": round(ms_t, 4), "frac_of_hbm_peak": round(nbytes / (ms_t * 1e-3) / 1e9 / peak, 4),
+                     "row_structured_ms": round(ms_r, 4)}
+    del g, gr, offset, ids, x, da, out
+    torch.cuda.empty_cache()
     return res
 
 

@@ -109,6 +109,7 @@ struct LinearParams {
     float* __restrict__ att_out;      // [2, M]
     int64_t M;
     int K, N, relu;
+    int round_robin;                  // v2 kernel: tiles dealt round-robin (1) or one contiguous row range per CTA (0)
     MultiOut mo;                      // count > 0: output rows pushed to every GPU instead of Y
     MultiOut att_mo;                  // count > 0: the second projection (attenR, one float per row) is ALSO stored
                                       // at element `row` of every GPU's gathered vector
@@ -440,8 +441,18 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
     // the bytes per CTA are equal whatever M is.  (Round-robin over fixed 128-row tiles left the last wave mostly empty
     // when a rank holds only ~1.5 tiles per SM: 228 tiles on 148 CTAs at 8 GPUs.)
     const int64_t rows_per_cta = ((p.M + gridDim.x - 1) / gridDim.x + 7) & ~int64_t(7);
-    const int64_t row_lo = min(p.M, (int64_t)blockIdx.x * rows_per_cta), row_hi = min(p.M, row_lo + rows_per_cta);
-    const uint32_t my_tiles = (uint32_t)((row_hi - row_lo + kBM - 1) / kBM);
+    const int64_t row_lo = min(p.M, (int64_t)blockIdx.x * rows_per_cta);
+    // Measured on B200 (profiles/r02_linear_tile_assignment.txt): the contiguous ranges win when a CTA holds few tiles and at
+    // small K (Products K = 100: 0.695 -> 0.654 ms), round-robin tiles win at large K with many tiles per CTA (Reddit
+    // K = 602: 0.239 vs 0.220 ms -- every CTA's last, partial tile pays a full tile's MMA chain and epilogue).
+    const int64_t ntiles_all = (p.M + kBM - 1) / kBM;
+    const int64_t row_end = p.round_robin ? p.M : min(p.M, row_lo + rows_per_cta);
+    const uint32_t my_tiles = p.round_robin
+        ? ((int64_t)blockIdx.x < ntiles_all ? (uint32_t)((ntiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u)
+        : (uint32_t)((row_end - row_lo + kBM - 1) / kBM);
+    auto tile_row = [&](uint32_t it) -> int64_t {
+        return p.round_robin ? ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM : row_lo + (int64_t)it * kBM;
+    };
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -490,7 +501,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    v[i] = (kok && wrow0 + i < row_hi) ? __ldg(reinterpret_cast<const float2*>(xc + (uint64_t)i * pitch)) : zero2;
+                    v[i] = (kok && wrow0 + i < row_end) ? __ldg(reinterpret_cast<const float2*>(xc + (uint64_t)i * pitch)) : zero2;
             }
         };
         auto store_ss = [&](uint32_t g, const float2 (&v)[16]) {
@@ -543,9 +554,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
             if (g >= total) return;
             const uint32_t it = g / (uint32_t)nss;
             const int ss = (int)(g - it * (uint32_t)nss);
-            const int64_t wrow0 = row_lo + (int64_t)it * kBM + warp * 16;
+            const int64_t wrow0 = tile_row(it) + warp * 16;
             const char* xlane = reinterpret_cast<const char*>(p.X + wrow0 * p.K + 2 * lane);
-            load_ss(xlane, wrow0 + 16 <= row_hi, wrow0, ss, v);
+            load_ss(xlane, wrow0 + 16 <= row_end, wrow0, ss, v);
         };
 #if GALA_LINEAR_REGBUF == 3
         float2 vc[16];
@@ -616,7 +627,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
             const uint32_t aset = it & 1;
             mbar_wait(&accf_bar[aset], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int64_t r = row_lo + (int64_t)it * kBM + q * 32 + lane;
+            const int64_t r = tile_row(it) + q * 32 + lane;
             float acc[NPAD];
 #pragma unroll
             for (int n = 0; n < NPAD; ++n) acc[n] = 0.0f;
@@ -637,7 +648,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acce_bar[aset]);        // the accumulator set may be overwritten
             float a0 = p.att_b_dev ? __ldg(p.att_b_dev) : p.att_b0, a1 = p.att_b_dev ? __ldg(p.att_b_dev + 1) : p.att_b1;
-            if (r < row_hi) {
+            if (r < row_end) {
                 const float rscale = p.row_scale ? __ldg(p.row_scale + r) : 1.0f;
 #pragma unroll
                 for (int n = 0; n < NPAD; ++n) {
@@ -670,11 +681,11 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
                     if (n < p.N) *reinterpret_cast<float4*>(&st[lane][n]) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
                 __syncwarp();
                 const int vec_per_row = p.N >> 2;
-                const int64_t tile_row0 = row_lo + (int64_t)it * kBM + q * 32;
+                const int64_t tile_row0 = tile_row(it) + q * 32;
                 for (int idx = lane; idx < 32 * vec_per_row; idx += 32) {
                     const int rr = idx / vec_per_row, cv = idx - rr * vec_per_row;
                     const int64_t row = tile_row0 + rr;
-                    if (row < row_hi) {
+                    if (row < row_end) {
                         const float4 v = *reinterpret_cast<const float4*>(&st[rr][cv * 4]);
                         Vec<4> o;
                         o.v[0] = v.x; o.v[1] = v.y; o.v[2] = v.z; o.v[3] = v.w;
@@ -683,7 +694,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) linear_tf32x3_v2_kernel(const _
                     }
                 }
                 __syncwarp();
-            } else if (r < row_hi) {
+            } else if (r < row_end) {
                 float* yrow = p.Y + r * p.N;
 #pragma unroll
                 for (int n = 0; n < NPAD; ++n)
@@ -1061,6 +1072,7 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
     const bool v2 = (K % 2 == 0) && (reinterpret_cast<uintptr_t>(X) % 8 == 0) && (reinterpret_cast<uintptr_t>(W) % 8 == 0) &&
                     M >= 4 * kBM;
     if (v2) {
+        p.round_robin = (K >= 256 && ntiles >= 4 * (int64_t)device_sm_count()) ? 1 : 0;
         if (N <= 16) return launch_linear_v2<16>(p, st);
         if (N <= 32) return launch_linear_v2<32>(p, st);
         if (N <= 48) return launch_linear_v2<48>(p, st);
