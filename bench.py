@@ -220,7 +220,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU feature exchange: fused into the kernels over peer memory, or NCCL all-gather")
-    ap.add_argument("--mode", default="folded", choices=["folded", "folded_dot", "fused", "literal", "dot"],
+    ap.add_argument("--mode", default="reflected", choices=["folded", "folded_dot", "reflected", "fused", "literal", "dot"],
                     help="how the dense ops around the fused GAT kernel run (gala_b200/gat_model.py)")
     ap.add_argument("--dense", default="tcgen05", choices=["tcgen05", "torch"],
                     help="layer-1 feature transform: hand-written tcgen05 3xTF32 kernel or cuBLAS fp32 via torch")
@@ -304,7 +304,8 @@ def main():
         X_in = X
         mode = args.mode
         step_fn = lambda hook=None: model.forward(g, X_in, hook, mode=mode, dense=args.dense)   # noqa: E731
-        launches_per_step = {"folded": 5, "folded_dot": 5, "fused": 3}.get(mode, 2) if args.dense == "tcgen05" else 2
+        launches_per_step = ({"folded": 5, "folded_dot": 5, "reflected": 5, "fused": 3}.get(mode, 2)
+                             if args.dense == "tcgen05" else 2)
         config["parallelism"] = "single GPU"
         config["dense"] = ("layer-1 X*W + attention projections: gala_linear_f32 (tcgen05 kind::tf32, 3xTF32)"
                            if args.dense == "tcgen05" else "cuBLAS fp32 through torch")
@@ -397,7 +398,7 @@ def main():
     out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
     X_stage = torch.empty_like(X_in)
 
-    e2e_chunks = 8 if (world == 1 and args.dense == "tcgen05" and mode in ("folded", "folded_dot")) else 1
+    e2e_chunks = 8 if (world == 1 and args.dense == "tcgen05" and mode in ("folded", "folded_dot", "reflected")) else 1
 
     def e2e_step():
         if e2e_chunks > 1:
@@ -438,6 +439,13 @@ def main():
         dist.all_reduce(tt)
         parity = float((tt[0] / tt[1]).sqrt().item())
         del g_full, want, got
+    else:
+        # N = 1: the timed mode (folded / reflected / ...: own kernels everywhere) against the op-by-op forward of the
+        # same model with cuBLAS dense parts, outside the timed region
+        want = model.forward(g, X, mode="literal", dense="torch")
+        got = model.forward(g, X, mode=mode, dense=args.dense)
+        parity = float(((got.double() - want.double()).norm() / want.double().norm()).item())
+        del want, got
 
     def finish():
         """Leave without tearing NCCL down: destroy_process_group() after a captured collective can
@@ -458,11 +466,18 @@ def main():
     peak, peak_src = peaks()
     rows_local = (runner.row_hi - runner.row_lo) if world > 1 else n
     e_local = runner.local_nvals if world > 1 else nvals
-    alg_bytes = 4 * (rows_local + 1) + 4 * e_local + 4 * (rows_local + n) + 4 * hidden * (n + rows_local)
+    # mode "reflected" (gala_gat_forward_col_f32): aR rides in the last column of the gathered rows -- no [N] aR
+    # vector in the byte model and no second 4-byte gather per edge
+    col_mode = world == 1 and mode == "reflected"
+    alg_bytes = (4 * (rows_local + 1) + 4 * e_local + 4 * rows_local + (0 if col_mode else 4 * n)
+                 + 4 * hidden * (n + rows_local))
     kms = float(np.mean([kern_ms[k] for k in ("gat_layer1", "gat_layer2") if k in kern_ms]))
     achieved = alg_bytes / (kms * 1e-3) / 1e9
-    gather_bytes = 4 * (rows_local + 1) + 4 * e_local + 4 * e_local + 4 * hidden * e_local + 4 * hidden * rows_local
-    roofline = {"kernel": "gala::spmm_kernel<4,8,1,MODE_GAT> (fused SDDVV+LeakyReLU+edge-softmax+SpMM, K=32)",
+    gather_bytes = (4 * (rows_local + 1) + 4 * e_local + (0 if col_mode else 4 * e_local) + 4 * hidden * e_local
+                    + 4 * hidden * rows_local)
+    roofline = {"kernel": ("gala::spmm_kernel<4,8,1,MODE_GAT_COL> (fused SDDVV+LeakyReLU+edge-softmax+SpMM, K=32, attention "
+                           "term read from the last column of the gathered row)" if col_mode else
+                           "gala::spmm_kernel<4,8,1,MODE_GAT> (fused SDDVV+LeakyReLU+edge-softmax+SpMM, K=32)"),
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kms, 4),
@@ -484,7 +499,8 @@ def main():
     tfile = os.path.join(ROOT, "profiles", "traffic.json")
     if world == 1 and os.path.exists(tfile):
         try:
-            roofline["traffic"] = json.load(open(tfile)).get("gat_fused_k32_bytes_per_launch")
+            roofline["traffic"] = json.load(open(tfile)).get(
+                "gat_fused_col_k32_bytes_per_launch" if col_mode else "gat_fused_k32_bytes_per_launch")
         except (ValueError, OSError):
             pass
 
@@ -615,6 +631,9 @@ def kernel_sweep(g, n, nvals, K, peak, dev, l2_gbs=None):
     wR = (torch.rand(K, generator=gen, device=dev) - 0.5).contiguous()
     rec("gat_fused_dot_k32", time_op(lambda: ops.gat_forward_dot(g, a, wR, 0.1, X, out=Y)), rp + 4 * nvals + 4 * n + 8 * n * K,
         gth)
+    # reflected basis: the attention scalar is the last element of the gathered row (gala_gat_forward_col_f32)
+    rec("gat_fused_col_k32", time_op(lambda: ops.gat_forward_col(g, a, 1.0, 0.1, X, reflect_in=wR, reflect_out=wR, relu=True,
+                                                                 out=Y)), rp + 4 * nvals + 4 * n + 8 * n * K, gth)
     rec("edge_softmax_fwd", time_op(lambda: ops.edge_softmax_fwd(g, w, out=ev)), rp + 8 * nvals)
     rec("edge_rowsum", time_op(lambda: ops.edge_rowsum(g, w)), rp + 4 * nvals + 4 * n)
     # K4 row scaling runs edge-parallel (csrc/edge_tiles.cuh: nnz-split tiles staged by bulk copies) on every shape

@@ -601,6 +601,69 @@ int gala_gat_forward_dot_f32(const gala_graph_t* g, const float* aL, const float
     return last_error();
 }
 
+int gala_reflection_f32(const float* w, int32_t K, float* v, float* sR) {
+    if (!w || !v || !sR) return GALA_ERR_NULL_POINTER;
+    if (K <= 0) return GALA_ERR_BAD_SHAPE;
+    double n2 = 0.0;
+    for (int i = 0; i < K; ++i) n2 += (double)w[i] * (double)w[i];
+    if (!(n2 > 0.0)) return GALA_ERR_BAD_SHAPE;
+    const double n = std::sqrt(n2);
+    const double sgn = w[K - 1] < 0.0f ? -1.0 : 1.0;
+    // v ~ e_{K-1} + sgn * w/|w|: the last component 1 + |w[K-1]|/|w| >= 1, no cancellation
+    double vn2 = 0.0;
+    std::vector<double> t(K);
+    for (int i = 0; i < K; ++i) {
+        t[i] = sgn * (double)w[i] / n + (i == K - 1 ? 1.0 : 0.0);
+        vn2 += t[i] * t[i];
+    }
+    const double vn = std::sqrt(vn2);
+    for (int i = 0; i < K; ++i) v[i] = (float)(t[i] / vn);
+    *sR = (float)(-sgn * n);
+    return GALA_OK;
+}
+
+int gala_gat_forward_col_f32(const gala_graph_t* g, const float* aL, float sR, float bR, const float* X, int32_t K,
+                             int64_t ldx, float slope, float* Y, int64_t ldy, float* alpha_out, int32_t relu,
+                             const float* reflect_in, const float* reflect_out, const gala_plan_t* plan,
+                             gala_stream_t stream) {
+    if (int rc = check_graph(g)) return rc;
+    if (K != 4 && K != 8 && K != 16 && K != 32) return GALA_ERR_UNSUPPORTED;   // K/4 lanes hold the row, last lane the scalar
+    if (g->nrows > 0 && (!aL || !X || !Y)) return GALA_ERR_NULL_POINTER;
+    if (ldx <= 0) ldx = K;
+    if (ldy <= 0) ldy = K;
+    if (ldx < K || ldy < K) return GALA_ERR_BAD_SHAPE;
+    if (!aligned(X, 16) || !aligned(Y, 16) || ldx % 4 != 0 || ldy % 4 != 0) return GALA_ERR_UNSUPPORTED;
+    if (g->nrows == 0) return GALA_OK;
+    SpmmParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.g = make_dev(g);
+    p.X = X;
+    p.Y = Y;
+    p.K = K;
+    p.ldx = ldx;
+    p.ldy = ldy;
+    p.relu = relu;
+    p.aL = aL;
+    p.sR = sR;
+    p.bR = bR;
+    p.refl_in = reflect_in;
+    p.refl_out = reflect_out;
+    p.slope = slope;
+    p.alpha_out = alpha_out;
+    p.seed_total = (float)g->segments * 1e-12f;
+    HubView h = hub_of(plan, g);
+    p.t = task_of(h);
+    dim3 grid(p.t.n_hub + (p.t.n_ordered + kWarpsPerCta - 1) / kWarpsPerCta, 1);
+    cudaStream_t st = S(stream);
+    switch (K) {
+        case 4: spmm_kernel<4, 1, 1, MODE_GAT_COL, true><<<grid, kCtaThreads, 0, st>>>(p); break;
+        case 8: spmm_kernel<4, 2, 1, MODE_GAT_COL, true><<<grid, kCtaThreads, 0, st>>>(p); break;
+        case 16: spmm_kernel<4, 4, 1, MODE_GAT_COL, true><<<grid, kCtaThreads, 0, st>>>(p); break;
+        default: spmm_kernel<4, 8, 1, MODE_GAT_COL, true><<<grid, kCtaThreads, 0, st>>>(p); break;
+    }
+    return last_error();
+}
+
 int gala_spmm_sampled_f32(const gala_graph_t* g, const float* vals, const float* X, int32_t K, float* Y,
                           int32_t nsamples, int32_t ra, int32_t rb, int32_t accumulate, int64_t ldx, int64_t ldy,
                           gala_stream_t stream) {

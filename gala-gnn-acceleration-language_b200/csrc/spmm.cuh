@@ -20,8 +20,12 @@ namespace gala {
 
 // MODE_GAT_DOT: like MODE_GAT, but aR[col] = dot(X[col,:], wR) + bR is recomputed from the
 // gathered feature row itself, which removes the second random gather per edge.
-enum { MODE_PLAIN = 0, MODE_GAT = 1, MODE_GAT_DOT = 2 };
-#define GALA_IS_GAT(M) ((M) == MODE_GAT || (M) == MODE_GAT_DOT)
+// MODE_GAT_COL: the caller stores the features in a reflected basis whose LAST column is (a multiple of) the
+// right-hand attention term, aR[j] = sR * X[j, K-1] + bR (see gala_gat_forward_col_f32): the scalar arrives with
+// the 128-byte row the edge gathers anyway, so an edge costs 4 sectors instead of 4 + 1, and no dot product.
+enum { MODE_PLAIN = 0, MODE_GAT = 1, MODE_GAT_DOT = 2, MODE_GAT_COL = 3 };
+#define GALA_IS_GAT(M) ((M) == MODE_GAT || (M) == MODE_GAT_DOT || (M) == MODE_GAT_COL)
+#define GALA_GAT_FROM_ROW(M) ((M) == MODE_GAT_DOT || (M) == MODE_GAT_COL)   // edge weight known only after the gather
 
 struct SpmmParams {
     GraphDev g;
@@ -44,6 +48,11 @@ struct SpmmParams {
     float seed_total;                     // S * 1e-12f
     const float* __restrict__ wR;         // MODE_GAT_DOT: aR[j] = dot(X[j,:], wR) + bR
     float bR;
+    float sR;                             // MODE_GAT_COL: aR[j] = sR * X[j, K-1] + bR
+    const float* __restrict__ refl_in;    // MODE_GAT_COL, nullable [K] unit vector v: y <- y - 2 v (v.y) on the normalised
+                                          // sum (back from the reflected basis), before the ReLU
+    const float* __restrict__ refl_out;   // nullable [K]: the same reflection with this vector after the ReLU (into the
+                                          // basis the NEXT layer gathers in)
     // fused dense epilogue on the finished output row y (K <= 128, one feature tile):
     const float* __restrict__ att_w;      // [2, K]: att_out[row] = y.att_w[0] + att_b0, att_out[nrows+row] = y.att_w[1] + att_b1
     float att_b0, att_b1;
@@ -168,6 +177,109 @@ __device__ __forceinline__ void gather_chunk_dot(const char* __restrict__ xlane,
 }
 
 
+// MODE_GAT_COL chunk: gather the 32 rows (LPR loads per lane, all in flight).  The lane that holds the last 16-byte
+// piece of a row (sub == LPR-1) has that edge's attention scalar in its last element: it drops the LPR scalars of its
+// group into the warp's 32-float staging line, every lane picks up the scalar of ITS OWN edge (slot = lane), evaluates
+// the softmax numerator once, writes it back to the same slot, and the LPR weights of the group come back with
+// vector loads; the column ids reach the groups the same way (one store, LPR/4 vector loads).  Three warp-local
+// syncs and a handful of shared-memory instructions per chunk replace the second global gather of MODE_GAT with its
+// 2 x LPR shuffles, and the LPR-1 shuffles + LPR*VEC FMAs of MODE_GAT_DOT.  TW == K (one exact tile).
+#ifndef GALA_GATCOL_SMEM_COLS
+#define GALA_GATCOL_SMEM_COLS 1   // 1: the column ids also travel through the staging line (no shuffles at all)
+#endif
+template <int VEC, int LPR, bool FULL>
+__device__ __forceinline__ void gather_chunk_col(const char* __restrict__ xlane, uint32_t row_bytes, int sub, int grp,
+                                                 int lane, int c, int base, int e1, float aL_row, float sR, float bR,
+                                                 float slope, float* __restrict__ alpha_out, float& rs,
+                                                 float (&acc)[1][VEC], float* __restrict__ line,
+                                                 int* __restrict__ cline) {
+    // Edge at chunk position q = grp*LPR + u is gathered by group grp in sub-iteration u; lane q evaluates its weight.
+    int cj[LPR];
+    Vec<VEC> x[LPR];
+#if GALA_GATCOL_SMEM_COLS
+    cline[lane] = c;
+    __syncwarp();       // also orders the previous chunk's reads of `line` before this chunk's writes
+    if constexpr (LPR % 4 == 0) {
+#pragma unroll
+        for (int u = 0; u < LPR; u += 4) {
+            const int4 t = *reinterpret_cast<const int4*>(cline + grp * LPR + u);
+            cj[u] = t.x; cj[u + 1] = t.y; cj[u + 2] = t.z; cj[u + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < LPR; ++u) cj[u] = cline[grp * LPR + u];
+    }
+#else
+#pragma unroll
+    for (int u = 0; u < LPR; ++u) cj[u] = __shfl_sync(kFull, c, grp * LPR + u);   // (also a warp-wide sync point)
+#endif
+#pragma unroll
+    for (int u = 0; u < LPR; ++u) {
+        const uint32_t cc = (uint32_t)(FULL ? cj[u] : max(cj[u], 0));
+        x[u].load(reinterpret_cast<const float*>(xlane + (uint64_t)cc * row_bytes));
+    }
+    if (sub == LPR - 1) {
+        if constexpr (LPR % 4 == 0) {
+#pragma unroll
+            for (int u = 0; u < LPR; u += 4)
+                *reinterpret_cast<float4*>(line + grp * LPR + u) =
+                    make_float4(x[u].v[VEC - 1], x[u + 1].v[VEC - 1], x[u + 2].v[VEC - 1], x[u + 3].v[VEC - 1]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < LPR; ++u) line[grp * LPR + u] = x[u].v[VEC - 1];
+        }
+    }
+    __syncwarp();
+    // slot `lane` is this lane's own edge (column c, chunk position lane); it is read and rewritten by this lane only
+    float e = 0.0f;
+    if (FULL || c >= 0) {
+        e = softmax_num(leaky(aL_row + fmaf(sR, line[lane], bR), slope));
+        rs += e;
+        if (alpha_out) alpha_out[base + lane] = e;
+    }
+    line[lane] = e;     // 0 for the positions past the row's end
+    __syncwarp();
+    float wj[LPR];
+    if constexpr (LPR % 4 == 0) {
+#pragma unroll
+        for (int u = 0; u < LPR; u += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(line + grp * LPR + u);
+            wj[u] = t.x; wj[u + 1] = t.y; wj[u + 2] = t.z; wj[u + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < LPR; ++u) wj[u] = line[grp * LPR + u];
+    }
+#pragma unroll
+    for (int u = 0; u < LPR; ++u) {
+        const bool ok = FULL || cj[u] >= 0;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[0][v] = fmaf(wj[u], ok ? x[u].v[v] : 0.0f, acc[0][v]);
+    }
+#if !GALA_GATCOL_SMEM_COLS
+    __syncwarp();       // the line is rewritten by the next chunk
+#endif
+}
+
+// y <- y - 2 v (v . y) for the K = VEC*LPR features a group of LPR lanes holds (VEC each); every lane of the group
+// returns with its reflected elements.  v is a unit vector (a Householder reflection: orthogonal and its own inverse).
+template <int VEC, int LPR>
+__device__ __forceinline__ void reflect_row(float (&y)[VEC], const float* __restrict__ v, int sub) {
+    float vv[VEC];
+    float d = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        vv[i] = __ldg(v + sub * VEC + i);
+        d = fmaf(vv[i], y[i], d);
+    }
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) d += __shfl_xor_sync(kFull, d, o);
+    d *= 2.0f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) y[i] = fmaf(-d, vv[i], y[i]);
+}
+
+
 constexpr int kRowBufMax = 128;   // widest output row the fused dense epilogue handles
 
 // Dense epilogue of one finished output row held in shared memory (K floats): the next layer's two
@@ -216,8 +328,15 @@ __device__ __forceinline__ void row_dense_epilogue(const SpmmParams& p, const fl
 //  two-gather MODE_GAT; profiles/r02_variants_dot_pipeline_softmax_cache.txt.  Occupancy, not the dependent chain, is
 //  what the gather lives on.)
 #endif
+#ifndef GALA_GATCOL_MINB
+#define GALA_GATCOL_MINB 4   // the column mode keeps the 8 gathered rows of a chunk live until all their weights are
+// known: 64 registers (4 CTAs per SM) hold that without spills -- 0.92 ms on the Reddit shape; squeezed to 48 registers
+// (5 CTAs) the accumulators spill inside the chunk loop, 1.40 ms; 3 CTAs 1.04 ms (profiles/r02_variants_col.txt)
+#endif
 #if GALA_SPMM_MINB > 0
-#define GALA_SPMM_BOUNDS __launch_bounds__(kCtaThreads, (MODE == MODE_GAT_DOT ? GALA_GATDOT_MINB : GALA_SPMM_MINB))
+#define GALA_SPMM_BOUNDS                                                                                   \
+    __launch_bounds__(kCtaThreads, (MODE == MODE_GAT_DOT ? GALA_GATDOT_MINB                                \
+                                                         : (MODE == MODE_GAT_COL ? GALA_GATCOL_MINB : GALA_SPMM_MINB)))
 #else
 #define GALA_SPMM_BOUNDS __launch_bounds__(kCtaThreads)
 #endif
@@ -237,7 +356,10 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
     const int row = task.row, lo = task.lo, hi = task.hi;
     // VEC == 8 is the bf16-feature flavour: X holds bf16 rows (2 bytes per feature), see Vec<8>
     constexpr uint32_t XB = VEC == 8 ? 2u : 4u;
-    static_assert(VEC != 8 || (ACC == 1 && EXACT && MODE != MODE_GAT_DOT), "bf16 rows: one exact tile, no dot mode");
+    static_assert(VEC != 8 || (ACC == 1 && EXACT && !GALA_GAT_FROM_ROW(MODE)), "bf16 rows: one exact tile, no dot mode");
+    static_assert(MODE != MODE_GAT_COL || (ACC == 1 && EXACT), "column mode: the row is one exact tile");
+    __shared__ __align__(16) float colline[MODE == MODE_GAT_COL ? kWarpsPerCta : 1][32];
+    __shared__ __align__(16) int colcols[MODE == MODE_GAT_COL ? kWarpsPerCta : 1][32];
     const uint32_t row_bytes = (uint32_t)p.ldx * XB;
     // Y rows go out as VEC-wide stores when their pitch and base keep that alignment; otherwise (packed rows of
     // odd width) element by element -- N*K*4 bytes once per launch, nothing next to the gather
@@ -275,8 +397,8 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
         w = 0.0f;
         if (idx < e1) {
             c = ld_stream(g.cols + idx);
-            if (MODE == MODE_GAT_DOT) {
-                // weight comes from the gathered row (gather_chunk_dot)
+            if (GALA_GAT_FROM_ROW(MODE)) {
+                // weight comes from the gathered row (gather_chunk_dot / gather_chunk_col)
             } else if (MODE == MODE_GAT) {
                 float e = softmax_num(leaky(aL_row + ld_keep(p.aR + c), p.slope));
                 rs += e;
@@ -305,6 +427,14 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
                 else
                     gather_chunk_dot<VEC, LPR, false>(xlane, row_bytes, sub, grp, c, base, e1, wreg, aL_row, p.bR,
                                                       p.slope, ao, rs, acc);
+            } else if constexpr (MODE == MODE_GAT_COL) {
+                float* ao = write_alpha ? p.alpha_out : nullptr;
+                if (base + 32 <= e1)
+                    gather_chunk_col<VEC, LPR, true>(xlane, row_bytes, sub, grp, lane, c, base, e1, aL_row, p.sR, p.bR,
+                                                     p.slope, ao, rs, acc, colline[warp], colcols[warp]);
+                else
+                    gather_chunk_col<VEC, LPR, false>(xlane, row_bytes, sub, grp, lane, c, base, e1, aL_row, p.sR, p.bR,
+                                                      p.slope, ao, rs, acc, colline[warp], colcols[warp]);
             } else if (base + 32 <= e1)
                 gather_chunk<VEC, LPR, ACC, true, EXACT>(xlane, row_bytes, grp, c, w, weighted, fvalid, acc);
             else
@@ -325,6 +455,56 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
 
     __shared__ float rowbuf[kWarpsPerCta][kRowBufMax];
     const bool dense_ep = p.att_w != nullptr || p.cls_wT != nullptr;   // host guarantees K <= kRowBufMax, one tile
+
+    if constexpr (MODE == MODE_GAT_COL) {
+        // One exact tile, K = VEC*LPR <= 32: normalise, reflect back from the gathered basis, ReLU, reflect into the
+        // next layer's basis.  Hub rows first combine their 8 warp partials in warp order (as below); every warp of
+        // the hub CTA then holds the same full sums and warp 0 finishes the row.
+        if (hub_cta) {
+            __shared__ float cpart[kWarpsPerCta * 32];
+            __shared__ float cpart_rs[kWarpsPerCta];
+            if (grp == 0) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) cpart[warp * 32 + sub * VEC + v] = acc[0][v];
+            }
+            if (lane == 0) cpart_rs[warp] = rs;
+            __syncthreads();
+            rs = 0.0f;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[0][v] = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kWarpsPerCta; ++w) {
+                rs += cpart_rs[w];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[0][v] += cpart[w * 32 + sub * VEC + v];
+            }
+        }
+        scale = 1.0f / (rs + p.seed_total);
+        if (!hub_cta || warp == 0) {
+            float y[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) y[v] = acc[0][v] * scale;
+            if (p.refl_in) reflect_row<VEC, LPR>(y, p.refl_in, sub);
+            if (p.relu) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) y[v] = fmaxf(y[v], 0.0f);
+            }
+            if (p.refl_out) reflect_row<VEC, LPR>(y, p.refl_out, sub);
+            if (grp == 0) {
+                Vec<VEC> o;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) o.v[v] = y[v];
+                o.store(p.Y + (int64_t)row * p.ldy + sub * VEC);
+            }
+        }
+        if (write_alpha) {
+            __syncwarp();   // the numerators were stored by other lanes of this warp
+            for_each_chunk(g, row, lo, hi, [&](int e0, int e1) {
+                for (int e = e0 + lane; e < e1; e += 32) p.alpha_out[e] *= scale;
+            });
+        }
+        return;
+    }
 
     if (!hub_cta) {
         if (GALA_IS_GAT(MODE)) scale = 1.0f / (rs + p.seed_total);

@@ -62,6 +62,25 @@ class GAT2:
         self.b_att2 = torch.tensor([self.bL2, self.bR2], device=W1.device)
         self.b_att2_host = [self.bL2, self.bR2]
         self.fc1_wT = W1.t().contiguous()
+        self._reflected = None
+
+    def fold_reflected(self):
+        """mode="reflected": every aggregation gathers its rows in a basis reflected so that the LAST feature column is
+        the right-hand attention term (gala_gat_forward_col_f32): H = I - 2 v v^T with H e_last = -+ wR/|wR|.  The
+        reflection of layer 1 folds into the layer-1 transform (W' = H1 W, b' = H1 b) and into the left-hand
+        projection (w' = H1 w); layer 1's kernel reflects its finished rows back, applies the ReLU and reflects them
+        into layer 2's basis (H2 from the folded projection wR2); layer 2's kernel reflects back before the
+        classifier.  Same math as "folded" up to fp32 rounding (H is orthogonal); one gather per edge instead of two.
+        Host arithmetic on [32] / [32, F] weights, done once per weight update."""
+        if self._reflected is None:
+            v1, s1 = ops.reflection(self.wR1)
+            v2, s2 = ops.reflection(self.wR2)
+            W0, b0 = self.fc0
+            self._reflected = dict(
+                v1=v1, s1=s1, v2=v2, s2=s2,
+                W0=ops.reflect(W0, v1, dim=0), b0=ops.reflect(b0, v1),
+                W_att1=ops.reflect(self.W_att1, v1), W_att2=ops.reflect(self.W_att2, v2))
+        return self._reflected
 
     def attention_inputs(self, t, wl, wr):
         return F.linear(t, *wl).reshape(-1), F.linear(t, *wr).reshape(-1)
@@ -76,6 +95,8 @@ class GAT2:
                           the kernels' epilogues (gala_linear_f32 + 2 x gala_gat_forward_ex_f32)
           mode="dot"    : aR recomputed inside the kernel (gala_gat_forward_dot_f32)
           mode="folded_dot": "folded" (own kernels for every dense op) + aR recomputed inside the kernel
+          mode="reflected": "folded" with the aggregated rows stored in a reflected basis whose last column IS the
+                          right-hand attention term (fold_reflected; gala_gat_forward_col_f32): one gather per edge
         dense="tcgen05" runs the layer-1 transform (and, in folded mode, its two attention
         projections, fused in the epilogue) on the tensor cores (gala_linear_f32); "torch" = cuBLAS."""
         run = hook if hook is not None else (lambda name, fn: fn())
@@ -94,6 +115,28 @@ class GAT2:
             _, _, out = run("gat_layer2", lambda: ops.gat_forward_ex(g, a2[0], a2[1], res, self.slope, relu=False,
                                                                      cls_wT=self.fc1_wT, cls_b=self.fc1[1], want_y=False))
             return out
+        if mode == "reflected" and hidden not in (4, 8, 16, 32):
+            mode = "folded"             # the column mode holds a row in hidden/4 lanes of one warp pass
+        if mode == "reflected":
+            r = self.fold_reflected()
+            if dense == "tcgen05":
+                res, a = run("linear1", lambda: ops.linear(X, r["W0"], r["b0"], att_w=r["W_att1"], att_b=self.b_att1_host))
+                aL = a[0]
+            else:
+                res = F.linear(X, r["W0"], r["b0"])
+                aL = F.linear(res, r["W_att1"][:1], self.b_att1[:1]).reshape(-1)
+            res = run("gat_layer1", lambda: ops.gat_forward_col(g, aL, r["s1"], self.bR1, res, self.slope, relu=True,
+                                                                reflect_in=r["v1"], reflect_out=r["v2"]))
+            if dense == "tcgen05":
+                a = run("att2", lambda: ops.linear_small(res, r["W_att2"], self.b_att2, transpose_out=True))
+                aL = a[0]
+            else:
+                aL = F.linear(res, r["W_att2"][:1], self.b_att2[:1]).reshape(-1)
+            agg = run("gat_layer2", lambda: ops.gat_forward_col(g, aL, r["s2"], self.bR2, res, self.slope, relu=False,
+                                                                reflect_in=r["v2"]))
+            if dense == "tcgen05":
+                return run("classifier", lambda: ops.linear_small(agg, self.fc1[0], self.fc1[1]))
+            return F.linear(agg, *self.fc1)
         if dense == "tcgen05" and mode == "folded_dot":
             # as "folded", with the right-hand attention term recomputed inside the aggregation kernel from the row
             # it gathers (gala_gat_forward_dot_f32: one gather per edge instead of two); aR is never read
@@ -140,6 +183,12 @@ class GAT2:
             stage = torch.empty(X_host.shape, dtype=torch.float32, device=dev)
         hidden = self.fc0[0].shape[0]
         res = torch.empty((n, hidden), dtype=torch.float32, device=dev)
+        if mode == "reflected" and hidden in (4, 8, 16, 32):
+            r = self.fold_reflected()
+            W0, b0, W_att1 = r["W0"], r["b0"], r["W_att1"]
+        else:
+            mode = "folded" if mode == "reflected" else mode
+            W0, b0, W_att1 = self.fc0[0], self.fc0[1], self.W_att1
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=dev)
         cs, main = self._copy_stream, torch.cuda.current_stream()
@@ -153,9 +202,14 @@ class GAT2:
                 ev = torch.cuda.Event()
                 ev.record(cs)
             main.wait_event(ev)
-            ops.linear(stage[lo:hi], self.fc0[0], self.fc0[1], out=res[lo:hi])
-        a = ops.linear_small(res, self.W_att1, self.b_att1, transpose_out=True)
-        if mode == "folded_dot":
+            ops.linear(stage[lo:hi], W0, b0, out=res[lo:hi])
+        a = ops.linear_small(res, W_att1, self.b_att1, transpose_out=True)
+        if mode == "reflected":
+            res = ops.gat_forward_col(g, a[0], r["s1"], self.bR1, res, self.slope, relu=True, reflect_in=r["v1"],
+                                      reflect_out=r["v2"])
+            a = ops.linear_small(res, r["W_att2"], self.b_att2, transpose_out=True)
+            agg = ops.gat_forward_col(g, a[0], r["s2"], self.bR2, res, self.slope, relu=False, reflect_in=r["v2"])
+        elif mode == "folded_dot":
             res = ops.gat_forward_dot(g, a[0], self.wR1, self.bR1, res, self.slope, relu=True)
             a = ops.linear_small(res, self.W_att2, self.b_att2, transpose_out=True)
             agg = ops.gat_forward_dot(g, a[0], self.wR2, self.bR2, res, self.slope, relu=False)

@@ -19,7 +19,7 @@ EXPORTS = [
     "gala_edge_scale_rows_f32", "gala_sddvv_f32", "gala_sddmm_f32", "gala_edge_softmax_fwd_f32",
     "gala_edge_softmax_bwd_f32", "gala_gat_forward_f32", "gala_gat_forward_dot_f32", "gala_linear_f32",
     "gala_gat_forward_ex_f32", "gala_linear_small_f32", "gala_linear_small_ex_f32", "gala_push_rows_f32", "gala_gat_backward_att_f32",
-    "gala_spmm_bf16", "gala_gat_forward_bf16", "gala_pad_rows_f32",
+    "gala_spmm_bf16", "gala_gat_forward_bf16", "gala_pad_rows_f32", "gala_gat_forward_col_f32", "gala_reflection_f32",
     "gala_csr_from_coo_workspace_bytes", "gala_csr_from_coo", "gala_csr_transpose",
     "gala_col_tile_segments", "gala_col_tile_workspace_bytes", "gala_col_tile", "gala_sample_ab",
     "gala_mask_subgraph_workspace_bytes", "gala_mask_subgraph",
@@ -99,6 +99,8 @@ def load():
         "gala_gat_forward_f32": [G, vp, vp, vp, i32, f32, vp, vp, i32, P, vp],
         "gala_gat_forward_dot_f32": [G, vp, vp, f32, vp, i32, f32, vp, vp, i32, P, vp],
         "gala_gat_forward_ex_f32": [G, vp, vp, vp, i32, f32, vp, vp, i32, C.POINTER(GalaDenseEpilogue), P, vp],
+        "gala_gat_forward_col_f32": [G, vp, f32, f32, vp, i32, C.c_int64, f32, vp, C.c_int64, vp, i32, vp, vp, P, vp],
+        "gala_reflection_f32": [C.POINTER(C.c_float), i32, C.POINTER(C.c_float), C.POINTER(C.c_float)],
     }
     i64, sz = C.c_int64, C.c_size_t
     sigs.update({

@@ -266,6 +266,46 @@ def gat_forward_dot(g, aL, wR, bR, X, slope=0.2, relu=False, out=None, alpha_out
     return out
 
 
+def reflection(w):
+    """Householder vector of gala_reflection_f32 for the projection weights w ([K] tensor, any device): returns
+    (v [K] on w's device, sR float) with H = I - 2 v v^T, H e_{K-1} = -sign(w[K-1]) w/|w| and (X H)[:, K-1] * sR = X w.
+    Host arithmetic (K <= a few hundred); call it when the weights change, never inside a step."""
+    wh = w.detach().reshape(-1).to("cpu", torch.float32).contiguous()
+    K = wh.numel()
+    w_arr = (C.c_float * K)(*wh.tolist())
+    v_arr = (C.c_float * K)()
+    sR = C.c_float()
+    _l.check(_l.load().gala_reflection_f32(w_arr, K, v_arr, C.byref(sR)))
+    return torch.tensor(list(v_arr), dtype=torch.float32, device=w.device), float(sR.value)
+
+
+def reflect(T, v, dim=-1):
+    """T H with H = I - 2 v v^T applied along `dim` (host-side folding of the reflection into weights / biases;
+    fp64 inside so that the folded weights carry no extra rounding)."""
+    Td, vd = T.double(), v.double()
+    if dim in (-1, T.dim() - 1):
+        return (Td - 2.0 * (Td @ vd).unsqueeze(-1) * vd).float().contiguous()
+    assert dim == 0
+    return (Td - 2.0 * vd.unsqueeze(-1) * (vd @ Td).unsqueeze(0)).float().contiguous()
+
+
+def gat_forward_col(g, aL, sR, bR, X, slope=0.2, relu=False, reflect_in=None, reflect_out=None, out=None,
+                    alpha_out=None):
+    """Fused GAT layer over features in a reflected basis whose last column carries the right-hand attention term:
+    aR[j] = sR * X[j, K-1] + bR (gala_gat_forward_col_f32).  reflect_in / reflect_out: [K] Householder vectors
+    applied to each finished output row before / after the ReLU.  K in {4, 8, 16, 32}."""
+    X, aL = _f32(X), _f32(aL)
+    K = X.shape[1]
+    rin = _f32(reflect_in) if reflect_in is not None else None
+    rout = _f32(reflect_out) if reflect_out is not None else None
+    if out is None:
+        out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
+    _l.check(_l.load().gala_gat_forward_col_f32(C.byref(g.c), _l.ptr(aL), float(sR), float(bR), _l.ptr(X), K, 0,
+                                                slope, _l.ptr(out), 0, _l.ptr(alpha_out), int(relu), _l.ptr(rin),
+                                                _l.ptr(rout), g._p(), _l.stream_ptr()))
+    return out
+
+
 def make_multi_out(bases, multicast_base=None, need_mask=None):
     """bases: per-GPU addresses (ints) of this rank's slab inside every peer-mapped gathered buffer.
     need_mask: uint8 device tensor [rows of this rank], bit q = GPU q references the row (peer stores only)."""

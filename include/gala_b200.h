@@ -48,7 +48,8 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define GALA_B200_ABI_VERSION 3   /* v2: row pitches ldx / ldy, gala_pad_rows_f32; v3: edge tiles in gala_plan_t */
+#define GALA_B200_ABI_VERSION 4   /* v2: row pitches ldx / ldy, gala_pad_rows_f32; v3: edge tiles in gala_plan_t;
+                                     v4: gala_gat_forward_col_f32, gala_reflection_f32 (additions only) */
 
 #define GALA_OK 0
 #define GALA_ERR_NULL_POINTER (-1)
@@ -294,6 +295,31 @@ int gala_gat_forward_ex_f32(const gala_graph_t *g, const float *aL, const float 
 int gala_gat_forward_dot_f32(const gala_graph_t *g, const float *aL, const float *wR, float bR,
                              const float *X, int32_t K, float slope, float *Y, float *alpha_out,
                              int32_t relu, const gala_plan_t *plan, gala_stream_t stream);
+
+/* Same layer for features stored in a REFLECTED basis whose last column carries the right-hand */
+/* attention term (ABI v4).  attenR = efc(res) is a linear function w.res + b of the rows the     */
+/* layer aggregates (common.h:1185-1281), and the aggregation is linear in those rows, so the     */
+/* producer may hand over X' = X H with H = I - 2 v v^T the Householder reflection that maps the  */
+/* last unit vector onto -+ w/|w| (gala_reflection_f32 below builds v and sR = -+|w|): then       */
+/*     aR[j] = sR * X'[j, K-1] + bR,     sum_j alpha_j X[j] = (sum_j alpha_j X'[j]) H,            */
+/* H is orthogonal and its own inverse, and it folds into the weights of the transform that       */
+/* produces X (W' = H W, b' = H b) at no cost.  The kernel reads the scalar from the 128-byte row  */
+/* it gathers anyway -- 4 sectors per edge instead of 4 + 1, no second random gather, no dot       */
+/* product -- and applies, per finished output row y (normalised sum):                             */
+/*     reflect_in  (device [K], nullable): y <- y - 2 v (v.y), back to the original basis;         */
+/*     ReLU if relu;                                                                               */
+/*     reflect_out (device [K], nullable): the same with the NEXT layer's vector.                   */
+/* K in {4, 8, 16, 32}; X, Y 16-byte aligned with row pitches ldx, ldy (0 = K) that are multiples  */
+/* of 4; otherwise GALA_ERR_UNSUPPORTED (use gala_gat_forward_f32).  alpha_out as above.           */
+int gala_gat_forward_col_f32(const gala_graph_t *g, const float *aL, float sR, float bR, const float *X,
+                             int32_t K, int64_t ldx, float slope, float *Y, int64_t ldy, float *alpha_out,
+                             int32_t relu, const float *reflect_in, const float *reflect_out,
+                             const gala_plan_t *plan, gala_stream_t stream);
+
+/* Host helper (no device work): the unit vector v[K] of the reflection H = I - 2 v v^T with      */
+/* H e_{K-1} = -sign(w[K-1]) w/|w| and *sR = -sign(w[K-1]) |w|, so that (X H)[:, K-1] * sR = X w.  */
+/* Accumulates in double.  w == 0 -> GALA_ERR_BAD_SHAPE (attention does not depend on the column). */
+int gala_reflection_f32(const float *w, int32_t K, float *v, float *sR);
 
 /* ---- dense feature transform on the tensor cores -------- */
 /* Replaces torch::nn::Linear of the generated model (common.h:1185-1281; cuBLAS fp32 SIMT   */

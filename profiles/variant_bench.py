@@ -35,6 +35,7 @@ Yf = torch.empty(n, K, device=dev)
 print(json.dumps({"linear_602_32": t(lambda: ops.linear(Xf, Wf, out=Yf)),
                   "gat": t(lambda: ops.gat_forward(g, a, a, X, out=Y)),
                   "gat_dot": t(lambda: ops.gat_forward_dot(g, a, X[0].contiguous(), 0.1, X, out=Y)),
+                  "gat_col": t(lambda: ops.gat_forward_col(g, a, 1.0, 0.1, X, reflect_in=X[1].contiguous(), reflect_out=X[2].contiguous(), relu=True, out=Y)) if hasattr(ops, "gat_forward_col") else None,
                   "spmm": t(lambda: ops.spmm(g, X, out=Y)),
                   "spmm_w": t(lambda: ops.spmm(g, X, vals=w, out=Y)),
                   "sddmm": t(lambda: ops.sddmm(g, X, X, out=ev)),

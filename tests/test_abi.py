@@ -31,7 +31,7 @@ def test_header_symbols_are_exported():
 
 def test_abi_version_and_error_strings():
     lib = L.load()
-    assert lib.gala_b200_abi_version() == 3
+    assert lib.gala_b200_abi_version() == 4
     assert lib.gala_b200_error_string(0) == b"success"
     for code in (-1, -2, -3, -4, -5):
         assert b"gala_b200" in lib.gala_b200_error_string(code)

@@ -257,6 +257,55 @@ def test_gat_dot_variant_matches_composition(orc, case, K):
         assert rel_err(got2, want2) < FP32_TOL
 
 
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("K", [4, 8, 16, 32])
+def test_gat_col_variant_matches_oracle(orc, case, K):
+    """gala_gat_forward_col_f32: features handed over in the reflected basis X' = X H (H = I - 2 v v^T maps the last
+    unit vector onto the direction of the right-hand projection), aR read from the last column of the gathered row.
+    The result must be the oracle's layer on the ORIGINAL X with the materialised aR = X.wR + bR."""
+    n, e, seed, T, empty, thr = case
+    t = graph_case(orc, n, e, seed, T, empty)
+    g = to_gpu_graph(t, thr)
+    rng = np.random.default_rng(seed + 17 * K)
+    aL = rng.normal(size=n).astype(np.float32)
+    wR = rng.normal(size=K).astype(np.float32)
+    if seed % 2:
+        wR[-1] = -abs(wR[-1])            # both signs of the pivot component
+    bR = 0.3
+    X = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    aR = (X.astype(np.float64) @ wR.astype(np.float64) + bR).astype(np.float32)
+    want_Y, want_alpha = orc.gat_forward(t, aL, aR, X)
+    v, sR = ops.reflection(dev(wR))
+    vd = v.double().cpu().numpy()
+    H = np.eye(K) - 2.0 * np.outer(vd, vd)
+    assert np.abs(H @ H - np.eye(K)).max() < 1e-6          # float32 v: orthogonal to rounding
+    assert np.abs(sR * H[:, -1] - wR).max() < 1e-5 * np.abs(wR).max()
+    Xr = (X.astype(np.float64) @ H).astype(np.float32)
+    alpha = torch.empty(t.nvals, device=DEV)
+    # back to the original basis, then ReLU
+    got = ops.gat_forward_col(g, dev(aL), sR, bR, dev(Xr), relu=True, reflect_in=v, alpha_out=alpha).cpu().numpy()
+    assert rel_err(got, np.maximum(want_Y, 0)) < FP32_TOL
+    assert rel_err(alpha.cpu().numpy(), want_alpha) < FP32_TOL
+    # ... and on into the next layer's basis (another reflection, after the ReLU)
+    w2 = rng.normal(size=K).astype(np.float32)
+    v2, _ = ops.reflection(dev(w2))
+    v2d = v2.double().cpu().numpy()
+    H2 = np.eye(K) - 2.0 * np.outer(v2d, v2d)
+    got2 = ops.gat_forward_col(g, dev(aL), sR, bR, dev(Xr), relu=True, reflect_in=v, reflect_out=v2).cpu().numpy()
+    assert rel_err(got2, np.maximum(want_Y, 0) @ H2) < FP32_TOL
+    # no reflections: the sum stays in the gathered basis
+    got3 = ops.gat_forward_col(g, dev(aL), sR, bR, dev(Xr)).cpu().numpy()
+    assert rel_err(got3, want_Y @ H) < FP32_TOL
+
+
+def test_gat_col_rejects_unsupported_widths(orc):
+    t = graph_case(orc, 300, 3000, 5)
+    g = to_gpu_graph(t, 64)
+    X = torch.rand(300, 12, device=DEV)
+    with pytest.raises(Exception):
+        ops.gat_forward_col(g, X[:, 0].contiguous(), 1.0, 0.0, X)
+
+
 def test_gat_model_dot_and_materialised_paths_agree(orc):
     from gala_b200.gat_model import GAT2
     n = 3000
@@ -265,7 +314,7 @@ def test_gat_model_dot_and_materialised_paths_agree(orc):
     model = GAT2(64, 32, 41, DEV, seed=3)
     X = torch.rand(n, 64, device=DEV) - 0.5
     b = model.forward(g, X, mode="literal", dense="torch")
-    for mode in ("folded", "dot", "literal", "fused"):
+    for mode in ("folded", "dot", "literal", "fused", "reflected"):
         for dense in ("torch", "tcgen05"):
             a = model.forward(g, X, mode=mode, dense=dense)
             assert float((a - b).double().norm() / b.double().norm()) < FP32_TOL
