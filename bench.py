@@ -220,7 +220,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU feature exchange: fused into the kernels over peer memory, or NCCL all-gather")
-    ap.add_argument("--mode", default="reflected", choices=["folded", "folded_dot", "reflected", "fused", "literal", "dot"],
+    ap.add_argument("--mode", default="reflected", choices=["folded", "folded_dot", "reflected", "reflected_fused", "fused", "literal", "dot"],
                     help="how the dense ops around the fused GAT kernel run (gala_b200/gat_model.py)")
     ap.add_argument("--dense", default="tcgen05", choices=["tcgen05", "torch"],
                     help="layer-1 feature transform: hand-written tcgen05 3xTF32 kernel or cuBLAS fp32 via torch")
@@ -292,8 +292,10 @@ def main():
 
         runner = dist_gat.PartitionedGAT(model, offset, ids, n, rank, world, dev, exchange=args.exchange)
         X_in = X[runner.row_lo:runner.row_hi].contiguous()
-        step_fn = lambda hook=None: runner.forward(X_in, hook)   # noqa: E731
+        mode = args.mode if args.mode in ("reflected", "folded", "fused", "dot", "literal") else "folded"
+        step_fn = lambda hook=None: runner.forward(X_in, hook, mode=mode)   # noqa: E731
         launches_per_step = runner.launches_per_step
+        config["mode"] = mode
         config["parallelism"] = (f"1D row partition over {world} GPUs (nnz-balanced); exchange of hidden features: "
                                  + {"p2p-multicast": "fused into the producing kernels (multimem.st through NVLS multicast "
                                                      "into every GPU's buffer + device barrier)",
@@ -304,7 +306,7 @@ def main():
         X_in = X
         mode = args.mode
         step_fn = lambda hook=None: model.forward(g, X_in, hook, mode=mode, dense=args.dense)   # noqa: E731
-        launches_per_step = ({"folded": 5, "folded_dot": 5, "reflected": 5, "fused": 3}.get(mode, 2)
+        launches_per_step = ({"folded": 5, "folded_dot": 5, "reflected": 4, "reflected_fused": 3, "fused": 3}.get(mode, 2)
                              if args.dense == "tcgen05" else 2)
         config["parallelism"] = "single GPU"
         config["dense"] = ("layer-1 X*W + attention projections: gala_linear_f32 (tcgen05 kind::tf32, 3xTF32)"
@@ -406,7 +408,7 @@ def main():
             model.forward_host(g, X_host, out_host, chunks=e2e_chunks, mode=mode, stage=X_stage)
             return
         X_stage.copy_(X_host, non_blocking=True)
-        o = (runner.forward(X_stage) if world > 1 else model.forward(g, X_stage, mode=mode, dense=args.dense))
+        o = (runner.forward(X_stage, mode=mode) if world > 1 else model.forward(g, X_stage, mode=mode, dense=args.dense))
         out_host.copy_(o, non_blocking=True)
 
     for _ in range(2):
@@ -434,7 +436,7 @@ def main():
     if world > 1:
         g_full = ops.TiledGraph(offset, ids, n).build_plan()
         want = model.forward(g_full, X, mode="literal", dense="torch")[runner.row_lo:runner.row_hi]
-        got = runner.forward(X_in)
+        got = runner.forward(X_in, mode=mode)
         tt = torch.stack([(got.double() - want.double()).pow(2).sum(), want.double().pow(2).sum()])
         dist.all_reduce(tt)
         parity = float((tt[0] / tt[1]).sqrt().item())
@@ -468,7 +470,7 @@ def main():
     e_local = runner.local_nvals if world > 1 else nvals
     # mode "reflected" (gala_gat_forward_col_f32): aR rides in the last column of the gathered rows -- no [N] aR
     # vector in the byte model and no second 4-byte gather per edge
-    col_mode = world == 1 and mode == "reflected"
+    col_mode = (mode in ("reflected", "reflected_fused") and world == 1) or (mode == "reflected" and world > 1 and runner.px is not None)
     alg_bytes = (4 * (rows_local + 1) + 4 * e_local + 4 * rows_local + (0 if col_mode else 4 * n)
                  + 4 * hidden * (n + rows_local))
     kms = float(np.mean([kern_ms[k] for k in ("gat_layer1", "gat_layer2") if k in kern_ms]))

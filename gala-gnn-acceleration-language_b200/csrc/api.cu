@@ -623,14 +623,17 @@ int gala_reflection_f32(const float* w, int32_t K, float* v, float* sR) {
 }
 
 int gala_gat_forward_col_f32(const gala_graph_t* g, const float* aL, float sR, float bR, const float* X, int32_t K,
-                             int64_t ldx, float slope, float* Y, int64_t ldy, float* alpha_out, int32_t relu,
-                             const float* reflect_in, const float* reflect_out, const gala_plan_t* plan,
+                             float slope, float* Y, float* alpha_out, int32_t relu, const float* reflect_in,
+                             const float* reflect_out, const gala_dense_epilogue_t* ep, const gala_plan_t* plan,
                              gala_stream_t stream) {
     if (int rc = check_graph(g)) return rc;
     if (K != 4 && K != 8 && K != 16 && K != 32) return GALA_ERR_UNSUPPORTED;   // K/4 lanes hold the row, last lane the scalar
-    if (g->nrows > 0 && (!aL || !X || !Y)) return GALA_ERR_NULL_POINTER;
-    if (ldx <= 0) ldx = K;
-    if (ldy <= 0) ldy = K;
+    const bool has_ep = ep && (ep->att_w || ep->cls_wT);
+    const bool multi = ep && ep->multi_out && ep->multi_out->count > 0;
+    if (g->nrows > 0 && (!aL || !X || (!Y && !(has_ep && ep->cls_wT) && !multi))) return GALA_ERR_NULL_POINTER;
+    if (multi && ep->multi_out->count > kMaxPeers) return GALA_ERR_UNSUPPORTED;
+    if (ep && ep->att_multi_out && ep->att_multi_out->count > 0) return GALA_ERR_UNSUPPORTED;   // no scalar to exchange here
+    const int64_t ldx = (ep && ep->ldx > 0) ? ep->ldx : K, ldy = (ep && ep->ldy > 0) ? ep->ldy : K;
     if (ldx < K || ldy < K) return GALA_ERR_BAD_SHAPE;
     if (!aligned(X, 16) || !aligned(Y, 16) || ldx % 4 != 0 || ldy % 4 != 0) return GALA_ERR_UNSUPPORTED;
     if (g->nrows == 0) return GALA_OK;
@@ -651,6 +654,24 @@ int gala_gat_forward_col_f32(const gala_graph_t* g, const float* aL, float sR, f
     p.slope = slope;
     p.alpha_out = alpha_out;
     p.seed_total = (float)g->segments * 1e-12f;
+    if (has_ep) {
+        if (ep->att_w && !ep->att_out) return GALA_ERR_NULL_POINTER;
+        if (ep->cls_wT && (!ep->cls_out || ep->cls_n <= 0)) return GALA_ERR_NULL_POINTER;
+        p.att_w = ep->att_w;
+        p.att_b0 = ep->att_b[0];
+        p.att_b1 = ep->att_b[1];
+        p.att_out = ep->att_out;
+        p.cls_wT = ep->cls_wT;
+        p.cls_b = ep->cls_b;
+        p.cls_out = ep->cls_out;
+        p.cls_n = ep->cls_n;
+    }
+    if (multi) {
+        p.mo.count = ep->multi_out->count;
+        p.mo.mc_base = ep->multi_out->multicast_base;
+        p.mo.need = ep->multi_out->need_mask;
+        for (int q = 0; q < p.mo.count; ++q) p.mo.base[q] = ep->multi_out->base[q];
+    }
     HubView h = hub_of(plan, g);
     p.t = task_of(h);
     dim3 grid(p.t.n_hub + (p.t.n_ordered + kWarpsPerCta - 1) / kWarpsPerCta, 1);

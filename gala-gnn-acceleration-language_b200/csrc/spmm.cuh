@@ -490,11 +490,30 @@ spmm_kernel(const __grid_constant__ SpmmParams p) {
                 for (int v = 0; v < VEC; ++v) y[v] = fmaxf(y[v], 0.0f);
             }
             if (p.refl_out) reflect_row<VEC, LPR>(y, p.refl_out, sub);
+            // the next layer's LEFT-hand projection of the final row (its right-hand one is that layer's last
+            // column): from the registers that hold the row, no staging -- att_out[0:nrows] only
+            const bool att_only = p.att_w != nullptr && p.cls_wT == nullptr;
+            if (att_only) {
+                float d = 0.0f;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) d = fmaf(y[v], __ldg(p.att_w + sub * VEC + v), d);
+#pragma unroll
+                for (int o = 1; o < LPR; o <<= 1) d += __shfl_xor_sync(kFull, d, o);
+                if (lane == 0) p.att_out[row] = d + p.att_b0;
+            }
             if (grp == 0) {
                 Vec<VEC> o;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) o.v[v] = y[v];
-                o.store(p.Y + (int64_t)row * p.ldy + sub * VEC);
+                for (int v = 0; v < VEC; ++v) {
+                    o.v[v] = y[v];
+                    if (dense_ep && !att_only) rowbuf[warp][sub * VEC + v] = y[v];
+                }
+                if (p.mo.count > 0) multi_store<VEC>(p.mo, (int64_t)row * p.K + sub * VEC, o, row);
+                else if (p.Y) o.store(p.Y + (int64_t)row * p.ldy + sub * VEC);
+            }
+            if (dense_ep && !att_only) {
+                __syncwarp();
+                row_dense_epilogue(p, rowbuf[warp], row, lane);
             }
         }
         if (write_alpha) {

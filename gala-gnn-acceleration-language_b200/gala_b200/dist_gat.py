@@ -423,13 +423,36 @@ class PartitionedGAT:
                                                                  want_y=False))
         return out
 
+    def forward_p2p_reflected(self, X_local, hook=None):
+        """forward_p2p with the hidden rows exchanged in the reflected basis of the layer that gathers them
+        (gat_model.GAT2.fold_reflected, gala_gat_forward_col_f32): the right-hand attention term is the last column
+        of every pushed row, so no scalar is exchanged or gathered, and each edge costs one gather instead of two."""
+        run = hook if hook is not None else (lambda name, fn: fn())
+        m, px, ops = self.model, self.px, self.ops
+        r = m.fold_reflected()
+        _, a = run("linear1", lambda: ops.linear(X_local, r["W0"], r["b0"], att_w=r["W_att1"], att_b=m.b_att1_host,
+                                                 multi_out=px.mos[0]))
+        px.barrier(0)
+        _, a2, _ = run("gat_layer1", lambda: ops.gat_forward_col_ex(
+            self.graph, a[0], r["s1"], m.bR1, px.bufs[0], m.slope, relu=True, reflect_in=r["v1"], reflect_out=r["v2"],
+            att_w=r["W_att2"], att_b=m.b_att2_host, multi_out=px.mos[1]))
+        px.barrier(1)
+        _, _, out = run("gat_layer2", lambda: ops.gat_forward_col_ex(
+            self.graph, a2[0], r["s2"], m.bR2, px.bufs[1], m.slope, relu=False, reflect_in=r["v2"],
+            cls_wT=m.fc1_wT, cls_b=m.fc1[1], want_y=False))
+        return out
+
     def _aggregate(self, aL, aR, feats, relu):
         return self.ops.gat_forward(self.graph, aL.contiguous(), aR.contiguous(), feats, self.model.slope, relu=relu)
 
     def _aggregate_dot(self, aL, wR, bR, feats, relu):
         return self.ops.gat_forward_dot(self.graph, aL.contiguous(), wR, bR, feats, self.model.slope, relu=relu)
 
-    def forward(self, X_local, hook=None, mode="folded"):
+    def forward(self, X_local, hook=None, mode="reflected"):
+        if mode == "reflected":
+            if self.px is not None and self.model.fc0[0].shape[0] in (4, 8, 16, 32):
+                return self.forward_p2p_reflected(X_local, hook)
+            mode = "folded"
         if self.px is not None and mode in ("folded", "fused"):
             return self.forward_p2p(X_local, hook)
         if mode == "dot":

@@ -95,6 +95,7 @@ class GAT2:
                           the kernels' epilogues (gala_linear_f32 + 2 x gala_gat_forward_ex_f32)
           mode="dot"    : aR recomputed inside the kernel (gala_gat_forward_dot_f32)
           mode="folded_dot": "folded" (own kernels for every dense op) + aR recomputed inside the kernel
+          mode="reflected_fused": "fused" in that basis (gala_gat_forward_col_f32 with its dense epilogue)
           mode="reflected": "folded" with the aggregated rows stored in a reflected basis whose last column IS the
                           right-hand attention term (fold_reflected; gala_gat_forward_col_f32): one gather per edge
         dense="tcgen05" runs the layer-1 transform (and, in folded mode, its two attention
@@ -117,6 +118,20 @@ class GAT2:
             return out
         if mode == "reflected" and hidden not in (4, 8, 16, 32):
             mode = "folded"             # the column mode holds a row in hidden/4 lanes of one warp pass
+        if mode == "reflected_fused" and (hidden not in (4, 8, 16, 32) or dense != "tcgen05"):
+            mode = "fused" if dense == "tcgen05" else "folded"
+        if mode == "reflected_fused":
+            # "fused" in the reflected basis: three launches, the left-hand projection of layer 2 and the classifier in
+            # the aggregation kernels' epilogues
+            r = self.fold_reflected()
+            res, a = run("linear1", lambda: ops.linear(X, r["W0"], r["b0"], att_w=r["W_att1"], att_b=self.b_att1_host))
+            res, a2, _ = run("gat_layer1", lambda: ops.gat_forward_col_ex(
+                g, a[0], r["s1"], self.bR1, res, self.slope, relu=True, reflect_in=r["v1"], reflect_out=r["v2"],
+                att_w=r["W_att2"], att_b=self.b_att2_host))
+            _, _, out = run("gat_layer2", lambda: ops.gat_forward_col_ex(
+                g, a2[0], r["s2"], self.bR2, res, self.slope, relu=False, reflect_in=r["v2"],
+                cls_wT=self.fc1_wT, cls_b=self.fc1[1], want_y=False))
+            return out
         if mode == "reflected":
             r = self.fold_reflected()
             if dense == "tcgen05":
@@ -125,13 +140,11 @@ class GAT2:
             else:
                 res = F.linear(X, r["W0"], r["b0"])
                 aL = F.linear(res, r["W_att1"][:1], self.b_att1[:1]).reshape(-1)
-            res = run("gat_layer1", lambda: ops.gat_forward_col(g, aL, r["s1"], self.bR1, res, self.slope, relu=True,
-                                                                reflect_in=r["v1"], reflect_out=r["v2"]))
-            if dense == "tcgen05":
-                a = run("att2", lambda: ops.linear_small(res, r["W_att2"], self.b_att2, transpose_out=True))
-                aL = a[0]
-            else:
-                aL = F.linear(res, r["W_att2"][:1], self.b_att2[:1]).reshape(-1)
+            # layer 2's left-hand projection of every finished (twice reflected) row comes from the kernel's epilogue
+            res, a, _ = run("gat_layer1", lambda: ops.gat_forward_col_ex(
+                g, aL, r["s1"], self.bR1, res, self.slope, relu=True, reflect_in=r["v1"], reflect_out=r["v2"],
+                att_w=r["W_att2"], att_b=self.b_att2_host))
+            aL = a[0]
             agg = run("gat_layer2", lambda: ops.gat_forward_col(g, aL, r["s2"], self.bR2, res, self.slope, relu=False,
                                                                 reflect_in=r["v2"]))
             if dense == "tcgen05":
@@ -205,9 +218,8 @@ class GAT2:
             ops.linear(stage[lo:hi], W0, b0, out=res[lo:hi])
         a = ops.linear_small(res, W_att1, self.b_att1, transpose_out=True)
         if mode == "reflected":
-            res = ops.gat_forward_col(g, a[0], r["s1"], self.bR1, res, self.slope, relu=True, reflect_in=r["v1"],
-                                      reflect_out=r["v2"])
-            a = ops.linear_small(res, r["W_att2"], self.b_att2, transpose_out=True)
+            res, a, _ = ops.gat_forward_col_ex(g, a[0], r["s1"], self.bR1, res, self.slope, relu=True, reflect_in=r["v1"],
+                                               reflect_out=r["v2"], att_w=r["W_att2"], att_b=self.b_att2_host)
             agg = ops.gat_forward_col(g, a[0], r["s2"], self.bR2, res, self.slope, relu=False, reflect_in=r["v2"])
         elif mode == "folded_dot":
             res = ops.gat_forward_dot(g, a[0], self.wR1, self.bR1, res, self.slope, relu=True)

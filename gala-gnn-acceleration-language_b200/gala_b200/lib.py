@@ -99,7 +99,7 @@ def load():
         "gala_gat_forward_f32": [G, vp, vp, vp, i32, f32, vp, vp, i32, P, vp],
         "gala_gat_forward_dot_f32": [G, vp, vp, f32, vp, i32, f32, vp, vp, i32, P, vp],
         "gala_gat_forward_ex_f32": [G, vp, vp, vp, i32, f32, vp, vp, i32, C.POINTER(GalaDenseEpilogue), P, vp],
-        "gala_gat_forward_col_f32": [G, vp, f32, f32, vp, i32, C.c_int64, f32, vp, C.c_int64, vp, i32, vp, vp, P, vp],
+        "gala_gat_forward_col_f32": [G, vp, f32, f32, vp, i32, f32, vp, vp, i32, vp, vp, C.POINTER(GalaDenseEpilogue), P, vp],
         "gala_reflection_f32": [C.POINTER(C.c_float), i32, C.POINTER(C.c_float), C.POINTER(C.c_float)],
     }
     i64, sz = C.c_int64, C.c_size_t

@@ -289,6 +289,33 @@ def reflect(T, v, dim=-1):
     return (Td - 2.0 * vd.unsqueeze(-1) * (vd @ Td).unsqueeze(0)).float().contiguous()
 
 
+def _dense_epilogue(g, dev, att_w, att_b, cls_wT, cls_b, multi_out, att_multi_out):
+    """gala_dense_epilogue_t + the tensors it writes (att [2, nrows], cls [nrows, C]) + the tensors it must keep alive."""
+    ep = _l.GalaDenseEpilogue()
+    keep = []
+    if multi_out is not None:
+        ep.multi_out = C.pointer(multi_out)
+    if att_multi_out is not None:
+        ep.att_multi_out = C.pointer(att_multi_out)
+    att = cls = None
+    if att_w is not None:
+        att = torch.empty((2, g.nrows), dtype=torch.float32, device=dev)
+        att_w = _f32(att_w)
+        keep.append(att_w)
+        ep.att_w = att_w.data_ptr()
+        ep.att_b[0], ep.att_b[1] = float(att_b[0]), float(att_b[1])
+        ep.att_out = att.data_ptr()
+    if cls_wT is not None:
+        cls_wT = _f32(cls_wT)
+        keep.append(cls_wT)
+        cls = torch.empty((g.nrows, cls_wT.shape[1]), dtype=torch.float32, device=dev)
+        ep.cls_wT = cls_wT.data_ptr()
+        ep.cls_b = cls_b.data_ptr() if cls_b is not None else None
+        ep.cls_out = cls.data_ptr()
+        ep.cls_n = cls_wT.shape[1]
+    return ep, att, cls, keep
+
+
 def gat_forward_col(g, aL, sR, bR, X, slope=0.2, relu=False, reflect_in=None, reflect_out=None, out=None,
                     alpha_out=None):
     """Fused GAT layer over features in a reflected basis whose last column carries the right-hand attention term:
@@ -300,10 +327,30 @@ def gat_forward_col(g, aL, sR, bR, X, slope=0.2, relu=False, reflect_in=None, re
     rout = _f32(reflect_out) if reflect_out is not None else None
     if out is None:
         out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
-    _l.check(_l.load().gala_gat_forward_col_f32(C.byref(g.c), _l.ptr(aL), float(sR), float(bR), _l.ptr(X), K, 0,
-                                                slope, _l.ptr(out), 0, _l.ptr(alpha_out), int(relu), _l.ptr(rin),
-                                                _l.ptr(rout), g._p(), _l.stream_ptr()))
+    _l.check(_l.load().gala_gat_forward_col_f32(C.byref(g.c), _l.ptr(aL), float(sR), float(bR), _l.ptr(X), K,
+                                                slope, _l.ptr(out), _l.ptr(alpha_out), int(relu), _l.ptr(rin),
+                                                _l.ptr(rout), None, g._p(), _l.stream_ptr()))
     return out
+
+
+def gat_forward_col_ex(g, aL, sR, bR, X, slope=0.2, relu=False, reflect_in=None, reflect_out=None, out=None,
+                       att_w=None, att_b=None, cls_wT=None, cls_b=None, want_y=True, multi_out=None):
+    """gat_forward_col + the dense epilogue of gat_forward_ex on every FINAL output row (after reflect_out): att_w
+    [2, K] are the next layer's projections expressed in the basis the rows leave in.  Returns (Y, att, cls)."""
+    X, aL = _f32(X), _f32(aL)
+    K = X.shape[1]
+    rin = _f32(reflect_in) if reflect_in is not None else None
+    rout = _f32(reflect_out) if reflect_out is not None else None
+    if multi_out is not None:
+        want_y = False
+    if want_y and out is None:
+        out = torch.empty((g.nrows, K), dtype=torch.float32, device=X.device)
+    ep, att, cls, keep = _dense_epilogue(g, X.device, att_w, att_b, cls_wT, cls_b, multi_out, None)
+    _l.check(_l.load().gala_gat_forward_col_f32(C.byref(g.c), _l.ptr(aL), float(sR), float(bR), _l.ptr(X), K,
+                                                slope, _l.ptr(out) if want_y else None, None, int(relu), _l.ptr(rin),
+                                                _l.ptr(rout), C.byref(ep), g._p(), _l.stream_ptr()))
+    del keep
+    return out, att, cls
 
 
 def make_multi_out(bases, multicast_base=None, need_mask=None):

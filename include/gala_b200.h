@@ -309,12 +309,16 @@ int gala_gat_forward_dot_f32(const gala_graph_t *g, const float *aL, const float
 /*     reflect_in  (device [K], nullable): y <- y - 2 v (v.y), back to the original basis;         */
 /*     ReLU if relu;                                                                               */
 /*     reflect_out (device [K], nullable): the same with the NEXT layer's vector.                   */
-/* K in {4, 8, 16, 32}; X, Y 16-byte aligned with row pitches ldx, ldy (0 = K) that are multiples  */
-/* of 4; otherwise GALA_ERR_UNSUPPORTED (use gala_gat_forward_f32).  alpha_out as above.           */
+/* ep (nullable) as for gala_gat_forward_ex_f32: row pitches, the dense epilogue on the FINAL row   */
+/* (after reflect_out: att_w then holds the next layer's projections expressed in that basis; only   */
+/* att_out[0:nrows] is needed by a next layer of this kind, and with att_w alone -- no cls_wT -- only  */
+/* that half is written, straight from the registers holding the row), multi_out; att_multi_out unset */
+/* (there is no scalar left to exchange).  K in {4, 8, 16, 32}; X, Y 16-byte aligned, row pitches     */
+/* multiples of 4; otherwise GALA_ERR_UNSUPPORTED (use gala_gat_forward_f32).  alpha_out as above.   */
 int gala_gat_forward_col_f32(const gala_graph_t *g, const float *aL, float sR, float bR, const float *X,
-                             int32_t K, int64_t ldx, float slope, float *Y, int64_t ldy, float *alpha_out,
-                             int32_t relu, const float *reflect_in, const float *reflect_out,
-                             const gala_plan_t *plan, gala_stream_t stream);
+                             int32_t K, float slope, float *Y, float *alpha_out, int32_t relu,
+                             const float *reflect_in, const float *reflect_out,
+                             const gala_dense_epilogue_t *ep, const gala_plan_t *plan, gala_stream_t stream);
 
 /* Host helper (no device work): the unit vector v[K] of the reflection H = I - 2 v v^T with      */
 /* H e_{K-1} = -sign(w[K-1]) w/|w| and *sR = -sign(w[K-1]) |w|, so that (X H)[:, K-1] * sR = X w.  */

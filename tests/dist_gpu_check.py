@@ -25,13 +25,15 @@ want = model.forward(g, X, mode="literal", dense="torch")
 err = 0.0
 for exchange in ("nccl", "p2p", "p2p-needed"):
     runner = dist_gat.PartitionedGAT(model, offset, ids, n, rank, world, dev, exchange=exchange)
-    for rep in range(3):    # repeated steps exercise the buffer re-use ordering of the peer exchange
-        out_loc = runner.forward(X[runner.row_lo:runner.row_hi].contiguous())
-    full = runner.part.unpad(runner.part.all_gather(out_loc))
-    e = float((full - want).double().norm() / want.double().norm())
-    err = max(err, e)
-    print(f"rank {rank}/{world} [{runner.exchange}]: rows [{runner.row_lo},{runner.row_hi}) nnz {runner.local_nvals} "
-          f"rel err {e:.3e}", flush=True)
+    # "reflected": rows exchanged in the reflected basis (gala_gat_forward_col_f32; peer exchange only, NCCL -> folded)
+    for mode in ("reflected", "folded"):
+        for rep in range(3):    # repeated steps exercise the buffer re-use ordering of the peer exchange
+            out_loc = runner.forward(X[runner.row_lo:runner.row_hi].contiguous(), mode=mode)
+        full = runner.part.unpad(runner.part.all_gather(out_loc))
+        e = float((full - want).double().norm() / want.double().norm())
+        err = max(err, e)
+        print(f"rank {rank}/{world} [{runner.exchange}, {mode}]: rows [{runner.row_lo},{runner.row_hi}) nnz "
+              f"{runner.local_nvals} rel err {e:.3e}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if err < 1e-5 else 1)

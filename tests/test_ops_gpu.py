@@ -298,6 +298,49 @@ def test_gat_col_variant_matches_oracle(orc, case, K):
     assert rel_err(got3, want_Y @ H) < FP32_TOL
 
 
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("K,C", [(32, 41), (8, 3), (16, 47)])
+def test_gat_col_dense_epilogue(orc, case, K, C):
+    """gala_gat_forward_col_f32 with the dense epilogue: projections and classifier of the FINAL row (after both
+    reflections), against the oracle's layer + numpy."""
+    n, e, seed, T, empty, thr = case
+    t = graph_case(orc, n, e, seed, T, empty)
+    g = to_gpu_graph(t, thr)
+    rng = np.random.default_rng(seed + K + C)
+    aL = rng.normal(size=n).astype(np.float32)
+    wR = rng.normal(size=K).astype(np.float32)
+    X = rng.uniform(-0.5, 0.5, (n, K)).astype(np.float32)
+    aR = (X.astype(np.float64) @ wR.astype(np.float64) + 0.1).astype(np.float32)
+    want_Y, _ = orc.gat_forward(t, aL, aR, X)
+    want_Y = np.maximum(want_Y, 0).astype(np.float64)
+    v, sR = ops.reflection(dev(wR))
+    v2, _ = ops.reflection(dev(rng.normal(size=K).astype(np.float32)))
+    H = np.eye(K) - 2.0 * np.outer(v.double().cpu().numpy(), v.double().cpu().numpy())
+    H2 = np.eye(K) - 2.0 * np.outer(v2.double().cpu().numpy(), v2.double().cpu().numpy())
+    Xr = (X.astype(np.float64) @ H).astype(np.float32)
+    att_w = rng.normal(size=(2, K)).astype(np.float32)
+    att_b = [0.25, -0.5]
+    cls_w = rng.normal(size=(C, K)).astype(np.float32)
+    cls_b = rng.normal(size=C).astype(np.float32)
+    Y, att, cls = ops.gat_forward_col_ex(g, dev(aL), sR, 0.1, dev(Xr), relu=True, reflect_in=v, reflect_out=v2,
+                                         att_w=dev(att_w), att_b=att_b, cls_wT=dev(np.ascontiguousarray(cls_w.T)),
+                                         cls_b=dev(cls_b))
+    final = want_Y @ H2
+    assert rel_err(Y.cpu().numpy(), final) < FP32_TOL
+    assert rel_err(att.cpu().numpy(), (final @ att_w.T.astype(np.float64) + np.array(att_b)).T) < FP32_TOL
+    assert rel_err(cls.cpu().numpy(), final @ cls_w.T.astype(np.float64) + cls_b) < FP32_TOL
+    # projections alone: the register path writes the left-hand one only
+    Y3, att3, _ = ops.gat_forward_col_ex(g, dev(aL), sR, 0.1, dev(Xr), relu=True, reflect_in=v, reflect_out=v2,
+                                         att_w=dev(att_w), att_b=att_b)
+    assert rel_err(Y3.cpu().numpy(), final) < FP32_TOL
+    assert rel_err(att3[0].cpu().numpy(), final @ att_w[0].astype(np.float64) + att_b[0]) < FP32_TOL
+    # classifier only (Y not written)
+    Y2, _, cls2 = ops.gat_forward_col_ex(g, dev(aL), sR, 0.1, dev(Xr), relu=True, reflect_in=v,
+                                         cls_wT=dev(np.ascontiguousarray(cls_w.T)), cls_b=dev(cls_b), want_y=False)
+    assert Y2 is None
+    assert rel_err(cls2.cpu().numpy(), want_Y @ cls_w.T.astype(np.float64) + cls_b) < FP32_TOL
+
+
 def test_gat_col_rejects_unsupported_widths(orc):
     t = graph_case(orc, 300, 3000, 5)
     g = to_gpu_graph(t, 64)
@@ -314,7 +357,7 @@ def test_gat_model_dot_and_materialised_paths_agree(orc):
     model = GAT2(64, 32, 41, DEV, seed=3)
     X = torch.rand(n, 64, device=DEV) - 0.5
     b = model.forward(g, X, mode="literal", dense="torch")
-    for mode in ("folded", "dot", "literal", "fused", "reflected"):
+    for mode in ("folded", "dot", "literal", "fused", "reflected", "reflected_fused"):
         for dense in ("torch", "tcgen05"):
             a = model.forward(g, X, mode=mode, dense=dense)
             assert float((a - b).double().norm() / b.double().norm()) < FP32_TOL
