@@ -294,7 +294,7 @@ def main():
         X_in = X[runner.row_lo:runner.row_hi].contiguous()
         mode = args.mode if args.mode in ("reflected", "folded", "fused", "dot", "literal") else "folded"
         step_fn = lambda hook=None: runner.forward(X_in, hook, mode=mode)   # noqa: E731
-        launches_per_step = runner.launches_per_step
+        launches_per_step = 4 if (mode == "reflected" and runner.px is not None) else 3
         config["mode"] = mode
         config["parallelism"] = (f"1D row partition over {world} GPUs (nnz-balanced); exchange of hidden features: "
                                  + {"p2p-multicast": "fused into the producing kernels (multimem.st through NVLS multicast "

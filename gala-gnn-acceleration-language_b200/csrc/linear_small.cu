@@ -85,6 +85,99 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const __grid_constant
     }
 }
 
+// Row-per-thread form of the same transform for N > 4, row-major output (the classifier that follows the last
+// aggregation: [233K x 32] x [32 x 41] on the Reddit shape).  The warp-per-row kernel above keeps 4 rows = 512 bytes in
+// flight per warp -- latency-bound at ~1.1 TB/s.  Here a warp owns 32 consecutive rows: their K-float inputs are one
+// contiguous span (32*K*4 bytes: 8 independent 128-bit loads per lane, all in flight) staged through shared memory,
+// lane l then holds row l in registers and walks the N outputs with the weights broadcast from shared memory
+// (LDS.128, 4 weights per instruction), and the 32 x N outputs leave through the same staging tile as one contiguous,
+// fully coalesced span.  Same arithmetic as above: one accumulator per output, bias first, k ascending.
+template <int KP>   // K rounded up to 32 or 64
+__global__ void __launch_bounds__(128) linear_rows_kernel(const __grid_constant__ SmallParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N4 = (p.N + 3) & ~3;                  // weight rows, zero-padded to a multiple of 4 outputs
+    const int NP = p.N | 1;                          // odd output pitch of the staging tile: conflict-free per-lane writes
+    constexpr int XP = KP + 4;                       // input pitch: 16-byte aligned rows, conflict-free 128-bit reads
+    const int TS = 32 * (XP > NP ? XP : NP);
+    float* sW = smem;                                // [N4][KP]
+    float* sB = smem + N4 * KP;                      // [N4]
+    float* tile = sB + N4 + warp * TS;
+    for (int i = threadIdx.x; i < N4 * KP; i += blockDim.x) {
+        const int n = i / KP, k = i % KP;
+        sW[i] = (n < p.N && k < p.K) ? __ldg(p.W + n * p.K + k) : 0.0f;
+    }
+    for (int i = threadIdx.x; i < N4; i += blockDim.x) sB[i] = (p.bias && i < p.N) ? __ldg(p.bias + i) : 0.0f;
+    __syncthreads();
+    const int64_t ntiles = (p.M + 31) / 32;
+    const bool vec_in = p.K == KP && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0;
+    for (int64_t t = (int64_t)blockIdx.x * 4 + warp; t < ntiles; t += (int64_t)gridDim.x * 4) {
+        const int64_t row0 = t * 32;
+        const int rows = (int)(p.M - row0 < 32 ? p.M - row0 : 32);
+        if (vec_in) {
+            const float4* src = reinterpret_cast<const float4*>(p.X + row0 * KP);
+            constexpr int C4 = KP / 4;
+#pragma unroll
+            for (int j = 0; j < C4; ++j) {           // 32 * C4 float4 of the tile, 32 per step
+                const int i = j * 32 + lane;
+                const int r = i / C4, c4 = i % C4;
+                if (r < rows) *reinterpret_cast<float4*>(tile + r * XP + c4 * 4) = __ldcs(src + i);
+            }
+        } else {
+            const float* src = p.X + row0 * p.K;
+            for (int r = 0; r < rows; ++r)
+                for (int c = lane; c < KP; c += 32) tile[r * XP + c] = c < p.K ? ld_stream(src + r * p.K + c) : 0.0f;
+        }
+        __syncwarp();
+        float x[KP];
+        if (lane < rows) {
+#pragma unroll
+            for (int c4 = 0; c4 < KP / 4; ++c4) {
+                const float4 v = *reinterpret_cast<const float4*>(tile + lane * XP + c4 * 4);
+                x[c4 * 4] = v.x; x[c4 * 4 + 1] = v.y; x[c4 * 4 + 2] = v.z; x[c4 * 4 + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) x[k] = 0.0f;
+        }
+        __syncwarp();                                // the tile now takes the outputs
+        for (int n0 = 0; n0 < N4; n0 += 4) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = sB[n0 + j];
+#pragma unroll
+            for (int k4 = 0; k4 < KP / 4; ++k4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 w = *reinterpret_cast<const float4*>(sW + (n0 + j) * KP + k4 * 4);
+                    o[j] = fmaf(x[k4 * 4], w.x, o[j]);
+                    o[j] = fmaf(x[k4 * 4 + 1], w.y, o[j]);
+                    o[j] = fmaf(x[k4 * 4 + 2], w.z, o[j]);
+                    o[j] = fmaf(x[k4 * 4 + 3], w.w, o[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n0 + j < p.N) tile[lane * NP + n0 + j] = p.relu ? fmaxf(o[j], 0.0f) : o[j];
+        }
+        __syncwarp();
+        float* dst = p.Y + row0 * p.N;
+        const int total = rows * p.N;
+        int r = 0, c = lane;
+        for (int i = lane; i < total; i += 32) {
+            while (c >= p.N) { c -= p.N; ++r; }
+            st_stream(dst + i, tile[r * NP + c]);
+            c += 32;
+        }
+        __syncwarp();                                // before the next tile's inputs overwrite it
+    }
+}
+
+static size_t rows_kernel_smem(int N, int KP) {
+    const int N4 = (N + 3) & ~3, NP = N | 1, XP = KP + 4;
+    return (size_t)(N4 * KP + N4 + 4 * 32 * std::max(XP, NP)) * sizeof(float);
+}
+
 // N <= 4 (the attention projections): lane l multiplies its input element with W[n, l] and the
 // warp reduces -- 5 shuffles per output instead of one broadcast shuffle per input element.
 template <int NT>
@@ -249,7 +342,22 @@ extern "C" int gala_linear_small_f32(const float* X, int64_t M, int32_t K, const
     const unsigned grid = (unsigned)std::min<int64_t>((warps_needed + 7) / 8, 148 * 2);   // persistent: weights are loaded once per CTA
     if (N <= 2) linear_tiny_kernel<2><<<(unsigned)std::min<int64_t>((M + 63) / 64, 148 * 8), 256, 0, st>>>(p);
     else if (N <= 4) linear_tiny_kernel<4><<<(unsigned)std::min<int64_t>((M + 63) / 64, 148 * 8), 256, 0, st>>>(p);
-    else if (K <= 32) linear_small_kernel<32><<<grid, 256, 0, st>>>(p);
+    else if (!transpose_out) {
+        // row-per-thread kernel: 128-thread CTAs, up to 8 per SM (26 KB of shared memory each on the classifier shape)
+        const int KP = K <= 32 ? 32 : 64;
+        const size_t smem = rows_kernel_smem(N, KP);
+        const int64_t tiles = (M + 31) / 32;
+        // equal tile counts per warp: as many rounds as one resident wave (7 CTAs per SM at 67 registers) needs
+        const int64_t ctas = (tiles + 3) / 4, wave = 148 * 7, rounds = (ctas + wave - 1) / wave;
+        const unsigned g2 = (unsigned)((ctas + rounds - 1) / rounds);
+        if (KP == 32) {
+            cudaFuncSetAttribute(linear_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            linear_rows_kernel<32><<<g2, 128, smem, st>>>(p);
+        } else {
+            cudaFuncSetAttribute(linear_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            linear_rows_kernel<64><<<g2, 128, smem, st>>>(p);
+        }
+    } else if (K <= 32) linear_small_kernel<32><<<grid, 256, 0, st>>>(p);
     else linear_small_kernel<64><<<grid, 256, 0, st>>>(p);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GALA_OK : (int)e;

@@ -75,7 +75,8 @@ def test_linear_row_scale_epilogue():
     assert float((got.double() - want).norm() / want.norm()) < 1e-5
 
 
-@pytest.mark.parametrize("M,K,N", [(1000, 32, 41), (233, 32, 2), (5000, 64, 64), (77, 7, 3), (4096, 47, 33), (1, 1, 1)])
+@pytest.mark.parametrize("M,K,N", [(1000, 32, 41), (233, 32, 2), (5000, 64, 64), (77, 7, 3), (4096, 47, 33), (1, 1, 1),
+                                   (100003, 32, 41), (1000, 32, 47), (65, 33, 64), (31, 64, 5), (32, 32, 32), (4097, 16, 7)])
 def test_linear_small_matches_fp64(M, K, N):
     X = torch.rand(M, K, device=DEV) - 0.5
     W = torch.rand(N, K, device=DEV) - 0.5
