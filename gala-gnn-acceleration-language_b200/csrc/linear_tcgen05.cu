@@ -1022,6 +1022,12 @@ int launch_linear(const LinearParams& p, cudaStream_t st) {
 
 }  // namespace
 
+// Fewest 128-row tiles for which the persistent kernel (one CTA per SM) is used; below, the 2-CTA/SM kernel runs every
+// tile in one wave.
+#ifndef GALA_LINEAR_V2_MIN_TILES
+#define GALA_LINEAR_V2_MIN_TILES 4
+#endif
+
 extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float* W, const float* bias, int32_t N, float* Y,
                                const float* row_scale, int32_t relu, const float* att_w, const float* att_b,
                                int32_t att_b_on_device, float* att_out, const gala_multi_out_t* multi_out,
@@ -1070,7 +1076,7 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int64_t ntiles = (M + kBM - 1) / kBM;
     const bool v2 = (K % 2 == 0) && (reinterpret_cast<uintptr_t>(X) % 8 == 0) && (reinterpret_cast<uintptr_t>(W) % 8 == 0) &&
-                    M >= 4 * kBM;
+                    ntiles >= GALA_LINEAR_V2_MIN_TILES;
     if (v2) {
         p.round_robin = (K >= 256 && ntiles >= 4 * (int64_t)device_sm_count()) ? 1 : 0;
         if (N <= 16) return launch_linear_v2<16>(p, st);

@@ -467,8 +467,13 @@ class PartitionedGATN:
     """L-layer runner (gat_model.GATN).  `part` is any object with RowPartition's interface, so that a
     rank can build its slab without ever holding the whole graph."""
 
-    def __init__(self, model, part, device, exchange="p2p", need_mask=None, pipeline=0, push_ctas=0, phases="m"):
-        """pipeline = B > 1 (fused exchanges only): producers of exchanged rows run in B row blocks and a finished block
+    def __init__(self, model, part, device, exchange="p2p", need_mask=None, pipeline=0, push_ctas=0, phases="m",
+                 reflected=False):
+        """reflected (fused exchanges, hidden widths in {4, 8, 16, 32}): every exchanged row travels in the reflected
+        basis of the layer that gathers it (gat_model.GATN.fold_reflected, gala_gat_forward_col_f32) -- its last column
+        is the right-hand attention term, so no scalar is exchanged and an edge costs one gather; kernel pushes only
+        (no copy-engine phases).
+        pipeline = B > 1 (fused exchanges only): producers of exchanged rows run in B row blocks and a finished block
         is sent from a side stream under the computation of the following blocks.  phases: which exchanges do so --
         f(irst transform), m(iddle: aggregation || next transform + push), l(ast hidden aggregation); the others keep
         the push in the producing kernel's epilogue.  Upper case (F, M, L): the finished block travels by copy engine
@@ -482,12 +487,18 @@ class PartitionedGATN:
         self.exchange = "nccl"
         self.blocks = None
         self.push_ctas, self.phases = push_ctas, phases
+        self.reflected = bool(reflected) and exchange in ("p2p", "p2p-needed") and model.reflected_ok()
+        if self.reflected:
+            assert not any(c in phases for c in "FML"), "reflected rows are pushed by kernels, not by copy engines"
+            self.r = model.fold_reflected()
         if exchange in ("p2p", "p2p-needed"):
             assert (exchange == "p2p-needed") == (need_mask is not None), "p2p-needed takes RowPartition.need_masks()"
             self.px = PeerExchange(part, [model.dims[i + 1] for i in range(model.L - 1)] + [model.dims[-2]], device,
                                    need_mask=need_mask)
             self.exchange = ("p2p-needed" if need_mask is not None else
                              "p2p-multicast" if self.px.mos[0].multicast_base else "p2p")
+            if self.reflected:
+                self.exchange += "+reflected"
             if pipeline > 1 and max(model.dims[1:-1]) <= 64:
                 self.blocks = RowBlocks(part, pipeline, device)
                 self.exchange += f"+pipeline{pipeline}" + ("" if phases == "m" else ":" + phases)
@@ -503,6 +514,48 @@ class PartitionedGATN:
 
     def _aggregate(self, aL, aR, feats, relu):
         return self.ops.gat_forward(self.graph, aL.contiguous(), aR.contiguous(), feats, self.model.slope, relu=relu)
+
+    # ---- the three kinds of aggregation of the fused-exchange forward, in either basis -----------------------------
+    def _fc(self, i):
+        """(W, b, W_att) of transform i as the kernels take them."""
+        if self.reflected:
+            return self.r["W"][i], self.r["b"][i], self.r["W_att"][i]
+        return self.model.fc[i][0], self.model.fc[i][1], self.model.W_att[i]
+
+    def _amo(self, att_mo):
+        """The right-hand attention scalar's exchange: none in the reflected basis."""
+        return None if self.reflected else att_mo
+
+    def _agg_hidden(self, graph, i, aL, out=None):
+        m, px, ops = self.model, self.px, self.ops
+        if self.reflected:
+            r = self.r
+            return ops.gat_forward_col(graph, aL, r["s"][i], r["bR"][i], px.bufs[i], m.slope, relu=True,
+                                       reflect_in=r["v"][i], out=out)
+        return ops.gat_forward(graph, aL, px.att_bufs[i], px.bufs[i], m.slope, relu=True, out=out)
+
+    def _agg_last_hidden(self, graph, aL, out=None, multi_out=None, att_multi_out=None):
+        """-> (y or None, att [2, rows]: att[0] = the final layer's left-hand term; att[1] only in the original basis)"""
+        m, px, ops = self.model, self.px, self.ops
+        i, L = m.L - 2, m.L
+        if self.reflected:
+            r = self.r
+            y, att, _ = ops.gat_forward_col_ex(graph, aL, r["s"][i], r["bR"][i], px.bufs[i], m.slope, relu=True,
+                                               reflect_in=r["v"][i], reflect_out=r["v"][L - 1], att_w=r["W_att"][L - 1],
+                                               att_b=m._bh[-1], out=out, multi_out=multi_out)
+            return y, att
+        y, att, _ = ops.gat_forward_ex(graph, aL, px.att_bufs[i], px.bufs[i], m.slope, relu=True, att_w=m.W_att[-1],
+                                       att_b=m._bh[-1], out=out, multi_out=multi_out, att_multi_out=att_multi_out)
+        return y, att
+
+    def _agg_final(self, aL):
+        m, px, ops = self.model, self.px, self.ops
+        L = m.L
+        if self.reflected:
+            r = self.r
+            return ops.gat_forward_col(self.graph, aL, r["s"][L - 1], r["bR"][L - 1], px.bufs[L - 1], m.slope,
+                                       relu=False, reflect_in=r["v"][L - 1])
+        return ops.gat_forward(self.graph, aL, px.att_bufs[L - 1], px.bufs[L - 1], m.slope, relu=False)
 
     def forward(self, X_local, hook=None, mark=None):
         """mark(name), if given, is called at every phase boundary (bench scripts record an event there)."""
@@ -528,25 +581,22 @@ class PartitionedGATN:
         for i in range(L - 1):
             # the transform pushes its rows to every GPU while it computes, projects them onto the attention
             # vectors in its epilogue and pushes the right-hand scalar of every row the same way
-            _, a = run(f"linear{i + 1}", lambda: ops.linear(res_loc, m.fc[i][0], m.fc[i][1], att_w=m.W_att[i],
-                                                            att_b=bh[i], multi_out=px.mos[i], att_multi_out=px.att_mos[i]))
+            W, b, Wa = self._fc(i)
+            _, a = run(f"linear{i + 1}", lambda: ops.linear(res_loc, W, b, att_w=Wa, att_b=bh[i], multi_out=px.mos[i],
+                                                            att_multi_out=self._amo(px.att_mos[i])))
             mark(f"linear{i + 1}+push")
             px.barrier(i)
-            aR_all = px.att_bufs[i]
             mark(f"exchange{i + 1}")
             if i == L - 2:
-                _, att, _ = run(f"gat_layer{i + 1}", lambda: ops.gat_forward_ex(
-                    self.graph, a[0], aR_all, px.bufs[i], m.slope, relu=True, att_w=m.W_att[-1], att_b=bh[-1],
-                    multi_out=px.mos[L - 1], att_multi_out=px.att_mos[L - 1]))
+                _, att = run(f"gat_layer{i + 1}", lambda: self._agg_last_hidden(
+                    self.graph, a[0], multi_out=px.mos[L - 1], att_multi_out=px.att_mos[L - 1]))
                 mark(f"gat_layer{i + 1}+push")
             else:
-                res_loc = run(f"gat_layer{i + 1}", lambda: ops.gat_forward(self.graph, a[0], aR_all, px.bufs[i],
-                                                                           m.slope, relu=True))
+                res_loc = run(f"gat_layer{i + 1}", lambda: self._agg_hidden(self.graph, i, a[0]))
                 mark(f"gat_layer{i + 1}")
         px.barrier(L - 1)
-        aR_all = px.att_bufs[L - 1]
         mark(f"exchange{L}")
-        agg = run(f"gat_layer{L}", lambda: ops.gat_forward(self.graph, att[0], aR_all, px.bufs[L - 1], m.slope, relu=False))
+        agg = run(f"gat_layer{L}", lambda: self._agg_final(att[0]))
         mark(f"gat_layer{L}")
         out = run("classifier", lambda: ops.dense(agg, *m.fc[-1]))
         mark("classifier")
@@ -589,19 +639,21 @@ class PartitionedGATN:
             px.dma_join(main)
             mark("linear1 || copy")
         elif "f" in self.phases:
+            W, b, Wa = self._fc(0)
             for j in range(bl.n):
                 lo, hi = bl.span(j)
-                _, a = ops.linear(X_local[lo:hi], m.fc[0][0], m.fc[0][1], att_w=m.W_att[0], att_b=bh[0], out=t0[lo:hi])
+                _, a = ops.linear(X_local[lo:hi], W, b, att_w=Wa, att_b=bh[0], out=t0[lo:hi])
                 aL[lo:hi].copy_(a[0])
                 keep.append(a)
                 mo, att_mo = self._outs[0][j]
-                after_block(lambda: ops.push_rows(t0[lo:hi], mo, scalars=a[1], scalar_multi_out=att_mo,
-                                                  max_ctas=self.push_ctas))
+                after_block(lambda: ops.push_rows(t0[lo:hi], mo, scalars=None if self.reflected else a[1],
+                                                  scalar_multi_out=self._amo(att_mo), max_ctas=self.push_ctas))
             join()
             mark("linear1 || push")
         else:
-            _, a = ops.linear(X_local, m.fc[0][0], m.fc[0][1], att_w=m.W_att[0], att_b=bh[0],
-                              multi_out=px.mos[0], att_multi_out=px.att_mos[0])
+            W, b, Wa = self._fc(0)
+            _, a = ops.linear(X_local, W, b, att_w=Wa, att_b=bh[0], multi_out=px.mos[0],
+                              att_multi_out=self._amo(px.att_mos[0]))
             aL = a[0]
             mark("linear1+push")
         px.barrier(0)
@@ -627,11 +679,12 @@ class PartitionedGATN:
                 mark(f"exchange{i + 2}")
                 aL = aL_next
                 continue
+            W, b, Wa = self._fc(i + 1)
             if "m" not in self.phases:
-                ops.gat_forward(self.graph, aL, px.att_bufs[i], px.bufs[i], m.slope, relu=True, out=res)
+                self._agg_hidden(self.graph, i, aL, out=res)
                 mark(f"gat_layer{i + 1}")
-                _, a = ops.linear(res, m.fc[i + 1][0], m.fc[i + 1][1], att_w=m.W_att[i + 1], att_b=bh[i + 1],
-                                  multi_out=px.mos[i + 1], att_multi_out=px.att_mos[i + 1])
+                _, a = ops.linear(res, W, b, att_w=Wa, att_b=bh[i + 1], multi_out=px.mos[i + 1],
+                                  att_multi_out=self._amo(px.att_mos[i + 1]))
                 mark(f"linear{i + 2}+push")
                 px.barrier(i + 1)
                 mark(f"exchange{i + 2}")
@@ -639,12 +692,12 @@ class PartitionedGATN:
                 continue
             for j in range(bl.n):
                 lo, hi = bl.span(j)
-                ops.gat_forward(bl.graphs[j], aL[lo:hi], px.att_bufs[i], px.bufs[i], m.slope, relu=True, out=res[lo:hi])
+                self._agg_hidden(bl.graphs[j], i, aL[lo:hi], out=res[lo:hi])
                 mo, att_mo = self._outs[i + 1][j]
 
-                def transform_push(lo=lo, hi=hi, j=j, mo=mo, att_mo=att_mo):
-                    ops.linear_small_ex(res[lo:hi], m.fc[i + 1][0], m.fc[i + 1][1], att_w=m.W_att[i + 1], att_b=bh[i + 1],
-                                        att_out=self._att[i][j], multi_out=mo, att_multi_out=att_mo,
+                def transform_push(lo=lo, hi=hi, j=j, mo=mo, att_mo=att_mo, W=W, b=b, Wa=Wa):
+                    ops.linear_small_ex(res[lo:hi], W, b, att_w=Wa, att_b=bh[i + 1],
+                                        att_out=self._att[i][j], multi_out=mo, att_multi_out=self._amo(att_mo),
                                         max_ctas=self.push_ctas)
                     aL_next[lo:hi].copy_(self._att[i][j][0])
                 after_block(transform_push)
@@ -670,24 +723,21 @@ class PartitionedGATN:
         elif "l" in self.phases:
             for j in range(bl.n):
                 lo, hi = bl.span(j)
-                _, att, _ = ops.gat_forward_ex(bl.graphs[j], aL[lo:hi], px.att_bufs[L - 2], px.bufs[L - 2], m.slope,
-                                               relu=True, att_w=m.W_att[-1], att_b=bh[-1], out=res[lo:hi])
+                _, att = self._agg_last_hidden(bl.graphs[j], aL[lo:hi], out=res[lo:hi])
                 aL_last[lo:hi].copy_(att[0])
                 keep.append(att)
                 mo, att_mo = self._outs[L - 1][j]
-                after_block(lambda: ops.push_rows(res[lo:hi], mo, scalars=att[1], scalar_multi_out=att_mo,
-                                                  max_ctas=self.push_ctas))
+                after_block(lambda: ops.push_rows(res[lo:hi], mo, scalars=None if self.reflected else att[1],
+                                                  scalar_multi_out=self._amo(att_mo), max_ctas=self.push_ctas))
             join()
             mark(f"gat_layer{L - 1} || push")
         else:
-            _, att, _ = ops.gat_forward_ex(self.graph, aL, px.att_bufs[L - 2], px.bufs[L - 2], m.slope, relu=True,
-                                           att_w=m.W_att[-1], att_b=bh[-1], multi_out=px.mos[L - 1],
-                                           att_multi_out=px.att_mos[L - 1])
+            _, att = self._agg_last_hidden(self.graph, aL, multi_out=px.mos[L - 1], att_multi_out=px.att_mos[L - 1])
             aL_last = att[0]
             mark(f"gat_layer{L - 1}+push")
         px.barrier(L - 1)
         mark(f"exchange{L}")
-        agg = ops.gat_forward(self.graph, aL_last, px.att_bufs[L - 1], px.bufs[L - 1], m.slope, relu=False)
+        agg = self._agg_final(aL_last)
         mark(f"gat_layer{L}")
         out = ops.dense(agg, *m.fc[-1])
         mark("classifier")

@@ -261,6 +261,32 @@ class GATN:
         self.b_att.append(torch.cat([self.efcL[-1][0] @ b + self.efcL[-1][1],
                                      self.efcR[-1][0] @ b + self.efcR[-1][1]], 0).contiguous())
 
+    def reflected_ok(self):
+        return all(d in (4, 8, 16, 32) for d in self.dims[1:-1])
+
+    def fold_reflected(self):
+        """The reflected basis of gala_gat_forward_col_f32 for every aggregation (see GAT2.fold_reflected): layer i
+        gathers rows whose last column is its right-hand attention term.  Hidden layer i < L-1 gathers t_i = fc_i(res):
+        H_i (from efcR_i) folds into fc_i and into the left-hand projection; its kernel reflects the finished rows back
+        (they feed the next transform in the original basis) -- except the last hidden layer, whose rows the final
+        layer gathers directly: those leave in H_{L-1}'s basis (from the folded right-hand projection).
+        Returns dict(v, s, bR: per aggregation; W, b: per transform; W_att: left-hand rows, reflected)."""
+        if getattr(self, "_reflected", None) is None:
+            if not hasattr(self, "_bh"):
+                self.host_biases()
+            L = self.L
+            v, s = [], []
+            for i in range(L):
+                vi, si = ops.reflection(self.W_att[i][1])
+                v.append(vi)
+                s.append(si)
+            self._reflected = dict(
+                v=v, s=s, bR=[self._bh[i][1] for i in range(L)],
+                W=[ops.reflect(self.fc[i][0], v[i], dim=0) for i in range(L - 1)],
+                b=[ops.reflect(self.fc[i][1], v[i]) for i in range(L - 1)],
+                W_att=[ops.reflect(self.W_att[i], v[i]) for i in range(L)])
+        return self._reflected
+
     def forward_literal(self, g, X):
         """Op by op (one Linear per projection, logits of the last layer from fc_L(res))."""
         res = X
@@ -275,14 +301,30 @@ class GATN:
         agg = ops.gat_forward(g, aL, aR, res, self.slope, relu=False)
         return F.linear(agg, *self.fc[-1])
 
-    def forward(self, g, X, hook=None, logits_chunk=None):
+    def forward(self, g, X, hook=None, logits_chunk=None, mode="folded"):
         """Own kernels for the transforms (tcgen05 + folded projections in its epilogue).
+        mode="reflected": every aggregation in the reflected basis (fold_reflected; hidden widths in {4, 8, 16, 32}).
         logits_chunk = (rows, buffer): the classifier runs in row chunks into a re-used buffer (for
         graphs whose [N, classes] logits do not fit next to the features on one GPU); returns None."""
         run = hook if hook is not None else (lambda name, fn: fn())
         if not hasattr(self, "_bh"):
             self.host_biases()
         res, a_last = X, None
+        if mode == "reflected" and self.reflected_ok():
+            r, L = self.fold_reflected(), self.L
+            for i in range(L - 1):
+                t, a = run(f"linear{i + 1}", lambda: ops.linear(res, r["W"][i], r["b"][i], att_w=r["W_att"][i],
+                                                                att_b=self._bh[i]))
+                if i == L - 2:
+                    res, a_last, _ = run(f"gat_layer{i + 1}", lambda: ops.gat_forward_col_ex(
+                        g, a[0], r["s"][i], r["bR"][i], t, self.slope, relu=True, reflect_in=r["v"][i],
+                        reflect_out=r["v"][L - 1], att_w=r["W_att"][L - 1], att_b=self._bh[L - 1]))
+                else:
+                    res = run(f"gat_layer{i + 1}", lambda: ops.gat_forward_col(
+                        g, a[0], r["s"][i], r["bR"][i], t, self.slope, relu=True, reflect_in=r["v"][i]))
+            agg = run(f"gat_layer{L}", lambda: ops.gat_forward_col(
+                g, a_last[0], r["s"][L - 1], r["bR"][L - 1], res, self.slope, relu=False, reflect_in=r["v"][L - 1]))
+            return self._classify(run, agg, logits_chunk)
         for i in range(self.L - 1):
             t, a = run(f"linear{i + 1}", lambda: ops.linear(res, self.fc[i][0], self.fc[i][1], att_w=self.W_att[i],
                                                             att_b=self._bh[i]))
@@ -292,6 +334,9 @@ class GATN:
             else:
                 res = run(f"gat_layer{i + 1}", lambda: ops.gat_forward(g, a[0], a[1], t, self.slope, relu=True))
         agg = run(f"gat_layer{self.L}", lambda: ops.gat_forward(g, a_last[0], a_last[1], res, self.slope, relu=False))
+        return self._classify(run, agg, logits_chunk)
+
+    def _classify(self, run, agg, logits_chunk):
         if logits_chunk is not None:
             rows, buf = logits_chunk
             for lo in range(0, agg.shape[0], rows):

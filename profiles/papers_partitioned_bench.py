@@ -47,6 +47,11 @@ def split_mode(mode):
     return base, int(pipe) if pipe else 0, int(ctas) if ctas else PUSH_CTAS, phases or "m"
 
 
+def split_refl(mode):
+    """"p2p-needed+refl+pipe8" -> ("p2p-needed+pipe8", True): rows exchanged in the reflected basis (GAT only)"""
+    return mode.replace("+refl", ""), "+refl" in mode
+
+
 def say(*a):
     if rank == 0:
         print(*a, flush=True)
@@ -94,11 +99,19 @@ model = GATN(dims, dev, seed=0).host_biases()
 X = torch.rand(n, dims[0], generator=torch.Generator(device=dev).manual_seed(1), device=dev) - 0.5
 want = model.forward_literal(ops.TiledGraph(offset, ids, n).build_plan(), X)
 worst = 0.0
-for mode in (("nccl", "p2p", "p2p-needed", "p2p+pipe3:fml", "p2p-needed+pipe4", "p2p-needed+pipe3:FML") if world > 1 else ("nccl",)):
+g_small = ops.TiledGraph(offset, ids, n).build_plan()
+err = float((model.forward(g_small, X, mode="reflected") - want).double().norm() / want.double().norm())
+worst = max(worst, err)
+say(f"parity [single GPU, reflected basis] 3-layer GAT: rel err {err:.2e}")
+del g_small
+for mode in (("nccl", "p2p", "p2p-needed", "p2p+pipe3:fml", "p2p-needed+pipe4", "p2p-needed+pipe3:FML", "p2p+refl",
+              "p2p-needed+refl", "p2p+refl+pipe3:fml", "p2p-needed+refl+pipe4") if world > 1 else ("nccl",)):
+    mode, refl = split_refl(mode)
     exchange, pipe, _, phases = split_mode(mode)
     part = dist_gat.RowPartition(offset, ids, n, rank, world)
     need = part.need_masks(ids, offset) if exchange == "p2p-needed" else None
-    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange, need_mask=need, pipeline=pipe, phases=phases)
+    runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange, need_mask=need, pipeline=pipe, phases=phases,
+                                      reflected=refl)
     for _ in range(3):
         out_loc = runner.forward(X[part.row_lo:part.row_hi].contiguous())
     full = part.unpad(part.all_gather(out_loc))
@@ -132,7 +145,7 @@ dims = [feats, hidden, hidden, classes]
 offset, ids = build(n, e, 0)
 part = dist_gat.RowPartition(offset, ids, n, rank, world)
 need_mask = None
-if world > 1 and any(split_mode(m)[0] == "p2p-needed" for m in EXCHANGES):
+if world > 1 and any(split_mode(split_refl(m)[0])[0] == "p2p-needed" for m in EXCHANGES):
     need_mask = part.need_masks(ids, offset)
     say(f"needed-rows masks: rank 0's rows are referenced by {part.need_fraction:.1%} of the (row, peer) pairs")
 del ids
@@ -142,9 +155,10 @@ X_loc = torch.rand(part.rows, feats, device=dev) - 0.5
 say(f"papers shape x{scale}: n={n} E={e}; rank 0 holds rows [{part.row_lo},{part.row_hi}) nnz {part.local_nvals}")
 res = {"workload": f"3-layer GAT forward, papers100M shape x{scale}", "n_gpus": world, "nodes": n, "edges": e}
 for mode in (EXCHANGES if world > 1 else ()):
+    mode, refl = split_refl(mode)
     exchange, pipe, ctas, phases = split_mode(mode)
     runner = dist_gat.PartitionedGATN(model, part, dev, exchange=exchange, pipeline=pipe, push_ctas=ctas, phases=phases,
-                                      need_mask=need_mask if exchange == "p2p-needed" else None)
+                                      need_mask=need_mask if exchange == "p2p-needed" else None, reflected=refl)
     if ctas:
         runner.exchange += f"@{ctas}"
     ms = timed(lambda: runner.forward(X_loc))
@@ -179,7 +193,9 @@ if world > 1 and "--needed" in sys.argv:
     del runner, npart
     torch.cuda.empty_cache()
 gcn = GCNN(dims, dev, seed=2)
-for mode in (EXCHANGES if world > 1 else ()):
+for mode in (EXCHANGES if world > 1 and "--no-gcn" not in sys.argv else ()):
+    if "+refl" in mode:          # GCN has no attention term to fold
+        continue
     exchange, pipe, ctas, phases = split_mode(mode)
     runner = dist_gat.PartitionedGCNN(gcn, part, dev, exchange=exchange, pipeline=pipe, push_ctas=ctas, phases=phases,
                                       need_mask=need_mask if exchange == "p2p-needed" else None)
@@ -223,6 +239,12 @@ if world == 1:
     model.forward(g1, X_loc, hook=hook, logits_chunk=sink)
     res["phases_ms"] = phases
     say(f"  single-GPU GATN.forward {ms:.2f} ms; kernels: {phases}")
+    ms = timed(lambda: model.forward(g1, X_loc, logits_chunk=sink, mode="reflected"))
+    res["ms_single_gpu_model_reflected"] = round(ms, 3)
+    phases = {}
+    model.forward(g1, X_loc, hook=hook, logits_chunk=sink, mode="reflected")
+    res["phases_ms_reflected"] = phases
+    say(f"  single-GPU GATN.forward, reflected basis {ms:.2f} ms; kernels: {phases}")
     gcn.prepare(g1)
 
     def gcn_step():

@@ -298,6 +298,22 @@ def test_gat_col_variant_matches_oracle(orc, case, K):
     assert rel_err(got3, want_Y @ H) < FP32_TOL
 
 
+def test_gatn_reflected_and_folded_forwards_match_literal(orc):
+    """3-layer GATN (the Papers-shape program): own-kernel forward in the original and in the reflected basis against
+    the op-by-op forward with cuBLAS dense parts."""
+    from gala_b200.gat_model import GATN
+    n = 4000
+    t = graph_case(orc, n, 150000, 7)
+    g = to_gpu_graph(t, 256)
+    for dims in ([64, 32, 32, 41], [20, 16, 32, 172], [33, 32, 7]):
+        model = GATN(dims, DEV, seed=5).host_biases()
+        X = torch.rand(n, dims[0], device=DEV) - 0.5
+        want = model.forward_literal(g, X)
+        for mode in ("folded", "reflected"):
+            got = model.forward(g, X, mode=mode)
+            assert float((got - want).double().norm() / want.double().norm()) < FP32_TOL, (dims, mode)
+
+
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("K,C", [(32, 41), (8, 3), (16, 47)])
 def test_gat_col_dense_epilogue(orc, case, K, C):

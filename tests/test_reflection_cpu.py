@@ -109,3 +109,39 @@ def test_reflected_model_equals_literal_model():
     agg = _gat_layer_col(A, aL, r["s2"], m.bR2, res, 0.2, False, d(r["v2"]), None)
     got = lin(agg, m.fc1)
     assert np.linalg.norm(got - want) / np.linalg.norm(want) < 2e-6
+
+
+def test_reflected_gatn_equals_literal_model():
+    """GATN.fold_reflected (3 layers: hidden rows reflected back after each aggregation, the last hidden layer's rows
+    leaving in the final layer's basis) + the restated column-mode layer reproduce GATN.forward_literal's math."""
+    from gala_b200.gat_model import GATN
+    n, dims = 90, [12, 32, 16, 5]
+    rng = np.random.default_rng(2)
+    A = (rng.uniform(size=(n, n)) < 0.12).astype(np.float64)
+    A[np.arange(n), np.arange(n)] = 1.0
+    m = GATN(dims, "cpu", seed=4)
+    m.host_biases()
+    assert m.reflected_ok()
+    X = rng.uniform(-0.5, 0.5, (n, dims[0]))
+    d = lambda t: t.double().numpy()
+    lin = lambda x, wb: x @ d(wb[0]).T + d(wb[1])
+    L = m.L
+    res = X
+    for i in range(L - 1):
+        t = lin(res, m.fc[i])
+        res = _gat_layer(A, lin(t, m.efcL[i])[:, 0], lin(t, m.efcR[i])[:, 0], t, 0.2, True)
+    t = lin(res, m.fc[-1])
+    agg = _gat_layer(A, lin(t, m.efcL[-1])[:, 0], lin(t, m.efcR[-1])[:, 0], res, 0.2, False)
+    want = lin(agg, m.fc[-1])
+    r = m.fold_reflected()
+    res, aL_last = X, None
+    for i in range(L - 1):
+        t = res @ d(r["W"][i]).T + d(r["b"][i])
+        aL = t @ d(r["W_att"][i])[0] + m._bh[i][0]
+        last = i == L - 2
+        res = _gat_layer_col(A, aL, r["s"][i], r["bR"][i], t, 0.2, True, d(r["v"][i]), d(r["v"][L - 1]) if last else None)
+        if last:
+            aL_last = res @ d(r["W_att"][L - 1])[0] + m._bh[L - 1][0]
+    agg = _gat_layer_col(A, aL_last, r["s"][L - 1], r["bR"][L - 1], res, 0.2, False, d(r["v"][L - 1]), None)
+    got = lin(agg, m.fc[-1])
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 2e-6
