@@ -245,6 +245,11 @@ if world == 1:
     model.forward(g1, X_loc, hook=hook, logits_chunk=sink, mode="reflected")
     res["phases_ms_reflected"] = phases
     say(f"  single-GPU GATN.forward, reflected basis {ms:.2f} ms; kernels: {phases}")
+    if "--no-gcn" in sys.argv:
+        say(json.dumps(res))
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0)
     gcn.prepare(g1)
 
     def gcn_step():
