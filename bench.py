@@ -514,7 +514,8 @@ def main():
                     "h2d_bytes_per_step": int(X_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
                     "h2d_chunks": e2e_chunks,
                     "call": ("GAT2.forward_host: pinned host features uploaded in row blocks on a copy stream, each block "
-                             "consumed by the row-tiled transform as it lands; logits copied back to pinned host memory")
+                             "consumed by the row-tiled transform as it lands; logits copied back to pinned host memory; consecutive "
+                             "calls pipeline (the next upload runs under this step's aggregation layers and download)")
                             if e2e_chunks > 1 else "H2D copy, forward, D2H copy on one stream"},
             "roofline": roofline, "kernel_ms": {k: round(v, 4) for k, v in kern_ms.items()},
             "eager_ms_per_step": round(eager_ms, 4),

@@ -190,7 +190,9 @@ class GAT2:
         """The same forward for features that live in (pinned) HOST memory: the [N, F] matrix is uploaded in `chunks`
         row blocks on a copy stream while the row-tiled layer-1 transform already consumes the blocks that have
         landed (it reads X front to back exactly once), so the PCIe transfer and the transform overlap; the logits
-        are copied back into out_host (pinned) if given.  Returns the device logits."""
+        are copied back into out_host (pinned) if given.  Returns the device logits (asynchronously: synchronise the
+        stream before reading out_host).  Consecutive calls pipeline: the next call's upload starts as soon as this
+        call's transform has consumed the staging buffer, i.e. under this call's aggregation layers and download."""
         n, dev = X_host.shape[0], g.device
         if stage is None:
             stage = torch.empty(X_host.shape, dtype=torch.float32, device=dev)
@@ -205,7 +207,15 @@ class GAT2:
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=dev)
         cs, main = self._copy_stream, torch.cuda.current_stream()
-        cs.wait_stream(main)                      # the staging buffer may still be read by the previous step
+        # The staging buffer may still be read by the previous call's transform -- and by nothing later in that call:
+        # waiting for that point only (not for the whole stream) lets this call's upload run under the previous call's
+        # aggregation layers and under its logits download (PCIe is full duplex), so that back-to-back calls are paced by
+        # the upload alone.  All compute stays in order on the caller's stream.
+        free = getattr(self, "_stage_free", None)
+        if free is not None and free[0] == stage.data_ptr():
+            cs.wait_event(free[1])
+        else:
+            cs.wait_stream(main)
         step = (n + chunks - 1) // chunks
         step = (step + 127) // 128 * 128          # whole 128-row tiles per block
         for lo in range(0, n, step):
@@ -216,6 +226,9 @@ class GAT2:
                 ev.record(cs)
             main.wait_event(ev)
             ops.linear(stage[lo:hi], W0, b0, out=res[lo:hi])
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._stage_free = (stage.data_ptr(), ev)
         a = ops.linear_small(res, W_att1, self.b_att1, transpose_out=True)
         if mode == "reflected":
             res, a, _ = ops.gat_forward_col_ex(g, a[0], r["s1"], self.bR1, res, self.slope, relu=True, reflect_in=r["v1"],

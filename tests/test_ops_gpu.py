@@ -298,6 +298,27 @@ def test_gat_col_variant_matches_oracle(orc, case, K):
     assert rel_err(got3, want_Y @ H) < FP32_TOL
 
 
+def test_forward_host_back_to_back_calls_do_not_clobber_the_staging_buffer(orc):
+    """GAT2.forward_host lets the next call's upload start while the previous call's aggregation still runs; three
+    un-synchronised calls with different inputs through ONE staging buffer must each give their own forward."""
+    from gala_b200.gat_model import GAT2
+    n, F_in = 30000, 602
+    t = graph_case(orc, n, 3000000, 21)
+    g = to_gpu_graph(t, 2048)
+    model = GAT2(F_in, 32, 41, DEV, seed=9)
+    gen = torch.Generator().manual_seed(4)
+    Xs = [(torch.rand(n, F_in, generator=gen) - 0.5).pin_memory() for _ in range(2)]
+    outs = [torch.empty(n, 41).pin_memory() for _ in range(3)]
+    stage = torch.empty(n, F_in, device=DEV)
+    for mode in ("reflected", "folded"):
+        for i, X in enumerate((Xs[0], Xs[1], Xs[0])):
+            model.forward_host(g, X, outs[i], chunks=4, mode=mode, stage=stage)
+        torch.cuda.synchronize()
+        want = [model.forward(g, X.to(DEV), mode="literal", dense="torch").cpu() for X in Xs]
+        for i, w in enumerate((want[0], want[1], want[0])):
+            assert float((outs[i] - w).double().norm() / w.double().norm()) < FP32_TOL, (mode, i)
+
+
 def test_gatn_reflected_and_folded_forwards_match_literal(orc):
     """3-layer GATN (the Papers-shape program): own-kernel forward in the original and in the reflected basis against
     the op-by-op forward with cuBLAS dense parts."""
