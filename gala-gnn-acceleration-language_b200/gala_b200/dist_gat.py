@@ -214,6 +214,23 @@ def gat2_forward_partitioned_folded(model, part, X_local, aggregate, hook=None):
     return F.linear(agg, *model.fc1)
 
 
+def gat2_forward_partitioned_reflected(model, part, X_local, aggregate_col, hook=None):
+    """The same forward with the hidden rows exchanged in the reflected basis of the layer that gathers them
+    (gat_model.GAT2.fold_reflected): the right-hand attention term is the last column of every exchanged row, so
+    nothing but the rows is exchanged and nothing is derived from gathered rows.  All-gather exchange (NCCL / gloo).
+      aggregate_col(aL_local, sR, bR, feats_all, relu, v_in, v_out) -> [rows, K]   (ops.gat_forward_col on the slab)"""
+    run = hook if hook is not None else (lambda name, fn: fn())
+    r = model.fold_reflected()
+    res_loc = F.linear(X_local, r["W0"], r["b0"])
+    aL = F.linear(res_loc, r["W_att1"][:1], model.b_att1[:1]).reshape(-1)
+    res_all = part.all_gather(res_loc)
+    y_loc = run("gat_layer1", lambda: aggregate_col(aL, r["s1"], model.bR1, res_all, True, r["v1"], r["v2"]))
+    aL = F.linear(y_loc, r["W_att2"][:1], model.b_att2[:1]).reshape(-1)
+    y_all = part.all_gather(y_loc)
+    agg = run("gat_layer2", lambda: aggregate_col(aL, r["s2"], model.bR2, y_all, False, r["v2"], None))
+    return F.linear(agg, *model.fc1)
+
+
 def gat2_forward_partitioned_dot(model, part, X_local, aggregate_dot, hook=None):
     """Same forward with the right-hand attention term recomputed inside the kernel
     (ops.gat_forward_dot): nothing but the hidden features is exchanged or re-derived."""
@@ -446,14 +463,21 @@ class PartitionedGAT:
     def _aggregate(self, aL, aR, feats, relu):
         return self.ops.gat_forward(self.graph, aL.contiguous(), aR.contiguous(), feats, self.model.slope, relu=relu)
 
+    def _aggregate_col(self, aL, sR, bR, feats, relu, v_in, v_out):
+        return self.ops.gat_forward_col(self.graph, aL.contiguous(), sR, bR, feats, self.model.slope, relu=relu,
+                                        reflect_in=v_in, reflect_out=v_out)
+
     def _aggregate_dot(self, aL, wR, bR, feats, relu):
         return self.ops.gat_forward_dot(self.graph, aL.contiguous(), wR, bR, feats, self.model.slope, relu=relu)
 
     def forward(self, X_local, hook=None, mode="reflected"):
         if mode == "reflected":
-            if self.px is not None and self.model.fc0[0].shape[0] in (4, 8, 16, 32):
+            if self.model.fc0[0].shape[0] not in (4, 8, 16, 32):
+                mode = "folded"
+            elif self.px is not None:
                 return self.forward_p2p_reflected(X_local, hook)
-            mode = "folded"
+            else:
+                return gat2_forward_partitioned_reflected(self.model, self.part, X_local, self._aggregate_col, hook)
         if self.px is not None and mode in ("folded", "fused"):
             return self.forward_p2p(X_local, hook)
         if mode == "dot":

@@ -33,6 +33,29 @@ def _oracle_aggregate(orc, part):
     return agg
 
 
+def _oracle_aggregate_col(orc, part):
+    """What gala_gat_forward_col_f32 computes on the slab, through the oracle's layer: the right-hand term from the last
+    column of the gathered rows, the finished rows reflected back / ReLU'd / reflected on."""
+    t = orc.Tiled.from_csr(part.rows, part.padded_n, part.offset.numpy(), part.cols.numpy())
+
+    def refl(y, v):
+        return y - 2.0 * (y @ v)[:, None] * v[None, :]
+
+    def agg(aL, sR, bR, feats, relu, v_in, v_out):
+        f = feats.numpy()
+        aR = (sR * f[:, -1].astype(np.float64) + bR).astype(np.float32)
+        y, _ = orc.gat_forward(t, aL.numpy(), aR, f)
+        y = torch.from_numpy(y).double()
+        if v_in is not None:
+            y = refl(y, v_in.double())
+        if relu:
+            y = torch.relu(y)
+        if v_out is not None:
+            y = refl(y, v_out.double())
+        return y.float()
+    return agg
+
+
 def rank_mode(rank):
     return "folded"     # both ranks must take the same collective sequence
 
@@ -50,8 +73,13 @@ def _worker(rank, world, port, n, e, feats, out_path):
     fwd = dist_gat.gat2_forward_partitioned if rank_mode(rank) == 'literal' else dist_gat.gat2_forward_partitioned_folded
     out_loc = fwd(model, part, X[part.row_lo:part.row_hi], _oracle_aggregate(orc, part))
     gathered = part.unpad(part.all_gather(out_loc))
+    # rows exchanged in the reflected basis (hidden width 8: one of the widths the column-mode kernel takes)
+    out_refl = dist_gat.gat2_forward_partitioned_reflected(model, part, X[part.row_lo:part.row_hi],
+                                                           _oracle_aggregate_col(orc, part))
+    gathered_refl = part.unpad(part.all_gather(out_refl))
     if rank == 0:
         np.save(out_path, gathered.numpy())
+        np.save(out_path + ".reflected.npy", gathered_refl.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -102,6 +130,7 @@ def test_two_rank_gloo_forward_matches_single_process(orc, tmp_path):
     a2 = agg(F.linear(tt, *model.efc2).reshape(-1), F.linear(tt, *model.efc3).reshape(-1), y, False)
     want = F.linear(a2, *model.fc1).numpy()
     assert rel_err(got, want) < 1e-5
+    assert rel_err(np.load(out_path + ".reflected.npy"), want) < 1e-5
 
 
 def _worker_deep(rank, world, port, n, e, dims, out_path):
