@@ -1022,8 +1022,9 @@ int launch_linear(const LinearParams& p, cudaStream_t st) {
 
 }  // namespace
 
-// Fewest 128-row tiles for which the persistent kernel (one CTA per SM) is used; below, the 2-CTA/SM kernel runs every
-// tile in one wave.
+// Fewest full 128-row tiles for which the persistent kernel (one CTA per SM) is used; below, the 2-CTA/SM kernel runs
+// every tile in one wave.  (Measured at the row counts a rank holds on 8 GPUs, profiles/r02_linear_small_m.txt: 29 121
+// rows 39.4 us persistent vs 35.1 us one-wave; equal from 58 242 rows on -- the default stays at 4.)
 #ifndef GALA_LINEAR_V2_MIN_TILES
 #define GALA_LINEAR_V2_MIN_TILES 4
 #endif
@@ -1076,7 +1077,7 @@ extern "C" int gala_linear_f32(const float* X, int64_t M, int32_t K, const float
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int64_t ntiles = (M + kBM - 1) / kBM;
     const bool v2 = (K % 2 == 0) && (reinterpret_cast<uintptr_t>(X) % 8 == 0) && (reinterpret_cast<uintptr_t>(W) % 8 == 0) &&
-                    ntiles >= GALA_LINEAR_V2_MIN_TILES;
+                    M >= (int64_t)GALA_LINEAR_V2_MIN_TILES * kBM;
     if (v2) {
         p.round_robin = (K >= 256 && ntiles >= 4 * (int64_t)device_sm_count()) ? 1 : 0;
         if (N <= 16) return launch_linear_v2<16>(p, st);
